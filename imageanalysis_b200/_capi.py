@@ -1,0 +1,271 @@
+"""ctypes binding of libiamatch.so (include/iamatch.h).
+
+This is the only place Python touches the native library.  There is no CPU
+fallback: if the shared object is missing or no sm_100 device is visible the
+constructor raises, and the `matcher` module surfaces that error instead of
+quietly calling OpenCV (BASELINE.json north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libiamatch.so")
+
+NORM_L2, NORM_HAMMING = 0, 1
+DTYPE_U8, DTYPE_F32 = 0, 1
+ENGINE_AUTO, ENGINE_UMMA, ENGINE_SIMT = 0, 1, 2
+REDUCE_LOWE, REDUCE_REF_METRIC = 0, 1
+MODEL_ESSENTIAL, MODEL_HOMOGRAPHY = 0, 1
+
+# every symbol include/iamatch.h declares; tests check the library exports them all
+EXPORTS = (
+    "iam_create", "iam_destroy", "iam_last_error", "iam_abi_version", "iam_set_stream",
+    "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
+    "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_release_descriptors", "iam_num_descriptors",
+    "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device",
+    "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+)
+
+
+class MatchParams(C.Structure):
+    _fields_ = [
+        ("match_ratio", C.c_double),
+        ("max_distance", C.c_double),
+        ("reduce_mode", C.c_int),
+        ("cap", C.c_int),
+        ("min_pairs", C.c_int),
+        ("cross_check", C.c_int),
+        ("dedupe", C.c_int),
+        ("reserved", C.c_int * 3),
+    ]
+
+
+class Timing(C.Structure):
+    _fields_ = [
+        ("knn_ms", C.c_float),
+        ("reduce_ms", C.c_float),
+        ("convert_ms", C.c_float),
+        ("knn_launches", C.c_int),
+        ("total_launches", C.c_int),
+        ("engine_used", C.c_int),
+        ("reserved", C.c_int * 2),
+    ]
+
+
+class IamError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libiamatch.so and declare signatures.  Raises IamError when the
+    library has not been built (run `python -m imageanalysis_b200.build`)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise IamError(
+            f"{p} not found: the CUDA extension is not built. "
+            "Run `python -m imageanalysis_b200.build` (needs nvcc); there is no CPU fallback."
+        )
+    lib = C.CDLL(p)
+    vp, ip, i32p, f32p = C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+    lib.iam_create.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.iam_destroy.argtypes = [vp]
+    lib.iam_last_error.restype = C.c_char_p
+    lib.iam_abi_version.restype = C.c_int
+    lib.iam_set_stream.argtypes = [vp, vp]
+    lib.iam_set_engine.argtypes = [vp, C.c_int]
+    lib.iam_synchronize.argtypes = [vp]
+    lib.iam_upload_descriptors.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+    lib.iam_upload_descriptors_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
+    lib.iam_upload_keypoint_keys.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.iam_release_descriptors.argtypes = [vp, C.c_int]
+    lib.iam_num_descriptors.argtypes = [vp, C.c_int]
+    lib.iam_descriptors_exact.argtypes = [vp, C.c_int]
+    lib.iam_knn_pairs.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.iam_match_pairs.argtypes = [vp, vp, C.c_int, C.POINTER(MatchParams), vp, vp, vp, vp]
+    lib.iam_match_pairs_device.argtypes = [vp, vp, C.c_int, C.POINTER(MatchParams), C.POINTER(vp), C.POINTER(vp)]
+    lib.iam_fetch_tables.argtypes = [vp, vp, vp]
+    lib.iam_ransac_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int,
+                                     C.c_uint32, vp, vp, vp]
+    lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
+    lib.iam_set_profiling.argtypes = [vp, C.c_int]
+    lib.iam_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("iam_last_error",):
+            fn.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One matching context on one GPU (wraps iam_ctx)."""
+
+    def __init__(self, norm: int, desc_bytes: int, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.norm = norm
+        self.desc_bytes = desc_bytes
+        self.device = device
+        rc = self._lib.iam_create(device, norm, desc_bytes, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise IamError(f"iam_create failed ({rc}): {self._lib.iam_last_error().decode()}")
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise IamError(f"{what} failed ({rc}): {self._lib.iam_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.iam_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        self._check(self._lib.iam_set_stream(self._h, C.c_void_p(cuda_stream or 0)), "iam_set_stream")
+
+    def set_engine(self, engine: int):
+        self._check(self._lib.iam_set_engine(self._h, engine), "iam_set_engine")
+
+    def synchronize(self):
+        self._check(self._lib.iam_synchronize(self._h), "iam_synchronize")
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.iam_set_profiling(self._h, int(on)), "iam_set_profiling")
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self._check(self._lib.iam_get_timing(self._h, C.byref(t)), "iam_get_timing")
+        return t
+
+    # -- descriptors --------------------------------------------------------
+    def upload(self, image_id: int, des: np.ndarray, pinned: bool = False):
+        """des: [N, D] float32 (SIFT) or uint8 (SIFT-as-u8 / ORB)."""
+        des = np.ascontiguousarray(des)
+        if des.ndim != 2 or des.shape[1] != self.desc_bytes:
+            raise IamError(f"descriptor array must be [N,{self.desc_bytes}], got {des.shape}")
+        if des.dtype == np.uint8:
+            dt = DTYPE_U8
+        elif des.dtype == np.float32:
+            dt = DTYPE_F32
+        else:
+            raise IamError(f"descriptor dtype {des.dtype} unsupported (uint8 / float32)")
+        self._check(self._lib.iam_upload_descriptors(self._h, image_id, _ptr(des), des.shape[0], dt, int(pinned)),
+                    "iam_upload_descriptors")
+
+    def upload_device(self, image_id: int, dptr: int, n: int, dtype: int):
+        self._check(self._lib.iam_upload_descriptors_device(self._h, image_id, C.c_void_p(dptr), n, dtype),
+                    "iam_upload_descriptors_device")
+
+    def upload_keypoint_keys(self, image_id: int, keys: np.ndarray):
+        keys = np.ascontiguousarray(keys, np.int32)
+        self._check(self._lib.iam_upload_keypoint_keys(self._h, image_id, _ptr(keys), keys.shape[0]),
+                    "iam_upload_keypoint_keys")
+
+    def release(self, image_id: int):
+        self._check(self._lib.iam_release_descriptors(self._h, image_id), "iam_release_descriptors")
+
+    def num_descriptors(self, image_id: int) -> int:
+        return self._lib.iam_num_descriptors(self._h, image_id)
+
+    def descriptors_exact(self, image_id: int) -> int:
+        return self._lib.iam_descriptors_exact(self._h, image_id)
+
+    # -- kNN ------------------------------------------------------------------
+    def knn_pairs(self, pairs: Sequence[Tuple[int, int]], k: int, n_stride: int, reverse: bool = True):
+        """Returns (idx_fwd, dist_fwd, idx_rev, dist_rev); arrays are [P, n_stride, k]
+        with -1 / NaN in rows beyond an image's descriptor count."""
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        P = pr.shape[0]
+        idx_f = np.full((P, n_stride, k), -1, np.int32)
+        dst_f = np.full((P, n_stride, k), np.nan, np.float32)
+        idx_r = np.full((P, n_stride, k), -1, np.int32) if reverse else None
+        dst_r = np.full((P, n_stride, k), np.nan, np.float32) if reverse else None
+        self._check(self._lib.iam_knn_pairs(self._h, _ptr(pr), P, k, n_stride, _ptr(idx_f), _ptr(dst_f), _ptr(idx_r),
+                                            _ptr(dst_r)), "iam_knn_pairs")
+        return idx_f, dst_f, idx_r, dst_r
+
+    # -- full match -------------------------------------------------------------
+    @staticmethod
+    def make_params(match_ratio=0.75, max_distance=270.0, reduce_mode=REDUCE_REF_METRIC, cap=2000, min_pairs=25,
+                    cross_check=True, dedupe=False) -> MatchParams:
+        p = MatchParams()
+        p.match_ratio = float(match_ratio)
+        p.max_distance = float(max_distance)
+        p.reduce_mode = int(reduce_mode)
+        p.cap = int(cap)
+        p.min_pairs = int(min_pairs)
+        p.cross_check = int(bool(cross_check))
+        p.dedupe = int(bool(dedupe))
+        return p
+
+    def match_pairs(self, pairs, params: MatchParams, want_reverse: bool = False):
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        P = pr.shape[0]
+        table = np.empty((P, params.cap, 2), np.int32)
+        count = np.zeros((P,), np.int32)
+        rtable = np.empty((P, params.cap, 2), np.int32) if want_reverse else None
+        rcount = np.zeros((P,), np.int32) if want_reverse else None
+        self._check(self._lib.iam_match_pairs(self._h, _ptr(pr), P, C.byref(params), _ptr(table), _ptr(count),
+                                              _ptr(rtable), _ptr(rcount)), "iam_match_pairs")
+        if want_reverse:
+            return table, count, rtable, rcount
+        return table, count
+
+    def match_pairs_device(self, pairs: np.ndarray, params: MatchParams) -> Tuple[int, int]:
+        """Enqueue only; results stay on the device.  Returns (d_table, d_count) raw pointers."""
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        dt, dc = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.iam_match_pairs_device(self._h, _ptr(pr), pr.shape[0], C.byref(params), C.byref(dt),
+                                                     C.byref(dc)), "iam_match_pairs_device")
+        return dt.value or 0, dc.value or 0
+
+    def fetch_tables(self, n_pairs: int, cap: int):
+        table = np.empty((n_pairs, cap, 2), np.int32)
+        count = np.zeros((n_pairs,), np.int32)
+        self._check(self._lib.iam_fetch_tables(self._h, _ptr(table), _ptr(count)), "iam_fetch_tables")
+        return table, count
+
+    def debug_tile(self, q_id, t_id, q_tile=0, t_tile=0, lbo=128, sbo=2304, kstep_bytes=256, ksteps=9):
+        out = np.zeros((128, 128), np.float32)
+        self._check(self._lib.iam_debug_tile(self._h, q_id, t_id, q_tile, t_tile, lbo, sbo, kstep_bytes, ksteps,
+                                             _ptr(out)), "iam_debug_tile")
+        return out
+
+    # -- RANSAC -----------------------------------------------------------------
+    def ransac_pairs(self, model: int, pts1: np.ndarray, pts2: np.ndarray, offsets: np.ndarray, K: Optional[np.ndarray],
+                     threshold: float, prob: float = 0.999, max_iters: int = 1000, seed: int = 0):
+        pts1 = np.ascontiguousarray(pts1, np.float32).reshape(-1, 2)
+        pts2 = np.ascontiguousarray(pts2, np.float32).reshape(-1, 2)
+        off = np.ascontiguousarray(offsets, np.int32)
+        P = off.shape[0] - 1
+        Kc = None if K is None else np.ascontiguousarray(K, np.float64).reshape(3, 3)
+        mask = np.zeros((pts1.shape[0],), np.uint8)
+        model_out = np.zeros((P, 9), np.float64)
+        inl = np.zeros((P,), np.int32)
+        self._check(self._lib.iam_ransac_pairs(self._h, model, _ptr(pts1), _ptr(pts2), _ptr(off), P, _ptr(Kc),
+                                               float(threshold), float(prob), int(max_iters), int(seed), _ptr(mask),
+                                               _ptr(model_out), _ptr(inl)), "iam_ransac_pairs")
+        return mask, model_out.reshape(P, 3, 3), inl

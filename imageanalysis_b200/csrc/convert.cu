@@ -1,0 +1,225 @@
+// convert.cu — descriptor upload-side layout conversion.
+//
+// Host rows (what OpenCV produced: float32 [N,128] integer-valued SIFT, or
+// uint8 [N,32] ORB; reference image.py:160-180) become
+//   raw    : packed u8 rows for the SIMT engine
+//   a_form : query-role tcgen05 operand  [q , 1, 2048, 2048, 1, nq0..nq3 ...]
+//   b_form : train-role tcgen05 operand  [-2t, nt0..nt3, 1, 2048, 2048, 1 ...]
+// in the tiled layout of layout.h, so that A'.B' = ||q||^2 + ||t||^2 - 2 q.t
+// = the exact squared distance.  For Hamming the 256 bits become e4m3
+// {0,1} / {0,-2} bytes and the popcounts ride in the augmentation step.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "knn.h"
+#include "layout.h"
+
+namespace iam {
+namespace {
+
+__device__ __forceinline__ size_t row_base(int r) {
+  return static_cast<size_t>(r >> 3) * kGroupBytes + static_cast<size_t>(r & 7) * 16;
+}
+
+// e4m3 encodings of the small integers 0..16 and 256.
+__device__ __forceinline__ uint8_t e4m3_small(int n) {
+  const uint8_t tbl[17] = {0x00, 0x38, 0x40, 0x44, 0x48, 0x4A, 0x4C, 0x4E, 0x50,
+                           0x51, 0x52, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58};
+  return tbl[n];
+}
+
+// norm -> four fp16 terms with  n = x0 + 2048*x1 + 2048*x2 + x3  (exact for
+// integer n < 2^24; ~33 significant bits otherwise)
+__device__ __forceinline__ void split_norm(float n, __half (&x)[4]) {
+  const float h2 = floorf(n * (1.0f / 4194304.0f));        // n / 2^22
+  const float r = n - h2 * 4194304.0f;
+  const float h1 = floorf(r * (1.0f / 2048.0f));
+  const float h0 = r - h1 * 2048.0f;
+  x[0] = __float2half_rn(h0);
+  x[1] = __float2half_rn(h1);
+  x[2] = __float2half_rn(h2 * 2048.0f);
+  x[3] = __float2half_rn(h0 - __half2float(x[0]));
+}
+
+// One warp per row, 8 warps (one 8-row core-matrix group) per block.
+template <typename SrcT>
+__global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict__ src, int dim, int n, int n_pad,
+                                                         uint8_t* __restrict__ raw, uint8_t* __restrict__ a_form,
+                                                         uint8_t* __restrict__ b_form, int* __restrict__ exact_flag) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n_pad) return;
+  const bool valid = r < n;
+
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  bool exact = true;
+  if (valid) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = lane * 4 + e;
+      if (k < dim) {
+        const float x = static_cast<float>(src[static_cast<size_t>(r) * dim + k]);
+        exact = exact && (x == rintf(x)) && (x >= 0.f) && (x <= 255.f);
+        v[e] = x;
+      }
+    }
+  }
+  __half h[4];
+  float nrm = 0.f;
+  uint32_t rawword = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = __float2half_rn(v[e]);
+    const float hv = __half2float(h[e]);
+    nrm += hv * hv;  // exact for integer inputs: every partial < 2^24
+    const int q = static_cast<int>(fminf(fmaxf(rintf(v[e]), 0.f), 255.f));
+    rawword |= static_cast<uint32_t>(q) << (8 * e);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
+  if (!__all_sync(0xffffffffu, exact) && lane == 0) atomicAnd(exact_flag, 0);
+
+  // raw u8 row (dim bytes, word `lane`)
+  if (lane * 4 < dim) reinterpret_cast<uint32_t*>(raw + static_cast<size_t>(r) * dim)[lane] = rawword;
+
+  // data chunks: lane -> chunk lane/2, half-chunk lane%2 (8 bytes = 4 halfs)
+  const size_t base = row_base(r) + static_cast<size_t>(lane >> 1) * 128 + static_cast<size_t>(lane & 1) * 8;
+  {
+    __half2 a01 = __halves2half2(h[0], h[1]), a23 = __halves2half2(h[2], h[3]);
+    uint2 av;
+    av.x = *reinterpret_cast<uint32_t*>(&a01);
+    av.y = *reinterpret_cast<uint32_t*>(&a23);
+    *reinterpret_cast<uint2*>(a_form + base) = av;
+    __half2 b01 = __halves2half2(__float2half_rn(-2.f * __half2float(h[0])), __float2half_rn(-2.f * __half2float(h[1])));
+    __half2 b23 = __halves2half2(__float2half_rn(-2.f * __half2float(h[2])), __float2half_rn(-2.f * __half2float(h[3])));
+    uint2 bv;
+    bv.x = *reinterpret_cast<uint32_t*>(&b01);
+    bv.y = *reinterpret_cast<uint32_t*>(&b23);
+    *reinterpret_cast<uint2*>(b_form + base) = bv;
+  }
+  // augmentation chunks 16 and 17 (16 halfs): lanes 0..15 write one half each
+  if (lane < 16) {
+    __half x[4];
+    split_norm(nrm, x);
+    const __half one = __float2half_rn(1.f), k2048 = __float2half_rn(2048.f), zero = __float2half_rn(0.f);
+    __half av = zero, bv = zero;
+    if (valid) {
+      // A: [1, 2048, 2048, 1, n0, n1, n2, n3, 0...]   B: [n0, n1, n2, n3, 1, 2048, 2048, 1, 0...]
+      switch (lane) {
+        case 0: av = one;   bv = x[0]; break;
+        case 1: av = k2048; bv = x[1]; break;
+        case 2: av = k2048; bv = x[2]; break;
+        case 3: av = one;   bv = x[3]; break;
+        case 4: av = x[0];  bv = one; break;
+        case 5: av = x[1];  bv = k2048; break;
+        case 6: av = x[2];  bv = k2048; break;
+        case 7: av = x[3];  bv = one; break;
+        default: break;
+      }
+    } else {
+      // padding train rows: distance = ||q||^2 + 2^24, larger than any real one
+      if (lane == 1) bv = __float2half_rn(8192.f);
+    }
+    const size_t abase = row_base(r) + static_cast<size_t>(16 + (lane >> 3)) * 128 + static_cast<size_t>(lane & 7) * 2;
+    *reinterpret_cast<__half*>(a_form + abase) = av;
+    *reinterpret_cast<__half*>(b_form + abase) = bv;
+  }
+}
+
+__global__ void __launch_bounds__(256) convert_hamming_kernel(const uint8_t* __restrict__ src, int nbytes, int n,
+                                                              int n_pad, uint8_t* __restrict__ raw,
+                                                              uint8_t* __restrict__ a_form,
+                                                              uint8_t* __restrict__ b_form) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= n_pad) return;
+  const bool valid = r < n;
+  uint32_t byte = 0;
+  if (valid && lane < nbytes) byte = src[static_cast<size_t>(r) * nbytes + lane];
+  if (lane < nbytes) raw[static_cast<size_t>(r) * nbytes + lane] = static_cast<uint8_t>(byte);
+  int pc = __popc(byte);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+
+  // element index = 8*lane + bit (bit 0 = LSB; any fixed order works as both operands agree)
+  uint32_t a_lo = 0, a_hi = 0, b_lo = 0, b_hi = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    if (byte & (1u << b)) {
+      a_lo |= 0x38u << (8 * b);  // 1.0
+      b_lo |= 0xC0u << (8 * b);  // -2.0
+    }
+    if (byte & (1u << (b + 4))) {
+      a_hi |= 0x38u << (8 * b);
+      b_hi |= 0xC0u << (8 * b);
+    }
+  }
+  const size_t base = row_base(r) + static_cast<size_t>(lane >> 1) * 128 + static_cast<size_t>(lane & 1) * 8;
+  *reinterpret_cast<uint2*>(a_form + base) = make_uint2(a_lo, a_hi);
+  *reinterpret_cast<uint2*>(b_form + base) = make_uint2(b_lo, b_hi);
+
+  // augmentation: 32 e4m3 elements in chunks 16,17; one byte per lane
+  const int d0 = pc & 15, d1 = pc >> 4;  // pc = d0 + 16*d1, d1 <= 16
+  uint8_t av = 0, bv = 0;
+  if (valid) {
+    // A: [1, 16, p0, p1, 16, ...]   B: [p0, p1, 1, 16, 0, ...]
+    switch (lane) {
+      case 0: av = 0x38; bv = e4m3_small(d0); break;
+      case 1: av = 0x58; bv = e4m3_small(d1); break;
+      case 2: av = e4m3_small(d0); bv = 0x38; break;
+      case 3: av = e4m3_small(d1); bv = 0x58; break;
+      case 4: av = 0x58; bv = 0x00; break;
+      default: break;
+    }
+  } else {
+    if (lane == 4) bv = 0x78;  // 16 * 256 = 4096 > any Hamming distance
+  }
+  const size_t abase = row_base(r) + static_cast<size_t>(16 + (lane >> 4)) * 128 + static_cast<size_t>(lane & 15);
+  a_form[abase] = av;
+  b_form[abase] = bv;
+}
+
+__global__ void finish_dist_kernel(int norm, float* __restrict__ d, int* __restrict__ idx, size_t count) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float x = d[i];
+  const float pad_thr = (norm == 0) ? 16777216.0f : 257.0f;  // padding rows sit at >= 2^24 (L2) / >= 4096 (Hamming)
+  if (x >= pad_thr || idx[i] < 0) {  // neighbour slot filled by a padding row (fewer than k train rows)
+    idx[i] = -1;
+    d[i] = __int_as_float(0x7f800000);
+    return;
+  }
+  if (norm == 0) d[i] = sqrtf(x);  // correctly rounded; matches cv2's float sqrt of the exact sum
+}
+
+}  // namespace
+
+cudaError_t launch_convert(int norm, int raw_bytes, const void* src, int src_dtype, int n, int n_pad, uint8_t* raw,
+                           uint8_t* a_form, uint8_t* b_form, int* exact_flag, cudaStream_t stream) {
+  const int blocks = n_pad / 8;
+  if (blocks <= 0) return cudaSuccess;
+  if (norm == 0) {
+    if (raw_bytes > 128 || (raw_bytes & 3)) return cudaErrorInvalidValue;
+    if (src_dtype == 0)
+      convert_l2_kernel<uint8_t><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(src), raw_bytes, n, n_pad,
+                                                             raw, a_form, b_form, exact_flag);
+    else
+      convert_l2_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), raw_bytes, n, n_pad, raw,
+                                                           a_form, b_form, exact_flag);
+  } else {
+    if (raw_bytes > 32 || src_dtype != 0) return cudaErrorInvalidValue;
+    convert_hamming_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(src), raw_bytes, n, n_pad, raw,
+                                                       a_form, b_form);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finish_dist(int norm, float* d, int* idx, size_t count, cudaStream_t stream) {
+  if (count == 0) return cudaSuccess;
+  const int threads = 256;
+  const size_t blocks = (count + threads - 1) / threads;
+  finish_dist_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(norm, d, idx, count);
+  return cudaGetLastError();
+}
+
+}  // namespace iam

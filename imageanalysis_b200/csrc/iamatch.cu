@@ -1,0 +1,696 @@
+// iamatch.cu — the C-ABI of libiamatch.so (declared in include/iamatch.h):
+// context, descriptor residency, work-list construction and kernel
+// sequencing.  Device code lives in knn_umma.cu / knn_simt.cu / convert.cu /
+// reduce.cu / ransac.cu.  No CPU compute path exists here by design: every
+// entry point either runs CUDA kernels or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/iamatch.h"
+#include "knn.h"
+#include "layout.h"
+#include "ransac.h"
+#include "reduce.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(e__ == cudaErrorMemoryAllocation ? IAM_E_NOMEM : IAM_E_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                               \
+  } while (0)
+
+struct Buffer {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct Image {
+  int* keys = nullptr;
+  uint8_t* block = nullptr;
+  size_t block_bytes = 0;
+  int n = -1;
+  int n_pad = 0;
+  int exact = 1;
+  iam::ImgDev dev{};
+};
+
+struct Plan {
+  std::vector<iam::KnnUnit> units;
+  std::vector<iam::RedJob> jobs;
+  std::vector<int> chunk_pair_begin;  // pair index where each chunk starts (+ sentinel)
+  std::vector<int> chunk_unit_begin;
+  std::vector<size_t> chunk_rows;
+  int max_n = 0;
+  size_t max_chunk_rows = 0;
+};
+
+}  // namespace
+
+struct iam_ctx {
+  int device = 0;
+  int norm = 0;
+  int desc_bytes = 0;
+  int num_sms = 0;
+  int engine = IAM_ENGINE_AUTO;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<Image> images;
+  bool imgs_dirty = true;
+  Buffer d_imgs, stage, exact_flag;
+  Buffer units, jobs, knn_idx, knn_dist, cand_metric, cand_qt, job_table, job_count, out_table, out_count, packed_i,
+      packed_d;
+  int last_pairs = 0, last_cap = 0;
+  Plan plan;                 // cached work list: rebuilt only when the pair list or an image's size changes
+  uint64_t plan_key = 0;
+  bool plan_valid = false;
+  uint64_t shape_epoch = 1;
+  bool timing_pending = false;
+  bool profiling = false;
+  cudaEvent_t ev[6] = {};
+  iam_timing timing{};
+};
+
+namespace {
+
+int bind(iam_ctx* c) {
+  if (!c) return fail(IAM_E_ARG, "null context");
+  CU(cudaSetDevice(c->device));
+  return IAM_OK;
+}
+
+int raw_row_bytes(const iam_ctx* c) { return c->desc_bytes; }
+
+bool umma_capable(const iam_ctx* c) {
+  return (c->norm == IAM_NORM_L2 && c->desc_bytes <= 128 && c->desc_bytes % 4 == 0) ||
+         (c->norm == IAM_NORM_HAMMING && c->desc_bytes <= 32);
+}
+bool simt_capable(const iam_ctx* c) { return c->desc_bytes == 32 || c->desc_bytes == 64 || c->desc_bytes == 128; }
+
+int sync_imgs(iam_ctx* c) {
+  if (!c->imgs_dirty) return IAM_OK;
+  const size_t n = c->images.size();
+  if (n == 0) return IAM_OK;
+  std::vector<iam::ImgDev> host(n);
+  for (size_t i = 0; i < n; ++i) host[i] = c->images[i].dev;
+  CU(c->d_imgs.ensure(n * sizeof(iam::ImgDev)));
+  CU(cudaMemcpyAsync(c->d_imgs.p, host.data(), n * sizeof(iam::ImgDev), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // `host` goes out of scope
+  c->imgs_dirty = false;
+  return IAM_OK;
+}
+
+int check_image(const iam_ctx* c, int id) {
+  if (id < 0 || id >= (int)c->images.size() || c->images[id].n < 0)
+    return fail(IAM_E_STATE, "image %d has no descriptors uploaded", id);
+  return IAM_OK;
+}
+
+int pick_engine(const iam_ctx* c, const int32_t* pairs, int n_pairs, int* engine) {
+  int e = c->engine;
+  if (e == IAM_ENGINE_AUTO) e = umma_capable(c) ? IAM_ENGINE_UMMA : IAM_ENGINE_SIMT;
+  if (e == IAM_ENGINE_UMMA && !umma_capable(c)) return fail(IAM_E_UNSUPPORTED, "descriptor size %d has no tensor-core layout", c->desc_bytes);
+  if (e == IAM_ENGINE_SIMT) {
+    if (!simt_capable(c)) return fail(IAM_E_UNSUPPORTED, "SIMT engine supports 32/64/128-byte descriptors, got %d", c->desc_bytes);
+    for (int p = 0; p < n_pairs * 2; ++p)
+      if (!c->images[pairs[p]].exact) return fail(IAM_E_UNSUPPORTED, "SIMT engine needs integer-valued descriptors (image %d)", pairs[p]);
+  }
+  *engine = e;
+  return IAM_OK;
+}
+
+// Two directed jobs per pair (2p: i->j, 2p+1: j->i); out_base restarts per chunk.
+int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, Plan* pl) {
+  size_t budget_mb = 768;  // kNN output workspace per chunk; IAM_CHUNK_MB overrides (tests force many chunks)
+  if (const char* env = getenv("IAM_CHUNK_MB")) budget_mb = std::max(1, atoi(env));
+  const size_t budget_rows = (budget_mb << 20) / (size_t(k) * 8);
+  size_t rows = 0;
+  pl->chunk_pair_begin.push_back(0);
+  pl->chunk_unit_begin.push_back(0);
+  for (int p = 0; p < n_pairs; ++p) {
+    const int i = pairs[2 * p], j = pairs[2 * p + 1];
+    int rc;
+    if ((rc = check_image(c, i)) != IAM_OK || (rc = check_image(c, j)) != IAM_OK) return rc;
+    const Image& a = c->images[i];
+    const Image& b = c->images[j];
+    const size_t need = size_t(a.n_pad) + (both ? size_t(b.n_pad) : 0);
+    if (rows > 0 && rows + need > budget_rows) {
+      pl->chunk_rows.push_back(rows);
+      pl->max_chunk_rows = std::max(pl->max_chunk_rows, rows);
+      pl->chunk_pair_begin.push_back(p);
+      pl->chunk_unit_begin.push_back((int)pl->units.size());
+      rows = 0;
+    }
+    for (int dir = 0; dir < (both ? 2 : 1); ++dir) {
+      const int qs = dir ? j : i, ts = dir ? i : j;
+      const Image& q = c->images[qs];
+      const Image& t = c->images[ts];
+      iam::RedJob jb{(int)rows, q.n, t.n, qs, ts, {0, 0, 0}};
+      pl->jobs.push_back(jb);
+      const int supers = (q.n + iam::kSuperRows - 1) / iam::kSuperRows;
+      for (int s = 0; s < supers; ++s) pl->units.push_back(iam::KnnUnit{qs, ts, s, (int)rows});
+      rows += q.n_pad;
+      pl->max_n = std::max(pl->max_n, std::max(q.n, t.n));
+    }
+  }
+  pl->chunk_rows.push_back(rows);
+  pl->max_chunk_rows = std::max(pl->max_chunk_rows, rows);
+  pl->chunk_pair_begin.push_back(n_pairs);
+  pl->chunk_unit_begin.push_back((int)pl->units.size());
+  return IAM_OK;
+}
+
+uint64_t plan_hash(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](uint64_t v) {
+    for (int b = 0; b < 8; ++b) {
+      h ^= (v >> (8 * b)) & 0xff;
+      h *= 1099511628211ull;
+    }
+  };
+  mix(c->shape_epoch);
+  mix(uint64_t(n_pairs));
+  mix(uint64_t(k) * 2 + (both ? 1 : 0));
+  if (const char* env = getenv("IAM_CHUNK_MB")) mix(uint64_t(atoi(env)) + 77);
+  for (int i = 0; i < 2 * n_pairs; ++i) mix(uint64_t(uint32_t(pairs[i])));
+  return h | 1ull;
+}
+
+int upload_plan(iam_ctx* c, const Plan& pl);
+
+// Build (or reuse) the work list for this pair list and make it resident.
+int prepare_plan(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both) {
+  const uint64_t key = plan_hash(c, pairs, n_pairs, k, both);
+  if (c->plan_valid && c->plan_key == key) return IAM_OK;
+  c->plan_valid = false;
+  c->plan = Plan{};
+  int rc = build_plan(c, pairs, n_pairs, k, both, &c->plan);
+  if (rc != IAM_OK) return rc;
+  if ((rc = upload_plan(c, c->plan)) != IAM_OK) return rc;
+  c->plan_key = key;
+  c->plan_valid = true;
+  return IAM_OK;
+}
+
+int upload_plan(iam_ctx* c, const Plan& pl) {
+  CU(c->units.ensure(std::max<size_t>(1, pl.units.size()) * sizeof(iam::KnnUnit)));
+  CU(c->jobs.ensure(std::max<size_t>(1, pl.jobs.size()) * sizeof(iam::RedJob)));
+  if (!pl.units.empty())
+    CU(cudaMemcpyAsync(c->units.p, pl.units.data(), pl.units.size() * sizeof(iam::KnnUnit), cudaMemcpyHostToDevice, c->stream));
+  if (!pl.jobs.empty())
+    CU(cudaMemcpyAsync(c->jobs.p, pl.jobs.data(), pl.jobs.size() * sizeof(iam::RedJob), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // pageable sources must outlive the copies
+  return IAM_OK;
+}
+
+int launch_knn(iam_ctx* c, int engine, int k, int unit_begin, int n_units) {
+  const iam::KnnUnit* u = c->units.as<iam::KnnUnit>() + unit_begin;
+  cudaError_t e;
+  if (engine == IAM_ENGINE_UMMA)
+    e = iam::launch_knn_umma(c->norm, k, c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->num_sms, c->stream);
+  else
+    e = iam::launch_knn_simt(c->norm, k, raw_row_bytes(c), c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "kNN launch failed: %s", cudaGetErrorString(e));
+  c->timing.knn_launches += 1;
+  c->timing.total_launches += 1;
+  c->timing.engine_used = engine;
+  return IAM_OK;
+}
+
+__global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jobs, int dirs, int dir, int k, int n_stride,
+                                const int* idx, const float* dist, int* out_i, float* out_d) {
+  // grid.x = job (of this direction) within the chunk, threads stride over rows*k
+  const int jl = blockIdx.x;
+  const iam::RedJob jb = jobs[job_begin + jl * dirs + dir];
+  const size_t src = size_t(jb.out_base) * k;
+  const size_t dst = size_t(jl) * n_stride * k;
+  const int rows = min(jb.n_q, n_stride);
+  for (int e = threadIdx.x; e < rows * k; e += blockDim.x) {
+    out_i[dst + e] = idx[src + e];
+    out_d[dst + e] = dist[src + e];
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int iam_abi_version(void) { return 1; }
+const char* iam_last_error(void) { return g_err.c_str(); }
+
+int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
+  if (!out) return fail(IAM_E_ARG, "out is null");
+  *out = nullptr;
+  if (norm != IAM_NORM_L2 && norm != IAM_NORM_HAMMING) return fail(IAM_E_ARG, "unknown norm %d", norm);
+  if (desc_bytes <= 0 || desc_bytes > 128 || (desc_bytes & 3)) return fail(IAM_E_ARG, "descriptor size %d not in 4..128 (multiple of 4)", desc_bytes);
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(IAM_E_CUDA, "CUDA device %d not present (%d visible)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(IAM_E_CUDA, "libiamatch is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+  iam_ctx* c = new (std::nothrow) iam_ctx();
+  if (!c) return fail(IAM_E_NOMEM, "host allocation failed");
+  c->device = device;
+  c->norm = norm;
+  c->desc_bytes = desc_bytes;
+  c->num_sms = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(IAM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  c->stream = c->own_stream;
+  for (auto& ev : c->ev) cudaEventCreate(&ev);
+  *out = c;
+  return IAM_OK;
+}
+
+int iam_destroy(iam_ctx* c) {
+  if (!c) return IAM_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& im : c->images) {
+    if (im.block) cudaFree(im.block);
+    if (im.keys) cudaFree(im.keys);
+  }
+  Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->exact_flag, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
+                    &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
+  for (Buffer* b : bufs) b->release();
+  for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return IAM_OK;
+}
+
+int iam_set_stream(iam_ctx* c, void* s) {
+  int rc = bind(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+  return IAM_OK;
+}
+
+int iam_set_engine(iam_ctx* c, int engine) {
+  if (!c) return fail(IAM_E_ARG, "null context");
+  if (engine < IAM_ENGINE_AUTO || engine > IAM_ENGINE_SIMT) return fail(IAM_E_ARG, "unknown engine %d", engine);
+  c->engine = engine;
+  return IAM_OK;
+}
+
+int iam_synchronize(iam_ctx* c) {
+  int rc = bind(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_set_profiling(iam_ctx* c, int enable) {
+  if (!c) return fail(IAM_E_ARG, "null context");
+  c->profiling = enable != 0;
+  return IAM_OK;
+}
+
+int iam_get_timing(iam_ctx* c, iam_timing* out) {
+  if (!c || !out) return fail(IAM_E_ARG, "null argument");
+  if (c->timing_pending) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->ev[2]));
+    CU(cudaEventElapsedTime(&c->timing.knn_ms, c->ev[0], c->ev[1]));
+    CU(cudaEventElapsedTime(&c->timing.reduce_ms, c->ev[1], c->ev[2]));
+    c->timing_pending = false;
+  }
+  *out = c->timing;
+  return IAM_OK;
+}
+
+static int upload_common(iam_ctx* c, int id, const void* dsrc, int n, int dtype) {
+  if ((int)c->images.size() <= id) c->images.resize(id + 1);
+  Image& im = c->images[id];
+  const int n_pad = std::max(iam::kSuperRows, iam::round_up(n, iam::kSuperRows));
+  const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
+  const size_t form_b = iam::form_bytes(n_pad);
+  const size_t total = raw_b + 2 * form_b;
+  if (im.block_bytes < total) {
+    if (im.block) CU(cudaFree(im.block));
+    im.block = nullptr;
+    im.block_bytes = 0;
+    CU(cudaMalloc(reinterpret_cast<void**>(&im.block), total));
+    im.block_bytes = total;
+  }
+  if (im.n != n || im.n_pad != n_pad) c->shape_epoch++;
+  im.n = n;
+  im.n_pad = n_pad;
+  im.dev.raw = im.block;
+  im.dev.a_form = im.block + raw_b;
+  im.dev.b_form = im.block + raw_b + form_b;
+  im.dev.n = n;
+  im.dev.n_pad = n_pad;
+  if (im.keys) {  // keys belong to the previous descriptor set
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(im.keys));
+    im.keys = nullptr;
+  }
+  im.dev.kp_key = nullptr;
+  c->imgs_dirty = true;
+
+  CU(c->exact_flag.ensure(sizeof(int)));
+  const int one = 1;
+  CU(cudaMemcpyAsync(c->exact_flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (c->profiling) CU(cudaEventRecord(c->ev[4], c->stream));
+  cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block, im.block + raw_b,
+                                      im.block + raw_b + form_b, c->exact_flag.as<int>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "convert launch: %s", cudaGetErrorString(e));
+  c->timing.total_launches += 1;
+  if (c->profiling) CU(cudaEventRecord(c->ev[5], c->stream));
+  int flag = 1;
+  if (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) {
+    CU(cudaMemcpyAsync(&flag, c->exact_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  im.exact = flag;
+  if (c->profiling) {
+    CU(cudaEventSynchronize(c->ev[5]));
+    CU(cudaEventElapsedTime(&c->timing.convert_ms, c->ev[4], c->ev[5]));
+  }
+  return IAM_OK;
+}
+
+int iam_upload_descriptors(iam_ctx* c, int id, const void* ptr, int n, int dtype, int pinned) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (id < 0 || id > (1 << 24)) return fail(IAM_E_ARG, "bad image id %d", id);
+  if (n < 0 || (n > 0 && !ptr)) return fail(IAM_E_ARG, "bad descriptor buffer");
+  if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
+  if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
+  const size_t bytes = size_t(n) * c->desc_bytes * (dtype == IAM_DTYPE_F32 ? 4 : 1);
+  CU(c->stage.ensure(std::max<size_t>(bytes, 256)));
+  if (bytes) CU(cudaMemcpyAsync(c->stage.p, ptr, bytes, cudaMemcpyHostToDevice, c->stream));
+  (void)pinned;
+  return upload_common(c, id, c->stage.p, n, dtype);
+}
+
+int iam_upload_descriptors_device(iam_ctx* c, int id, const void* dptr, int n, int dtype) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (id < 0 || id > (1 << 24)) return fail(IAM_E_ARG, "bad image id %d", id);
+  if (n < 0 || (n > 0 && !dptr)) return fail(IAM_E_ARG, "bad descriptor buffer");
+  if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
+  if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
+  return upload_common(c, id, dptr, n, dtype);
+}
+
+int iam_release_descriptors(iam_ctx* c, int id) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (id < 0 || id >= (int)c->images.size()) return IAM_OK;
+  Image& im = c->images[id];
+  CU(cudaStreamSynchronize(c->stream));
+  if (im.block) CU(cudaFree(im.block));
+  if (im.keys) CU(cudaFree(im.keys));
+  im = Image{};
+  c->shape_epoch++;
+  c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+int iam_upload_keypoint_keys(iam_ctx* c, int id, const int32_t* keys, int n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = check_image(c, id)) != IAM_OK) return rc;
+  Image& im = c->images[id];
+  if (n != im.n || (n > 0 && !keys)) return fail(IAM_E_ARG, "keys must have one entry per descriptor (%d), got %d", im.n, n);
+  for (int i = 0; i < n; ++i)
+    if (keys[i] < 0 || keys[i] >= n) return fail(IAM_E_ARG, "key %d out of range [0,%d) at %d", keys[i], n, i);
+  if (im.keys) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(im.keys));
+    im.keys = nullptr;
+  }
+  if (n > 0) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&im.keys), size_t(n) * sizeof(int)));
+    CU(cudaMemcpyAsync(im.keys, keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  im.dev.kp_key = im.keys;
+  c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+int iam_num_descriptors(iam_ctx* c, int id) {
+  if (!c || id < 0 || id >= (int)c->images.size()) return -1;
+  return c->images[id].n;
+}
+
+int iam_descriptors_exact(iam_ctx* c, int id) {
+  if (!c || id < 0 || id >= (int)c->images.size() || c->images[id].n < 0) return -1;
+  return c->images[id].exact;
+}
+
+int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_stride, int32_t* out_idx_fwd,
+                  float* out_dist_fwd, int32_t* out_idx_rev, float* out_dist_rev) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_pairs < 0 || (n_pairs && !pairs)) return fail(IAM_E_ARG, "bad pair list");
+  if (k < 1 || k > 3) return fail(IAM_E_ARG, "k=%d unsupported (1..3; the reference uses 2 and 3)", k);
+  if (!out_idx_fwd || !out_dist_fwd) return fail(IAM_E_ARG, "forward outputs are required");
+  if ((out_idx_rev == nullptr) != (out_dist_rev == nullptr)) return fail(IAM_E_ARG, "reverse outputs must both be given or both be null");
+  if (n_stride <= 0) return fail(IAM_E_ARG, "n_stride must be positive");
+  const bool both = out_idx_rev != nullptr;
+  if ((rc = prepare_plan(c, pairs, n_pairs, k, both)) != IAM_OK) return rc;
+  const Plan& pl = c->plan;
+  int engine;
+  if ((rc = pick_engine(c, pairs, n_pairs, &engine)) != IAM_OK) return rc;
+  if ((rc = sync_imgs(c)) != IAM_OK) return rc;
+  CU(c->knn_idx.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(int)));
+  CU(c->knn_dist.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(float)));
+  c->timing.knn_launches = 0;
+  c->timing.knn_ms = 0.f;
+  c->timing.reduce_ms = 0.f;
+  const int dirs = both ? 2 : 1;
+  const int n_chunks = (int)pl.chunk_rows.size();
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
+    const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
+    if (p1 == p0) continue;
+    if (c->profiling) CU(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
+    cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
+    if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
+    c->timing.total_launches += 1;
+    if (c->profiling) CU(cudaEventRecord(c->ev[1], c->stream));
+    const size_t per = size_t(p1 - p0) * n_stride * k;
+    CU(c->packed_i.ensure(per * sizeof(int)));
+    CU(c->packed_d.ensure(per * sizeof(float)));
+    for (int dir = 0; dir < dirs; ++dir) {
+      pack_knn_kernel<<<p1 - p0, 256, 0, c->stream>>>(c->jobs.as<iam::RedJob>(), p0 * dirs, p1 - p0, dirs, dir, k, n_stride,
+                                                      c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->packed_i.as<int>(), c->packed_d.as<float>());
+      CU(cudaGetLastError());
+      c->timing.total_launches += 1;
+      int32_t* oi = (dir ? out_idx_rev : out_idx_fwd) + size_t(p0) * n_stride * k;
+      float* od = (dir ? out_dist_rev : out_dist_fwd) + size_t(p0) * n_stride * k;
+      CU(cudaMemcpyAsync(oi, c->packed_i.p, per * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(od, c->packed_d.p, per * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    }
+    if (c->profiling) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+      c->timing.knn_ms += ms;
+    }
+  }
+  return IAM_OK;
+}
+
+int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, void** d_table,
+                           void** d_count) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_pairs < 0 || (n_pairs && !pairs) || !prm) return fail(IAM_E_ARG, "bad arguments");
+  if (prm->cap <= 0 || prm->cap > 65536) return fail(IAM_E_ARG, "cap=%d out of range", prm->cap);
+  if (prm->reduce_mode != IAM_REDUCE_LOWE && prm->reduce_mode != IAM_REDUCE_REF_METRIC) return fail(IAM_E_ARG, "unknown reduce mode %d", prm->reduce_mode);
+  const int k = 2;
+  if ((rc = prepare_plan(c, pairs, n_pairs, k, true)) != IAM_OK) return rc;
+  const Plan& pl = c->plan;
+  int engine;
+  if ((rc = pick_engine(c, pairs, n_pairs, &engine)) != IAM_OK) return rc;
+  if ((rc = sync_imgs(c)) != IAM_OK) return rc;
+
+  const size_t cap = prm->cap;
+  int max_chunk_pairs = 1;
+  for (size_t ch = 0; ch + 1 < pl.chunk_pair_begin.size(); ++ch)
+    max_chunk_pairs = std::max(max_chunk_pairs, pl.chunk_pair_begin[ch + 1] - pl.chunk_pair_begin[ch]);
+  const int cand_stride = std::max(1, pl.max_n);
+  CU(c->knn_idx.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(int)));
+  CU(c->knn_dist.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(float)));
+  CU(c->cand_metric.ensure(size_t(max_chunk_pairs) * 2 * cand_stride * sizeof(double)));
+  CU(c->cand_qt.ensure(size_t(max_chunk_pairs) * 2 * cand_stride * sizeof(int2)));
+  CU(c->job_table.ensure(size_t(max_chunk_pairs) * 2 * cap * 2 * sizeof(int)));
+  CU(c->job_count.ensure(size_t(max_chunk_pairs) * 2 * sizeof(int)));
+  CU(c->out_table.ensure(std::max<size_t>(1, size_t(n_pairs)) * cap * 2 * sizeof(int)));
+  CU(c->out_count.ensure(std::max<size_t>(1, size_t(n_pairs)) * sizeof(int)));
+
+  iam::ReduceParams rp{};
+  rp.ratio = prm->match_ratio;
+  rp.thresh = prm->max_distance * prm->match_ratio;  // double product, as Python evaluates matcher.py:261
+  rp.mode = prm->reduce_mode;
+  rp.cap = prm->cap;
+  rp.min_pairs = prm->min_pairs;
+
+  c->timing.knn_launches = 0;
+  c->timing.knn_ms = 0.f;
+  c->timing.reduce_ms = 0.f;
+  const int n_chunks = (int)pl.chunk_rows.size();
+  std::vector<std::pair<int, int>> ran;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
+    const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
+    if (p1 == p0) continue;
+    const bool prof = c->profiling && n_chunks == 1;
+    if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
+    if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
+    if (prof) CU(cudaEventRecord(c->ev[1], c->stream));
+    cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
+    if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
+    const iam::RedJob* jobs = c->jobs.as<iam::RedJob>() + size_t(p0) * 2;
+    e = iam::launch_reduce(jobs, (p1 - p0) * 2, c->knn_idx.as<int>(), c->knn_dist.as<float>(), k, rp, c->cand_metric.as<double>(),
+                           c->cand_qt.as<int2>(), cand_stride, c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
+    if (e != cudaSuccess) return fail(IAM_E_CUDA, "reduce launch: %s", cudaGetErrorString(e));
+    if (prm->dedupe) {
+      e = iam::launch_dedupe(jobs, (p1 - p0) * 2, c->d_imgs.as<iam::ImgDev>(), prm->cap, prm->min_pairs, pl.max_n,
+                             c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
+      if (e != cudaSuccess) return fail(IAM_E_CUDA, "dedupe launch: %s", cudaGetErrorString(e));
+      c->timing.total_launches += 1;
+    }
+    e = iam::launch_crosscheck(jobs, p1 - p0, c->job_table.as<int>(), c->job_count.as<int>(), prm->cap, prm->cross_check, pl.max_n,
+                               c->out_table.as<int>() + size_t(p0) * cap * 2, c->out_count.as<int>() + p0, c->stream);
+    if (e != cudaSuccess) return fail(IAM_E_CUDA, "cross-check launch: %s", cudaGetErrorString(e));
+    c->timing.total_launches += 3;
+    if (prof) CU(cudaEventRecord(c->ev[2], c->stream));
+  }
+  c->timing_pending = c->profiling && n_chunks == 1 && n_pairs > 0;  // resolved lazily in iam_get_timing
+  c->last_pairs = n_pairs;
+  c->last_cap = prm->cap;
+  if (d_table) *d_table = c->out_table.p;
+  if (d_count) *d_count = c->out_count.p;
+  return IAM_OK;
+}
+
+int iam_fetch_tables(iam_ctx* c, int32_t* out_table, int32_t* out_count) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!out_table || !out_count) return fail(IAM_E_ARG, "null output");
+  if (c->last_pairs > 0) {
+    CU(cudaMemcpyAsync(out_count, c->out_count.p, size_t(c->last_pairs) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(out_table, c->out_table.p, size_t(c->last_pairs) * c->last_cap * 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_match_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int32_t* out_table,
+                    int32_t* out_count, int32_t* out_table_rev, int32_t* out_count_rev) {
+  if (!out_table || !out_count) return fail(IAM_E_ARG, "null output");
+  if ((out_table_rev == nullptr) != (out_count_rev == nullptr)) return fail(IAM_E_ARG, "reverse outputs must both be given or both be null");
+  int rc = iam_match_pairs_device(c, pairs, n_pairs, prm, nullptr, nullptr);
+  if (rc) return rc;
+  rc = iam_fetch_tables(c, out_table, out_count);
+  if (rc) return rc;
+  if (out_table_rev) {
+    // independent reverse direction = the same pipeline on the swapped pair list
+    std::vector<int32_t> sw(size_t(n_pairs) * 2);
+    for (int p = 0; p < n_pairs; ++p) {
+      sw[2 * p] = pairs[2 * p + 1];
+      sw[2 * p + 1] = pairs[2 * p];
+    }
+    rc = iam_match_pairs_device(c, sw.data(), n_pairs, prm, nullptr, nullptr);
+    if (rc) return rc;
+    rc = iam_fetch_tables(c, out_table_rev, out_count_rev);
+  }
+  return rc;
+}
+
+int iam_debug_tile(iam_ctx* c, int q_id, int t_id, int q_tile, int t_tile, uint32_t lbo, uint32_t sbo,
+                   uint32_t kstep_bytes, int ksteps, float* out_host) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if ((rc = check_image(c, q_id)) != IAM_OK || (rc = check_image(c, t_id)) != IAM_OK) return rc;
+  if (!out_host) return fail(IAM_E_ARG, "null output");
+  const Image& q = c->images[q_id];
+  const Image& t = c->images[t_id];
+  if (q_tile < 0 || t_tile < 0 || (q_tile + 1) * iam::kTileRows > q.n_pad || (t_tile + 1) * iam::kTileRows > t.n_pad)
+    return fail(IAM_E_ARG, "tile index out of range");
+  CU(c->packed_d.ensure(128 * 128 * sizeof(float)));
+  cudaError_t e = iam::launch_umma_tile_debug(c->norm, q.dev.a_form + size_t(q_tile) * iam::kTileBytes,
+                                              t.dev.b_form + size_t(t_tile) * iam::kTileBytes, lbo, sbo, kstep_bytes,
+                                              ksteps, c->packed_d.as<float>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "debug tile launch: %s", cudaGetErrorString(e));
+  CU(cudaMemcpyAsync(out_host, c->packed_d.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2, const int32_t* off, int n_pairs,
+                     const double* K, double threshold_px, double prob, int max_iters, uint32_t seed, uint8_t* out_mask,
+                     double* out_model, int32_t* out_inliers) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_pairs < 0 || !off || !out_mask || !out_model || !out_inliers) return fail(IAM_E_ARG, "bad arguments");
+  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY) return fail(IAM_E_ARG, "unknown model %d", model);
+  if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
+  std::string err;
+  rc = iam::ransac_pairs(model, pts1, pts2, off, n_pairs, K, threshold_px, prob, max_iters, seed, out_mask, out_model,
+                         out_inliers, c->stream, &err);
+  if (rc != 0) return fail(rc, "%s", err.c_str());
+  c->timing.total_launches += 1;
+  return IAM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), pair list sharded in
+contiguous blocks, ONE all-gather of the per-pair match tables over
+NCCL/NVLink at the end.  The reference is single
+process (matcher.py:928 walks the work list serially); pairs are independent,
+so no other communication exists on this path.
+
+Works with backend "nccl" (GPU tensors) and "gloo" (CPU tensors; used by the
+world_size-2 tests that run without a GPU).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+from . import pairs as _pairs
+
+
+def env_world() -> Tuple[int, int, int]:
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def init(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Initialise torch.distributed from the torchrun environment (no-op for a
+    single process).  Returns (rank, world, local_rank)."""
+    rank, world, local = env_world()
+    if world > 1 and not td.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        td.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_pairs(pair_array: np.ndarray, rank: int, world: int) -> Tuple[np.ndarray, int, int]:
+    b, e = _pairs.shard(len(pair_array), rank, world)
+    return pair_array[b:e], b, e
+
+
+class DevicePtr:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<i4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def as_tensor(ptr: int, shape, device: int) -> torch.Tensor:
+    return torch.as_tensor(DevicePtr(ptr, shape), device=torch.device("cuda", device))
+
+
+def allgather_tables(table: torch.Tensor, count: torch.Tensor, n_total: int, rank: int, world: int):
+    """table [P_local, cap, 2] int32, count [P_local] int32 on every rank (the
+    rank's contiguous shard) -> (table [n_total, cap, 2], count [n_total]) on
+    every rank.  One collective: counts ride in an extra table row so a single
+    all_gather moves everything (padded to the largest shard)."""
+    if world == 1:
+        return table, count
+    cap = table.shape[1]
+    sizes = [_pairs.shard(n_total, r, world) for r in range(world)]
+    p_max = max(e - b for b, e in sizes)
+    send = torch.zeros((p_max, cap + 1, 2), dtype=torch.int32, device=table.device)
+    p_loc = table.shape[0]
+    send[:p_loc, :cap] = table
+    send[:p_loc, cap, 0] = count
+    recv = torch.empty((world * p_max, cap + 1, 2), dtype=torch.int32, device=table.device)
+    td.all_gather_into_tensor(recv, send)      # THE collective of this path
+    recv = recv.view(world, p_max, cap + 1, 2)
+    out_t = torch.empty((n_total, cap, 2), dtype=torch.int32, device=table.device)
+    out_c = torch.empty((n_total,), dtype=torch.int32, device=table.device)
+    for r, (b, e) in enumerate(sizes):
+        out_t[b:e] = recv[r, :e - b, :cap]
+        out_c[b:e] = recv[r, :e - b, cap, 0]
+    return out_t, out_c

@@ -1,0 +1,207 @@
+/*
+ * iamatch.h — C-ABI of libiamatch.so, the B200-native (sm_100a) pairwise
+ * feature-matching engine that sits behind the `matcher` module of
+ * NorthStarUAS/ImageAnalysis.
+ *
+ * The reference has no FFI layer of its own: its numeric seam is the Python
+ * call `the_matcher.knnMatch(des1, des2, k)` inside `raw_matches`
+ * (reference scripts/lib/matcher.py:203-216, matcher object built at :62-79)
+ * and the Python reductions that follow it.  Every entry point below names
+ * the reference code it stands in for.  Plain C types only; the caller owns
+ * all host buffers; the library owns device memory until iam_destroy().
+ *
+ * Error convention: every function returns 0 on success or a negative
+ * IAM_E_* code; iam_last_error() returns a human-readable string for the
+ * last failure on the calling thread.  There is no CPU fallback: if no
+ * CUDA device / kernel image is usable the call fails with IAM_E_CUDA.
+ */
+#ifndef IAMATCH_H
+#define IAMATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums ----------------------------------------------------------- */
+
+/* Norm selected by matcher.configure() (matcher.py:49-56):
+ * SIFT/SURF -> cv2.NORM_L2, ORB/Star -> cv2.NORM_HAMMING. */
+#define IAM_NORM_L2       0
+#define IAM_NORM_HAMMING  1
+
+/* Host descriptor element types accepted by iam_upload_descriptors():
+ * OpenCV SIFT hands back float32 [N,128] (integer valued, 0..255),
+ * ORB uint8 [N,32] (image.py:160-180 loads exactly those). */
+#define IAM_DTYPE_U8   0
+#define IAM_DTYPE_F32  1
+
+/* kNN engine selection (debug / validation aid; IAM_ENGINE_AUTO in
+ * production).  UMMA = tcgen05 tensor-core kernel, SIMT = exact CUDA-core
+ * kernel used as the on-device cross-check. */
+#define IAM_ENGINE_AUTO  0
+#define IAM_ENGINE_UMMA  1
+#define IAM_ENGINE_SIMT  2
+
+/* Reduction applied to the k=2 neighbour lists of one direction. */
+#define IAM_REDUCE_LOWE        0  /* keep d0 <= d1*ratio          (find_obj.py:50-60, matcher.py:227) */
+#define IAM_REDUCE_REF_METRIC  1  /* metric=d0*(d0/d1) sorted, < max_distance*ratio, best `cap`  (matcher.py:253-269) */
+
+/* RANSAC models of filter_by_transform (matcher.py:121-128). */
+#define IAM_MODEL_ESSENTIAL   0
+#define IAM_MODEL_HOMOGRAPHY  1
+
+#define IAM_OK           0
+#define IAM_E_ARG       -1
+#define IAM_E_CUDA      -2
+#define IAM_E_NOMEM     -3
+#define IAM_E_STATE     -4
+#define IAM_E_UNSUPPORTED -5
+
+typedef struct iam_ctx iam_ctx;
+
+/* ---- lifetime -------------------------------------------------------- */
+
+/* Replaces the matcher construction in matcher.configure() (matcher.py:62-79).
+ * `desc_bytes` is the descriptor row size in bytes as OpenCV stores it for
+ * u8 data (128 for SIFT-as-u8, 32 for ORB); for float32 SIFT pass 128 too
+ * (the element count).  Only 128 (L2) and 32 (Hamming) take the tensor-core
+ * path; other sizes up to 128 use the SIMT engine. */
+int iam_create(int device, int norm, int desc_bytes, iam_ctx** out);
+int iam_destroy(iam_ctx* ctx);
+const char* iam_last_error(void);
+/* Library/ABI version, bumped on any signature change. */
+int iam_abi_version(void);
+
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*), e.g.
+ * torch.cuda.current_stream().cuda_stream, so that callers can bracket work
+ * with their own events.  NULL restores the context's private stream. */
+int iam_set_stream(iam_ctx* ctx, void* cuda_stream);
+int iam_set_engine(iam_ctx* ctx, int engine);
+int iam_synchronize(iam_ctx* ctx);
+
+/* ---- descriptors ----------------------------------------------------- */
+
+/* Stands in for `np.array(i1.des_list)` being handed to knnMatch
+ * (matcher.py:212-213).  Copies `n` descriptors from HOST memory `ptr`
+ * (row-major, `desc_bytes` elements per row of `dtype`) to the device and
+ * converts them into the tiled tensor-core operand layout.  `image_id` is a
+ * small non-negative integer chosen by the caller (index into
+ * proj.image_list).  Re-uploading an id replaces it.  `pinned` != 0 promises
+ * that `ptr` is page-locked so the copy can be asynchronous. */
+int iam_upload_descriptors(iam_ctx* ctx, int image_id, const void* ptr,
+                           int n, int dtype, int pinned);
+/* Same, but `dptr` already lives in device memory (no H2D copy). */
+int iam_upload_descriptors_device(iam_ctx* ctx, int image_id, const void* dptr,
+                                  int n, int dtype);
+/* Keypoint position ids for filter_duplicates (matcher.py:157-182): two
+ * keypoints of one image get the same id iff their '%.2f-%.2f' pixel keys
+ * (matcher.py:165-166) are equal.  `keys` is a HOST array [n] with values in
+ * [0, n); the image's descriptors must already be uploaded. */
+int iam_upload_keypoint_keys(iam_ctx* ctx, int image_id, const int32_t* keys, int n);
+/* Mirrors the LRU flush that sets des_list=None (matcher.py:1022-1026). */
+int iam_release_descriptors(iam_ctx* ctx, int image_id);
+/* Number of descriptors held for image_id, or <0 if absent. */
+int iam_num_descriptors(iam_ctx* ctx, int image_id);
+/* 1 if the image's descriptors were integer valued in [0,255] (exact path,
+ * SURVEY D8), 0 if they were rounded to fp16 (tolerance path). */
+int iam_descriptors_exact(iam_ctx* ctx, int image_id);
+
+/* ---- kNN: replaces cv2 DescriptorMatcher.knnMatch -------------------- */
+
+/* For every pair p = (pairs[2p], pairs[2p+1]) = (i, j) computes
+ *   forward : for each descriptor of image i its k nearest in image j
+ *   reverse : for each descriptor of image j its k nearest in image i
+ * exactly as cv2.BFMatcher(norm).knnMatch(des_i, des_j, k) would
+ * (ascending distance, ties -> lowest trainIdx).  Outputs are HOST buffers
+ * laid out [P][n_stride][k]; rows >= n(image) are left untouched.  Distances
+ * are float32: sqrt(sum of squared differences) for L2, the bit count for
+ * Hamming.  `out_*_rev` may be NULL to skip the reverse direction.
+ * Reference: matcher.py:203-216 (raw_matches), called with k=2 (:219,:600)
+ * and k=3 (:465,:707). */
+int iam_knn_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs, int k,
+                  int n_stride,
+                  int32_t* out_idx_fwd, float* out_dist_fwd,
+                  int32_t* out_idx_rev, float* out_dist_rev);
+
+/* ---- full per-pair match: kNN (both ways) + reduction + cross-check --- */
+
+typedef struct iam_match_params {
+  double match_ratio;   /* /config/matcher/match_ratio (3a-matching.py:40), 0.75; a Python float, hence double */
+  double max_distance;  /* matcher.max_distance: 270.0 L2 / 64 Hamming (matcher.py:53,56) */
+  int    reduce_mode;   /* IAM_REDUCE_*                                            */
+  int    cap;           /* `mymax` = 2000 (matcher.py:265)                         */
+  int    min_pairs;     /* /config/matcher/min_pairs (matcher.py:80,271,312)       */
+  int    cross_check;   /* !=0: filter_cross_check (matcher.py:187-200)            */
+  int    dedupe;        /* !=0: filter_duplicates (matcher.py:157-182, :294) + its min_pairs gate (:296-298);
+                           uses the keys given to iam_upload_keypoint_keys (identity keys if none)  */
+  int    reserved[3];
+} iam_match_params;
+
+/* Device pipeline for the 'traditional' strategy minus GMS
+ * (bidirectional_pair_matches, matcher.py:304-318, with basic_pair_matches
+ * :218-273 for each direction).  Writes per pair a table of [queryIdx,
+ * trainIdx] rows in the order the reference would produce (ascending
+ * metric, stable) into HOST buffers:
+ *   out_table : [P][cap][2] int32,  out_count : [P] int32.
+ * The reverse table is by construction the column swap of the forward one
+ * after cross-check (matcher.py:195-196); without cross-check pass
+ * out_table_rev/out_count_rev to receive the independent reverse table. */
+int iam_match_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs,
+                    const iam_match_params* prm,
+                    int32_t* out_table, int32_t* out_count,
+                    int32_t* out_table_rev, int32_t* out_count_rev);
+
+/* Same work, but results stay in device memory owned by the context (the
+ * "inputs and outputs resident in HBM" form used for kernel-level timing and
+ * by the multi-GPU gather).  Pointers returned are DEVICE pointers valid
+ * until the next call on this context. */
+int iam_match_pairs_device(iam_ctx* ctx, const int32_t* pairs, int n_pairs,
+                           const iam_match_params* prm,
+                           void** d_table, void** d_count);
+/* Copy the device tables of the last iam_match_pairs_device() to the host. */
+int iam_fetch_tables(iam_ctx* ctx, int32_t* out_table, int32_t* out_count);
+
+/* ---- RANSAC: replaces cv2.findEssentialMat(..., RANSAC, threshold) ---- */
+
+/* Batched robust model fit for filter_by_transform (matcher.py:90-142;
+ * the call being replaced is :126 / :122).  Pair p owns points
+ * pts1[off[p] .. off[p+1]) / pts2[...] (float32 xy, pixel coordinates, HOST).
+ * K is the row-major 3x3 camera matrix (double).  Outputs (HOST):
+ * out_mask[off[P]] (1 = inlier), out_model[P][9] double (E or H, row-major),
+ * out_inliers[P].  `seed` makes the sampler reproducible. */
+int iam_ransac_pairs(iam_ctx* ctx, int model, const float* pts1, const float* pts2,
+                     const int32_t* off, int n_pairs, const double* K,
+                     double threshold_px, double prob, int max_iters, uint32_t seed,
+                     uint8_t* out_mask, double* out_model, int32_t* out_inliers);
+
+/* ---- instrumentation ------------------------------------------------- */
+
+/* When enabled, the context brackets its kernels with CUDA events on the
+ * launching stream. */
+int iam_set_profiling(iam_ctx* ctx, int enable);
+typedef struct iam_timing {
+  float knn_ms;        /* distance+top-k kernel(s) of the last call          */
+  float reduce_ms;     /* ratio/metric reduction + cross-check kernels       */
+  float convert_ms;    /* descriptor layout conversion (last upload)         */
+  int   knn_launches;  /* kernels launched by the last match/knn call        */
+  int   total_launches;/* all kernel launches since context creation         */
+  int   engine_used;   /* IAM_ENGINE_UMMA or IAM_ENGINE_SIMT                 */
+  int   reserved[2];
+} iam_timing;
+int iam_get_timing(iam_ctx* ctx, iam_timing* out);
+
+/* Debug aid (no reference counterpart): raw fp32 accumulators of one 128x128
+ * tensor-core distance tile (query tile `q_tile` of image q_id x train tile
+ * `t_tile` of image t_id) with explicit UMMA descriptor strides, into
+ * out_host[128*128].  Production values: lbo=128, sbo=2304, kstep_bytes=256,
+ * ksteps=9. */
+int iam_debug_tile(iam_ctx* ctx, int q_id, int t_id, int q_tile, int t_tile,
+                   uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, int ksteps,
+                   float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAMATCH_H */

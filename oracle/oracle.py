@@ -1,0 +1,230 @@
+"""oracle.py — CPU restatement of the reference's pairwise matching path.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module, and
+only as the checker or as the timed CPU baseline.  Nothing under
+imageanalysis_b200/ imports it; the product fails loudly when its CUDA
+library is missing instead of falling back to this code.
+
+Every function cites the reference lines it follows (paths relative to the
+reference repo root).  The k-NN arithmetic itself lives in OpenCV, which the
+reference does not vendor (environment.yml:13 pins opencv 4.0.1; this image
+ships 4.13.0): `knn()` restates BFMatcher.knnMatch and is PINNED against
+live cv2 output committed under tests/golden/ (tests/golden/make_golden.py
+is the generator).  The Python-level reductions are restated from
+scripts/lib/matcher.py and pinned against the reference module itself,
+imported with shims by the same generator.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "liboracle_knn.so")
+_lib = None
+
+NORM_L2, NORM_HAMMING = 0, 1
+
+
+def _load():
+    global _lib
+    if _lib is None and os.path.exists(_SO):
+        lib = C.CDLL(_SO)
+        for name in ("oracle_knn_l2_u8", "oracle_knn_l2_f32", "oracle_knn_hamming"):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def have_c_oracle() -> bool:
+    return _load() is not None
+
+
+# --------------------------------------------------------------------------
+# k-NN  (matcher.py:203-216 raw_matches -> cv2 BFMatcher.knnMatch)
+# --------------------------------------------------------------------------
+def knn_numpy(q: np.ndarray, t: np.ndarray, k: int, norm: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Pure-numpy restatement (small sizes).  Returns (idx [N,k] int32, dist [N,k] float32).
+    Ordering: ascending distance, ties by ascending train index (stable argsort)."""
+    if norm == NORM_L2:
+        qa = q.astype(np.float64)
+        ta = t.astype(np.float64)
+        d2 = ((qa[:, None, :] - ta[None, :, :]) ** 2).sum(-1)
+    else:
+        x = np.bitwise_xor(q[:, None, :], t[None, :, :])
+        d2 = np.unpackbits(x, axis=-1).sum(-1).astype(np.float64)
+    order = np.argsort(d2, axis=1, kind="stable")[:, :k]
+    dsel = np.take_along_axis(d2, order, axis=1)
+    dist = (np.sqrt(dsel) if norm == NORM_L2 else dsel).astype(np.float32)
+    idx = order.astype(np.int32)
+    if idx.shape[1] < k:  # fewer train rows than k
+        pad = k - idx.shape[1]
+        idx = np.concatenate([idx, np.full((idx.shape[0], pad), -1, np.int32)], 1)
+        dist = np.concatenate([dist, np.full((dist.shape[0], pad), np.inf, np.float32)], 1)
+    return idx, dist
+
+
+def knn(q: np.ndarray, t: np.ndarray, k: int, norm: int, threads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
+    """C restatement (oracle_knn.c) fanned out over `threads` row blocks; falls
+    back to knn_numpy when the shared object has not been built."""
+    lib = _load()
+    if lib is None:
+        return knn_numpy(q, t, k, norm)
+    q = np.ascontiguousarray(q)
+    t = np.ascontiguousarray(t)
+    nq, dim = q.shape
+    nt = t.shape[0]
+    idx = np.empty((nq, k), np.int32)
+    dist = np.empty((nq, k), np.float32)
+    if norm == NORM_HAMMING:
+        fn = lib.oracle_knn_hamming
+        assert q.dtype == np.uint8 and t.dtype == np.uint8
+    elif q.dtype == np.uint8:
+        fn = lib.oracle_knn_l2_u8
+    else:
+        q = q.astype(np.float32, copy=False)
+        t = t.astype(np.float32, copy=False)
+        fn = lib.oracle_knn_l2_f32
+
+    def run(lo, hi):
+        if hi > lo:
+            fn(q[lo:hi].ctypes.data, hi - lo, t.ctypes.data, nt, dim, k, idx[lo:hi].ctypes.data, dist[lo:hi].ctypes.data)
+
+    threads = max(1, min(threads, nq))
+    if threads == 1:
+        run(0, nq)
+    else:
+        bounds = np.linspace(0, nq, threads + 1).astype(int)
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(lambda b: run(int(b[0]), int(b[1])), zip(bounds[:-1], bounds[1:])))
+    return idx, dist
+
+
+# --------------------------------------------------------------------------
+# reductions  (matcher.py:218-273, 187-200, 157-182)
+# --------------------------------------------------------------------------
+def reduce_ref_metric(idx: np.ndarray, dist: np.ndarray, match_ratio: float, max_distance: float, cap: int = 2000,
+                      min_pairs: int = 25) -> List[List[int]]:
+    """matcher.py:253-273.  metric = d0 * (d0/d1) in Python floats, stable
+    ascending sort, keep metric < max_distance*match_ratio, clip to `cap`,
+    gate on min_pairs.  Rows whose d1 is 0 would raise ZeroDivisionError in
+    the reference; they are dropped here and on the device (documented)."""
+    by_metric = []
+    for qi in range(idx.shape[0]):
+        if idx[qi, 0] < 0 or idx[qi, 1] < 0:
+            continue
+        d0 = float(dist[qi, 0])
+        d1 = float(dist[qi, 1])
+        if d1 == 0.0:
+            continue
+        ratio = d0 / d1
+        metric = d0 * ratio
+        by_metric.append([metric, qi, int(idx[qi, 0])])
+    by_metric = sorted(by_metric, key=lambda f: f[0])
+    out = [[qi, ti] for metric, qi, ti in by_metric if metric < max_distance * match_ratio]
+    if len(out) > cap:
+        out = out[:cap]
+    if len(out) < min_pairs:
+        return []
+    return out
+
+
+def reduce_lowe(idx: np.ndarray, dist: np.ndarray, match_ratio: float, cap: int = 2000,
+                min_pairs: int = 0) -> List[List[int]]:
+    """Plain Lowe gate, matcher.py:227 (`m[0].distance <= m[1].distance * match_ratio`),
+    same test as find_obj.py:50-60 filter_matches."""
+    out = []
+    for qi in range(idx.shape[0]):
+        if idx[qi, 0] < 0 or idx[qi, 1] < 0:
+            continue
+        if float(dist[qi, 0]) <= float(dist[qi, 1]) * match_ratio:
+            out.append([qi, int(idx[qi, 0])])
+    out = out[:cap]
+    if len(out) < min_pairs:
+        return []
+    return out
+
+
+def filter_cross_check(p1: Sequence[Sequence[int]], p2: Sequence[Sequence[int]]):
+    """matcher.py:187-200."""
+    s2 = {(int(a), int(b)) for a, b in p2}
+    new1, new2 = [], []
+    for q, t in p1:
+        if (int(t), int(q)) in s2:
+            new1.append([int(q), int(t)])
+            new2.append([int(t), int(q)])
+    return new1, new2
+
+
+def filter_duplicates(pts1: np.ndarray, pts2: np.ndarray, idx_pairs: Sequence[Sequence[int]]):
+    """matcher.py:157-182: first-seen-wins on '%.2f-%.2f' keypoint keys."""
+    result = []
+    d1, d2 = {}, {}
+    for q, t in idx_pairs:
+        k1 = "%.2f-%.2f" % (pts1[q][0], pts1[q][1])
+        k2 = "%.2f-%.2f" % (pts2[t][0], pts2[t][1])
+        if k1 in d1 or k2 in d2:
+            continue
+        d1[k1] = True
+        d2[k2] = True
+        result.append([int(q), int(t)])
+    return result
+
+
+def bidirectional(q: np.ndarray, t: np.ndarray, norm: int, match_ratio: float, max_distance: float, cap: int = 2000,
+                  min_pairs: int = 25, threads: int = 1, mode: str = "ref_metric", cross_check: bool = True):
+    """bidirectional_pair_matches (matcher.py:304-318) without the GMS stage
+    (cv2.xfeatures2d is contrib-only) and without filter_duplicates
+    (needs keypoints): forward reduce, reverse only if forward >= min_pairs,
+    cross-check."""
+    i1, d1 = knn(q, t, 2, norm, threads)
+    red = (lambda i, d: reduce_ref_metric(i, d, match_ratio, max_distance, cap, min_pairs)) if mode == "ref_metric" \
+        else (lambda i, d: reduce_lowe(i, d, match_ratio, cap, min_pairs))
+    p1 = red(i1, d1)
+    if not cross_check:
+        return p1, None
+    if len(p1) >= min_pairs and len(p1) > 0:
+        i2, d2 = knn(t, q, 2, norm, threads)
+        p2 = red(i2, d2)
+    else:
+        p2 = []
+    return filter_cross_check(p1, p2)
+
+
+# --------------------------------------------------------------------------
+# pair work-list  (matcher.py:858-903)
+# --------------------------------------------------------------------------
+def worklist(neds: np.ndarray, mode: str = "sequential", min_dist: float = 0.0, max_dist: float | None = None,
+             seq_k: int = 4):
+    """matcher.py:858-903.  `sequential` is the live branch (:899), `geotag`
+    the documented distance window (:896, disabled by `if False` in the
+    snapshot).  Returns [[ddist, i, j], ...] in generation order."""
+    n = len(neds)
+    intervals = [float(np.linalg.norm(np.array(neds[i + 1]) - np.array(neds[i]))) for i in range(n - 1)]
+    median = float(np.median(intervals))
+    average = float(np.average(intervals))
+    if median < average:
+        median = average
+    median_int = int(round(median))
+    if median_int == 0:
+        median_int = 1
+    if max_dist is None:
+        max_dist = median_int * 4
+    interval = median_int * 1.3
+    work = []
+    for i in range(n):
+        for j in range(i + 1, n):
+            dist = float(np.linalg.norm(np.array(neds[j]) - np.array(neds[i])))
+            if mode == "geotag":
+                if dist >= min_dist and dist <= max_dist:
+                    work.append([int(round(dist / interval)) * interval, i, j])
+            elif abs(i - j) <= seq_k:
+                work.append([int(round(dist / interval)) * interval, i, j])
+    return work

@@ -1,0 +1,64 @@
+"""World-size-2 test of the pair sharding + table all-gather on the gloo
+backend (CPU), exercising the same code the NCCL path runs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, cap, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from imageanalysis_b200 import dist
+    r, w, _ = dist.init("gloo")
+    assert (r, w) == (rank, world)
+    pairs = np.stack([np.arange(n_total), np.arange(n_total) + 1], 1).astype(np.int32)
+    local, b, e = dist.shard_pairs(pairs, rank, world)
+    # fake per-pair tables: pair p has (p % cap) entries [p, e]
+    table = torch.zeros((e - b, cap, 2), dtype=torch.int32)
+    count = torch.zeros((e - b,), dtype=torch.int32)
+    for li, p in enumerate(range(b, e)):
+        c = p % cap
+        count[li] = c
+        for k in range(c):
+            table[li, k, 0] = p
+            table[li, k, 1] = k
+    t, c = dist.allgather_tables(table, count, n_total, rank, world)
+    torch.save((t, c), os.path.join(out_dir, "r%d.pt" % rank))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_allgather_tables_world2(tmp_path):
+    world, n_total, cap = 2, 11, 5
+    mp.spawn(_worker, args=(world, _free_port(), n_total, cap, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(world)]
+    for t, c in res:
+        assert t.shape == (n_total, cap, 2) and c.tolist() == [p % cap for p in range(n_total)]
+        for p in range(n_total):
+            for k in range(p % cap):
+                assert t[p, k].tolist() == [p, k]
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])   # byte-identical on all ranks
+
+
+def test_allgather_single_rank_is_identity():
+    sys.path.insert(0, ROOT)
+    from imageanalysis_b200 import dist
+    t = torch.arange(24, dtype=torch.int32).reshape(3, 4, 2)
+    c = torch.tensor([1, 2, 3], dtype=torch.int32)
+    t2, c2 = dist.allgather_tables(t, c, 3, 0, 1)
+    assert t2 is t and c2 is c

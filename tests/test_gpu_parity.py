@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against
+the oracle and the committed golden vectors.  Integer paths are compared
+bit-for-bit (indices AND float32 distances)."""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from imageanalysis_b200 import _capi, synth
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = [(_capi.ENGINE_UMMA, "umma"), (_capi.ENGINE_SIMT, "simt")]
+KNN_CASES = [("knn_l2_synth.npz", _capi.NORM_L2), ("knn_hamming_synth.npz", _capi.NORM_HAMMING),
+             ("knn_sift_real.npz", _capi.NORM_L2), ("knn_orb_real.npz", _capi.NORM_HAMMING)]
+
+
+def run_knn(norm, q, t, k, engine, reverse=True):
+    eng = _capi.Engine(norm, q.shape[1], 0)
+    eng.set_engine(engine)
+    eng.upload(0, q)
+    eng.upload(1, t)
+    n = max(q.shape[0], t.shape[0])
+    out = eng.knn_pairs([(0, 1)], k, n, reverse=reverse)
+    used = eng.timing().engine_used
+    eng.close()
+    assert used == engine
+    return out
+
+
+@pytest.mark.parametrize("engine,ename", ENGINES)
+@pytest.mark.parametrize("name,norm", KNN_CASES)
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_knn_equals_cv2_golden(engine, ename, name, norm, k):
+    g = load_golden(name)
+    q, t = g["q"], g["t"]
+    idx, dist, ridx, rdist = run_knn(norm, q, t, k, engine)
+    assert (idx[0, :len(q)] == g["idx"][:, :k]).all()
+    assert (dist[0, :len(q)] == g["dist"][:, :k]).all()
+    assert (ridx[0, :len(t)] == g["ridx"][:, :k]).all()
+    assert (rdist[0, :len(t)] == g["rdist"][:, :k]).all()
+
+
+@pytest.mark.parametrize("engine,ename", ENGINES)
+def test_float32_sift_input_is_exact_path(engine, ename):
+    g = load_golden("knn_sift_real.npz")
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.set_engine(engine)
+    eng.upload(0, g["q"].astype(np.float32))     # what cv2.SIFT hands the reference (image.py:324)
+    eng.upload(1, g["t"].astype(np.float32))
+    assert eng.descriptors_exact(0) == 1 and eng.num_descriptors(1) == len(g["t"])
+    idx, dist, _, _ = eng.knn_pairs([(0, 1)], 2, len(g["q"]), reverse=False)
+    assert (idx[0] == g["idx"][:, :2]).all() and (dist[0] == g["dist"][:, :2]).all()
+
+
+@pytest.mark.parametrize("norm,gen,nb", [(_capi.NORM_L2, synth.sift_like, 128), (_capi.NORM_HAMMING, synth.orb_like, 32)])
+@pytest.mark.parametrize("nq,nt", [(1, 5), (2, 2), (127, 129), (128, 128), (129, 127), (255, 257), (256, 256),
+                                   (300, 1), (513, 1025), (1000, 3), (2000, 1777)])
+def test_knn_ragged_sizes(norm, gen, nb, nq, nt):
+    q, t = gen(nq, seed=nq), gen(nt, seed=1000 + nt)
+    if nt > 4 and nq > 4:
+        t[nt // 2] = q[1]
+        t[nt - 1] = q[1]                      # duplicate at the very last valid column of the last tile
+        t[0] = q[nq - 1]
+    for engine, _ in ENGINES:
+        idx, dist, ridx, rdist = run_knn(norm, q, t, 3, engine)
+        oi, od = oracle.knn(q, t, 3, norm, threads=4)
+        ri, rd = oracle.knn(t, q, 3, norm, threads=4)
+        assert (idx[0, :nq] == oi).all() and (dist[0, :nq] == od).all()
+        assert (ridx[0, :nt] == ri).all() and (rdist[0, :nt] == rd).all()
+
+
+def test_extreme_values_stay_exact():
+    """all-255 vs all-0 rows: d^2 = 128*255^2 = 8 323 200, the largest value the
+    fp32 accumulator must hold exactly."""
+    q = np.zeros((130, 128), np.uint8)
+    q[::2] = 255
+    q[5, :64] = 255
+    t = np.zeros((140, 128), np.uint8)
+    t[1::2] = 255
+    t[7, 64:] = 254
+    for engine, _ in ENGINES:
+        idx, dist, _, _ = run_knn(_capi.NORM_L2, q, t, 3, engine, reverse=False)
+        oi, od = oracle.knn(q, t, 3, _capi.NORM_L2)
+        assert (idx[0, :130] == oi).all() and (dist[0, :130] == od).all()
+    assert od.max() > 2880
+
+
+@pytest.mark.parametrize("norm,gen,nb", [(_capi.NORM_L2, synth.sift_like, 128), (_capi.NORM_HAMMING, synth.orb_like, 32)])
+def test_full_size_5000_umma_equals_simt_and_oracle_rows(norm, gen, nb):
+    """BASELINE config 2/3 shape (5000 x 5000).  Full-matrix check: the tcgen05
+    engine against the independent CUDA-core engine; plus a 300-row slice
+    against the CPU oracle."""
+    rng = np.random.default_rng(5)
+    q, t = gen(5000, seed=71), gen(5000, seed=72)
+    src = rng.permutation(5000)[:2000]
+    if norm == _capi.NORM_L2:
+        q[:2000] = np.clip(t[src].astype(np.int32) + rng.integers(-3, 4, (2000, 128)), 0, 255)
+    else:
+        q[:2000] = synth.flip_bits(t[src], 20, rng)
+    a = run_knn(norm, q, t, 2, _capi.ENGINE_UMMA)
+    b = run_knn(norm, q, t, 2, _capi.ENGINE_SIMT)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    rows = rng.permutation(5000)[:300]
+    oi, od = oracle.knn(q[rows], t, 2, norm, threads=8)
+    assert (a[0][0, rows] == oi).all() and (a[1][0, rows] == od).all()
+
+
+def test_many_pairs_and_chunking(monkeypatch):
+    """Several images, all pairs, forced through multiple workspace chunks."""
+    des, _, _ = synth.sift_project(6, 700, seed=2)
+    pairs = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    ref = {}
+    for engine, _ in ENGINES:
+        for chunk in ("", "1"):
+            if chunk:
+                monkeypatch.setenv("IAM_CHUNK_MB", chunk)
+            else:
+                monkeypatch.delenv("IAM_CHUNK_MB", raising=False)
+            eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+            eng.set_engine(engine)
+            for i, d in enumerate(des):
+                eng.upload(i, d)
+            out = eng.knn_pairs(pairs, 2, 700)
+            prm = _capi.Engine.make_params()
+            tab = eng.match_pairs(pairs, prm)
+            eng.close()
+            if not ref:
+                ref["knn"], ref["tab"] = out, tab
+            else:
+                for x, y in zip(out, ref["knn"]):
+                    assert np.array_equal(x, y, equal_nan=True)
+                assert (tab[1] == ref["tab"][1]).all()
+                for p in range(len(pairs)):
+                    assert (tab[0][p, :tab[1][p]] == ref["tab"][0][p, :tab[1][p]]).all()
+    for p, (i, j) in enumerate(pairs):
+        oi, od = oracle.knn(des[i], des[j], 2, oracle.NORM_L2, threads=4)
+        assert (ref["knn"][0][p] == oi).all() and (ref["knn"][1][p] == od).all()
+
+
+@pytest.mark.parametrize("mode", [_capi.REDUCE_REF_METRIC, _capi.REDUCE_LOWE])
+@pytest.mark.parametrize("cross", [True, False])
+def test_match_tables_equal_oracle(mode, cross):
+    des, _, _ = synth.sift_project(5, 1500, seed=4)
+    pairs = [(0, 1), (1, 2), (0, 2), (0, 4), (3, 4)]
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i, d in enumerate(des):
+        eng.upload(i, d)
+    prm = _capi.Engine.make_params(reduce_mode=mode, cross_check=cross, min_pairs=25, cap=500)
+    table, count = eng.match_pairs(pairs, prm)
+    for p, (i, j) in enumerate(pairs):
+        f, _ = oracle.bidirectional(des[i], des[j], oracle.NORM_L2, 0.75, 270.0, cap=500, min_pairs=25, threads=4,
+                                    mode="ref_metric" if mode == _capi.REDUCE_REF_METRIC else "lowe",
+                                    cross_check=cross)
+        assert table[p, :count[p]].tolist() == f
+    assert count[0] > 100 and count[3] == 0      # neighbours match, distant frames do not
+
+
+def test_orb_match_tables_equal_oracle():
+    des, _, _ = synth.sift_project(3, 1200, seed=6, kind="orb")
+    eng = _capi.Engine(_capi.NORM_HAMMING, 32, 0)
+    for i, d in enumerate(des):
+        eng.upload(i, d)
+    prm = _capi.Engine.make_params(max_distance=64.0)
+    table, count = eng.match_pairs([(0, 1), (1, 2)], prm)
+    for p, (i, j) in enumerate([(0, 1), (1, 2)]):
+        f, _ = oracle.bidirectional(des[i], des[j], oracle.NORM_HAMMING, 0.75, 64.0, threads=4)
+        assert table[p, :count[p]].tolist() == f
+    assert count.min() > 50
+
+
+def test_dedupe_and_cross_check_equal_reference_module():
+    """Device filter_duplicates + cross-check against what the reference's own
+    lib.matcher produced (golden reference_reductions.npz)."""
+    from imageanalysis_b200 import matcher
+    g = load_golden("reference_reductions.npz")
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i in range(4):
+        eng.upload(i, g["des%d" % i])
+        kps = [types.SimpleNamespace(pt=(float(x), float(y))) for x, y in g["pts%d" % i]]
+        eng.upload_keypoint_keys(i, matcher.keypoint_keys(kps))
+    prm = _capi.Engine.make_params(dedupe=True, cross_check=True)
+    table, count = eng.match_pairs([(0, 1), (0, 2)], prm)
+    assert table[0, :count[0]].tolist() == g["cross01"].tolist()
+    assert table[1, :count[1]].tolist() == g["bidir02_fwd"].tolist()
+    prm = _capi.Engine.make_params(dedupe=True, cross_check=False)
+    table, count, rtable, rcount = eng.match_pairs([(0, 1)], prm, want_reverse=True)
+    assert table[0, :count[0]].tolist() == g["basic01"].tolist()
+    assert rtable[0, :rcount[0]].tolist() == g["basic10"].tolist()
+
+
+class FakeImage:
+    def __init__(self, name, des, pts, ned):
+        self.name = name
+        self.des_list = des
+        self.kp_list = [types.SimpleNamespace(pt=(float(p[0]), float(p[1]))) for p in pts]
+        self.uv_list = [list(map(float, p)) for p in pts]
+        self.match_list = {}
+        self.matches_clean = True
+        self.desc_timestamp = 0.0
+        self._ned = list(map(float, ned))
+        self.saved = 0
+
+    def get_camera_pose(self, opt=False):
+        return self._ned, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]
+
+    def detect_features(self, scale):
+        raise AssertionError("descriptors are preloaded")
+
+    def save_matches(self):
+        self.saved += 1
+        self.matches_clean = True
+
+    def set_aircraft_yaw_error_estimate(self, v):
+        pass
+
+
+def _configure_matcher(detector="SIFT"):
+    from imageanalysis_b200 import matcher
+    from imageanalysis_b200.propshim import getNode
+    det = getNode("/config/detector", True)
+    det.setString("detector", detector)
+    det.setFloat("scale", 1.0)
+    mn = getNode("/config/matcher", True)
+    mn.setFloat("match_ratio", 0.75)
+    mn.setFloat("min_pairs", 25)
+    cam = getNode("/config/camera", True)
+    cam.setInt("width_px", 5472)
+    cam.setInt("height_px", 3648)
+    matcher.configure()
+    return matcher
+
+
+def test_find_matches_equals_reference_driver():
+    """The drop-in find_matches() against the match_list the reference's own
+    find_matches produced on the same 7-frame project (golden)."""
+    g = load_golden("reference_find_matches.npz")
+    matcher = _configure_matcher()
+    n = int(g["n"])
+    imgs = [FakeImage("frame%02d" % i, g["des%d" % i].astype(np.float32), g["pts%d" % i], g["ned%d" % i])
+            for i in range(n)]
+    proj = types.SimpleNamespace(image_list=imgs, analysis_dir="/tmp")
+    K = np.array([[3666.666504, 0, 2736], [0, 3666.666504, 1824], [0, 0, 1]])
+    matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
+    checked = 0
+    for im in imgs:
+        assert im.saved == 1
+        for other, lst in im.match_list.items():
+            want = g["match_%s_%s" % (im.name, other)].tolist()
+            assert lst == want, (im.name, other)
+            checked += 1
+    assert checked == 2 * 18
+    # resume rule (matcher.py:945-951): a second call skips finished pairs, retries empty ones
+    before = {im.name: {k: list(v) for k, v in im.match_list.items()} for im in imgs}
+    matcher.find_matches(proj, K, strategy="traditional")
+    assert before == {im.name: im.match_list for im in imgs}
+
+
+def test_raw_matches_and_pair_functions():
+    g = load_golden("reference_reductions.npz")
+    matcher = _configure_matcher()
+    i1 = FakeImage("a", g["des0"].astype(np.float32), g["pts0"], [0, 0, 0])
+    i2 = FakeImage("b", g["des1"].astype(np.float32), g["pts1"], [15, 0, 0])
+    m = matcher.raw_matches(i1, i2, k=3)
+    oi, od = oracle.knn(g["des0"], g["des1"], 3, oracle.NORM_L2, threads=4)
+    assert len(m) == len(oi) and all(len(r) == 3 for r in m)
+    assert [[d.trainIdx for d in r] for r in m] == oi.tolist()
+    assert np.float32([[d.distance for d in r] for r in m]).tolist() == od.tolist()
+    assert m[5][0].queryIdx == 5
+    assert matcher.basic_pair_matches(i1, i2) == g["basic01"].tolist()
+    f, r = matcher.bidirectional_pair_matches(i1, i2)
+    assert f == g["cross01"].tolist() and r == g["cross10"].tolist()
+    empty = FakeImage("c", None, [], [0, 0, 0])
+    assert matcher.raw_matches(i1, empty) == []
+
+
+def test_non_integer_descriptors_tolerance_path():
+    """SURF/RootSIFT-like float descriptors go through fp16 operands: distances
+    agree with float64 arithmetic to 2e-3 relative (tolerance path)."""
+    rng = np.random.default_rng(8)
+    q = np.abs(rng.normal(size=(400, 128))).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t = q[rng.permutation(400)] + rng.normal(0, 0.02, (400, 128)).astype(np.float32)
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.upload(0, q)
+    eng.upload(1, t.astype(np.float32))
+    assert eng.descriptors_exact(0) == 0
+    idx, dist, _, _ = eng.knn_pairs([(0, 1)], 2, 400, reverse=False)
+    oi, od = oracle.knn(q, t.astype(np.float32), 2, oracle.NORM_L2)
+    assert (idx[0, :, 0] == oi[:, 0]).mean() > 0.99
+    assert np.allclose(dist[0, :, 0], od[:, 0], rtol=2e-3, atol=2e-3)
+
+
+def test_error_paths():
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    with pytest.raises(_capi.IamError, match="no descriptors"):
+        eng.knn_pairs([(0, 1)], 2, 10)
+    eng.upload(0, synth.sift_like(10, 1))
+    eng.upload(1, synth.sift_like(10, 2))
+    with pytest.raises(_capi.IamError, match="k=4"):
+        eng.knn_pairs([(0, 1)], 4, 10)
+    with pytest.raises(_capi.IamError):
+        eng.upload(2, np.zeros((4, 64), np.uint8))
+    eng.release(1)
+    assert eng.num_descriptors(1) < 0
+    with pytest.raises(_capi.IamError):
+        _capi.Engine(7, 128, 0)

@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""GPU debug aid: dump one 128x128 tcgen05 distance tile with several UMMA
+descriptor stride settings and compare with exact integer arithmetic."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imageanalysis_b200 import _capi, synth  # noqa: E402
+
+
+def main():
+    out = {}
+    for norm, gen, nb, name in ((_capi.NORM_L2, synth.sift_like, 128, "l2"), (_capi.NORM_HAMMING, synth.orb_like, 32, "ham")):
+        q, t = gen(300, seed=1), gen(300, seed=2)
+        eng = _capi.Engine(norm, nb, 0)
+        eng.upload(0, q)
+        eng.upload(1, t)
+        if norm == _capi.NORM_L2:
+            exp = ((q[:128, None].astype(np.int64) - t[None, :128].astype(np.int64)) ** 2).sum(-1)
+            dot = -2 * (q[:128].astype(np.int64) @ t[:128].astype(np.int64).T)
+        else:
+            exp = np.unpackbits(q[:128, None] ^ t[None, :128], axis=-1).sum(-1)
+            dot = -2 * (np.unpackbits(q[:128], axis=-1).astype(np.int64) @ np.unpackbits(t[:128], axis=-1).astype(np.int64).T)
+        for tag, kw in (("prod", dict()), ("swapped", dict(lbo=2304, sbo=128)), ("data_only", dict(ksteps=8)),
+                        ("first_kstep", dict(ksteps=1))):
+            try:
+                got = eng.debug_tile(0, 1, **kw)
+            except Exception as e:  # noqa: BLE001
+                print(name, tag, "FAILED:", e)
+                continue
+            ref = exp if tag in ("prod", "swapped") else dot
+            diff = np.abs(got.astype(np.float64) - ref)
+            print("%s %-11s max|diff|=%g  exact=%d/16384  got[0,:4]=%s ref[0,:4]=%s" % (
+                name, tag, diff.max(), int((diff == 0).sum()), got[0, :4].tolist(), ref[0, :4].tolist()))
+            out["%s_%s" % (name, tag)] = got
+        out[name + "_exp"] = exp
+        eng.close()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.savez_compressed(os.path.join(ROOT, "gpurun_out", "debug_tile.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()
