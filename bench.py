@@ -263,7 +263,10 @@ def main():
 
     eng = _capi.Engine(norm, nbytes, local)
     eng.set_engine({"auto": _capi.ENGINE_AUTO, "umma": _capi.ENGINE_UMMA, "simt": _capi.ENGINE_SIMT}[args.engine])
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library, so that the
+    # CUDA events below bracket exactly the stream the kernels are launched on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     eng.set_profiling(True)
     prm = _capi.Engine.make_params(max_distance=270.0 if args.detector == "SIFT" else 64.0)

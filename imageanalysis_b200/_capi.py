@@ -29,6 +29,7 @@ EXPORTS = (
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device",
     "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_debug_minimal_solver",
 )
 
 
@@ -98,6 +99,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_ransac_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int,
                                      C.c_uint32, vp, vp, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
+    lib.iam_debug_minimal_solver.argtypes = [C.c_int, vp, vp, vp, vp, vp]
     lib.iam_set_profiling.argtypes = [vp, C.c_int]
     lib.iam_get_timing.argtypes = [vp, C.POINTER(Timing)]
     for name in EXPORTS:
@@ -107,6 +109,17 @@ def load_library(path: Optional[str] = None):
     if path is None:
         _lib = lib
     return lib
+
+
+def minimal_solver_host(model: int, x1, y1, x2, y2) -> np.ndarray:
+    """Host run of the RANSAC minimal solver (no GPU needed); returns [n_models, 3, 3]."""
+    lib = load_library()
+    arrs = [np.ascontiguousarray(a, np.float32) for a in (x1, y1, x2, y2)]
+    out = np.zeros((10, 9), np.float32)
+    n = lib.iam_debug_minimal_solver(model, *[a.ctypes.data_as(C.c_void_p) for a in arrs], out.ctypes.data_as(C.c_void_p))
+    if n < 0:
+        raise IamError("minimal solver failed: %s" % lib.iam_last_error().decode())
+    return out[:n].reshape(n, 3, 3)
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -677,6 +677,12 @@ int iam_debug_tile(iam_ctx* c, int q_id, int t_id, int q_tile, int t_tile, uint3
   return IAM_OK;
 }
 
+int iam_debug_minimal_solver(int model, const float* x1, const float* y1, const float* x2, const float* y2,
+                              float* out_models) {
+  if (!x1 || !y1 || !x2 || !y2 || !out_models) return fail(IAM_E_ARG, "null argument");
+  return iam::debug_minimal_solver(model, x1, y1, x2, y2, out_models);
+}
+
 int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2, const int32_t* off, int n_pairs,
                      const double* K, double threshold_px, double prob, int max_iters, uint32_t seed, uint8_t* out_mask,
                      double* out_model, int32_t* out_inliers) {

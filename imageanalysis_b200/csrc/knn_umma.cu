@@ -11,13 +11,17 @@
 // the N x M distance matrix never leaves the SM: eight epilogue warps read
 // it from TMEM and keep a per-row running top-k in registers.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over units):
+// Warp roles (640 threads, 1 CTA / SM, persistent over units):
 //   warp 0      : B-tile producer  (bulk copy  -> b_full[stage])
 //   warp 1      : MMA issuer       (one elected lane issues 18 tcgen05.mma / B tile)
 //   warp 2      : TMEM allocator / deallocator
 //   warp 3      : A-tile producer  (bulk copy  -> a_full[half])
-//   warps 4..11 : epilogue, warp e -> accumulator e/4, TMEM lane quadrant (warp_id % 4)
+//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (accumulator, 64-column part,
+//                 TMEM lane quadrant = warp_id % 4); the two column parts of a row merge
+//                 their top-k lists through shared memory once per unit
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "knn.h"
 #include "layout.h"
@@ -29,8 +33,6 @@ namespace {
 
 constexpr int kBStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
 constexpr uint32_t kTmemCols = 512;  // 2 stages x 2 accumulators x 128 fp32 columns
 
 struct __align__(8) Barriers {
@@ -46,7 +48,8 @@ struct __align__(8) Barriers {
 
 constexpr size_t kSmemA = 2 * kTileBytes;
 constexpr size_t kSmemB = kBStages * kTileBytes;
-constexpr size_t kSmemTotal = kSmemA + kSmemB + sizeof(Barriers) + 128;
+constexpr size_t kSmemMerge = 2 * 128 * 3 * 8;  // [A tile][row][k] (dist, idx) hand-over between column parts
+constexpr size_t kSmemTotal = kSmemA + kSmemB + sizeof(Barriers) + kSmemMerge + 128;
 
 constexpr float kInf = 3.0e38f;
 
@@ -58,18 +61,34 @@ struct TopK {
 #pragma unroll
     for (int s = 0; s < KTOP; ++s) {
       d[s] = kInf;
-      i[s] = -1;
+      i[s] = 0x7fffffff;
     }
   }
   __device__ __forceinline__ float thr() const { return d[KTOP - 1]; }
-  // Insert (x, col); caller guarantees x < thr().  Strict '<' everywhere keeps
-  // the earliest (lowest) column first among equal distances, which is the
-  // order cv2.BFMatcher reports ties in.
+  // Insert (x, col); caller guarantees x < thr().  Columns arrive in ascending
+  // order, so strict '<' keeps the earliest (lowest) column first among equal
+  // distances, which is the order cv2.BFMatcher reports ties in.
   __device__ __forceinline__ void insert(float x, int col) {
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
-      const bool lt_prev = (s > 0) ? (x < d[s - 1]) : false;
+      const bool lt_prev = (s > 0) ? (x < d[s > 0 ? s - 1 : 0]) : false;
       const bool lt_cur = x < d[s];
+      if (s > 0) {
+        d[s] = lt_prev ? d[s - 1] : (lt_cur ? x : d[s]);
+        i[s] = lt_prev ? i[s - 1] : (lt_cur ? col : i[s]);
+      } else {
+        d[s] = lt_cur ? x : d[s];
+        i[s] = lt_cur ? col : i[s];
+      }
+    }
+  }
+  // Order-independent insert: (distance, index) lexicographic.  Used to merge the
+  // partial lists of the two column parts of a row.
+  __device__ __forceinline__ void insert_lex(float x, int col) {
+#pragma unroll
+    for (int s = KTOP - 1; s >= 0; --s) {
+      const bool lt_prev = (s > 0) ? (x < d[s > 0 ? s - 1 : 0] || (x == d[s > 0 ? s - 1 : 0] && col < i[s > 0 ? s - 1 : 0])) : false;
+      const bool lt_cur = x < d[s] || (x == d[s] && col < i[s]);
       if (s > 0) {
         d[s] = lt_prev ? d[s - 1] : (lt_cur ? x : d[s]);
         i[s] = lt_prev ? i[s - 1] : (lt_cur ? col : i[s]);
@@ -81,34 +100,50 @@ struct TopK {
   }
 };
 
-// 32 accumulator columns of one row: cheap FMNMX3 min-tree per group of 8,
-// full insertion only for groups that can beat the current k-th best.
+__device__ __forceinline__ float min8(const float* w) {
+  return fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
+}
+
+// 64 accumulator columns of one row (two 32-column TMEM loads).  All eight
+// group minima are formed first (independent FMNMX3 chains), one combined test
+// skips the whole block, and only groups that can beat the running k-th best
+// take the insertion path.
 template <int KTOP>
-__device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk) {
+__device__ __forceinline__ void consume64(const float (&v0)[32], const float (&v1)[32], int col0, TopK<KTOP>& tk) {
+  float m[8];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float* w = &v[g * 8];
-    float m = fmin3(w[0], w[1], w[2]);
-    m = fmin3(m, w[3], w[4]);
-    m = fmin3(m, w[5], w[6]);
-    m = fminf(m, w[7]);
-    if (m < tk.thr()) {
+    m[g] = min8(&v0[g * 8]);
+    m[4 + g] = min8(&v1[g * 8]);
+  }
+  const float mall = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]), fminf(m[6], m[7]));
+  if (mall < tk.thr()) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (w[j] < tk.thr()) tk.insert(w[j], col0 + g * 8 + j);
+    for (int g = 0; g < 8; ++g) {
+      if (m[g] < tk.thr()) {
+        const float* w = (g < 4) ? &v0[g * 8] : &v1[(g - 4) * 8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (w[j] < tk.thr()) tk.insert(w[j], col0 + g * 8 + j);
+        }
       }
     }
   }
 }
 
-template <Kind kKind, int KTOP>
-__global__ void __launch_bounds__(kThreads, 1)
+// NPART = number of column parts an accumulator tile is split into among
+// epilogue warps (1: 8 epilogue warps, 2: 16 epilogue warps = 4 per SM sub-partition).
+template <Kind kKind, int KTOP, int NPART>
+__global__ void __launch_bounds__(128 + 256 * NPART, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
-                int* __restrict__ out_idx, float* __restrict__ out_d2) {
+                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
+  constexpr int kEpiWarps = 8 * NPART;
+  constexpr int kCols = 128 / NPART;  // accumulator columns per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
+  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + ((sizeof(Barriers) + 15) / 16) * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -210,8 +245,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
-    const int e = warp - 4;
-    const int h = e >> 2;               // which accumulator / A tile
+    const int g = (warp - 4) >> 2;      // 0 .. 2*NPART-1
+    const int h = g / NPART;            // which accumulator / A tile
+    const int part = g % NPART;         // which column part of it
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;
     TopK<KTOP> tk;
@@ -227,25 +263,53 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         const uint32_t apar = (it / kAccStages) & 1;
         mbar_wait(&bars->t_full[acc], apar, 40);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + h * 128;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + h * 128 + part * kCols;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
+        for (int c = 0; c < kCols / 64; ++c) {
+          if (dbg_flags == 1) break;
+          float v0[32], v1[32];
           __syncwarp();
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait(v);
-          consume32<KTOP>(v, tb * kTileRows + c * 32, tk);
+          tmem_ld32(taddr + c * 64, v0);
+          tmem_ld32(taddr + c * 64 + 32, v1);
+          tmem_ld_wait(v0);
+          tmem_ld_wait(v1);
+          if (dbg_flags == 0) {
+            consume64<KTOP>(v0, v1, tb * kTileRows + part * kCols + c * 64, tk);
+          } else if (dbg_flags == 2) {  // profiling aid: fast path only (results are NOT valid)
+            float m = v0[0];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m = fminf(m, fminf(min8(&v0[j * 8]), min8(&v1[j * 8])));
+            tk.d[0] = fminf(tk.d[0], m);
+          }  // dbg_flags == 1: MMA/TMA pipeline only, accumulators dropped
         }
         __syncwarp();
         tc_fence_before();
         if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
       }
+      if (NPART == 2) {
+        // hand the upper column part's list to the lower part's thread of the same row
+        if (part == 1) {
+#pragma unroll
+          for (int s = 0; s < KTOP; ++s)
+            merge[(h * 128 + row_in_tile) * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(256 * NPART) : "memory");
+        if (part == 0) {
+#pragma unroll
+          for (int s = 0; s < KTOP; ++s) {
+            const float2 e = merge[(h * 128 + row_in_tile) * KTOP + s];
+            tk.insert_lex(e.x, __float_as_int(e.y));
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(256 * NPART) : "memory");
+      }
       const int row = unit.super * kSuperRows + h * kTileRows + row_in_tile;
-      if (row < q.n) {
+      if (part == 0 && row < q.n) {
         const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
 #pragma unroll
         for (int s = 0; s < KTOP; ++s) {
-          out_idx[o + s] = tk.i[s];
+          out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : tk.i[s];
           out_d2[o + s] = tk.d[s];
         }
       }
@@ -312,15 +376,30 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   }
 }
 
-template <Kind kKind, int KTOP>
-cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
+template <Kind kKind, int KTOP, int NPART>
+cudaError_t launch_p(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
                      cudaStream_t stream) {
-  auto kern = knn_umma_kernel<kKind, KTOP>;
+  auto kern = knn_umma_kernel<kKind, KTOP, NPART>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
   const int grid = n_units < num_sms ? n_units : num_sms;
-  kern<<<grid, kThreads, kSmemTotal, stream>>>(imgs, units, n_units, out_idx, out_d2);
+  static const int flags = [] {
+    const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
+    return e ? atoi(e) : 0;
+  }();
+  kern<<<grid, 128 + 256 * NPART, kSmemTotal, stream>>>(imgs, units, n_units, out_idx, out_d2, flags);
   return cudaGetLastError();
+}
+
+template <Kind kKind, int KTOP>
+cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
+                     cudaStream_t stream) {
+  static const int parts = [] {
+    const char* e = getenv("IAM_UMMA_PARTS");  // tuning / A-B aid: 1 = 8 epilogue warps, 2 = 16 (default)
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  return parts == 1 ? launch_p<kKind, KTOP, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream)
+                    : launch_p<kKind, KTOP, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
 }
 
 }  // namespace

@@ -17,4 +17,9 @@ int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t*
                  double threshold_px, double prob, int max_iters, uint32_t seed, uint8_t* out_mask, double* out_model,
                  int32_t* out_inliers, cudaStream_t stream, std::string* err);
 
+// Host-side run of the minimal solvers (same source as the device code) on the
+// first 5 (essential) / 4 (homography) normalised correspondences; returns the
+// number of models written to out[10][9].  Used by the CPU tests.
+int debug_minimal_solver(int model, const float* x1, const float* y1, const float* x2, const float* y2, float* out);
+
 }  // namespace iam

@@ -201,6 +201,13 @@ int iam_debug_tile(iam_ctx* ctx, int q_id, int t_id, int q_tile, int t_tile,
                    uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, int ksteps,
                    float* out_host);
 
+/* Debug aid: run the minimal solver of iam_ransac_pairs (5-point essential /
+ * 4-point homography; same source as the device code) on the HOST for the
+ * first 5 / 4 normalised correspondences.  Returns the number of models
+ * written to out_models[10][9] (row-major), or <0.  Needs no GPU. */
+int iam_debug_minimal_solver(int model, const float* x1, const float* y1,
+                             const float* x2, const float* y2, float* out_models);
+
 #ifdef __cplusplus
 }
 #endif
