@@ -72,11 +72,13 @@ struct Buffer {
 
 struct Image {
   int* keys = nullptr;
-  uint8_t* block = nullptr;
+  uint8_t* block = nullptr;   // [256 B flag word][raw][a_form][b_form]
   size_t block_bytes = 0;
   int n = -1;
   int n_pad = 0;
-  int exact = 1;
+  int exact = 1;              // -1: not read back from the device yet
+  cudaEvent_t ready = nullptr;  // recorded on the upload stream after the layout conversion
+  uint64_t seq = 0;           // upload order; a later seq completing implies every earlier one did
   iam::ImgDev dev{};
 };
 
@@ -99,10 +101,14 @@ struct iam_ctx {
   int num_sms = 0;
   int engine = IAM_ENGINE_AUTO;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;     // compute stream (own_stream or the caller's)
+  cudaStream_t up_stream = nullptr;  // H2D + layout conversion; overlaps with matching of earlier pair chunks
+  cudaEvent_t compute_done = nullptr;
+  bool compute_pending = false;
+  uint64_t up_seq = 0;
   std::vector<Image> images;
   bool imgs_dirty = true;
-  Buffer d_imgs, stage, exact_flag;
+  Buffer d_imgs, stage;
   Buffer units, jobs, knn_idx, knn_dist, cand_metric, cand_qt, job_table, job_count, out_table, out_count, packed_i,
       packed_d;
   int last_pairs = 0, last_cap = 0;
@@ -151,6 +157,41 @@ int check_image(const iam_ctx* c, int id) {
   return IAM_OK;
 }
 
+// Read an image's exactness flag back from the device on first use.
+int resolve_exact(iam_ctx* c, int id) {
+  Image& im = c->images[id];
+  if (im.exact < 0) {
+    int flag = 0;
+    if (cudaMemcpyAsync(&flag, im.block, sizeof(int), cudaMemcpyDeviceToHost, c->up_stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->up_stream) != cudaSuccess)
+      return -1;
+    im.exact = flag != 0;
+  }
+  return im.exact;
+}
+
+// Make the compute stream wait for the uploads of every image a chunk of pairs touches.
+int wait_uploads(iam_ctx* c, const int32_t* pairs, int p0, int p1) {
+  uint64_t best = 0;
+  int best_id = -1;
+  for (int i = 2 * p0; i < 2 * p1; ++i) {
+    const Image& im = c->images[pairs[i]];
+    if (im.seq > best) {
+      best = im.seq;
+      best_id = pairs[i];
+    }
+  }
+  if (best_id >= 0 && c->images[best_id].ready) CU(cudaStreamWaitEvent(c->stream, c->images[best_id].ready, 0));
+  return IAM_OK;
+}
+
+// After the last kernel of a call: later uploads must not overwrite operands still being read.
+int mark_compute(iam_ctx* c) {
+  CU(cudaEventRecord(c->compute_done, c->stream));
+  c->compute_pending = true;
+  return IAM_OK;
+}
+
 int pick_engine(const iam_ctx* c, const int32_t* pairs, int n_pairs, int* engine) {
   int e = c->engine;
   if (e == IAM_ENGINE_AUTO) e = umma_capable(c) ? IAM_ENGINE_UMMA : IAM_ENGINE_SIMT;
@@ -158,14 +199,16 @@ int pick_engine(const iam_ctx* c, const int32_t* pairs, int n_pairs, int* engine
   if (e == IAM_ENGINE_SIMT) {
     if (!simt_capable(c)) return fail(IAM_E_UNSUPPORTED, "SIMT engine supports 32/64/128-byte descriptors, got %d", c->desc_bytes);
     for (int p = 0; p < n_pairs * 2; ++p)
-      if (!c->images[pairs[p]].exact) return fail(IAM_E_UNSUPPORTED, "SIMT engine needs integer-valued descriptors (image %d)", pairs[p]);
+      if (resolve_exact(const_cast<iam_ctx*>(c), pairs[p]) == 0) return fail(IAM_E_UNSUPPORTED, "SIMT engine needs integer-valued descriptors (image %d)", pairs[p]);
   }
   *engine = e;
   return IAM_OK;
 }
 
 // Two directed jobs per pair (2p: i->j, 2p+1: j->i); out_base restarts per chunk.
-int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, Plan* pl) {
+int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, int waves, Plan* pl) {
+  const int max_pairs = waves > 1 ? std::max(64, (n_pairs + waves - 1) / waves) : (1 << 30);
+  int in_chunk = 0;
   size_t budget_mb = 768;  // kNN output workspace per chunk; IAM_CHUNK_MB overrides (tests force many chunks)
   if (const char* env = getenv("IAM_CHUNK_MB")) budget_mb = std::max(1, atoi(env));
   const size_t budget_rows = (budget_mb << 20) / (size_t(k) * 8);
@@ -179,13 +222,15 @@ int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool 
     const Image& a = c->images[i];
     const Image& b = c->images[j];
     const size_t need = size_t(a.n_pad) + (both ? size_t(b.n_pad) : 0);
-    if (rows > 0 && rows + need > budget_rows) {
+    if (rows > 0 && (rows + need > budget_rows || in_chunk >= max_pairs)) {
+      in_chunk = 0;
       pl->chunk_rows.push_back(rows);
       pl->max_chunk_rows = std::max(pl->max_chunk_rows, rows);
       pl->chunk_pair_begin.push_back(p);
       pl->chunk_unit_begin.push_back((int)pl->units.size());
       rows = 0;
     }
+    ++in_chunk;
     for (int dir = 0; dir < (both ? 2 : 1); ++dir) {
       const int qs = dir ? j : i, ts = dir ? i : j;
       const Image& q = c->images[qs];
@@ -205,7 +250,26 @@ int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool 
   return IAM_OK;
 }
 
-uint64_t plan_hash(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both) {
+// Uploads still in flight on the upload stream?  Then matching is cut into waves so
+// that early pair chunks run while later images are still crossing PCIe.
+int pick_waves(iam_ctx* c) {
+  uint64_t best = 0;
+  cudaEvent_t ev = nullptr;
+  for (const Image& im : c->images)
+    if (im.seq > best) {
+      best = im.seq;
+      ev = im.ready;
+    }
+  if (!ev) return 1;
+  const cudaError_t q = cudaEventQuery(ev);
+  if (q == cudaErrorNotReady) {
+    cudaGetLastError();
+    return 8;
+  }
+  return 1;
+}
+
+uint64_t plan_hash(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, int waves) {
   uint64_t h = 1469598103934665603ull;
   auto mix = [&h](uint64_t v) {
     for (int b = 0; b < 8; ++b) {
@@ -215,7 +279,7 @@ uint64_t plan_hash(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, b
   };
   mix(c->shape_epoch);
   mix(uint64_t(n_pairs));
-  mix(uint64_t(k) * 2 + (both ? 1 : 0));
+  mix(uint64_t(k) * 2 + (both ? 1 : 0) + 16 * uint64_t(waves));
   if (const char* env = getenv("IAM_CHUNK_MB")) mix(uint64_t(atoi(env)) + 77);
   for (int i = 0; i < 2 * n_pairs; ++i) mix(uint64_t(uint32_t(pairs[i])));
   return h | 1ull;
@@ -225,11 +289,12 @@ int upload_plan(iam_ctx* c, const Plan& pl);
 
 // Build (or reuse) the work list for this pair list and make it resident.
 int prepare_plan(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both) {
-  const uint64_t key = plan_hash(c, pairs, n_pairs, k, both);
+  const int waves = pick_waves(c);
+  const uint64_t key = plan_hash(c, pairs, n_pairs, k, both, waves);
   if (c->plan_valid && c->plan_key == key) return IAM_OK;
   c->plan_valid = false;
   c->plan = Plan{};
-  int rc = build_plan(c, pairs, n_pairs, k, both, &c->plan);
+  int rc = build_plan(c, pairs, n_pairs, k, both, waves, &c->plan);
   if (rc != IAM_OK) return rc;
   if ((rc = upload_plan(c, c->plan)) != IAM_OK) return rc;
   c->plan_key = key;
@@ -307,6 +372,12 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
     return fail(IAM_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   c->stream = c->own_stream;
+  e = cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(IAM_E_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
+  }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   *out = c;
   return IAM_OK;
@@ -316,11 +387,15 @@ int iam_destroy(iam_ctx* c) {
   if (!c) return IAM_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->up_stream) cudaStreamSynchronize(c->up_stream);
   for (auto& im : c->images) {
     if (im.block) cudaFree(im.block);
     if (im.keys) cudaFree(im.keys);
+    if (im.ready) cudaEventDestroy(im.ready);
   }
-  Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->exact_flag, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
+  if (c->compute_done) cudaEventDestroy(c->compute_done);
+  if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
                     &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
   for (Buffer* b : bufs) b->release();
   for (auto& ev : c->ev)
@@ -348,6 +423,7 @@ int iam_set_engine(iam_ctx* c, int engine) {
 int iam_synchronize(iam_ctx* c) {
   int rc = bind(c);
   if (rc) return rc;
+  CU(cudaStreamSynchronize(c->up_stream));
   CU(cudaStreamSynchronize(c->stream));
   return IAM_OK;
 }
@@ -360,6 +436,11 @@ int iam_set_profiling(iam_ctx* c, int enable) {
 
 int iam_get_timing(iam_ctx* c, iam_timing* out) {
   if (!c || !out) return fail(IAM_E_ARG, "null argument");
+  if (c->profiling && c->up_seq > 0) {
+    CU(cudaSetDevice(c->device));
+    if (cudaEventSynchronize(c->ev[5]) == cudaSuccess) cudaEventElapsedTime(&c->timing.convert_ms, c->ev[4], c->ev[5]);
+    cudaGetLastError();
+  }
   if (c->timing_pending) {
     CU(cudaSetDevice(c->device));
     CU(cudaEventSynchronize(c->ev[2]));
@@ -371,26 +452,33 @@ int iam_get_timing(iam_ctx* c, iam_timing* out) {
   return IAM_OK;
 }
 
-static int upload_common(iam_ctx* c, int id, const void* dsrc, int n, int dtype) {
+static int upload_common(iam_ctx* c, int id, const void* src, bool src_on_host, int n, int dtype) {
   if ((int)c->images.size() <= id) c->images.resize(id + 1);
   Image& im = c->images[id];
   const int n_pad = std::max(iam::kSuperRows, iam::round_up(n, iam::kSuperRows));
   const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
   const size_t form_b = iam::form_bytes(n_pad);
-  const size_t total = raw_b + 2 * form_b;
+  const size_t total = 256 + raw_b + 2 * form_b;
+  if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
+    CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    c->compute_pending = false;
+  }
   if (im.block_bytes < total) {
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->up_stream));
     if (im.block) CU(cudaFree(im.block));
     im.block = nullptr;
     im.block_bytes = 0;
     CU(cudaMalloc(reinterpret_cast<void**>(&im.block), total));
     im.block_bytes = total;
   }
+  if (!im.ready) CU(cudaEventCreateWithFlags(&im.ready, cudaEventDisableTiming));
   if (im.n != n || im.n_pad != n_pad) c->shape_epoch++;
   im.n = n;
   im.n_pad = n_pad;
-  im.dev.raw = im.block;
-  im.dev.a_form = im.block + raw_b;
-  im.dev.b_form = im.block + raw_b + form_b;
+  im.dev.raw = im.block + 256;
+  im.dev.a_form = im.block + 256 + raw_b;
+  im.dev.b_form = im.block + 256 + raw_b + form_b;
   im.dev.n = n;
   im.dev.n_pad = n_pad;
   if (im.keys) {  // keys belong to the previous descriptor set
@@ -401,25 +489,26 @@ static int upload_common(iam_ctx* c, int id, const void* dsrc, int n, int dtype)
   im.dev.kp_key = nullptr;
   c->imgs_dirty = true;
 
-  CU(c->exact_flag.ensure(sizeof(int)));
-  const int one = 1;
-  CU(cudaMemcpyAsync(c->exact_flag.p, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  if (c->profiling) CU(cudaEventRecord(c->ev[4], c->stream));
-  cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block, im.block + raw_b,
-                                      im.block + raw_b + form_b, c->exact_flag.as<int>(), c->stream);
+  const void* dsrc = src;
+  if (src_on_host) {
+    const size_t bytes = size_t(n) * c->desc_bytes * (dtype == IAM_DTYPE_F32 ? 4 : 1);
+    if (c->stage.cap < bytes) {
+      CU(cudaStreamSynchronize(c->up_stream));  // a conversion may still be reading the old staging buffer
+      CU(c->stage.ensure(std::max<size_t>(bytes, 256)));
+    }
+    if (bytes) CU(cudaMemcpyAsync(c->stage.p, src, bytes, cudaMemcpyHostToDevice, c->up_stream));
+    dsrc = c->stage.p;
+  }
+  CU(cudaMemsetAsync(im.block, 1, sizeof(int), c->up_stream));  // exactness flag: non-zero = exact
+  if (c->profiling) CU(cudaEventRecord(c->ev[4], c->up_stream));
+  cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block + 256, im.block + 256 + raw_b,
+                                      im.block + 256 + raw_b + form_b, reinterpret_cast<int*>(im.block), c->up_stream);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "convert launch: %s", cudaGetErrorString(e));
   c->timing.total_launches += 1;
-  if (c->profiling) CU(cudaEventRecord(c->ev[5], c->stream));
-  int flag = 1;
-  if (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) {
-    CU(cudaMemcpyAsync(&flag, c->exact_flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-  }
-  im.exact = flag;
-  if (c->profiling) {
-    CU(cudaEventSynchronize(c->ev[5]));
-    CU(cudaEventElapsedTime(&c->timing.convert_ms, c->ev[4], c->ev[5]));
-  }
+  if (c->profiling) CU(cudaEventRecord(c->ev[5], c->up_stream));
+  CU(cudaEventRecord(im.ready, c->up_stream));
+  im.seq = ++c->up_seq;
+  im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
   return IAM_OK;
 }
 
@@ -430,11 +519,8 @@ int iam_upload_descriptors(iam_ctx* c, int id, const void* ptr, int n, int dtype
   if (n < 0 || (n > 0 && !ptr)) return fail(IAM_E_ARG, "bad descriptor buffer");
   if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
   if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
-  const size_t bytes = size_t(n) * c->desc_bytes * (dtype == IAM_DTYPE_F32 ? 4 : 1);
-  CU(c->stage.ensure(std::max<size_t>(bytes, 256)));
-  if (bytes) CU(cudaMemcpyAsync(c->stage.p, ptr, bytes, cudaMemcpyHostToDevice, c->stream));
   (void)pinned;
-  return upload_common(c, id, c->stage.p, n, dtype);
+  return upload_common(c, id, ptr, true, n, dtype);
 }
 
 int iam_upload_descriptors_device(iam_ctx* c, int id, const void* dptr, int n, int dtype) {
@@ -444,7 +530,7 @@ int iam_upload_descriptors_device(iam_ctx* c, int id, const void* dptr, int n, i
   if (n < 0 || (n > 0 && !dptr)) return fail(IAM_E_ARG, "bad descriptor buffer");
   if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
   if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
-  return upload_common(c, id, dptr, n, dtype);
+  return upload_common(c, id, dptr, false, n, dtype);
 }
 
 int iam_release_descriptors(iam_ctx* c, int id) {
@@ -453,8 +539,10 @@ int iam_release_descriptors(iam_ctx* c, int id) {
   if (id < 0 || id >= (int)c->images.size()) return IAM_OK;
   Image& im = c->images[id];
   CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamSynchronize(c->up_stream));
   if (im.block) CU(cudaFree(im.block));
   if (im.keys) CU(cudaFree(im.keys));
+  if (im.ready) CU(cudaEventDestroy(im.ready));
   im = Image{};
   c->shape_epoch++;
   c->imgs_dirty = true;
@@ -476,8 +564,8 @@ int iam_upload_keypoint_keys(iam_ctx* c, int id, const int32_t* keys, int n) {
   }
   if (n > 0) {
     CU(cudaMalloc(reinterpret_cast<void**>(&im.keys), size_t(n) * sizeof(int)));
-    CU(cudaMemcpyAsync(im.keys, keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(im.keys, keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
+    CU(cudaStreamSynchronize(c->up_stream));
   }
   im.dev.kp_key = im.keys;
   c->imgs_dirty = true;
@@ -491,7 +579,8 @@ int iam_num_descriptors(iam_ctx* c, int id) {
 
 int iam_descriptors_exact(iam_ctx* c, int id) {
   if (!c || id < 0 || id >= (int)c->images.size() || c->images[id].n < 0) return -1;
-  return c->images[id].exact;
+  if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+  return resolve_exact(c, id);
 }
 
 int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_stride, int32_t* out_idx_fwd,
@@ -520,6 +609,7 @@ int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_st
     const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
     const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
     if (p1 == p0) continue;
+    if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) return rc;
     if (c->profiling) CU(cudaEventRecord(c->ev[0], c->stream));
     if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
     cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
@@ -546,7 +636,7 @@ int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_st
       c->timing.knn_ms += ms;
     }
   }
-  return IAM_OK;
+  return mark_compute(c);
 }
 
 int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, void** d_table,
@@ -593,6 +683,7 @@ int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const 
     const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
     const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
     if (p1 == p0) continue;
+    if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) return rc;
     const bool prof = c->profiling && n_chunks == 1;
     if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
     if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
@@ -616,6 +707,7 @@ int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const 
     if (prof) CU(cudaEventRecord(c->ev[2], c->stream));
   }
   c->timing_pending = c->profiling && n_chunks == 1 && n_pairs > 0;  // resolved lazily in iam_get_timing
+  if ((rc = mark_compute(c)) != IAM_OK) return rc;
   c->last_pairs = n_pairs;
   c->last_cap = prm->cap;
   if (d_table) *d_table = c->out_table.p;

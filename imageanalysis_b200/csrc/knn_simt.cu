@@ -21,10 +21,11 @@ __global__ void __launch_bounds__(128) knn_simt_kernel(const ImgDev* __restrict_
   __shared__ __align__(16) uint32_t s_t[kTrainTile * WORDS];
   __shared__ uint32_t s_norm[kTrainTile];
 
-  const KnnUnit unit = units[blockIdx.x >> 1];
+  constexpr int kSub = kSuperRows / 128;
+  const KnnUnit unit = units[blockIdx.x / kSub];
   const ImgDev q = imgs[unit.q_slot];
   const ImgDev t = imgs[unit.t_slot];
-  const int row = unit.super * kSuperRows + (blockIdx.x & 1) * 128 + threadIdx.x;
+  const int row = unit.super * kSuperRows + (blockIdx.x % kSub) * 128 + threadIdx.x;
 
   uint32_t qw[WORDS];
   {
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(128) knn_simt_kernel(const ImgDev* __restrict_
 template <int NORM, int WORDS>
 cudaError_t launch_w(int k, const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2,
                      cudaStream_t stream) {
-  const int grid = n_units * 2;
+  const int grid = n_units * (kSuperRows / 128);
   switch (k) {
     case 1: knn_simt_kernel<NORM, WORDS, 1><<<grid, 128, 0, stream>>>(imgs, units, out_idx, out_d2); break;
     case 2: knn_simt_kernel<NORM, WORDS, 2><<<grid, 128, 0, stream>>>(imgs, units, out_idx, out_d2); break;

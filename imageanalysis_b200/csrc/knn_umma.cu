@@ -3,8 +3,8 @@
 // cv2.DescriptorMatcher.knnMatch as called from raw_matches()
 // (reference scripts/lib/matcher.py:203-216).
 //
-// One work unit = 256 query descriptors (two 128-row A tiles, resident in
-// shared memory) against every descriptor of the train image (128-row B tiles
+// One work unit = 512 query descriptors (four 128-row A tiles, resident in
+// shared memory) against every descriptor of the train image (64-row B tiles
 // streamed by cp.async.bulk through a 4-deep mbarrier ring).  The augmented
 // K-step makes every accumulator element the exact squared L2 distance
 // (integer valued < 2^23, exact in fp32) or the exact Hamming distance, so
@@ -13,12 +13,12 @@
 //
 // Warp roles (640 threads, 1 CTA / SM, persistent over units):
 //   warp 0      : B-tile producer  (bulk copy  -> b_full[stage])
-//   warp 1      : MMA issuer       (one elected lane issues 18 tcgen05.mma / B tile)
+//   warp 1      : MMA issuer       (one elected lane issues 36 tcgen05.mma M128xN64xK16 / B tile)
 //   warp 2      : TMEM allocator / deallocator
 //   warp 3      : A-tile producer  (bulk copy  -> a_full[half])
-//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (accumulator, 64-column part,
-//                 TMEM lane quadrant = warp_id % 4); the two column parts of a row merge
-//                 their top-k lists through shared memory once per unit
+//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (A tile, TMEM lane quadrant
+//                 = warp_id % 4); each thread owns ONE query row for all train columns, so
+//                 its running top-k needs no cross-thread merge
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -33,11 +33,14 @@ namespace {
 
 constexpr int kBStages = 4;
 constexpr int kAccStages = 2;
-constexpr uint32_t kTmemCols = 512;  // 2 stages x 2 accumulators x 128 fp32 columns
+constexpr int kEpiWarps = 4 * kATiles;           // one warp per (A tile, TMEM lane quadrant)
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 640
+constexpr uint32_t kTmemCols = 512;              // 2 stages x 4 accumulators x 64 fp32 columns
+constexpr uint32_t kAccCols = kATiles * kBRows;  // 256 TMEM columns per accumulator stage
 
 struct __align__(8) Barriers {
-  uint64_t a_full[2];
-  uint64_t a_empty[2];
+  uint64_t a_full[kATiles];
+  uint64_t a_empty[kATiles];
   uint64_t b_full[kBStages];
   uint64_t b_empty[kBStages];
   uint64_t t_full[kAccStages];
@@ -46,10 +49,9 @@ struct __align__(8) Barriers {
   uint32_t pad;
 };
 
-constexpr size_t kSmemA = 2 * kTileBytes;
-constexpr size_t kSmemB = kBStages * kTileBytes;
-constexpr size_t kSmemMerge = 2 * 128 * 3 * 8;  // [A tile][row][k] (dist, idx) hand-over between column parts
-constexpr size_t kSmemTotal = kSmemA + kSmemB + sizeof(Barriers) + kSmemMerge + 128;
+constexpr size_t kSmemA = kATiles * kTileBytes;       // 147456: four resident query tiles
+constexpr size_t kSmemB = kBStages * kBTileBytes;     //  73728: streamed train tiles
+constexpr size_t kSmemTotal = kSmemA + kSmemB + sizeof(Barriers) + 128;
 
 constexpr float kInf = 3.0e38f;
 
@@ -61,13 +63,13 @@ struct TopK {
 #pragma unroll
     for (int s = 0; s < KTOP; ++s) {
       d[s] = kInf;
-      i[s] = 0x7fffffff;
+      i[s] = -1;
     }
   }
   __device__ __forceinline__ float thr() const { return d[KTOP - 1]; }
-  // Insert (x, col); caller guarantees x < thr().  Columns arrive in ascending
-  // order, so strict '<' keeps the earliest (lowest) column first among equal
-  // distances, which is the order cv2.BFMatcher reports ties in.
+  // Branch-free insertion network; a no-op when x >= thr().  Columns arrive in
+  // ascending order and every comparison is strict, so among equal distances the
+  // earliest (lowest) column stays first: the order cv2.BFMatcher reports ties in.
   __device__ __forceinline__ void insert(float x, int col) {
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
@@ -82,74 +84,42 @@ struct TopK {
       }
     }
   }
-  // Order-independent insert: (distance, index) lexicographic.  Used to merge the
-  // partial lists of the two column parts of a row.
-  __device__ __forceinline__ void insert_lex(float x, int col) {
-#pragma unroll
-    for (int s = KTOP - 1; s >= 0; --s) {
-      const bool lt_prev = (s > 0) ? (x < d[s > 0 ? s - 1 : 0] || (x == d[s > 0 ? s - 1 : 0] && col < i[s > 0 ? s - 1 : 0])) : false;
-      const bool lt_cur = x < d[s] || (x == d[s] && col < i[s]);
-      if (s > 0) {
-        d[s] = lt_prev ? d[s - 1] : (lt_cur ? x : d[s]);
-        i[s] = lt_prev ? i[s - 1] : (lt_cur ? col : i[s]);
-      } else {
-        d[s] = lt_cur ? x : d[s];
-        i[s] = lt_cur ? col : i[s];
-      }
-    }
-  }
 };
 
-__device__ __forceinline__ float min8(const float* w) {
-  return fminf(fmin3(fmin3(w[0], w[1], w[2]), w[3], w[4]), fmin3(w[5], w[6], w[7]));
-}
-
-// 64 accumulator columns of one row (two 32-column TMEM loads).  All eight
-// group minima are formed first (independent FMNMX3 chains), one combined test
-// skips the whole block, and only groups that can beat the running k-th best
-// take the insertion path.
+// 64 accumulator columns of one row.  Fast path: one FMNMX3-based minimum per
+// group of 4 columns and a warp vote; the insertion network runs (for the whole
+// warp, uniformly: no divergence) only for columns where some lane can beat its
+// running k-th best.  Expected insertions per row over M columns are ~k*ln(M/k),
+// so almost every group takes the 4-instruction fast path.
 template <int KTOP>
 __device__ __forceinline__ void consume64(const float (&v0)[32], const float (&v1)[32], int col0, TopK<KTOP>& tk) {
-  float m[8];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    m[g] = min8(&v0[g * 8]);
-    m[4 + g] = min8(&v1[g * 8]);
-  }
-  const float mall = fmin3(fmin3(m[0], m[1], m[2]), fmin3(m[3], m[4], m[5]), fminf(m[6], m[7]));
-  if (mall < tk.thr()) {
+  for (int g = 0; g < 16; ++g) {
+    const float* w = (g < 8) ? &v0[g * 4] : &v1[(g - 8) * 4];
+    const float m = fminf(fmin3(w[0], w[1], w[2]), w[3]);
+    if (__any_sync(0xffffffffu, m < tk.thr())) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (m[g] < tk.thr()) {
-        const float* w = (g < 4) ? &v0[g * 8] : &v1[(g - 4) * 8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (w[j] < tk.thr()) tk.insert(w[j], col0 + g * 8 + j);
-        }
+      for (int j = 0; j < 4; ++j) {
+        if (__any_sync(0xffffffffu, w[j] < tk.thr())) tk.insert(w[j], col0 + g * 4 + j);
       }
     }
   }
 }
 
-// NPART = number of column parts an accumulator tile is split into among
-// epilogue warps (1: 8 epilogue warps, 2: 16 epilogue warps = 4 per SM sub-partition).
-template <Kind kKind, int KTOP, int NPART>
-__global__ void __launch_bounds__(128 + 256 * NPART, 1)
+template <Kind kKind, int KTOP>
+__global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
-  constexpr int kEpiWarps = 8 * NPART;
-  constexpr int kCols = 128 / NPART;  // accumulator columns per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
-  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + ((sizeof(Barriers) + 15) / 16) * 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kATiles; ++i) {
       mbar_init(&bars->a_full[i], 1);
       mbar_init(&bars->a_empty[i], 1);
     }
@@ -177,13 +147,13 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
-        const int n_tb = (t.n + kTileRows - 1) / kTileRows;
+        const int n_tb = (t.n + kBRows - 1) / kBRows;
         for (int tb = 0; tb < n_tb; ++tb, ++it) {
           const uint32_t stage = it % kBStages;
           const uint32_t par = (it / kBStages) & 1;
           mbar_wait(&bars->b_empty[stage], par ^ 1, 10);
-          mbar_arrive_expect_tx(&bars->b_full[stage], kTileBytes);
-          bulk_g2s(smem_b + stage * kTileBytes, t.b_form + static_cast<size_t>(tb) * kTileBytes, kTileBytes,
+          mbar_arrive_expect_tx(&bars->b_full[stage], kBTileBytes);
+          bulk_g2s(smem_b + stage * kBTileBytes, t.b_form + static_cast<size_t>(tb) * kBTileBytes, kBTileBytes,
                    &bars->b_full[stage]);
         }
       }
@@ -197,24 +167,24 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         const ImgDev q = imgs[unit.q_slot];
         const uint8_t* src = q.a_form + static_cast<size_t>(unit.super) * kSuperRows * kRowBytes;
         const uint32_t par = it & 1;
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&bars->a_empty[h], par ^ 1, 20 + h);
-          mbar_arrive_expect_tx(&bars->a_full[h], kTileBytes);
-          bulk_g2s(smem_a + h * kTileBytes, src + static_cast<size_t>(h) * kTileBytes, kTileBytes, &bars->a_full[h]);
+        for (int a = 0; a < kATiles; ++a) {
+          mbar_wait(&bars->a_empty[a], par ^ 1, 20 + a);
+          mbar_arrive_expect_tx(&bars->a_full[a], kTileBytes);
+          bulk_g2s(smem_a + a * kTileBytes, src + static_cast<size_t>(a) * kTileBytes, kTileBytes, &bars->a_full[a]);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+      constexpr uint32_t idesc = make_idesc(128, kBRows, 0, 0);
       const uint32_t a_addr = smem_u32(smem_a);
       const uint32_t b_addr = smem_u32(smem_b);
       uint32_t it = 0, uit = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uit) {
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
-        const int n_tb = (t.n + kTileRows - 1) / kTileRows;
+        const int n_tb = (t.n + kBRows - 1) / kBRows;
         for (int tb = 0; tb < n_tb; ++tb, ++it) {
           const uint32_t stage = it % kBStages;
           const uint32_t par = (it / kBStages) & 1;
@@ -222,21 +192,21 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           const uint32_t apar = (it / kAccStages) & 1;
           mbar_wait(&bars->b_full[stage], par, 30);
           mbar_wait(&bars->t_empty[acc], apar ^ 1, 31);
-          if (tb == 0) {
-            mbar_wait(&bars->a_full[0], uit & 1, 32);
-            mbar_wait(&bars->a_full[1], uit & 1, 33);
-          }
           tc_fence_after();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t taddr = tmem_base + acc * 256 + h * 128;
+          for (int a = 0; a < kATiles; ++a) {
+            if (tb == 0) {
+              mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
+              tc_fence_after();
+            }
+            const uint32_t taddr = tmem_base + acc * kAccCols + a * kBRows;
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks) {
-              const uint64_t adesc = make_smem_desc(a_addr + h * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
-              const uint64_t bdesc = make_smem_desc(b_addr + stage * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
+              const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
+              const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
               umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
             }
-            if (tb == n_tb - 1) umma_commit(&bars->a_empty[h]);  // A half free for the next unit
+            if (tb == n_tb - 1) umma_commit(&bars->a_empty[a]);  // this A tile is free for the next unit
           }
           umma_commit(&bars->b_empty[stage]);
           umma_commit(&bars->t_full[acc]);
@@ -244,10 +214,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue
-    const int g = (warp - 4) >> 2;      // 0 .. 2*NPART-1
-    const int h = g / NPART;            // which accumulator / A tile
-    const int part = g % NPART;         // which column part of it
+    // ------------------------------------------------ epilogue: one row per thread, all columns
+    const int a = (warp - 4) >> 2;      // which accumulator / A tile
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int row_in_tile = quad * 32 + lane;
     TopK<KTOP> tk;
@@ -256,60 +224,42 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const KnnUnit unit = units[u];
       const ImgDev q = imgs[unit.q_slot];
       const ImgDev t = imgs[unit.t_slot];
-      const int n_tb = (t.n + kTileRows - 1) / kTileRows;
+      const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
       for (int tb = 0; tb < n_tb; ++tb, ++it) {
         const uint32_t acc = it % kAccStages;
         const uint32_t apar = (it / kAccStages) & 1;
         mbar_wait(&bars->t_full[acc], apar, 40);
         tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + h * 128 + part * kCols;
-#pragma unroll 1
-        for (int c = 0; c < kCols / 64; ++c) {
-          if (dbg_flags == 1) break;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols + a * kBRows;
+        if (dbg_flags != 1) {
           float v0[32], v1[32];
           __syncwarp();
-          tmem_ld32(taddr + c * 64, v0);
-          tmem_ld32(taddr + c * 64 + 32, v1);
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
           tmem_ld_wait(v0);
           tmem_ld_wait(v1);
           if (dbg_flags == 0) {
-            consume64<KTOP>(v0, v1, tb * kTileRows + part * kCols + c * 64, tk);
-          } else if (dbg_flags == 2) {  // profiling aid: fast path only (results are NOT valid)
+            consume64<KTOP>(v0, v1, tb * kBRows, tk);
+          } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v0[0];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m = fminf(m, fminf(min8(&v0[j * 8]), min8(&v1[j * 8])));
+            for (int j = 0; j < 8; ++j)
+              m = fminf(m, fmin3(fminf(v0[j * 4], v0[j * 4 + 1]), fminf(v0[j * 4 + 2], v0[j * 4 + 3]),
+                                 fmin3(fminf(v1[j * 4], v1[j * 4 + 1]), v1[j * 4 + 2], v1[j * 4 + 3])));
             tk.d[0] = fminf(tk.d[0], m);
-          }  // dbg_flags == 1: MMA/TMA pipeline only, accumulators dropped
-        }
+          }
+        }  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
         __syncwarp();
         tc_fence_before();
         if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
       }
-      if (NPART == 2) {
-        // hand the upper column part's list to the lower part's thread of the same row
-        if (part == 1) {
-#pragma unroll
-          for (int s = 0; s < KTOP; ++s)
-            merge[(h * 128 + row_in_tile) * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(256 * NPART) : "memory");
-        if (part == 0) {
-#pragma unroll
-          for (int s = 0; s < KTOP; ++s) {
-            const float2 e = merge[(h * 128 + row_in_tile) * KTOP + s];
-            tk.insert_lex(e.x, __float_as_int(e.y));
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(256 * NPART) : "memory");
-      }
-      const int row = unit.super * kSuperRows + h * kTileRows + row_in_tile;
-      if (part == 0 && row < q.n) {
+      const int row = unit.super * kSuperRows + a * kTileRows + row_in_tile;
+      if (row < q.n) {
         const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
 #pragma unroll
         for (int s = 0; s < KTOP; ++s) {
-          out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : tk.i[s];
+          out_idx[o + s] = tk.i[s];
           out_d2[o + s] = tk.d[s];
         }
       }
@@ -376,30 +326,19 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   }
 }
 
-template <Kind kKind, int KTOP, int NPART>
-cudaError_t launch_p(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
+template <Kind kKind, int KTOP>
+cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
                      cudaStream_t stream) {
-  auto kern = knn_umma_kernel<kKind, KTOP, NPART>;
+  auto kern = knn_umma_kernel<kKind, KTOP>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
-  const int grid = n_units < num_sms ? n_units : num_sms;
   static const int flags = [] {
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
     return e ? atoi(e) : 0;
   }();
-  kern<<<grid, 128 + 256 * NPART, kSmemTotal, stream>>>(imgs, units, n_units, out_idx, out_d2, flags);
+  const int grid = n_units < num_sms ? n_units : num_sms;
+  kern<<<grid, kThreads, kSmemTotal, stream>>>(imgs, units, n_units, out_idx, out_d2, flags);
   return cudaGetLastError();
-}
-
-template <Kind kKind, int KTOP>
-cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
-                     cudaStream_t stream) {
-  static const int parts = [] {
-    const char* e = getenv("IAM_UMMA_PARTS");  // tuning / A-B aid: 1 = 8 epilogue warps, 2 = 16 (default)
-    return (e && atoi(e) == 1) ? 1 : 2;
-  }();
-  return parts == 1 ? launch_p<kKind, KTOP, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream)
-                    : launch_p<kKind, KTOP, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
 }
 
 }  // namespace

@@ -20,7 +20,10 @@ constexpr int kGroupRows = 8;
 constexpr int kGroupBytes = kGroupRows * kRowBytes;  // 2304
 constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows * kRowBytes;    // 36864
-constexpr int kSuperRows = 256;                      // rows of the query image one work unit owns
+constexpr int kATiles = 4;                           // resident query tiles per work unit
+constexpr int kSuperRows = kATiles * kTileRows;      // 512 rows of the query image one work unit owns
+constexpr int kBRows = 64;                           // train rows per streamed B tile (= UMMA N)
+constexpr int kBTileBytes = kBRows * kRowBytes;      // 18432
 constexpr int kKSteps = 9;                           // 8 data K-steps + 1 augmentation step
 constexpr int kKStepBytes = 256;                     // 2 chunks * 128 B
 constexpr uint32_t kLBO = 128;
@@ -39,7 +42,7 @@ struct ImgDev {
   int n_pad;              // rows allocated, multiple of kSuperRows
 };
 
-// One unit of work for the kNN kernels: 256 query rows of q_slot against all
+// One unit of work for the kNN kernels: kSuperRows query rows of q_slot against all
 // descriptors of t_slot.
 struct KnnUnit {
   int q_slot;

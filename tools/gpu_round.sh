@@ -5,12 +5,11 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -25
 echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tee gpurun_out/smoke.log | tail -3
-B="timeout 600 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu"
-echo "== bench parts=2"; $B 2>&1 | tee gpurun_out/bench_p2.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['clocks'])"
-echo "== bench parts=1"; IAM_UMMA_PARTS=1 $B 2>&1 | tee gpurun_out/bench_p1.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'])"
+B="timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu"
+echo "== bench new"; $B 2>&1 | tee gpurun_out/bench_new.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['clocks'])"
 echo "== bench no-epilogue (MMA+TMA only)"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['clocks'])"
 echo "== bench fast-path only"; IAM_UMMA_DEBUG=2 $B 2>&1 | tee gpurun_out/bench_dbg2.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'])"
-echo "== bench full"; timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1
+echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1
 echo "== bench ORB"; timeout 600 python bench.py --steps 3 --warmup 3 --detector ORB --no-e2e 2>&1 | tee gpurun_out/bench_orb.log | tail -1
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 120 --no-e2e --no-cpu > gpurun_out/ncu_list.log 2>&1
