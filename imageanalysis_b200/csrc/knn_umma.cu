@@ -3,9 +3,11 @@
 // cv2.DescriptorMatcher.knnMatch as called from raw_matches()
 // (reference scripts/lib/matcher.py:203-216).
 //
-// One work unit = 512 query descriptors (four 128-row A tiles, resident in
-// shared memory) against every descriptor of the train image (64-row B tiles
-// streamed by cp.async.bulk through a 4-deep mbarrier ring).  The augmented
+// One work unit = 256 query descriptors (two 128-row A tiles, copied once per
+// unit from a shared-memory staging buffer into TENSOR MEMORY with tcgen05.cp,
+// so the MMAs read only the B operand from shared memory) against every
+// descriptor of the train image (64-row B tiles streamed by cp.async.bulk
+// through a 6-deep mbarrier ring).  The augmented
 // K-step makes every accumulator element the exact squared L2 distance
 // (integer valued < 2^23, exact in fp32) or the exact Hamming distance, so
 // the N x M distance matrix never leaves the SM: eight epilogue warps read
@@ -13,12 +15,13 @@
 //
 // Warp roles (640 threads, 1 CTA / SM, persistent over units):
 //   warp 0      : B-tile producer  (bulk copy  -> b_full[stage])
-//   warp 1      : MMA issuer       (one elected lane issues 36 tcgen05.mma M128xN64xK16 / B tile)
+//   warp 1      : MMA issuer       (one elected lane: 18 tcgen05.cp per unit, 18 tcgen05.mma M128xN64xK16 per B tile)
 //   warp 2      : TMEM allocator / deallocator
 //   warp 3      : A-tile producer  (bulk copy  -> a_full[half])
-//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (A tile, TMEM lane quadrant
-//                 = warp_id % 4); each thread owns ONE query row for all train columns, so
-//                 its running top-k needs no cross-thread merge
+//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (A tile, 32-column half of each
+//                 64-column accumulator tile, TMEM lane quadrant = warp_id % 4); the two threads
+//                 that share a row exchange their running bounds through shared memory every
+//                 tile (stale bounds are still valid) and merge their lists once per unit
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -31,12 +34,14 @@ namespace iam {
 
 namespace {
 
-constexpr int kBStages = 4;
+constexpr int kBStages = 6;
 constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 4 * kATiles;           // one warp per (A tile, TMEM lane quadrant)
+constexpr int kEpiWarps = 8 * kATiles;           // (A tile, 32-column half, TMEM lane quadrant): 16 warps, 4 per SM sub-partition
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 640
-constexpr uint32_t kTmemCols = 512;              // 2 stages x 4 accumulators x 64 fp32 columns
-constexpr uint32_t kAccCols = kATiles * kBRows;  // 256 TMEM columns per accumulator stage
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCols = kATiles * kBRows;  // 128 TMEM columns per accumulator stage  (columns 0..255)
+constexpr uint32_t kTmemA = kAccStages * kAccCols;  // A operand region starts at column 256
+constexpr uint32_t kTmemAColsPerTile = kKSteps * 8;  // 72 columns: 128 rows x 144 fp16 (two K elements per 32-bit cell)
 
 struct __align__(8) Barriers {
   uint64_t a_full[kATiles];
@@ -49,9 +54,12 @@ struct __align__(8) Barriers {
   uint32_t pad;
 };
 
-constexpr size_t kSmemA = kATiles * kTileBytes;       // 147456: four resident query tiles
-constexpr size_t kSmemB = kBStages * kBTileBytes;     //  73728: streamed train tiles
-constexpr size_t kSmemTotal = kSmemA + kSmemB + sizeof(Barriers) + 128;
+constexpr size_t kSmemA = kATiles * kTileBytes;         //  73728: staging for the next unit's query tiles
+constexpr size_t kSmemB = kBStages * kBTileBytes;       // 110592: streamed train tiles
+constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
+constexpr size_t kSmemShare = 2 * kSuperRows * 16;      //   8192: running bounds exchanged between the two column halves
+constexpr size_t kSmemMerge = kSuperRows * 3 * 8;       //   6144: end-of-unit hand-over of the upper half's list
+constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
 
 constexpr float kInf = 3.0e38f;
 
@@ -63,13 +71,14 @@ struct TopK {
 #pragma unroll
     for (int s = 0; s < KTOP; ++s) {
       d[s] = kInf;
-      i[s] = -1;
+      i[s] = 0x7fffffff;
     }
   }
   __device__ __forceinline__ float thr() const { return d[KTOP - 1]; }
-  // Branch-free insertion network; a no-op when x >= thr().  Columns arrive in
-  // ascending order and every comparison is strict, so among equal distances the
-  // earliest (lowest) column stays first: the order cv2.BFMatcher reports ties in.
+  // Branch-free insertion network; a no-op when x >= thr().  A thread sees its
+  // columns in ascending order and every comparison is strict, so among equal
+  // distances the earliest (lowest) column stays first: the order
+  // cv2.BFMatcher reports ties in.
   __device__ __forceinline__ void insert(float x, int col) {
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
@@ -84,29 +93,53 @@ struct TopK {
       }
     }
   }
+  // Order-independent insert ((distance, index) lexicographic): merges the list of
+  // the other column half at the end of a unit.
+  __device__ __forceinline__ void insert_lex(float x, int col) {
+#pragma unroll
+    for (int s = KTOP - 1; s >= 0; --s) {
+      const int sp = s > 0 ? s - 1 : 0;
+      const bool lt_prev = (s > 0) ? (x < d[sp] || (x == d[sp] && col < i[sp])) : false;
+      const bool lt_cur = x < d[s] || (x == d[s] && col < i[s]);
+      if (s > 0) {
+        d[s] = lt_prev ? d[s - 1] : (lt_cur ? x : d[s]);
+        i[s] = lt_prev ? i[s - 1] : (lt_cur ? col : i[s]);
+      } else {
+        d[s] = lt_cur ? x : d[s];
+        i[s] = lt_cur ? col : i[s];
+      }
+    }
+  }
 };
 
-// 64 accumulator columns of one row.  Fast path: one FMNMX3-based minimum per
+__device__ __forceinline__ float next_up(float x) {  // x >= 0
+  return __int_as_float(__float_as_int(x) + 1);
+}
+
+// 32 accumulator columns of one row.  Fast path: one FMNMX3-based minimum per
 // group of 4 columns and a warp vote; the insertion network runs (for the whole
 // warp, uniformly: no divergence) only for columns where some lane can beat its
-// running k-th best.  Expected insertions per row over M columns are ~k*ln(M/k),
-// so almost every group takes the 4-instruction fast path.
+// bound.  `pb_up` is the smallest value NOT admissible according to the partner
+// thread that owns the other 32 columns of this row (ties with the partner's
+// bound are admitted; the final merge orders them by index).  Expected
+// insertions per row over M columns are ~k*ln(M/k), so almost every group takes
+// the 5-instruction fast path.
 template <int KTOP>
-__device__ __forceinline__ void consume64(const float (&v0)[32], const float (&v1)[32], int col0, TopK<KTOP>& tk) {
+__device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up) {
 #pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    const float* w = (g < 8) ? &v0[g * 4] : &v1[(g - 8) * 4];
+  for (int g = 0; g < 8; ++g) {
+    const float* w = &v[g * 4];
     const float m = fminf(fmin3(w[0], w[1], w[2]), w[3]);
-    if (__any_sync(0xffffffffu, m < tk.thr())) {
+    if (__any_sync(0xffffffffu, m < fminf(tk.thr(), pb_up))) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (__any_sync(0xffffffffu, w[j] < tk.thr())) tk.insert(w[j], col0 + g * 4 + j);
+        if (__any_sync(0xffffffffu, w[j] < fminf(tk.thr(), pb_up))) tk.insert(w[j], col0 + g * 4 + j);
       }
     }
   }
 }
 
-template <Kind kKind, int KTOP>
+template <Kind kKind, int KTOP, bool kATmem>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
@@ -114,10 +147,13 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
+  float4* share = reinterpret_cast<float4*>(smem + kSmemA + kSmemB + kSmemBars);             // [half][row]
+  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + kSmemBars + kSmemShare);  // [row][k]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  for (int i = threadIdx.x; i < 2 * kSuperRows; i += blockDim.x) share[i] = make_float4(kInf, kInf, __int_as_float(-1), 0.f);
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kATiles; ++i) {
       mbar_init(&bars->a_full[i], 1);
@@ -185,6 +221,20 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
         const int n_tb = (t.n + kBRows - 1) / kBRows;
+        // query tiles: shared-memory staging -> tensor memory (tcgen05.cp), then the staging is free again.
+        // tcgen05 operations of one thread execute in issue order, so these copies run after every MMA of
+        // the previous unit that still reads the old A tiles.
+        for (int a = 0; a < kATiles; ++a) {
+          mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
+          tc_fence_after();
+          if (kATmem) {
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks)
+              tmem_cp_128x256b(tmem_base + kTmemA + a * kTmemAColsPerTile + ks * 8,
+                               make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO));
+            umma_commit(&bars->a_empty[a]);
+          }
+        }
         for (int tb = 0; tb < n_tb; ++tb, ++it) {
           const uint32_t stage = it % kBStages;
           const uint32_t par = (it / kBStages) & 1;
@@ -195,18 +245,18 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_after();
 #pragma unroll
           for (int a = 0; a < kATiles; ++a) {
-            if (tb == 0) {
-              mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
-              tc_fence_after();
-            }
             const uint32_t taddr = tmem_base + acc * kAccCols + a * kBRows;
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks) {
-              const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
               const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
-              umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+              if (kATmem) {
+                umma_ts<kKind>(taddr, tmem_base + kTmemA + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+              } else {
+                const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
+                umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+              }
             }
-            if (tb == n_tb - 1) umma_commit(&bars->a_empty[a]);  // this A tile is free for the next unit
+            if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
           }
           umma_commit(&bars->b_empty[stage]);
           umma_commit(&bars->t_full[acc]);
@@ -214,13 +264,16 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue: one row per thread, all columns
-    const int a = (warp - 4) >> 2;      // which accumulator / A tile
+    // ------------------------------------------------ epilogue
+    const int e = (warp - 4) >> 2;      // 0..3
+    const int a = e >> 1;               // which accumulator / A tile
+    const int half = e & 1;             // which 32 of the tile's 64 columns
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
-    const int row_in_tile = quad * 32 + lane;
+    const int urow = a * kTileRows + quad * 32 + lane;  // row within the unit
     TopK<KTOP> tk;
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int uit = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uit) {
       const KnnUnit unit = units[u];
       const ImgDev q = imgs[unit.q_slot];
       const ImgDev t = imgs[unit.t_slot];
@@ -229,38 +282,58 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       for (int tb = 0; tb < n_tb; ++tb, ++it) {
         const uint32_t acc = it % kAccStages;
         const uint32_t apar = (it / kAccStages) & 1;
+        // bound from the thread that owns the other half of this row's columns (stale values are still valid bounds)
+        float pb_up = kInf;
+        {
+          const float4 p = lds_volatile_v4(&share[(half ^ 1) * kSuperRows + urow]);
+          if (__float_as_int(p.z) == uit) {
+            const float merged = (KTOP == 2) ? fminf(fmaxf(tk.d[0], p.x), fminf(tk.d[KTOP - 1], p.y)) : fminf(tk.d[KTOP - 1], p.y);
+            pb_up = next_up(merged);
+          }
+        }
         mbar_wait(&bars->t_full[acc], apar, 40);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols + a * kBRows;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols + a * kBRows + half * 32;
         if (dbg_flags != 1) {
-          float v0[32], v1[32];
+          float v[32];
           __syncwarp();
-          tmem_ld32(taddr, v0);
-          tmem_ld32(taddr + 32, v1);
-          tmem_ld_wait(v0);
-          tmem_ld_wait(v1);
+          tmem_ld32(taddr, v);
+          tmem_ld_wait(v);
           if (dbg_flags == 0) {
-            consume64<KTOP>(v0, v1, tb * kBRows, tk);
+            consume32<KTOP>(v, tb * kBRows + half * 32, tk, pb_up);
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
-            float m = v0[0];
+            float m = v[0];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              m = fminf(m, fmin3(fminf(v0[j * 4], v0[j * 4 + 1]), fminf(v0[j * 4 + 2], v0[j * 4 + 3]),
-                                 fmin3(fminf(v1[j * 4], v1[j * 4 + 1]), v1[j * 4 + 2], v1[j * 4 + 3])));
+            for (int j = 0; j < 8; ++j) m = fminf(m, fminf(fmin3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
             tk.d[0] = fminf(tk.d[0], m);
           }
         }  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
         __syncwarp();
         tc_fence_before();
         if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
+        sts_volatile_v4(&share[half * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
       }
-      const int row = unit.super * kSuperRows + a * kTileRows + row_in_tile;
-      if (row < q.n) {
-        const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
+      // end of unit: the upper half hands its list to the lower half's thread of the same row
+      if (half == 1) {
+#pragma unroll
+        for (int s = 0; s < KTOP; ++s) merge[urow * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      const int row = unit.super * kSuperRows + urow;
+      if (half == 0) {
 #pragma unroll
         for (int s = 0; s < KTOP; ++s) {
-          out_idx[o + s] = tk.i[s];
-          out_d2[o + s] = tk.d[s];
+          const float2 m = merge[urow * KTOP + s];
+          tk.insert_lex(m.x, __float_as_int(m.y));
+        }
+        if (row < q.n) {
+          const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
+#pragma unroll
+          for (int s = 0; s < KTOP; ++s) {
+            out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : tk.i[s];
+            out_d2[o + s] = tk.d[s];
+          }
         }
       }
     }
@@ -279,7 +352,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 template <Kind kKind>
 __global__ void __launch_bounds__(128, 1)
 umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __restrict__ b_tile, uint32_t lbo,
-                       uint32_t sbo, uint32_t kstep_bytes, int ksteps, float* __restrict__ out) {
+                       uint32_t sbo, uint32_t kstep_bytes, int ksteps_in, float* __restrict__ out) {
+  const bool a_in_tmem = ksteps_in < 0;  // negative K-step count selects the TS form (A staged through tcgen05.cp)
+  const int ksteps = a_in_tmem ? -ksteps_in : ksteps_in;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full, bar_done;
   __shared__ uint32_t s_tmem;
@@ -289,7 +364,7 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
     mbar_init(&bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<128>(&s_tmem);
+  if (warp == 1) tmem_alloc<256>(&s_tmem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -301,10 +376,16 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
     mbar_wait(&bar_full, 0, 90);
     tc_fence_after();
     constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+    if (a_in_tmem)
+      for (int ks = 0; ks < ksteps; ++ks)
+        tmem_cp_128x256b(tmem + 128 + ks * 8, make_smem_desc(smem_u32(smem) + ks * kstep_bytes, lbo, sbo));
     for (int ks = 0; ks < ksteps; ++ks) {
       const uint64_t ad = make_smem_desc(smem_u32(smem) + ks * kstep_bytes, lbo, sbo);
       const uint64_t bd = make_smem_desc(smem_u32(smem + kTileBytes) + ks * kstep_bytes, lbo, sbo);
-      umma<kKind>(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      if (a_in_tmem)
+        umma_ts<kKind>(tmem, tmem + 128 + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
+      else
+        umma<kKind>(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
     }
     umma_commit(&bar_done);
   }
@@ -322,14 +403,18 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem);
+    tmem_dealloc<256>(tmem);
   }
 }
 
 template <Kind kKind, int KTOP>
 cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
                      cudaStream_t stream) {
-  auto kern = knn_umma_kernel<kKind, KTOP>;
+  static const bool a_tmem = [] {
+    const char* e = getenv("IAM_UMMA_A_SMEM");  // A/B aid: 1 = keep the A operand in shared memory (SS form)
+    return !(e && atoi(e) == 1);
+  }();
+  auto kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true> : knn_umma_kernel<kKind, KTOP, false>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
   static const int flags = [] {

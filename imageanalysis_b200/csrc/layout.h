@@ -20,8 +20,8 @@ constexpr int kGroupRows = 8;
 constexpr int kGroupBytes = kGroupRows * kRowBytes;  // 2304
 constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows * kRowBytes;    // 36864
-constexpr int kATiles = 4;                           // resident query tiles per work unit
-constexpr int kSuperRows = kATiles * kTileRows;      // 512 rows of the query image one work unit owns
+constexpr int kATiles = 2;                           // resident query tiles per work unit (A operand lives in TMEM)
+constexpr int kSuperRows = kATiles * kTileRows;      // 256 rows of the query image one work unit owns
 constexpr int kBRows = 64;                           // train rows per streamed B tile (= UMMA N)
 constexpr int kBTileBytes = kBRows * kRowBytes;      // 18432
 constexpr int kKSteps = 9;                           // 8 data K-steps + 1 augmentation step

@@ -44,22 +44,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware, do not spin on issue slots
       : "memory");
   return ok != 0;
 }
 
-#ifndef IAM_SPIN_LIMIT
-#define IAM_SPIN_LIMIT (1u << 27)   // ~seconds; a lost arrival traps instead of hanging the GPU
+#ifndef IAM_WAIT_TIMEOUT_NS
+#define IAM_WAIT_TIMEOUT_NS 8000000000ull   // a lost arrival traps after 8 s instead of hanging the GPU
 #endif
 
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > IAM_SPIN_LIMIT) {
+    if (global_timer_ns() - t0 > IAM_WAIT_TIMEOUT_NS) {
       printf("iamatch: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();
@@ -138,6 +145,33 @@ __device__ __forceinline__ void umma(uint32_t taddr, uint64_t adesc, uint64_t bd
   }
 }
 
+// A operand from tensor memory ("TS" form): D[tmem] (+)= A[tmem] . B[smem]
+template <Kind kKind>
+__device__ __forceinline__ void umma_ts(uint32_t taddr, uint32_t a_taddr, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (kKind == Kind::F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(taddr),
+        "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(taddr),
+        "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// shared memory -> tensor memory: 128 rows x 256 bits (one K-step slab of an A tile,
+// addressed by the same matrix descriptor the SS-form MMA would use) -> 128 lanes x 8 columns
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -164,6 +198,21 @@ __device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
                  "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
                  "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                :
+               : "memory");
+}
+
+// 16-byte shared-memory accesses that the compiler may neither cache nor split
+__device__ __forceinline__ float4 lds_volatile_v4(const void* p) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(smem_u32(p))
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_v4(void* p, float4 v) {
+  asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
                : "memory");
 }
 

@@ -24,14 +24,14 @@ def main():
         else:
             exp = np.unpackbits(q[:128, None] ^ t[None, :128], axis=-1).sum(-1)
             dot = -2 * (np.unpackbits(q[:128], axis=-1).astype(np.int64) @ np.unpackbits(t[:128], axis=-1).astype(np.int64).T)
-        for tag, kw in (("prod", dict()), ("swapped", dict(lbo=2304, sbo=128)), ("data_only", dict(ksteps=8)),
-                        ("first_kstep", dict(ksteps=1))):
+        for tag, kw in (("prod", dict()), ("prod_A_in_tmem", dict(ksteps=-9)), ("data_only", dict(ksteps=8)),
+                        ("data_only_A_in_tmem", dict(ksteps=-8))):
             try:
                 got = eng.debug_tile(0, 1, **kw)
             except Exception as e:  # noqa: BLE001
                 print(name, tag, "FAILED:", e)
                 continue
-            ref = exp if tag in ("prod", "swapped") else dot
+            ref = exp if tag.startswith("prod") else dot
             diff = np.abs(got.astype(np.float64) - ref)
             print("%s %-11s max|diff|=%g  exact=%d/16384  got[0,:4]=%s ref[0,:4]=%s" % (
                 name, tag, diff.max(), int((diff == 0).sum()), got[0, :4].tolist(), ref[0, :4].tolist()))

@@ -1,18 +1,22 @@
 #!/bin/bash
-# One GPU session: parity tests -> smoke -> bench A/B -> ncu.  Every stage has its own
+# One GPU session: debug tile -> parity tests -> smoke -> bench A/B -> ncu.  Every stage has its own
 # timeout so a wedged kernel cannot eat the box; logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -25
+echo "== debug tile"; timeout 180 python tools/debug_tile.py 2>&1 | tee gpurun_out/debug_tile.log | tail -12
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu.log | tail -25
+echo "== pytest gpu (A in smem)"; IAM_UMMA_A_SMEM=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu_smem.log | tail -5
 echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tee gpurun_out/smoke.log | tail -3
 B="timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu"
-echo "== bench new"; $B 2>&1 | tee gpurun_out/bench_new.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'], d['clocks'])"
-echo "== bench no-epilogue (MMA+TMA only)"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'], d['clocks'])"
-echo "== bench fast-path only"; IAM_UMMA_DEBUG=2 $B 2>&1 | tee gpurun_out/bench_dbg2.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['kernel_ms_per_launch'])"
+P='import sys,json; d=json.loads(sys.stdin.read()); print(d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_per_launch"], d["roofline"]["frac"], d["clocks"])'
+echo "== bench A-tmem"; $B 2>&1 | tee gpurun_out/bench_new.log | tail -1 | python -c "$P"
+echo "== bench A-smem"; IAM_UMMA_A_SMEM=1 $B 2>&1 | tee gpurun_out/bench_asmem.log | tail -1 | python -c "$P"
+echo "== bench no-epilogue (MMA+TMA only)"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "$P"
+echo "== bench fast-path only"; IAM_UMMA_DEBUG=2 $B 2>&1 | tee gpurun_out/bench_dbg2.log | tail -1 | python -c "$P"
 echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1
-echo "== bench ORB"; timeout 600 python bench.py --steps 3 --warmup 3 --detector ORB --no-e2e 2>&1 | tee gpurun_out/bench_orb.log | tail -1
+echo "== bench ORB"; timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e 2>&1 | tee gpurun_out/bench_orb.log | tail -1
 echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 120 --no-e2e --no-cpu > gpurun_out/ncu_list.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"knn_|reduce_kernel|dedupe_|crosscheck_|finish_dist|convert_" -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 120 --no-cpu > gpurun_out/ncu_list.log 2>&1
 echo "== ncu full (knn kernel)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:knn_umma -s 1 -c 1 -o gpurun_out/knn_umma python bench.py --steps 1 --warmup 1 --frames 60 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
