@@ -239,6 +239,9 @@ int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool 
       pl->jobs.push_back(jb);
       const int supers = (q.n + iam::kSuperRows - 1) / iam::kSuperRows;
       for (int s = 0; s < supers; ++s) pl->units.push_back(iam::KnnUnit{qs, ts, s, (int)rows});
+      // the clustered kernel walks units in pairs that share the train image: keep every job even
+      // (the duplicate recomputes and rewrites identical results)
+      if (supers & 1) pl->units.push_back(iam::KnnUnit{qs, ts, supers - 1, (int)rows});
       rows += q.n_pad;
       pl->max_n = std::max(pl->max_n, std::max(q.n, t.n));
     }

@@ -125,21 +125,42 @@ __device__ __forceinline__ float next_up(float x) {  // x >= 0
 // insertions per row over M columns are ~k*ln(M/k), so almost every group takes
 // the 5-instruction fast path.
 template <int KTOP>
+__device__ __forceinline__ void consume_group(const float* w, int col, TopK<KTOP>& tk, float te) {
+  // four votes issued back to back (computed against the bound at group entry: a superset of what
+  // the tightening bound would admit), then the branch-free network only where some lane qualifies
+  const bool e0 = __any_sync(0xffffffffu, w[0] < te);
+  const bool e1 = __any_sync(0xffffffffu, w[1] < te);
+  const bool e2 = __any_sync(0xffffffffu, w[2] < te);
+  const bool e3 = __any_sync(0xffffffffu, w[3] < te);
+  if (e0) tk.insert(w[0], col);
+  if (e1) tk.insert(w[1], col + 1);
+  if (e2) tk.insert(w[2], col + 2);
+  if (e3) tk.insert(w[3], col + 3);
+}
+
+template <int KTOP>
 __device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float* w = &v[g * 4];
-    const float m = fminf(fmin3(w[0], w[1], w[2]), w[3]);
-    if (__any_sync(0xffffffffu, m < fminf(tk.thr(), pb_up))) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (__any_sync(0xffffffffu, w[j] < fminf(tk.thr(), pb_up))) tk.insert(w[j], col0 + g * 4 + j);
-      }
-    }
+  for (int h = 0; h < 2; ++h) {
+    // bound admitted at batch entry; it only tightens, so votes taken against it stay conservative
+    const float te = fminf(tk.thr(), pb_up);
+    const float* w = &v[h * 16];
+    const float m0 = fminf(fmin3(w[0], w[1], w[2]), w[3]);
+    const float m1 = fminf(fmin3(w[4], w[5], w[6]), w[7]);
+    const float m2 = fminf(fmin3(w[8], w[9], w[10]), w[11]);
+    const float m3 = fminf(fmin3(w[12], w[13], w[14]), w[15]);
+    const bool t0 = __any_sync(0xffffffffu, m0 < te);
+    const bool t1 = __any_sync(0xffffffffu, m1 < te);
+    const bool t2 = __any_sync(0xffffffffu, m2 < te);
+    const bool t3 = __any_sync(0xffffffffu, m3 < te);
+    if (t0) consume_group<KTOP>(w, col0 + h * 16, tk, fminf(tk.thr(), pb_up));
+    if (t1) consume_group<KTOP>(w + 4, col0 + h * 16 + 4, tk, fminf(tk.thr(), pb_up));
+    if (t2) consume_group<KTOP>(w + 8, col0 + h * 16 + 8, tk, fminf(tk.thr(), pb_up));
+    if (t3) consume_group<KTOP>(w + 12, col0 + h * 16 + 12, tk, fminf(tk.thr(), pb_up));
   }
 }
 
-template <Kind kKind, int KTOP, bool kATmem>
+template <Kind kKind, int KTOP, bool kATmem, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
@@ -152,6 +173,13 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // With kCluster two CTAs (one cluster) walk the unit list in lock step on the two units 2p, 2p+1 of the
+  // same directed job: each CTA fetches HALF of every train tile and multicasts it to both, which halves
+  // the L2 -> SM traffic of the streamed operand.
+  constexpr int kCtas = kCluster ? 2 : 1;
+  const int cta_rank = kCluster ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_pu = blockIdx.x / kCtas;
+  const int pu_stride = gridDim.x / kCtas;
 
   for (int i = threadIdx.x; i < 2 * kSuperRows; i += blockDim.x) share[i] = make_float4(kInf, kInf, __int_as_float(-1), 0.f);
   if (warp == 1 && elect_one()) {
@@ -161,7 +189,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     }
     for (int i = 0; i < kBStages; ++i) {
       mbar_init(&bars->b_full[i], 1);
-      mbar_init(&bars->b_empty[i], 1);
+      mbar_init(&bars->b_empty[i], kCtas);  // every CTA that received the tile must be done with it
     }
     for (int i = 0; i < kAccStages; ++i) {
       mbar_init(&bars->t_full[i], 1);
@@ -173,6 +201,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
@@ -180,7 +209,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // ------------------------------------------------ B-tile producer
     if (elect_one()) {
       uint32_t it = 0;  // running B-tile counter across units
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride) {
+        const int u = pu * kCtas + cta_rank;
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
         const int n_tb = (t.n + kBRows - 1) / kBRows;
@@ -189,8 +219,15 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           const uint32_t par = (it / kBStages) & 1;
           mbar_wait(&bars->b_empty[stage], par ^ 1, 10);
           mbar_arrive_expect_tx(&bars->b_full[stage], kBTileBytes);
-          bulk_g2s(smem_b + stage * kBTileBytes, t.b_form + static_cast<size_t>(tb) * kBTileBytes, kBTileBytes,
-                   &bars->b_full[stage]);
+          if (kCluster) {
+            constexpr uint32_t kHalf = kBTileBytes / 2;  // 32 train rows = 4 core-matrix groups, contiguous
+            bulk_g2s_multicast(smem_b + stage * kBTileBytes + cta_rank * kHalf,
+                               t.b_form + static_cast<size_t>(tb) * kBTileBytes + cta_rank * kHalf, kHalf,
+                               &bars->b_full[stage], 0x3);
+          } else {
+            bulk_g2s(smem_b + stage * kBTileBytes, t.b_form + static_cast<size_t>(tb) * kBTileBytes, kBTileBytes,
+                     &bars->b_full[stage]);
+          }
         }
       }
     }
@@ -198,7 +235,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // ------------------------------------------------ A-tile producer
     if (elect_one()) {
       uint32_t it = 0;  // unit counter of this CTA
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++it) {
+        const int u = pu * kCtas + cta_rank;
         const KnnUnit unit = units[u];
         const ImgDev q = imgs[unit.q_slot];
         const uint8_t* src = q.a_form + static_cast<size_t>(unit.super) * kSuperRows * kRowBytes;
@@ -217,7 +255,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const uint32_t a_addr = smem_u32(smem_a);
       const uint32_t b_addr = smem_u32(smem_b);
       uint32_t it = 0, uit = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uit) {
+      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
+        const int u = pu * kCtas + cta_rank;
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
         const int n_tb = (t.n + kBRows - 1) / kBRows;
@@ -258,7 +297,10 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             }
             if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
           }
-          umma_commit(&bars->b_empty[stage]);
+          if (kCluster)
+            umma_commit_multicast(&bars->b_empty[stage], 0x3);
+          else
+            umma_commit(&bars->b_empty[stage]);
           umma_commit(&bars->t_full[acc]);
         }
       }
@@ -273,7 +315,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     TopK<KTOP> tk;
     uint32_t it = 0;
     int uit = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++uit) {
+    for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
+        const int u = pu * kCtas + cta_rank;
       const KnnUnit unit = units[u];
       const ImgDev q = imgs[unit.q_slot];
       const ImgDev t = imgs[unit.t_slot];
@@ -341,6 +384,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster) cluster_sync_all();  // no CTA leaves while its peer may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -414,16 +458,41 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     const char* e = getenv("IAM_UMMA_A_SMEM");  // A/B aid: 1 = keep the A operand in shared memory (SS form)
     return !(e && atoi(e) == 1);
   }();
-  auto kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true> : knn_umma_kernel<kKind, KTOP, false>;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
-  if (err != cudaSuccess) return err;
+  static const bool cluster = [] {
+    const char* e = getenv("IAM_UMMA_NO_CLUSTER");  // A/B aid: 1 = independent CTAs, no multicast of the train tiles
+    return !(e && atoi(e) == 1);
+  }();
   static const int flags = [] {
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
     return e ? atoi(e) : 0;
   }();
-  const int grid = n_units < num_sms ? n_units : num_sms;
-  kern<<<grid, kThreads, kSmemTotal, stream>>>(imgs, units, n_units, out_idx, out_d2, flags);
-  return cudaGetLastError();
+  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int);
+  KernT kern;
+  if (cluster && (n_units % 2 == 0))
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true> : knn_umma_kernel<kKind, KTOP, false, true>;
+  else
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false> : knn_umma_kernel<kKind, KTOP, false, false>;
+  const bool use_cluster = cluster && (n_units % 2 == 0);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
+  if (err != cudaSuccess) return err;
+  int grid = n_units < num_sms ? n_units : num_sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (use_cluster) {
+    grid &= ~1;
+    if (grid < 2) grid = 2;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  cfg.gridDim = dim3(grid);
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags);
 }
 
 }  // namespace

@@ -5,13 +5,14 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== debug tile"; timeout 180 python tools/debug_tile.py 2>&1 | tee gpurun_out/debug_tile.log | tail -12
 echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu.log | tail -25
-echo "== pytest gpu (A in smem)"; IAM_UMMA_A_SMEM=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu_smem.log | tail -5
+echo "== pytest gpu (no cluster)"; IAM_UMMA_NO_CLUSTER=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tee gpurun_out/pytest_gpu_nocluster.log | tail -5
 echo "== smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tee gpurun_out/smoke.log | tail -3
 B="timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu"
 P='import sys,json; d=json.loads(sys.stdin.read()); print(d["value"], d["ms_per_step"], d["roofline"]["kernel_ms_per_launch"], d["roofline"]["frac"], d["clocks"])'
-echo "== bench A-tmem"; $B 2>&1 | tee gpurun_out/bench_new.log | tail -1 | python -c "$P"
-echo "== bench A-smem"; IAM_UMMA_A_SMEM=1 $B 2>&1 | tee gpurun_out/bench_asmem.log | tail -1 | python -c "$P"
-echo "== bench no-epilogue (MMA+TMA only)"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "$P"
+echo "== bench cluster"; $B 2>&1 | tee gpurun_out/bench_new.log | tail -1 | python -c "$P"
+echo "== bench no cluster"; IAM_UMMA_NO_CLUSTER=1 $B 2>&1 | tee gpurun_out/bench_nocluster.log | tail -1 | python -c "$P"
+echo "== bench no-epilogue (MMA+TMA only), cluster"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "$P"
+echo "== bench no-epilogue (MMA+TMA only), no cluster"; IAM_UMMA_NO_CLUSTER=1 IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1_nc.log | tail -1 | python -c "$P"
 echo "== bench fast-path only"; IAM_UMMA_DEBUG=2 $B 2>&1 | tee gpurun_out/bench_dbg2.log | tail -1 | python -c "$P"
 echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1
 echo "== bench ORB"; timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e 2>&1 | tee gpurun_out/bench_orb.log | tail -1
