@@ -338,9 +338,19 @@ def main():
         if world > 1:
             torch.distributed.all_reduce(e_ms, op=torch.distributed.ReduceOp.MAX)
         n_e = max(1, args.steps // 2)
+        # context for the e2e number: what a bare pinned-host -> device copy of the same bytes costs on this box
+        dst = torch.empty_like(host, device=dev)
+        dst.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        c0 = time.perf_counter()
+        dst.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_ms = (time.perf_counter() - c0) * 1e3
+        del dst
         e2e = {"value": P * world * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e_ms.item()) / n_e,
-               "mean_matches_per_pair": float(count.mean())}
+               "mean_matches_per_pair": float(count.mean()), "bare_h2d_ms_same_bytes": h2d_ms,
+               "bare_h2d_gb_per_s": h2d / h2d_ms / 1e6}
 
     if rank != 0:
         return

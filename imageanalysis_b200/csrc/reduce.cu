@@ -19,7 +19,7 @@ constexpr int kRedThreads = 1024;
 constexpr int kRankTile = 1024;
 
 __global__ void __launch_bounds__(kRedThreads)
-reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ knn_idx, const float* __restrict__ knn_dist,
+metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ knn_idx, const float* __restrict__ knn_dist,
               int k, ReduceParams prm, double* __restrict__ cand_metric, int2* __restrict__ cand_qt, int cand_stride,
               int* __restrict__ job_table, int* __restrict__ job_count) {
   __shared__ int s_count;
@@ -218,7 +218,7 @@ cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, co
                           const ReduceParams& prm, double* cand_metric, int2* cand_qt, int cand_stride,
                           int* job_table, int* job_count, cudaStream_t stream) {
   if (n_jobs <= 0) return cudaSuccess;
-  reduce_kernel<<<n_jobs, kRedThreads, 0, stream>>>(jobs, knn_idx, knn_dist, k, prm, cand_metric, cand_qt,
+  metric_reduce_kernel<<<n_jobs, kRedThreads, 0, stream>>>(jobs, knn_idx, knn_dist, k, prm, cand_metric, cand_qt,
                                                     cand_stride, job_table, job_count);
   return cudaGetLastError();
 }
