@@ -140,23 +140,23 @@ __device__ __forceinline__ void consume_group(const float* w, int col, TopK<KTOP
 
 template <int KTOP>
 __device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up) {
-  // Per 16-column batch the four group tests are formed and voted on up front against the bound at
-  // entry (it only tightens, so the votes stay conservative): independent FMNMX3/FSETP/VOTE chains
-  // instead of serialised vote->branch round trips.
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
+    // bound admitted at batch entry; it only tightens, so votes taken against it stay conservative
     const float te = fminf(tk.thr(), pb_up);
     const float* w = &v[h * 16];
-    const unsigned h0 = __ballot_sync(0xffffffffu, fminf(fmin3(w[0], w[1], w[2]), w[3]) < te);
-    const unsigned h1 = __ballot_sync(0xffffffffu, fminf(fmin3(w[4], w[5], w[6]), w[7]) < te);
-    const unsigned h2 = __ballot_sync(0xffffffffu, fminf(fmin3(w[8], w[9], w[10]), w[11]) < te);
-    const unsigned h3 = __ballot_sync(0xffffffffu, fminf(fmin3(w[12], w[13], w[14]), w[15]) < te);
-    if ((h0 | h1 | h2 | h3) != 0u) {
-      if (h0) consume_group<KTOP>(w, col0 + h * 16, tk, fminf(tk.thr(), pb_up));
-      if (h1) consume_group<KTOP>(w + 4, col0 + h * 16 + 4, tk, fminf(tk.thr(), pb_up));
-      if (h2) consume_group<KTOP>(w + 8, col0 + h * 16 + 8, tk, fminf(tk.thr(), pb_up));
-      if (h3) consume_group<KTOP>(w + 12, col0 + h * 16 + 12, tk, fminf(tk.thr(), pb_up));
-    }
+    const float m0 = fminf(fmin3(w[0], w[1], w[2]), w[3]);
+    const float m1 = fminf(fmin3(w[4], w[5], w[6]), w[7]);
+    const float m2 = fminf(fmin3(w[8], w[9], w[10]), w[11]);
+    const float m3 = fminf(fmin3(w[12], w[13], w[14]), w[15]);
+    const bool t0 = __any_sync(0xffffffffu, m0 < te);
+    const bool t1 = __any_sync(0xffffffffu, m1 < te);
+    const bool t2 = __any_sync(0xffffffffu, m2 < te);
+    const bool t3 = __any_sync(0xffffffffu, m3 < te);
+    if (t0) consume_group<KTOP>(w, col0 + h * 16, tk, fminf(tk.thr(), pb_up));
+    if (t1) consume_group<KTOP>(w + 4, col0 + h * 16 + 4, tk, fminf(tk.thr(), pb_up));
+    if (t2) consume_group<KTOP>(w + 8, col0 + h * 16 + 8, tk, fminf(tk.thr(), pb_up));
+    if (t3) consume_group<KTOP>(w + 12, col0 + h * 16 + 12, tk, fminf(tk.thr(), pb_up));
   }
 }
 
@@ -282,14 +282,12 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           mbar_wait(&bars->b_full[stage], par, 30);
           mbar_wait(&bars->t_empty[acc], apar ^ 1, 31);
           tc_fence_after();
-          // K-step outer, A tile inner: consecutive MMAs accumulate into DIFFERENT TMEM tiles, so the
-          // tensor pipe never waits on the accumulator of the instruction in front of it
 #pragma unroll
-          for (int ks = 0; ks < kKSteps; ++ks) {
-            const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
+          for (int a = 0; a < kATiles; ++a) {
+            const uint32_t taddr = tmem_base + acc * kAccCols + a * kBRows;
 #pragma unroll
-            for (int a = 0; a < kATiles; ++a) {
-              const uint32_t taddr = tmem_base + acc * kAccCols + a * kBRows;
+            for (int ks = 0; ks < kKSteps; ++ks) {
+              const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
               if (kATmem) {
                 umma_ts<kKind>(taddr, tmem_base + kTmemA + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
               } else {
@@ -297,10 +295,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
                 umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
               }
             }
-          }
-          if (!kATmem && tb == n_tb - 1) {
-#pragma unroll
-            for (int a = 0; a < kATiles; ++a) umma_commit(&bars->a_empty[a]);
+            if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
           }
           if (kCluster)
             umma_commit_multicast(&bars->b_empty[stage], 0x3);
@@ -327,57 +322,47 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const ImgDev t = imgs[unit.t_slot];
       const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
-      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * kBRows + half * 32;
-      // Software pipeline over the unit's tiles: the TMEM load of tile tb+1 is in flight while tile tb is
-      // consumed out of registers, and the accumulator stage is handed back to the MMA issuer as soon as
-      // its values are in registers (before they are processed).
-      auto issue_load = [&](uint32_t itx, float (&buf)[32]) {
-        const uint32_t acc = itx % kAccStages;
-        mbar_wait(&bars->t_full[acc], (itx / kAccStages) & 1, 40);
-        tc_fence_after();
-        __syncwarp();
-        tmem_ld32(lane_base + acc * kAccCols, buf);
-      };
-      auto finish_load = [&](uint32_t itx, float (&buf)[32]) {
-        tmem_ld_wait(buf);
-        __syncwarp();
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(&bars->t_empty[itx % kAccStages]);
-      };
-      auto process = [&](int tb, float (&buf)[32]) {
+      for (int tb = 0; tb < n_tb; ++tb, ++it) {
+        const uint32_t acc = it % kAccStages;
+        const uint32_t apar = (it / kAccStages) & 1;
         // bound from the thread that owns the other half of this row's columns (stale values are still valid bounds)
         float pb_up = kInf;
-        const float4 p = lds_volatile_v4(&share[(half ^ 1) * kSuperRows + urow]);
-        if (__float_as_int(p.z) == uit) {
-          const float merged = (KTOP == 2) ? fminf(fmaxf(tk.d[0], p.x), fminf(tk.d[KTOP - 1], p.y)) : fminf(tk.d[KTOP - 1], p.y);
-          pb_up = next_up(merged);
+        {
+          const float4 p = lds_volatile_v4(&share[(half ^ 1) * kSuperRows + urow]);
+          if (__float_as_int(p.z) == uit) {
+            const float merged = (KTOP == 2) ? fminf(fmaxf(tk.d[0], p.x), fminf(tk.d[KTOP - 1], p.y)) : fminf(tk.d[KTOP - 1], p.y);
+            pb_up = next_up(merged);
+          }
         }
-        if (dbg_flags == 0) {
-          consume32<KTOP>(buf, tb * kBRows + half * 32, tk, pb_up);
-        } else if (dbg_flags == 2) {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
-          float m = buf[0];
+        mbar_wait(&bars->t_full[acc], apar, 40);
+        tc_fence_after();
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols + a * kBRows + half * 32;
+        if (dbg_flags != 1) {
+          float v[32];
+          __syncwarp();
+          tmem_ld32(taddr, v);
+          tmem_ld_wait(v);
+          // the values are in registers: hand the accumulator stage back to the MMA issuer before consuming them
+          __syncwarp();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
+          if (dbg_flags == 0) {
+            consume32<KTOP>(v, tb * kBRows + half * 32, tk, pb_up);
+          } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
+            float m = v[0];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) m = fminf(m, fminf(fmin3(buf[j * 4], buf[j * 4 + 1], buf[j * 4 + 2]), buf[j * 4 + 3]));
-          tk.d[0] = fminf(tk.d[0], m);
+            for (int j = 0; j < 8; ++j) m = fminf(m, fminf(fmin3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
+            tk.d[0] = fminf(tk.d[0], m);
+          }
         }  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
-        sts_volatile_v4(&share[half * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
-      };
-      float va[32], vb[32];
-      issue_load(it, va);
-      finish_load(it, va);
-      for (int tb = 0; tb < n_tb; tb += 2) {
-        const bool has1 = tb + 1 < n_tb;
-        if (has1) issue_load(it + tb + 1, vb);
-        process(tb, va);
-        if (has1) {
-          finish_load(it + tb + 1, vb);
-          const bool has2 = tb + 2 < n_tb;
-          if (has2) issue_load(it + tb + 2, va);
-          process(tb + 1, vb);
-          if (has2) finish_load(it + tb + 2, va);
+        if (dbg_flags == 1) {
+          __syncwarp();
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
         }
+        sts_volatile_v4(&share[half * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
       }
-      it += n_tb;
       // end of unit: the upper half hands its list to the lower half's thread of the same row
       if (half == 1) {
 #pragma unroll

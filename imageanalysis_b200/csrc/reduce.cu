@@ -21,7 +21,8 @@ constexpr int kRankTile = 1024;
 __global__ void __launch_bounds__(kRedThreads)
 metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ knn_idx, const float* __restrict__ knn_dist,
               int k, ReduceParams prm, double* __restrict__ cand_metric, int2* __restrict__ cand_qt, int cand_stride,
-              int* __restrict__ job_table, int* __restrict__ job_count) {
+              int* __restrict__ job_table, int* __restrict__ job_count, int sort_cap) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_count;
   __shared__ double s_m[kRankTile];
   __shared__ int s_q[kRankTile];
@@ -66,7 +67,50 @@ metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ kn
   }
   __threadfence_block();
 
-  // rank every candidate by (metric, queryIdx); candidates staged through smem tiles
+  // Order the candidates by (metric, queryIdx) = what Python's stable sorted() yields (matcher.py:258).
+  // Up to kSortMax candidates: bitonic sort in shared memory on the raw IEEE bits (positive doubles
+  // order like unsigned integers); beyond that, rank every candidate by counting.
+  int npow2 = 1;
+  while (npow2 < c) npow2 <<= 1;
+  if (npow2 <= sort_cap) {
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_dyn);
+    int2* s_qt = reinterpret_cast<int2*>(s_key + npow2);
+    for (int e = threadIdx.x; e < npow2; e += blockDim.x) {
+      if (e < c) {
+        s_key[e] = static_cast<unsigned long long>(__double_as_longlong(cm[e]));
+        s_qt[e] = cq[e];
+      } else {
+        s_key[e] = ~0ull;
+        s_qt[e] = make_int2(0x7fffffff, 0);
+      }
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= npow2; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int e = threadIdx.x; e < npow2; e += blockDim.x) {
+          const int x = e ^ j;
+          if (x > e) {
+            const unsigned long long ka = s_key[e], kb = s_key[x];
+            const int2 qa = s_qt[e], qb = s_qt[x];
+            const bool a_gt_b = ka > kb || (ka == kb && qa.x > qb.x);
+            const bool up = (e & k2) == 0;
+            if (a_gt_b == up) {
+              s_key[e] = kb;
+              s_key[x] = ka;
+              s_qt[e] = qb;
+              s_qt[x] = qa;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const int n_out = min(c, prm.cap);  // matcher.py:265-269
+    for (int e = threadIdx.x; e < n_out; e += blockDim.x) {
+      table[e * 2 + 0] = s_qt[e].x;
+      table[e * 2 + 1] = s_qt[e].y;
+    }
+  } else {
   const int n_slots = (c + blockDim.x - 1) / blockDim.x;
   for (int slot = 0; slot < n_slots; ++slot) {
     const int e = slot * blockDim.x + threadIdx.x;
@@ -97,6 +141,7 @@ metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ kn
       table[rank * 2 + 0] = qe.x;
       table[rank * 2 + 1] = qe.y;
     }
+  }
   }
   if (threadIdx.x == 0) job_count[job] = min(c, prm.cap);
 }
@@ -218,8 +263,16 @@ cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, co
                           const ReduceParams& prm, double* cand_metric, int2* cand_qt, int cand_stride,
                           int* job_table, int* job_count, cudaStream_t stream) {
   if (n_jobs <= 0) return cudaSuccess;
-  metric_reduce_kernel<<<n_jobs, kRedThreads, 0, stream>>>(jobs, knn_idx, knn_dist, k, prm, cand_metric, cand_qt,
-                                                    cand_stride, job_table, job_count);
+  // shared-memory sort capacity: next power of two of the largest possible candidate count, at most 8192
+  int sort_cap = 1;
+  while (sort_cap < cand_stride && sort_cap < 8192) sort_cap <<= 1;
+  const size_t smem = static_cast<size_t>(sort_cap) * 16;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(metric_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  metric_reduce_kernel<<<n_jobs, kRedThreads, smem, stream>>>(jobs, knn_idx, knn_dist, k, prm, cand_metric, cand_qt,
+                                                           cand_stride, job_table, job_count, sort_cap);
   return cudaGetLastError();
 }
 

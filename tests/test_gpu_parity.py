@@ -165,6 +165,23 @@ def test_match_tables_equal_oracle(mode, cross):
     assert count[0] > 100 and count[3] < count[0] // 4   # neighbours match strongly, frames 4 apart barely
 
 
+def test_reduce_paths_small_sort_and_large_rank():
+    """More than 8192 candidates per direction leaves the shared-memory sort for the
+    rank-by-counting path; both must order exactly like Python's stable sorted()."""
+    rng = np.random.default_rng(12)
+    a = synth.sift_like(9000, seed=91)
+    b = np.clip(a[rng.permutation(9000)].astype(np.int32) + rng.integers(-2, 3, (9000, 128)), 0, 255).astype(np.uint8)
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.upload(0, a)
+    eng.upload(1, b)
+    for cap in (2000, 9000):
+        prm = _capi.Engine.make_params(cap=cap, cross_check=False)
+        table, count = eng.match_pairs([(0, 1)], prm)
+        f, _ = oracle.bidirectional(a, b, oracle.NORM_L2, 0.75, 270.0, cap=cap, threads=8, cross_check=False)
+        assert count[0] == len(f) == cap
+        assert table[0, :count[0]].tolist() == f
+
+
 def test_orb_match_tables_equal_oracle():
     des, _, _ = synth.sift_project(3, 1200, seed=6, kind="orb")
     eng = _capi.Engine(_capi.NORM_HAMMING, 32, 0)
