@@ -284,6 +284,7 @@ def main():
             dist.allgather_tables(t, c, P * world, rank, world)
 
     upload_all()
+    eng.synchronize()
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
@@ -323,9 +324,12 @@ def main():
         h2d = int(host_np.nbytes)
         d2h = int(P * (prm.cap * 2 + 1) * 4)
 
+        ids = np.arange(args.frames, dtype=np.int32)
+        frames_host = [host_np[f] for f in range(args.frames)]
+
         def step_e2e():
-            upload_all()
-            return eng.match_pairs(pairs, prm)
+            # the public one-call API: host descriptors in, host match tables out (H2D + conversion + matching + D2H)
+            return eng.match_images(ids, frames_host, pairs, prm)
         step_e2e()
         torch.cuda.synchronize()
         if world > 1:

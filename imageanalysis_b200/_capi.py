@@ -27,7 +27,7 @@ EXPORTS = (
     "iam_create", "iam_destroy", "iam_last_error", "iam_abi_version", "iam_set_stream",
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_release_descriptors", "iam_num_descriptors",
-    "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device",
+    "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
     "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver",
 )
@@ -95,6 +95,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_knn_pairs.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
     lib.iam_match_pairs.argtypes = [vp, vp, C.c_int, C.POINTER(MatchParams), vp, vp, vp, vp]
     lib.iam_match_pairs_device.argtypes = [vp, vp, C.c_int, C.POINTER(MatchParams), C.POINTER(vp), C.POINTER(vp)]
+    lib.iam_match_images.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(MatchParams), vp, vp]
     lib.iam_fetch_tables.argtypes = [vp, vp, vp]
     lib.iam_ransac_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int,
                                      C.c_uint32, vp, vp, vp]
@@ -245,6 +246,37 @@ class Engine:
                                               _ptr(rtable), _ptr(rcount)), "iam_match_pairs")
         if want_reverse:
             return table, count, rtable, rcount
+        return table, count
+
+    def match_images(self, image_ids, arrays, pairs, params: MatchParams, keys=None):
+        """Upload + match in one call with PCIe/compute overlap (iam_match_images).
+        arrays[i]: [N_i, D] float32 or uint8 descriptors of image image_ids[i] (all the same dtype);
+        keys[i]: optional int32 [N_i] keypoint position ids."""
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        arrs = [np.ascontiguousarray(a) for a in arrays]
+        if len(arrs) != len(ids):
+            raise IamError("image_ids and arrays differ in length")
+        dts = {a.dtype for a in arrs}
+        if len(dts) > 1 or (arrs and arrs[0].dtype not in (np.uint8, np.float32)):
+            raise IamError("descriptor arrays must all be uint8 or all float32")
+        dt = DTYPE_U8 if (not arrs or arrs[0].dtype == np.uint8) else DTYPE_F32
+        for a in arrs:
+            if a.ndim != 2 or a.shape[1] != self.desc_bytes:
+                raise IamError(f"descriptor array must be [N,{self.desc_bytes}], got {a.shape}")
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        counts = np.ascontiguousarray([a.shape[0] for a in arrs], np.int32)
+        kptrs = None
+        karrs = None
+        if keys is not None:
+            karrs = [None if k is None else np.ascontiguousarray(k, np.int32) for k in keys]
+            kptrs = (C.c_void_p * max(n, 1))(*[None if k is None else k.ctypes.data for k in karrs])
+        pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+        P = pr.shape[0]
+        table = np.empty((P, params.cap, 2), np.int32)
+        count = np.zeros((P,), np.int32)
+        self._check(self._lib.iam_match_images(self._h, n, _ptr(ids), ptrs, _ptr(counts), dt, kptrs, _ptr(pr), P,
+                                               C.byref(params), _ptr(table), _ptr(count)), "iam_match_images")
         return table, count
 
     def match_pairs_device(self, pairs: np.ndarray, params: MatchParams) -> Tuple[int, int]:

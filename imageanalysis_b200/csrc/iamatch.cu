@@ -291,8 +291,8 @@ uint64_t plan_hash(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, b
 int upload_plan(iam_ctx* c, const Plan& pl);
 
 // Build (or reuse) the work list for this pair list and make it resident.
-int prepare_plan(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both) {
-  const int waves = pick_waves(c);
+int prepare_plan(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, int waves_override = 0) {
+  const int waves = waves_override > 0 ? waves_override : pick_waves(c);
   const uint64_t key = plan_hash(c, pairs, n_pairs, k, both, waves);
   if (c->plan_valid && c->plan_key == key) return IAM_OK;
   c->plan_valid = false;
@@ -455,17 +455,14 @@ int iam_get_timing(iam_ctx* c, iam_timing* out) {
   return IAM_OK;
 }
 
-static int upload_common(iam_ctx* c, int id, const void* src, bool src_on_host, int n, int dtype) {
+// Size an image slot (allocation, device record) without touching its contents.
+static int prepare_image(iam_ctx* c, int id, int n) {
   if ((int)c->images.size() <= id) c->images.resize(id + 1);
   Image& im = c->images[id];
   const int n_pad = std::max(iam::kSuperRows, iam::round_up(n, iam::kSuperRows));
   const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
   const size_t form_b = iam::form_bytes(n_pad);
   const size_t total = 256 + raw_b + 2 * form_b;
-  if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
-    CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
-    c->compute_pending = false;
-  }
   if (im.block_bytes < total) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->up_stream));
@@ -484,14 +481,33 @@ static int upload_common(iam_ctx* c, int id, const void* src, bool src_on_host, 
   im.dev.b_form = im.block + 256 + raw_b + form_b;
   im.dev.n = n;
   im.dev.n_pad = n_pad;
+  c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+// H2D copy (when the source is on the host) + layout conversion on the upload stream; records im.ready.
+static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host, int dtype, const int32_t* host_keys) {
+  Image& im = c->images[id];
+  const int n = im.n, n_pad = im.n_pad;
+  const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
+  const size_t form_b = iam::form_bytes(n_pad);
+  if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
+    CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    c->compute_pending = false;
+  }
   if (im.keys) {  // keys belong to the previous descriptor set
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(im.keys));
     im.keys = nullptr;
+    im.dev.kp_key = nullptr;
+    c->imgs_dirty = true;
   }
-  im.dev.kp_key = nullptr;
-  c->imgs_dirty = true;
-
+  if (host_keys && n > 0) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&im.keys), size_t(n) * sizeof(int)));
+    CU(cudaMemcpyAsync(im.keys, host_keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
+    im.dev.kp_key = im.keys;
+    c->imgs_dirty = true;
+  }
   const void* dsrc = src;
   if (src_on_host) {
     const size_t bytes = size_t(n) * c->desc_bytes * (dtype == IAM_DTYPE_F32 ? 4 : 1);
@@ -513,6 +529,12 @@ static int upload_common(iam_ctx* c, int id, const void* src, bool src_on_host, 
   im.seq = ++c->up_seq;
   im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
   return IAM_OK;
+}
+
+static int upload_common(iam_ctx* c, int id, const void* src, bool src_on_host, int n, int dtype) {
+  int rc = prepare_image(c, id, n);
+  if (rc) return rc;
+  return enqueue_upload(c, id, src, src_on_host, dtype, nullptr);
 }
 
 int iam_upload_descriptors(iam_ctx* c, int id, const void* ptr, int n, int dtype, int pinned) {
@@ -642,18 +664,97 @@ int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_st
   return mark_compute(c);
 }
 
+}  // extern "C"
+
+namespace {
+struct UploadFeed {  // host-side sources for iam_match_images: enqueue an image's upload right before its first use
+  const void* const* ptrs = nullptr;
+  const int32_t* const* keys = nullptr;
+  const int32_t* ids = nullptr;
+  int n_images = 0;
+  int dtype = 0;
+  std::vector<int> slot_of_id;   // image id -> index into ptrs
+  std::vector<char> done;
+};
+
+int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
+               void** d_table, void** d_count);
+}  // namespace
+
+extern "C" {
+
 int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, void** d_table,
                            void** d_count) {
   int rc = bind(c);
   if (rc) return rc;
+  return match_core(c, pairs, n_pairs, prm, 0, nullptr, d_table, d_count);
+}
+
+int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const void* const* host_ptrs,
+                     const int32_t* counts, int dtype, const int32_t* const* key_ptrs, const int32_t* pairs, int n_pairs,
+                     const iam_match_params* prm, int32_t* out_table, int32_t* out_count) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_images < 0 || (n_images && (!image_ids || !host_ptrs || !counts)) || !out_table || !out_count)
+    return fail(IAM_E_ARG, "bad arguments");
+  if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
+  if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
+  UploadFeed feed;
+  feed.ptrs = host_ptrs;
+  feed.keys = key_ptrs;
+  feed.ids = image_ids;
+  feed.n_images = n_images;
+  feed.dtype = dtype;
+  feed.done.assign(n_images, 0);
+  int max_id = -1;
+  for (int i = 0; i < n_images; ++i) {
+    if (image_ids[i] < 0 || image_ids[i] > (1 << 24)) return fail(IAM_E_ARG, "bad image id %d", image_ids[i]);
+    if (counts[i] < 0 || (counts[i] > 0 && !host_ptrs[i])) return fail(IAM_E_ARG, "bad descriptor buffer for image %d", image_ids[i]);
+    max_id = std::max(max_id, image_ids[i]);
+  }
+  feed.slot_of_id.assign(max_id + 1, -1);
+  for (int i = 0; i < n_images; ++i) {
+    feed.slot_of_id[image_ids[i]] = i;
+    if ((rc = prepare_image(c, image_ids[i], counts[i])) != IAM_OK) return rc;
+    c->images[image_ids[i]].seq = 0;  // contents are stale until this call uploads them
+  }
+  // enough waves that the first kernels start after a few per cent of the bytes have crossed PCIe
+  const int waves = std::max(1, std::min(16, n_pairs / 96));
+  if ((rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr)) != IAM_OK) return rc;
+  for (int i = 0; i < n_images; ++i)  // images no pair referenced are still part of the resident set
+    if (!feed.done[i] && (rc = enqueue_upload(c, image_ids[i], host_ptrs[i], true, dtype, key_ptrs ? key_ptrs[i] : nullptr)) != IAM_OK)
+      return rc;
+  return iam_fetch_tables(c, out_table, out_count);
+}
+
+}  // extern "C"
+
+namespace {
+
+int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
+               void** d_table, void** d_count) {
+  int rc;
   if (n_pairs < 0 || (n_pairs && !pairs) || !prm) return fail(IAM_E_ARG, "bad arguments");
   if (prm->cap <= 0 || prm->cap > 65536) return fail(IAM_E_ARG, "cap=%d out of range", prm->cap);
   if (prm->reduce_mode != IAM_REDUCE_LOWE && prm->reduce_mode != IAM_REDUCE_REF_METRIC) return fail(IAM_E_ARG, "unknown reduce mode %d", prm->reduce_mode);
   const int k = 2;
-  if ((rc = prepare_plan(c, pairs, n_pairs, k, true)) != IAM_OK) return rc;
+  if ((rc = prepare_plan(c, pairs, n_pairs, k, true, waves)) != IAM_OK) return rc;
   const Plan& pl = c->plan;
   int engine;
   if ((rc = pick_engine(c, pairs, n_pairs, &engine)) != IAM_OK) return rc;
+  if (feed && feed->keys) {  // device key pointers must be in the image table before it is made resident
+    for (int i = 0; i < feed->n_images; ++i) {
+      Image& im = c->images[feed->ids[i]];
+      if (im.keys) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaFree(im.keys));
+        im.keys = nullptr;
+      }
+      if (feed->keys[i] && im.n > 0) CU(cudaMalloc(reinterpret_cast<void**>(&im.keys), size_t(im.n) * sizeof(int)));
+      im.dev.kp_key = im.keys;
+      c->imgs_dirty = true;
+    }
+  }
   if ((rc = sync_imgs(c)) != IAM_OK) return rc;
 
   const size_t cap = prm->cap;
@@ -686,6 +787,24 @@ int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const 
     const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
     const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
     if (p1 == p0) continue;
+    if (feed) {  // enqueue the uploads this chunk is the first to need (upload stream; overlaps earlier chunks' kernels)
+      for (int i = 2 * p0; i < 2 * p1; ++i) {
+        const int id = pairs[i];
+        const int slot = id < (int)feed->slot_of_id.size() ? feed->slot_of_id[id] : -1;
+        if (slot >= 0 && !feed->done[slot]) {
+          feed->done[slot] = 1;
+          Image& im = c->images[id];
+          const int32_t* hk = feed->keys ? feed->keys[slot] : nullptr;
+          int* keep = im.keys;  // allocated above; enqueue_upload must reuse it, not free it
+          im.keys = nullptr;
+          if ((rc = enqueue_upload(c, id, feed->ptrs[slot], true, feed->dtype, nullptr)) != IAM_OK) return rc;
+          im.keys = keep;
+          im.dev.kp_key = keep;
+          if (hk && keep) CU(cudaMemcpyAsync(keep, hk, size_t(im.n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
+          if (hk && keep) CU(cudaEventRecord(im.ready, c->up_stream));
+        }
+      }
+    }
     if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) return rc;
     const bool prof = c->profiling && n_chunks == 1;
     if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
@@ -717,6 +836,10 @@ int iam_match_pairs_device(iam_ctx* c, const int32_t* pairs, int n_pairs, const 
   if (d_count) *d_count = c->out_count.p;
   return IAM_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int iam_fetch_tables(iam_ctx* c, int32_t* out_table, int32_t* out_count) {
   int rc = bind(c);

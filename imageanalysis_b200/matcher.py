@@ -497,18 +497,16 @@ def _batched_traditional(image_list, todo):
     used = sorted({i for p in todo for i in p})
     for i in used:
         _ensure_features(image_list[i])
-    eng = None
-    for i in used:
-        im = image_list[i]
-        des = GpuKnnMatcher._as_device_dtype(im.des_list, _norm)
-        if eng is None:
-            eng = the_matcher.engine(int(des.shape[1]))
-        eng.upload(i, des)
-        eng.upload_keypoint_keys(i, keypoint_keys(im.kp_list))
+    arrays = [GpuKnnMatcher._as_device_dtype(image_list[i].des_list, _norm) for i in used]
+    if len({a.dtype for a in arrays}) > 1:   # mixed caches: widen everything to float32
+        arrays = [np.ascontiguousarray(a, np.float32) for a in arrays]
+    keys = [keypoint_keys(image_list[i].kp_list) for i in used]
+    eng = the_matcher.engine(int(arrays[0].shape[1]))
     prm = _capi.Engine.make_params(match_ratio=matcher_node.getFloat('match_ratio'), max_distance=float(max_distance),
                                    reduce_mode=_capi.REDUCE_REF_METRIC, cap=2000, min_pairs=int(min_pairs),
                                    cross_check=True, dedupe=True)
-    table, count = eng.match_pairs(np.int32(todo), prm)
+    # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching
+    table, count = eng.match_images(used, arrays, np.int32(todo), prm, keys=keys)
     out = []
     for p in range(len(todo)):
         fwd = table[p, :count[p]].tolist()

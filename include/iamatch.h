@@ -153,6 +153,21 @@ int iam_match_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs,
                     int32_t* out_table, int32_t* out_count,
                     int32_t* out_table_rev, int32_t* out_count_rev);
 
+/* One-call form for a whole project step (what find_matches() does per call,
+ * matcher.py:852-1031): descriptors are still in HOST memory.  Image
+ * image_ids[i] has counts[i] rows of `dtype` at host_ptrs[i] (page-locked
+ * memory makes the copies asynchronous); key_ptrs (may be NULL, entries may
+ * be NULL) are the per-keypoint position ids of iam_upload_keypoint_keys.
+ * The pair list is cut into waves; each image's H2D copy + layout conversion
+ * is enqueued on an upload stream right before the first wave that needs it,
+ * so PCIe transfers overlap the matching of earlier waves.  Outputs as
+ * iam_match_pairs.  The images stay resident afterwards. */
+int iam_match_images(iam_ctx* ctx, int n_images, const int32_t* image_ids,
+                     const void* const* host_ptrs, const int32_t* counts, int dtype,
+                     const int32_t* const* key_ptrs,
+                     const int32_t* pairs, int n_pairs, const iam_match_params* prm,
+                     int32_t* out_table, int32_t* out_count);
+
 /* Same work, but results stay in device memory owned by the context (the
  * "inputs and outputs resident in HBM" form used for kernel-level timing and
  * by the multi-GPU gather).  Pointers returned are DEVICE pointers valid

@@ -215,6 +215,30 @@ def test_dedupe_and_cross_check_equal_reference_module():
     assert rtable[0, :rcount[0]].tolist() == g["basic10"].tolist()
 
 
+def test_match_images_one_call_equals_two_phase():
+    """iam_match_images (uploads enqueued wave by wave) == upload everything, then iam_match_pairs."""
+    from imageanalysis_b200 import matcher
+    des, pts, _ = synth.sift_project(40, 600, seed=21)
+    pairs = [(i, j) for i in range(40) for j in range(i + 1, min(40, i + 5))]
+    keys = [matcher.keypoint_keys([types.SimpleNamespace(pt=(float(x), float(y))) for x, y in p]) for p in pts]
+    prm = _capi.Engine.make_params(dedupe=True, cross_check=True)
+    ref = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i, d in enumerate(des):
+        ref.upload(i, d.astype(np.float32))
+        ref.upload_keypoint_keys(i, keys[i])
+    t0, c0 = ref.match_pairs(pairs, prm)
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for rep in range(2):      # second call re-uploads over resident images (WAR ordering between calls)
+        t1, c1 = eng.match_images(list(range(40)), [d.astype(np.float32) for d in des], pairs, prm, keys=keys)
+        assert (c0 == c1).all() and c0.max() > 100
+        for p in range(len(pairs)):
+            assert (t0[p, :c0[p]] == t1[p, :c1[p]]).all()
+    assert eng.descriptors_exact(3) == 1 and eng.num_descriptors(39) == 600
+    t2, c2 = eng.match_images(list(range(40)), des, pairs, prm)          # uint8 input, no keys
+    t3, c3 = ref.match_pairs(pairs, _capi.Engine.make_params(dedupe=False, cross_check=True))
+    assert (c2 == c3).all()
+
+
 class FakeImage:
     def __init__(self, name, des, pts, ned):
         self.name = name
