@@ -354,6 +354,9 @@ def main():
         e2e = {"value": P * world * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e_ms.item()) / n_e,
                "mean_matches_per_pair": float(count.mean()), "bare_h2d_ms_same_bytes": h2d_ms,
+               "timeline_ms": {"host_enqueue": eng.timing().host_enqueue_ms, "upload_span": eng.timing().upload_span_ms,
+                               "compute_span": eng.timing().compute_span_ms, "total_span": eng.timing().total_span_ms,
+                               "waves": eng.timing().waves},
                "bare_h2d_gb_per_s": h2d / h2d_ms / 1e6}
 
     if rank != 0:

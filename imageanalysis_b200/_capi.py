@@ -54,7 +54,12 @@ class Timing(C.Structure):
         ("knn_launches", C.c_int),
         ("total_launches", C.c_int),
         ("engine_used", C.c_int),
-        ("reserved", C.c_int * 2),
+        ("waves", C.c_int),
+        ("reserved", C.c_int),
+        ("host_enqueue_ms", C.c_float),
+        ("upload_span_ms", C.c_float),
+        ("compute_span_ms", C.c_float),
+        ("total_span_ms", C.c_float),
     ]
 
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -119,6 +120,8 @@ struct iam_ctx {
   bool timing_pending = false;
   bool profiling = false;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
+  bool span_pending = false;
   iam_timing timing{};
 };
 
@@ -348,7 +351,7 @@ __global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jo
 
 extern "C" {
 
-int iam_abi_version(void) { return 1; }
+int iam_abi_version(void) { return 2; }
 const char* iam_last_error(void) { return g_err.c_str(); }
 
 int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
@@ -382,6 +385,7 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
     return fail(IAM_E_CUDA, "stream/event creation: %s", cudaGetErrorString(e));
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
+  for (auto& ev : c->span) cudaEventCreate(&ev);
   *out = c;
   return IAM_OK;
 }
@@ -402,6 +406,8 @@ int iam_destroy(iam_ctx* c) {
                     &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
   for (Buffer* b : bufs) b->release();
   for (auto& ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->span)
     if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -444,6 +450,16 @@ int iam_get_timing(iam_ctx* c, iam_timing* out) {
     if (cudaEventSynchronize(c->ev[5]) == cudaSuccess) cudaEventElapsedTime(&c->timing.convert_ms, c->ev[4], c->ev[5]);
     cudaGetLastError();
   }
+  if (c->span_pending) {
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventSynchronize(c->span[1]));
+    CU(cudaEventSynchronize(c->span[3]));
+    cudaEventElapsedTime(&c->timing.upload_span_ms, c->span[0], c->span[1]);
+    cudaEventElapsedTime(&c->timing.compute_span_ms, c->span[2], c->span[3]);
+    cudaEventElapsedTime(&c->timing.total_span_ms, c->span[0], c->span[3]);
+    cudaGetLastError();
+    c->span_pending = false;
+  }
   if (c->timing_pending) {
     CU(cudaSetDevice(c->device));
     CU(cudaEventSynchronize(c->ev[2]));
@@ -459,7 +475,7 @@ int iam_get_timing(iam_ctx* c, iam_timing* out) {
 static int prepare_image(iam_ctx* c, int id, int n) {
   if ((int)c->images.size() <= id) c->images.resize(id + 1);
   Image& im = c->images[id];
-  const int n_pad = std::max(iam::kSuperRows, iam::round_up(n, iam::kSuperRows));
+  const int n_pad = std::max(iam::kSuperRows, iam::round_up(iam::round_up(n, iam::kBRows), iam::kSuperRows));  // whole B tiles and whole units
   const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
   const size_t form_b = iam::form_bytes(n_pad);
   const size_t total = 256 + raw_b + 2 * form_b;
@@ -720,10 +736,22 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   }
   // enough waves that the first kernels start after a few per cent of the bytes have crossed PCIe
   const int waves = std::max(1, std::min(16, n_pairs / 96));
+  const auto h0 = std::chrono::steady_clock::now();
+  if (c->compute_pending) {
+    CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    c->compute_pending = false;
+  }
+  CU(cudaEventRecord(c->span[0], c->up_stream));
+  CU(cudaEventRecord(c->span[2], c->stream));
   if ((rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr)) != IAM_OK) return rc;
   for (int i = 0; i < n_images; ++i)  // images no pair referenced are still part of the resident set
     if (!feed.done[i] && (rc = enqueue_upload(c, image_ids[i], host_ptrs[i], true, dtype, key_ptrs ? key_ptrs[i] : nullptr)) != IAM_OK)
       return rc;
+  CU(cudaEventRecord(c->span[1], c->up_stream));
+  CU(cudaEventRecord(c->span[3], c->stream));
+  c->timing.host_enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - h0).count();
+  c->timing.waves = waves;
+  c->span_pending = true;
   return iam_fetch_tables(c, out_table, out_count);
 }
 

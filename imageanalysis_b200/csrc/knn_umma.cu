@@ -34,22 +34,24 @@ namespace iam {
 
 namespace {
 
-constexpr int kBStages = 6;
-constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 8 * kATiles;           // (A tile, 32-column half, TMEM lane quadrant): 16 warps, 4 per SM sub-partition
-constexpr int kThreads = 128 + 32 * kEpiWarps;   // 640
+constexpr int kBStages = 4;
+constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
+constexpr int kWarpsPerATile = 4 * kParts;
+constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 896
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccCols = kATiles * kBRows;  // 128 TMEM columns per accumulator stage  (columns 0..255)
-constexpr uint32_t kTmemA = kAccStages * kAccCols;  // A operand region starts at column 256
 constexpr uint32_t kTmemAColsPerTile = kKSteps * 8;  // 72 columns: 128 rows x 144 fp16 (two K elements per 32-bit cell)
+// Accumulator slots of kBRows columns each, handed round-robin to successive (B tile, A tile) products.
+constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;  // 3 for 96-column tiles
+constexpr uint32_t kTmemA = kSlots * kBRows;     // A operand region behind the accumulator slots
 
 struct __align__(8) Barriers {
   uint64_t a_full[kATiles];
   uint64_t a_empty[kATiles];
   uint64_t b_full[kBStages];
   uint64_t b_empty[kBStages];
-  uint64_t t_full[kAccStages];
-  uint64_t t_empty[kAccStages];
+  uint64_t t_full[kSlots];
+  uint64_t t_empty[kSlots];
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -57,9 +59,11 @@ struct __align__(8) Barriers {
 constexpr size_t kSmemA = kATiles * kTileBytes;         //  73728: staging for the next unit's query tiles
 constexpr size_t kSmemB = kBStages * kBTileBytes;       // 110592: streamed train tiles
 constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
-constexpr size_t kSmemShare = 2 * kSuperRows * 16;      //   8192: running bounds exchanged between the two column halves
-constexpr size_t kSmemMerge = kSuperRows * 3 * 8;       //   6144: end-of-unit hand-over of the upper half's list
+constexpr size_t kSmemShare = kParts * kSuperRows * 16;       // 12288: running bounds exchanged between the column parts of a row
+constexpr size_t kSmemMerge = (kParts - 1) * kSuperRows * 3 * 8;  // 12288: end-of-unit hand-over of the other parts' lists
 constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
+static_assert(kSmemTotal <= 232448, "shared memory budget");
+static_assert(kTmemA + kATiles * kTmemAColsPerTile <= 512, "tensor memory budget");
 
 constexpr float kInf = 3.0e38f;
 
@@ -168,8 +172,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
-  float4* share = reinterpret_cast<float4*>(smem + kSmemA + kSmemB + kSmemBars);             // [half][row]
-  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + kSmemBars + kSmemShare);  // [row][k]
+  float4* share = reinterpret_cast<float4*>(smem + kSmemA + kSmemB + kSmemBars);             // [part][row]
+  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + kSmemBars + kSmemShare);  // [part-1][row][k]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,7 +185,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   const int first_pu = blockIdx.x / kCtas;
   const int pu_stride = gridDim.x / kCtas;
 
-  for (int i = threadIdx.x; i < 2 * kSuperRows; i += blockDim.x) share[i] = make_float4(kInf, kInf, __int_as_float(-1), 0.f);
+  for (int i = threadIdx.x; i < kParts * kSuperRows; i += blockDim.x) share[i] = make_float4(kInf, kInf, __int_as_float(-1), 0.f);
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kATiles; ++i) {
       mbar_init(&bars->a_full[i], 1);
@@ -191,9 +195,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       mbar_init(&bars->b_full[i], 1);
       mbar_init(&bars->b_empty[i], kCtas);  // every CTA that received the tile must be done with it
     }
-    for (int i = 0; i < kAccStages; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
       mbar_init(&bars->t_full[i], 1);
-      mbar_init(&bars->t_empty[i], kEpiWarps);
+      mbar_init(&bars->t_empty[i], kWarpsPerATile);  // the warps of whichever A tile last used the slot
     }
     fence_barrier_init();
   } else if (warp == 2) {
@@ -277,14 +281,14 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         for (int tb = 0; tb < n_tb; ++tb, ++it) {
           const uint32_t stage = it % kBStages;
           const uint32_t par = (it / kBStages) & 1;
-          const uint32_t acc = it % kAccStages;
-          const uint32_t apar = (it / kAccStages) & 1;
           mbar_wait(&bars->b_full[stage], par, 30);
-          mbar_wait(&bars->t_empty[acc], apar ^ 1, 31);
-          tc_fence_after();
 #pragma unroll
           for (int a = 0; a < kATiles; ++a) {
-            const uint32_t taddr = tmem_base + acc * kAccCols + a * kBRows;
+            const uint32_t sq = it * kATiles + a;          // running (B tile, A tile) product counter
+            const uint32_t slot = sq % kSlots;
+            mbar_wait(&bars->t_empty[slot], ((sq / kSlots) & 1) ^ 1, 31);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + slot * kBRows;
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks) {
               const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
@@ -296,85 +300,106 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
               }
             }
             if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
+            umma_commit(&bars->t_full[slot]);
           }
           if (kCluster)
             umma_commit_multicast(&bars->b_empty[stage], 0x3);
           else
             umma_commit(&bars->b_empty[stage]);
-          umma_commit(&bars->t_full[acc]);
         }
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
-    const int e = (warp - 4) >> 2;      // 0..3
-    const int a = e >> 1;               // which accumulator / A tile
-    const int half = e & 1;             // which 32 of the tile's 64 columns
+    const int e = (warp - 4) >> 2;      // 0 .. kATiles*kParts-1
+    const int a = e / kParts;           // which A tile
+    const int part = e % kParts;        // which 32 of the B tile's columns
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int urow = a * kTileRows + quad * 32 + lane;  // row within the unit
     TopK<KTOP> tk;
     uint32_t it = 0;
     int uit = 0;
     for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
-        const int u = pu * kCtas + cta_rank;
+      const int u = pu * kCtas + cta_rank;
       const KnnUnit unit = units[u];
       const ImgDev q = imgs[unit.q_slot];
       const ImgDev t = imgs[unit.t_slot];
       const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
       for (int tb = 0; tb < n_tb; ++tb, ++it) {
-        const uint32_t acc = it % kAccStages;
-        const uint32_t apar = (it / kAccStages) & 1;
-        // bound from the thread that owns the other half of this row's columns (stale values are still valid bounds)
+        const uint32_t sq = it * kATiles + a;
+        const uint32_t slot = sq % kSlots;
+        // Bound from the threads that own the other column parts of this row: the k-th best of the union of
+        // all lists (stale values are still valid bounds).  Ties with it are admitted; the final merge orders
+        // them by index.
         float pb_up = kInf;
         {
-          const float4 p = lds_volatile_v4(&share[(half ^ 1) * kSuperRows + urow]);
-          if (__float_as_int(p.z) == uit) {
-            const float merged = (KTOP == 2) ? fminf(fmaxf(tk.d[0], p.x), fminf(tk.d[KTOP - 1], p.y)) : fminf(tk.d[KTOP - 1], p.y);
-            pb_up = next_up(merged);
+          float f1 = kInf, g1 = kInf, f2 = kInf, g2 = kInf;
+          const float4 p1 = lds_volatile_v4(&share[((part + 1) % kParts) * kSuperRows + urow]);
+          if (__float_as_int(p1.z) == uit) {
+            f1 = p1.x;
+            g1 = p1.y;
           }
+          if (kParts > 2) {
+            const float4 p2 = lds_volatile_v4(&share[((part + 2) % kParts) * kSuperRows + urow]);
+            if (__float_as_int(p2.z) == uit) {
+              f2 = p2.x;
+              g2 = p2.y;
+            }
+          }
+          float merged;
+          if (KTOP == 2) {
+            const float f0 = tk.d[0];
+            const float second_of_firsts = fmaxf(fminf(f0, f1), fminf(fmaxf(f0, f1), f2));
+            merged = fminf(second_of_firsts, fmin3(tk.d[1], g1, g2));
+          } else {
+            merged = fmin3(tk.d[KTOP - 1], g1, g2);
+          }
+          if (merged < kInf) pb_up = next_up(merged);
         }
-        mbar_wait(&bars->t_full[acc], apar, 40);
+        mbar_wait(&bars->t_full[slot], (sq / kSlots) & 1, 40);
         tc_fence_after();
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kAccCols + a * kBRows + half * 32;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * kBRows + part * 32;
         if (dbg_flags != 1) {
           float v[32];
           __syncwarp();
           tmem_ld32(taddr, v);
           tmem_ld_wait(v);
-          // the values are in registers: hand the accumulator stage back to the MMA issuer before consuming them
+          // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
           __syncwarp();
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
+          if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
           if (dbg_flags == 0) {
-            consume32<KTOP>(v, tb * kBRows + half * 32, tk, pb_up);
+            consume32<KTOP>(v, tb * kBRows + part * 32, tk, pb_up);
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v[0];
 #pragma unroll
             for (int j = 0; j < 8; ++j) m = fminf(m, fminf(fmin3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
             tk.d[0] = fminf(tk.d[0], m);
           }
-        }  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
-        if (dbg_flags == 1) {
+        } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
           __syncwarp();
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&bars->t_empty[acc]);
+          if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
         }
-        sts_volatile_v4(&share[half * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
+        sts_volatile_v4(&share[part * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
       }
-      // end of unit: the upper half hands its list to the lower half's thread of the same row
-      if (half == 1) {
+      // end of unit: parts 1.. hand their lists to part 0's thread of the same row
+      if (part > 0) {
 #pragma unroll
-        for (int s = 0; s < KTOP; ++s) merge[urow * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
+        for (int s = 0; s < KTOP; ++s)
+          merge[((part - 1) * kSuperRows + urow) * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       const int row = unit.super * kSuperRows + urow;
-      if (half == 0) {
+      if (part == 0) {
 #pragma unroll
-        for (int s = 0; s < KTOP; ++s) {
-          const float2 m = merge[urow * KTOP + s];
-          tk.insert_lex(m.x, __float_as_int(m.y));
+        for (int pp = 0; pp < kParts - 1; ++pp) {
+#pragma unroll
+          for (int s = 0; s < KTOP; ++s) {
+            const float2 m = merge[(pp * kSuperRows + urow) * KTOP + s];
+            tk.insert_lex(m.x, __float_as_int(m.y));
+          }
         }
         if (row < q.n) {
           const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
@@ -385,6 +410,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           }
         }
       }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // merge area is free again
     }
   }
 

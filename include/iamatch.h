@@ -203,7 +203,13 @@ typedef struct iam_timing {
   int   knn_launches;  /* kernels launched by the last match/knn call        */
   int   total_launches;/* all kernel launches since context creation         */
   int   engine_used;   /* IAM_ENGINE_UMMA or IAM_ENGINE_SIMT                 */
-  int   reserved[2];
+  int   waves;         /* pair-list chunks of the last match call            */
+  int   reserved;
+  /* last iam_match_images call (device timeline from CUDA events, host time from a monotonic clock) */
+  float host_enqueue_ms;  /* host time spent enqueueing uploads + kernels          */
+  float upload_span_ms;   /* first H2D copy start -> last conversion end           */
+  float compute_span_ms;  /* first kernel start -> last kernel end                 */
+  float total_span_ms;    /* first H2D copy start -> last kernel end               */
 } iam_timing;
 int iam_get_timing(iam_ctx* ctx, iam_timing* out);
 
