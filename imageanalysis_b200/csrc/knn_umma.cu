@@ -35,6 +35,7 @@ namespace iam {
 namespace {
 
 constexpr int kBStages = 4;
+constexpr int kShareEvery = 4;                   // tiles between exchanges of running bounds (power of two)
 constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
 constexpr int kWarpsPerATile = 4 * kParts;
 constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
@@ -84,6 +85,22 @@ struct TopK {
   // distances the earliest (lowest) column stays first: the order
   // cv2.BFMatcher reports ties in.
   __device__ __forceinline__ void insert(float x, int col) {
+    if constexpr (KTOP == 2) {
+      // Same network as below, written with predicated moves: two compares on the ALU pipe, the six
+      // moves can issue as IMAD.MOV on the FMA pipe, which the (ALU-pipe-bound) epilogue leaves idle.
+      asm("{\n\t.reg .pred p0, p1;\n\t"
+          "setp.lt.f32 p0, %4, %0;\n\t"
+          "setp.lt.and.f32 p1, %4, %1, !p0;\n\t"
+          "@p1 mov.f32 %1, %4;\n\t"
+          "@p1 mov.b32 %3, %5;\n\t"
+          "@p0 mov.f32 %1, %0;\n\t"
+          "@p0 mov.b32 %3, %2;\n\t"
+          "@p0 mov.f32 %0, %4;\n\t"
+          "@p0 mov.b32 %2, %5;\n\t}"
+          : "+f"(d[0]), "+f"(d[1]), "+r"(i[0]), "+r"(i[1])
+          : "f"(x), "r"(col));
+      return;
+    }
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
       const bool lt_prev = (s > 0) ? (x < d[s > 0 ? s - 1 : 0]) : false;
@@ -326,14 +343,14 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const ImgDev t = imgs[unit.t_slot];
       const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
+      float pb_up = kInf;  // smallest value NOT admissible according to the other column parts of this row
       for (int tb = 0; tb < n_tb; ++tb, ++it) {
         const uint32_t sq = it * kATiles + a;
         const uint32_t slot = sq % kSlots;
         // Bound from the threads that own the other column parts of this row: the k-th best of the union of
         // all lists (stale values are still valid bounds).  Ties with it are admitted; the final merge orders
         // them by index.
-        float pb_up = kInf;
-        {
+        if ((tb & (kShareEvery - 1)) == 0) {  // refresh every few tiles: the exchange itself costs ALU-pipe instructions
           float f1 = kInf, g1 = kInf, f2 = kInf, g2 = kInf;
           const float4 p1 = lds_volatile_v4(&share[((part + 1) % kParts) * kSuperRows + urow]);
           if (__float_as_int(p1.z) == uit) {
@@ -355,7 +372,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           } else {
             merged = fmin3(tk.d[KTOP - 1], g1, g2);
           }
-          if (merged < kInf) pb_up = next_up(merged);
+          if (merged < kInf) pb_up = fminf(pb_up, next_up(merged));
         }
         mbar_wait(&bars->t_full[slot], (sq / kSlots) & 1, 40);
         tc_fence_after();
@@ -382,7 +399,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_before();
           if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
         }
-        sts_volatile_v4(&share[part * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
+        if ((tb & (kShareEvery - 1)) == kShareEvery - 1)
+          sts_volatile_v4(&share[part * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
       }
       // end of unit: parts 1.. hand their lists to part 0's thread of the same row
       if (part > 0) {

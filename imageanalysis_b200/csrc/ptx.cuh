@@ -52,21 +52,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-#ifndef IAM_WAIT_TIMEOUT_NS
-#define IAM_WAIT_TIMEOUT_NS 8000000000ull   // a lost arrival traps after 8 s instead of hanging the GPU
+#ifndef IAM_SPIN_LIMIT
+#define IAM_SPIN_LIMIT (1u << 26)   // failed try_waits (each a hardware sleep) before a lost arrival traps instead of hanging the GPU
 #endif
 
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
+// The spin body is deliberately tiny (TRYWAIT, BRA, IADD, ISETP): waiting warps share the ALU pipe
+// with the working epilogue warps, so every instruction spent polling is stolen from them.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (global_timer_ns() - t0 > IAM_WAIT_TIMEOUT_NS) {
+    if (++spins == IAM_SPIN_LIMIT) {
       printf("iamatch: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
              (int)threadIdx.x, parity);
       __trap();
