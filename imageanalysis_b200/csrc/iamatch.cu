@@ -120,6 +120,9 @@ struct iam_ctx {
   bool timing_pending = false;
   bool profiling = false;
   cudaEvent_t ev[6] = {};
+  std::vector<cudaEvent_t> wave_ev;   // one event per wave of uploads in iam_match_images
+  int reserve_sms = 0;                // SMs left free for conversion kernels while uploads are in flight
+  bool feed_mode = false;             // inside iam_match_images: no per-image memset / event
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -323,7 +326,7 @@ int launch_knn(iam_ctx* c, int engine, int k, int unit_begin, int n_units) {
   const iam::KnnUnit* u = c->units.as<iam::KnnUnit>() + unit_begin;
   cudaError_t e;
   if (engine == IAM_ENGINE_UMMA)
-    e = iam::launch_knn_umma(c->norm, k, c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->num_sms, c->stream);
+    e = iam::launch_knn_umma(c->norm, k, c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), std::max(2, c->num_sms - c->reserve_sms), c->stream);
   else
     e = iam::launch_knn_simt(c->norm, k, raw_row_bytes(c), c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->stream);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "kNN launch failed: %s", cudaGetErrorString(e));
@@ -408,6 +411,8 @@ int iam_destroy(iam_ctx* c) {
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->span)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->wave_ev)
     if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -534,15 +539,17 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
     if (bytes) CU(cudaMemcpyAsync(c->stage.p, src, bytes, cudaMemcpyHostToDevice, c->up_stream));
     dsrc = c->stage.p;
   }
-  CU(cudaMemsetAsync(im.block, 1, sizeof(int), c->up_stream));  // exactness flag: non-zero = exact
-  if (c->profiling) CU(cudaEventRecord(c->ev[4], c->up_stream));
+  // exactness flag: non-zero = exact.  u8 / Hamming sources are exact by construction: no flag traffic at all.
+  const bool need_flag = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32);
+  if (need_flag) CU(cudaMemsetAsync(im.block, 1, sizeof(int), c->up_stream));
+  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[4], c->up_stream));
   cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block + 256, im.block + 256 + raw_b,
                                       im.block + 256 + raw_b + form_b, reinterpret_cast<int*>(im.block), c->up_stream);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "convert launch: %s", cudaGetErrorString(e));
   c->timing.total_launches += 1;
-  if (c->profiling) CU(cudaEventRecord(c->ev[5], c->up_stream));
-  CU(cudaEventRecord(im.ready, c->up_stream));
-  im.seq = ++c->up_seq;
+  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[5], c->up_stream));
+  if (!c->feed_mode) CU(cudaEventRecord(im.ready, c->up_stream));  // feed mode: one event per wave instead
+  im.seq = c->feed_mode ? 0 : ++c->up_seq;
   im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
   return IAM_OK;
 }
@@ -743,7 +750,14 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   }
   CU(cudaEventRecord(c->span[0], c->up_stream));
   CU(cudaEventRecord(c->span[2], c->stream));
-  if ((rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr)) != IAM_OK) return rc;
+  // The matching kernel fills every SM it is given (registers, shared memory); leave a few SMs to the layout
+  // conversion kernels of later waves so that uploads really overlap the matching of earlier waves.
+  c->feed_mode = true;
+  c->reserve_sms = waves > 1 ? 8 : 0;
+  rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr);
+  c->feed_mode = false;
+  c->reserve_sms = 0;
+  if (rc != IAM_OK) return rc;
   for (int i = 0; i < n_images; ++i)  // images no pair referenced are still part of the resident set
     if (!feed.done[i] && (rc = enqueue_upload(c, image_ids[i], host_ptrs[i], true, dtype, key_ptrs ? key_ptrs[i] : nullptr)) != IAM_OK)
       return rc;
@@ -816,6 +830,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     const int u0 = pl.chunk_unit_begin[ch], u1 = pl.chunk_unit_begin[ch + 1];
     if (p1 == p0) continue;
     if (feed) {  // enqueue the uploads this chunk is the first to need (upload stream; overlaps earlier chunks' kernels)
+      bool any_upload = false;
       for (int i = 2 * p0; i < 2 * p1; ++i) {
         const int id = pairs[i];
         const int slot = id < (int)feed->slot_of_id.size() ? feed->slot_of_id[id] : -1;
@@ -829,11 +844,21 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
           im.keys = keep;
           im.dev.kp_key = keep;
           if (hk && keep) CU(cudaMemcpyAsync(keep, hk, size_t(im.n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
-          if (hk && keep) CU(cudaEventRecord(im.ready, c->up_stream));
+          any_upload = true;
         }
       }
+      if (any_upload) {  // the compute stream is in order: waiting for this wave's uploads covers all earlier ones
+        if ((int)c->wave_ev.size() <= ch) {
+          const size_t old = c->wave_ev.size();
+          c->wave_ev.resize(ch + 1, nullptr);
+          for (size_t w = old; w < c->wave_ev.size(); ++w) CU(cudaEventCreateWithFlags(&c->wave_ev[w], cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(c->wave_ev[ch], c->up_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->wave_ev[ch], 0));
+      }
+    } else if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) {
+      return rc;
     }
-    if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) return rc;
     const bool prof = c->profiling && n_chunks == 1;
     if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
     if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;

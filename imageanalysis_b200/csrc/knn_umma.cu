@@ -35,7 +35,7 @@ namespace iam {
 namespace {
 
 constexpr int kBStages = 4;
-constexpr int kShareEvery = 4;                   // tiles between exchanges of running bounds (power of two)
+constexpr int kShareEvery = 1;                   // tiles between exchanges of running bounds (power of two)
 constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
 constexpr int kWarpsPerATile = 4 * kParts;
 constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
@@ -43,7 +43,7 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;   // 896
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemAColsPerTile = kKSteps * 8;  // 72 columns: 128 rows x 144 fp16 (two K elements per 32-bit cell)
 // Accumulator slots of kBRows columns each, handed round-robin to successive (B tile, A tile) products.
-constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;  // 3 for 96-column tiles
+constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;  // 3 for 96-column tiles, 5 for 64
 constexpr uint32_t kTmemA = kSlots * kBRows;     // A operand region behind the accumulator slots
 
 struct __align__(8) Barriers {
@@ -61,7 +61,7 @@ constexpr size_t kSmemA = kATiles * kTileBytes;         //  73728: staging for t
 constexpr size_t kSmemB = kBStages * kBTileBytes;       // 110592: streamed train tiles
 constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
 constexpr size_t kSmemShare = kParts * kSuperRows * 16;       // 12288: running bounds exchanged between the column parts of a row
-constexpr size_t kSmemMerge = (kParts - 1) * kSuperRows * 3 * 8;  // 12288: end-of-unit hand-over of the other parts' lists
+constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kSuperRows * 3 * 8;  // end-of-unit hand-over of the other parts' lists
 constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
 static_assert(kTmemA + kATiles * kTmemAColsPerTile <= 512, "tensor memory budget");
@@ -374,7 +374,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           }
           if (merged < kInf) pb_up = fminf(pb_up, next_up(merged));
         }
-        mbar_wait(&bars->t_full[slot], (sq / kSlots) & 1, 40);
+        mbar_wait_bare(&bars->t_full[slot], (sq / kSlots) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * kBRows + part * 32;
         if (dbg_flags != 1) {

@@ -22,7 +22,10 @@ constexpr int kTileRows = 128;
 constexpr int kTileBytes = kTileRows * kRowBytes;    // 36864
 constexpr int kATiles = 2;                           // resident query tiles per work unit (A operand lives in TMEM)
 constexpr int kSuperRows = kATiles * kTileRows;      // 256 rows of the query image one work unit owns
-constexpr int kBRows = 96;                           // train rows per streamed B tile (= UMMA N), multiple of 32
+#ifndef IAM_BROWS
+#define IAM_BROWS 96
+#endif
+constexpr int kBRows = IAM_BROWS;                    // train rows per streamed B tile (= UMMA N), multiple of 32
 constexpr int kBTileBytes = kBRows * kRowBytes;      // 27648
 constexpr int kKSteps = 9;                           // 8 data K-steps + 1 augmentation step
 constexpr int kKStepBytes = 256;                     // 2 chunks * 128 B

@@ -69,6 +69,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// Hot-loop wait without the watchdog counter (two ALU-pipe instructions less per poll).  Only for waits
+// whose producer side is itself guarded by mbar_wait: a lost arrival still traps there.
+__device__ __forceinline__ void mbar_wait_bare(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
 // ------------------------------------------------------- bulk copy (TMA 1-D)
 // global -> shared, completion reported on an mbarrier in bytes.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
