@@ -104,6 +104,11 @@ struct iam_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;     // compute stream (own_stream or the caller's)
   cudaStream_t up_stream = nullptr;  // H2D + layout conversion; overlaps with matching of earlier pair chunks
+  cudaStream_t up_stream2 = nullptr; // second upload lane (iam_match_images alternates images between the two, so the
+                                     // copy of one image overlaps the conversion of the previous one)
+  Buffer stage2;
+  cudaEvent_t lane2_ev = nullptr;
+  unsigned up_rr = 0;
   cudaEvent_t compute_done = nullptr;
   bool compute_pending = false;
   uint64_t up_seq = 0;
@@ -382,6 +387,8 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
   }
   c->stream = c->own_stream;
   e = cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->up_stream2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2_ev, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete c;
@@ -398,6 +405,7 @@ int iam_destroy(iam_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->up_stream) cudaStreamSynchronize(c->up_stream);
+  if (c->up_stream2) cudaStreamSynchronize(c->up_stream2);
   for (auto& im : c->images) {
     if (im.block) cudaFree(im.block);
     if (im.keys) cudaFree(im.keys);
@@ -405,6 +413,9 @@ int iam_destroy(iam_ctx* c) {
   }
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
+  if (c->up_stream2) cudaStreamDestroy(c->up_stream2);
+  if (c->lane2_ev) cudaEventDestroy(c->lane2_ev);
+  c->stage2.release();
   Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
                     &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
   for (Buffer* b : bufs) b->release();
@@ -437,6 +448,7 @@ int iam_set_engine(iam_ctx* c, int engine) {
 int iam_synchronize(iam_ctx* c) {
   int rc = bind(c);
   if (rc) return rc;
+  CU(cudaStreamSynchronize(c->up_stream2));
   CU(cudaStreamSynchronize(c->up_stream));
   CU(cudaStreamSynchronize(c->stream));
   return IAM_OK;
@@ -514,8 +526,12 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
   const size_t form_b = iam::form_bytes(n_pad);
   if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
     CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    CU(cudaStreamWaitEvent(c->up_stream2, c->compute_done, 0));
     c->compute_pending = false;
   }
+  const bool lane2 = c->feed_mode && ((c->up_rr++ & 1u) != 0u);
+  cudaStream_t us = lane2 ? c->up_stream2 : c->up_stream;
+  Buffer& stg = lane2 ? c->stage2 : c->stage;
   if (im.keys) {  // keys belong to the previous descriptor set
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaFree(im.keys));
@@ -525,30 +541,30 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
   }
   if (host_keys && n > 0) {
     CU(cudaMalloc(reinterpret_cast<void**>(&im.keys), size_t(n) * sizeof(int)));
-    CU(cudaMemcpyAsync(im.keys, host_keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
+    CU(cudaMemcpyAsync(im.keys, host_keys, size_t(n) * sizeof(int), cudaMemcpyHostToDevice, us));
     im.dev.kp_key = im.keys;
     c->imgs_dirty = true;
   }
   const void* dsrc = src;
   if (src_on_host) {
     const size_t bytes = size_t(n) * c->desc_bytes * (dtype == IAM_DTYPE_F32 ? 4 : 1);
-    if (c->stage.cap < bytes) {
-      CU(cudaStreamSynchronize(c->up_stream));  // a conversion may still be reading the old staging buffer
-      CU(c->stage.ensure(std::max<size_t>(bytes, 256)));
+    if (stg.cap < bytes) {
+      CU(cudaStreamSynchronize(us));  // a conversion may still be reading the old staging buffer
+      CU(stg.ensure(std::max<size_t>(bytes, 256)));
     }
-    if (bytes) CU(cudaMemcpyAsync(c->stage.p, src, bytes, cudaMemcpyHostToDevice, c->up_stream));
-    dsrc = c->stage.p;
+    if (bytes) CU(cudaMemcpyAsync(stg.p, src, bytes, cudaMemcpyHostToDevice, us));
+    dsrc = stg.p;
   }
   // exactness flag: non-zero = exact.  u8 / Hamming sources are exact by construction: no flag traffic at all.
   const bool need_flag = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32);
-  if (need_flag) CU(cudaMemsetAsync(im.block, 1, sizeof(int), c->up_stream));
-  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[4], c->up_stream));
+  if (need_flag) CU(cudaMemsetAsync(im.block, 1, sizeof(int), us));
+  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[4], us));
   cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block + 256, im.block + 256 + raw_b,
-                                      im.block + 256 + raw_b + form_b, reinterpret_cast<int*>(im.block), c->up_stream);
+                                      im.block + 256 + raw_b + form_b, reinterpret_cast<int*>(im.block), us);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "convert launch: %s", cudaGetErrorString(e));
   c->timing.total_launches += 1;
-  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[5], c->up_stream));
-  if (!c->feed_mode) CU(cudaEventRecord(im.ready, c->up_stream));  // feed mode: one event per wave instead
+  if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[5], us));
+  if (!c->feed_mode) CU(cudaEventRecord(im.ready, us));  // feed mode: one event per wave instead
   im.seq = c->feed_mode ? 0 : ++c->up_seq;
   im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
   return IAM_OK;
@@ -746,6 +762,7 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   const auto h0 = std::chrono::steady_clock::now();
   if (c->compute_pending) {
     CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    CU(cudaStreamWaitEvent(c->up_stream2, c->compute_done, 0));
     c->compute_pending = false;
   }
   CU(cudaEventRecord(c->span[0], c->up_stream));
@@ -761,6 +778,8 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   for (int i = 0; i < n_images; ++i)  // images no pair referenced are still part of the resident set
     if (!feed.done[i] && (rc = enqueue_upload(c, image_ids[i], host_ptrs[i], true, dtype, key_ptrs ? key_ptrs[i] : nullptr)) != IAM_OK)
       return rc;
+  CU(cudaEventRecord(c->lane2_ev, c->up_stream2));
+  CU(cudaStreamWaitEvent(c->up_stream, c->lane2_ev, 0));
   CU(cudaEventRecord(c->span[1], c->up_stream));
   CU(cudaEventRecord(c->span[3], c->stream));
   c->timing.host_enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - h0).count();
@@ -853,6 +872,8 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
           c->wave_ev.resize(ch + 1, nullptr);
           for (size_t w = old; w < c->wave_ev.size(); ++w) CU(cudaEventCreateWithFlags(&c->wave_ev[w], cudaEventDisableTiming));
         }
+        CU(cudaEventRecord(c->lane2_ev, c->up_stream2));          // fold lane 2 into lane 1, then one event for both
+        CU(cudaStreamWaitEvent(c->up_stream, c->lane2_ev, 0));
         CU(cudaEventRecord(c->wave_ev[ch], c->up_stream));
         CU(cudaStreamWaitEvent(c->stream, c->wave_ev[ch], 0));
       }
