@@ -35,7 +35,10 @@ namespace iam {
 namespace {
 
 constexpr int kBStages = 4;
-constexpr int kShareEvery = 1;                   // tiles between exchanges of running bounds (power of two)
+#ifndef IAM_SHARE_EVERY
+#define IAM_SHARE_EVERY 1
+#endif
+constexpr int kShareEvery = IAM_SHARE_EVERY;                   // tiles between exchanges of running bounds (power of two)
 constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
 constexpr int kWarpsPerATile = 4 * kParts;
 constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
