@@ -63,7 +63,7 @@ struct __align__(8) Barriers {
 constexpr size_t kSmemA = kATiles * kTileBytes;         //  73728: staging for the next unit's query tiles
 constexpr size_t kSmemB = kBStages * kBTileBytes;       // 110592: streamed train tiles
 constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
-constexpr size_t kSmemShare = kParts * kSuperRows * 16;       // 12288: running bounds exchanged between the column parts of a row
+constexpr size_t kSmemShare = 2 * kParts * kSuperRows * 4;   //  6144: running k-th bests exchanged between the column parts of a row
 constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kSuperRows * 3 * 8;  // end-of-unit hand-over of the other parts' lists
 constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
 static_assert(kSmemTotal <= 232448, "shared memory budget");
@@ -192,7 +192,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
   Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
-  float4* share = reinterpret_cast<float4*>(smem + kSmemA + kSmemB + kSmemBars);             // [part][row]
+  float* share = reinterpret_cast<float*>(smem + kSmemA + kSmemB + kSmemBars);               // [unit parity][part][row]
   float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + kSmemBars + kSmemShare);  // [part-1][row][k]
 
   const int warp = threadIdx.x >> 5;
@@ -205,7 +205,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   const int first_pu = blockIdx.x / kCtas;
   const int pu_stride = gridDim.x / kCtas;
 
-  for (int i = threadIdx.x; i < kParts * kSuperRows; i += blockDim.x) share[i] = make_float4(kInf, kInf, __int_as_float(-1), 0.f);
+  for (int i = threadIdx.x; i < 2 * kParts * kSuperRows; i += blockDim.x) share[i] = kInf;
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kATiles; ++i) {
       mbar_init(&bars->a_full[i], 1);
@@ -347,34 +347,24 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
       float pb_up = kInf;  // smallest value NOT admissible according to the other column parts of this row
+      // Bounds live in a buffer selected by the unit's parity.  At the start of unit u every thread resets its
+      // slot in the OTHER buffer (the one unit u+1 will use); the end-of-unit barrier orders that reset before
+      // any partner reads it, so a slot only ever holds +inf or values of the unit being processed.
+      float* my_share = share + (uit & 1) * kParts * kSuperRows + urow;
+      sts_volatile_f32(share + ((uit + 1) & 1) * kParts * kSuperRows + part * kSuperRows + urow, kInf);
       for (int tb = 0; tb < n_tb; ++tb, ++it) {
         const uint32_t sq = it * kATiles + a;
         const uint32_t slot = sq % kSlots;
         // Bound from the threads that own the other column parts of this row: the k-th best of the union of
         // all lists (stale values are still valid bounds).  Ties with it are admitted; the final merge orders
         // them by index.
-        if ((tb & (kShareEvery - 1)) == 0) {  // refresh every few tiles: the exchange itself costs ALU-pipe instructions
-          float f1 = kInf, g1 = kInf, f2 = kInf, g2 = kInf;
-          const float4 p1 = lds_volatile_v4(&share[((part + 1) % kParts) * kSuperRows + urow]);
-          if (__float_as_int(p1.z) == uit) {
-            f1 = p1.x;
-            g1 = p1.y;
-          }
-          if (kParts > 2) {
-            const float4 p2 = lds_volatile_v4(&share[((part + 2) % kParts) * kSuperRows + urow]);
-            if (__float_as_int(p2.z) == uit) {
-              f2 = p2.x;
-              g2 = p2.y;
-            }
-          }
-          float merged;
-          if (KTOP == 2) {
-            const float f0 = tk.d[0];
-            const float second_of_firsts = fmaxf(fminf(f0, f1), fminf(fmaxf(f0, f1), f2));
-            merged = fminf(second_of_firsts, fmin3(tk.d[1], g1, g2));
-          } else {
-            merged = fmin3(tk.d[KTOP - 1], g1, g2);
-          }
+        // Bound from the threads that own the other column parts of this row: nothing worse than the smallest
+        // of their k-th bests can end up in the merged list (ties are admitted; the final merge orders them by
+        // index).  Stale values are still valid bounds, so plain volatile shared-memory traffic suffices.
+        if ((tb & (kShareEvery - 1)) == 0 && kParts > 1) {
+          const float g1 = lds_volatile_f32(&my_share[((part + 1) % kParts) * kSuperRows]);
+          const float g2 = kParts > 2 ? lds_volatile_f32(&my_share[((part + 2) % kParts) * kSuperRows]) : kInf;
+          const float merged = fminf(g1, g2);
           if (merged < kInf) pb_up = fminf(pb_up, next_up(merged));
         }
         mbar_wait_bare(&bars->t_full[slot], (sq / kSlots) & 1);
@@ -402,8 +392,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_before();
           if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
         }
-        if ((tb & (kShareEvery - 1)) == kShareEvery - 1)
-          sts_volatile_v4(&share[part * kSuperRows + urow], make_float4(tk.d[0], tk.d[KTOP - 1], __int_as_float(uit), 0.f));
+        if ((tb & (kShareEvery - 1)) == kShareEvery - 1 && kParts > 1) sts_volatile_f32(&my_share[part * kSuperRows], tk.d[KTOP - 1]);
       }
       // end of unit: parts 1.. hand their lists to part 0's thread of the same row
       if (part > 0) {

@@ -248,6 +248,15 @@ __device__ __forceinline__ void sts_volatile_v4(void* p, float4 v) {
                : "memory");
 }
 
+__device__ __forceinline__ float lds_volatile_f32(const void* p) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_f32(void* p, float v) {
+  asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }  // -> FMNMX3
 
 }  // namespace iam
