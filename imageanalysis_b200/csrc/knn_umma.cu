@@ -162,21 +162,53 @@ __device__ __forceinline__ void consume_group(const float* w, int col, TopK<KTOP
   if (e3) tk.insert(w[3], col + 3);
 }
 
+// Group test on the FMA pipe: the epilogue is bound by the ALU pipe (FMNMX / FSETP / SEL), while the FMA
+// pipe idles.  Non-negative floats order like their bit patterns, so (bits(x) - bits(te)) < 0  <=>  x < te;
+// IMAD forms the differences and IMAD.HI accumulates their sign words (-1 / 0), all on the FMA pipe.  `one`
+// is a kernel argument (always 1) so that the multiplies are not strength-reduced back into ALU adds.
+__device__ __forceinline__ bool group_below_fma(const float* w, int neg_te_bits, int one) {
+  int acc;
+  asm("{\n\t.reg .s32 d0, d1, d2, d3, a;\n\t"
+      "mad.lo.s32 d0, %1, %5, %6;\n\t"
+      "mad.lo.s32 d1, %2, %5, %6;\n\t"
+      "mad.lo.s32 d2, %3, %5, %6;\n\t"
+      "mad.lo.s32 d3, %4, %5, %6;\n\t"
+      "mad.hi.s32 a, d0, %5, 0;\n\t"
+      "mad.hi.s32 a, d1, %5, a;\n\t"
+      "mad.hi.s32 a, d2, %5, a;\n\t"
+      "mad.hi.s32 %0, d3, %5, a;\n\t}"
+      : "=r"(acc)
+      : "r"(__float_as_int(w[0])), "r"(__float_as_int(w[1])), "r"(__float_as_int(w[2])), "r"(__float_as_int(w[3])),
+        "r"(one), "r"(neg_te_bits));
+  return acc != 0;
+}
+
+#ifndef IAM_FMA_GROUPS
+#define IAM_FMA_GROUPS 6   // of the 8 four-column groups of a 32-column block, how many are tested on the FMA pipe
+#endif
+
 template <int KTOP>
-__device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up) {
+__device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up, int one) {
+  // Per 16-column batch the four group tests are formed and voted on up front against the bound at
+  // entry (it only tightens, so the votes stay conservative): independent chains instead of
+  // serialised vote->branch round trips.
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    // bound admitted at batch entry; it only tightens, so votes taken against it stay conservative
     const float te = fminf(tk.thr(), pb_up);
+    const int nte = -__float_as_int(te);
     const float* w = &v[h * 16];
-    const float m0 = fminf(fmin3(w[0], w[1], w[2]), w[3]);
-    const float m1 = fminf(fmin3(w[4], w[5], w[6]), w[7]);
-    const float m2 = fminf(fmin3(w[8], w[9], w[10]), w[11]);
-    const float m3 = fminf(fmin3(w[12], w[13], w[14]), w[15]);
-    const bool t0 = __any_sync(0xffffffffu, m0 < te);
-    const bool t1 = __any_sync(0xffffffffu, m1 < te);
-    const bool t2 = __any_sync(0xffffffffu, m2 < te);
-    const bool t3 = __any_sync(0xffffffffu, m3 < te);
+    bool b[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (h * 4 + g < IAM_FMA_GROUPS)
+        b[g] = group_below_fma(w + g * 4, nte, one);
+      else
+        b[g] = fminf(fmin3(w[g * 4], w[g * 4 + 1], w[g * 4 + 2]), w[g * 4 + 3]) < te;
+    }
+    const bool t0 = __any_sync(0xffffffffu, b[0]);
+    const bool t1 = __any_sync(0xffffffffu, b[1]);
+    const bool t2 = __any_sync(0xffffffffu, b[2]);
+    const bool t3 = __any_sync(0xffffffffu, b[3]);
     if (t0) consume_group<KTOP>(w, col0 + h * 16, tk, fminf(tk.thr(), pb_up));
     if (t1) consume_group<KTOP>(w + 4, col0 + h * 16 + 4, tk, fminf(tk.thr(), pb_up));
     if (t2) consume_group<KTOP>(w + 8, col0 + h * 16 + 8, tk, fminf(tk.thr(), pb_up));
@@ -187,7 +219,7 @@ __device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<K
 template <Kind kKind, int KTOP, bool kATmem, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
-                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
+                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags, int one) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
@@ -380,7 +412,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_before();
           if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
           if (dbg_flags == 0) {
-            consume32<KTOP>(v, tb * kBRows + part * 32, tk, pb_up);
+            consume32<KTOP>(v, tb * kBRows + part * 32, tk, pb_up, one);
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v[0];
 #pragma unroll
@@ -508,7 +540,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
     return e ? atoi(e) : 0;
   }();
-  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int);
+  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int, int);
   KernT kern;
   if (cluster && (n_units % 2 == 0))
     kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true> : knn_umma_kernel<kKind, KTOP, false, true>;
@@ -534,7 +566,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     cfg.numAttrs = 1;
   }
   cfg.gridDim = dim3(grid);
-  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags);
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags, 1);
 }
 
 }  // namespace
