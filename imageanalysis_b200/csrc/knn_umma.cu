@@ -148,78 +148,63 @@ __device__ __forceinline__ float next_up(float x) {  // x >= 0
 // bound are admitted; the final merge orders them by index).  Expected
 // insertions per row over M columns are ~k*ln(M/k), so almost every group takes
 // the 5-instruction fast path.
-template <int KTOP>
-__device__ __forceinline__ void consume_group(const float* w, int col, TopK<KTOP>& tk, float te) {
+// The running lists carry an ENCODED column index e = tp * 33 + j, where tp = tile * kParts + part numbers
+// the 32-column slices of the train image and j < 32 is the column inside the slice.  e is monotone in the real
+// column (tp * 32 + j), so ties order identically, and it is formed by ONE IMAD with an immediate addend: the
+// epilogue is ALU-pipe bound while the FMA pipe idles, and "base + j" would cost an ALU-pipe add per insert.
+constexpr int kEncMul = 33;
+template <int J>
+__device__ __forceinline__ int enc_index(int tp) {
+  int c;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(c) : "r"(tp), "n"(kEncMul), "n"(J));
+  return c;
+}
+__device__ __forceinline__ int dec_index(int e) {
+  const int tp = e / kEncMul;
+  return tp * 32 + (e - tp * kEncMul);
+}
+
+template <int KTOP, int J0>
+__device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>& tk, float te) {
   // four votes issued back to back (computed against the bound at group entry: a superset of what
   // the tightening bound would admit), then the branch-free network only where some lane qualifies
   const bool e0 = __any_sync(0xffffffffu, w[0] < te);
   const bool e1 = __any_sync(0xffffffffu, w[1] < te);
   const bool e2 = __any_sync(0xffffffffu, w[2] < te);
   const bool e3 = __any_sync(0xffffffffu, w[3] < te);
-  if (e0) tk.insert(w[0], col);
-  if (e1) tk.insert(w[1], col + 1);
-  if (e2) tk.insert(w[2], col + 2);
-  if (e3) tk.insert(w[3], col + 3);
+  if (e0) tk.insert(w[0], enc_index<J0>(tp));
+  if (e1) tk.insert(w[1], enc_index<J0 + 1>(tp));
+  if (e2) tk.insert(w[2], enc_index<J0 + 2>(tp));
+  if (e3) tk.insert(w[3], enc_index<J0 + 3>(tp));
 }
 
-// Group test on the FMA pipe: the epilogue is bound by the ALU pipe (FMNMX / FSETP / SEL), while the FMA
-// pipe idles.  Non-negative floats order like their bit patterns, so (bits(x) - bits(te)) < 0  <=>  x < te;
-// IMAD forms the differences and IMAD.HI accumulates their sign words (-1 / 0), all on the FMA pipe.  `one`
-// is a kernel argument (always 1) so that the multiplies are not strength-reduced back into ALU adds.
-__device__ __forceinline__ bool group_below_fma(const float* w, int neg_te_bits, int one) {
-  int acc;
-  asm("{\n\t.reg .s32 d0, d1, d2, d3, a;\n\t"
-      "mad.lo.s32 d0, %1, %5, %6;\n\t"
-      "mad.lo.s32 d1, %2, %5, %6;\n\t"
-      "mad.lo.s32 d2, %3, %5, %6;\n\t"
-      "mad.lo.s32 d3, %4, %5, %6;\n\t"
-      "mad.hi.s32 a, d0, %5, 0;\n\t"
-      "mad.hi.s32 a, d1, %5, a;\n\t"
-      "mad.hi.s32 a, d2, %5, a;\n\t"
-      "mad.hi.s32 %0, d3, %5, a;\n\t}"
-      : "=r"(acc)
-      : "r"(__float_as_int(w[0])), "r"(__float_as_int(w[1])), "r"(__float_as_int(w[2])), "r"(__float_as_int(w[3])),
-        "r"(one), "r"(neg_te_bits));
-  return acc != 0;
+// Per 16-column batch the four group tests are formed and voted on up front against the bound at
+// entry (it only tightens, so the votes stay conservative): independent FMNMX3/FSETP/VOTE chains
+// instead of serialised vote->branch round trips.  (Moving the tests to the idle FMA pipe with
+// IMAD/IMAD.HI sign accumulation was measured and is slower: IMAD.HI is not a full-rate instruction.)
+template <int KTOP, int H>
+__device__ __forceinline__ void consume16(const float* w, int tp, TopK<KTOP>& tk, float pb_up) {
+  const float te = fminf(tk.thr(), pb_up);
+  const bool t0 = __any_sync(0xffffffffu, fminf(fmin3(w[0], w[1], w[2]), w[3]) < te);
+  const bool t1 = __any_sync(0xffffffffu, fminf(fmin3(w[4], w[5], w[6]), w[7]) < te);
+  const bool t2 = __any_sync(0xffffffffu, fminf(fmin3(w[8], w[9], w[10]), w[11]) < te);
+  const bool t3 = __any_sync(0xffffffffu, fminf(fmin3(w[12], w[13], w[14]), w[15]) < te);
+  if (t0) consume_group<KTOP, H * 16>(w, tp, tk, fminf(tk.thr(), pb_up));
+  if (t1) consume_group<KTOP, H * 16 + 4>(w + 4, tp, tk, fminf(tk.thr(), pb_up));
+  if (t2) consume_group<KTOP, H * 16 + 8>(w + 8, tp, tk, fminf(tk.thr(), pb_up));
+  if (t3) consume_group<KTOP, H * 16 + 12>(w + 12, tp, tk, fminf(tk.thr(), pb_up));
 }
-
-#ifndef IAM_FMA_GROUPS
-#define IAM_FMA_GROUPS 6   // of the 8 four-column groups of a 32-column block, how many are tested on the FMA pipe
-#endif
 
 template <int KTOP>
-__device__ __forceinline__ void consume32(const float (&v)[32], int col0, TopK<KTOP>& tk, float pb_up, int one) {
-  // Per 16-column batch the four group tests are formed and voted on up front against the bound at
-  // entry (it only tightens, so the votes stay conservative): independent chains instead of
-  // serialised vote->branch round trips.
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const float te = fminf(tk.thr(), pb_up);
-    const int nte = -__float_as_int(te);
-    const float* w = &v[h * 16];
-    bool b[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (h * 4 + g < IAM_FMA_GROUPS)
-        b[g] = group_below_fma(w + g * 4, nte, one);
-      else
-        b[g] = fminf(fmin3(w[g * 4], w[g * 4 + 1], w[g * 4 + 2]), w[g * 4 + 3]) < te;
-    }
-    const bool t0 = __any_sync(0xffffffffu, b[0]);
-    const bool t1 = __any_sync(0xffffffffu, b[1]);
-    const bool t2 = __any_sync(0xffffffffu, b[2]);
-    const bool t3 = __any_sync(0xffffffffu, b[3]);
-    if (t0) consume_group<KTOP>(w, col0 + h * 16, tk, fminf(tk.thr(), pb_up));
-    if (t1) consume_group<KTOP>(w + 4, col0 + h * 16 + 4, tk, fminf(tk.thr(), pb_up));
-    if (t2) consume_group<KTOP>(w + 8, col0 + h * 16 + 8, tk, fminf(tk.thr(), pb_up));
-    if (t3) consume_group<KTOP>(w + 12, col0 + h * 16 + 12, tk, fminf(tk.thr(), pb_up));
-  }
+__device__ __forceinline__ void consume32(const float (&v)[32], int tp, TopK<KTOP>& tk, float pb_up) {
+  consume16<KTOP, 0>(&v[0], tp, tk, pb_up);
+  consume16<KTOP, 1>(&v[16], tp, tk, pb_up);
 }
 
 template <Kind kKind, int KTOP, bool kATmem, bool kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
-                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags, int one) {
+                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
@@ -412,7 +397,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_before();
           if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
           if (dbg_flags == 0) {
-            consume32<KTOP>(v, tb * kBRows + part * 32, tk, pb_up, one);
+            consume32<KTOP>(v, tb * kParts + part, tk, pb_up);
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v[0];
 #pragma unroll
@@ -447,7 +432,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
 #pragma unroll
           for (int s = 0; s < KTOP; ++s) {
-            out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : tk.i[s];
+            out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : dec_index(tk.i[s]);
             out_d2[o + s] = tk.d[s];
           }
         }
@@ -540,7 +525,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
     return e ? atoi(e) : 0;
   }();
-  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int, int);
+  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int);
   KernT kern;
   if (cluster && (n_units % 2 == 0))
     kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true> : knn_umma_kernel<kKind, KTOP, false, true>;
@@ -566,7 +551,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     cfg.numAttrs = 1;
   }
   cfg.gridDim = dim3(grid);
-  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags, 1);
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags);
 }
 
 }  // namespace
