@@ -14,7 +14,8 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libiamatch.so")
+# IAMATCH_LIB selects another build of the same library (A/B timing of kernel variants); default is the in-tree one
+LIB_PATH = os.environ.get("IAMATCH_LIB") or os.path.join(_HERE, "lib", "libiamatch.so")
 
 NORM_L2, NORM_HAMMING = 0, 1
 DTYPE_U8, DTYPE_F32 = 0, 1

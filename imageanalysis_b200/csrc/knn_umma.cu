@@ -164,14 +164,26 @@ __device__ __forceinline__ int dec_index(int e) {
   return tp * 32 + (e - tp * kEncMul);
 }
 
+// IAM_VOTE=1: warp-uniform branches decided by votes; 0: plain divergent branches (no VOTE on the ALU pipe)
+#ifndef IAM_VOTE
+#define IAM_VOTE 1
+#endif
+__device__ __forceinline__ bool any_lane(bool p) {
+#if IAM_VOTE
+  return __any_sync(0xffffffffu, p);
+#else
+  return p;
+#endif
+}
+
 template <int KTOP, int J0>
 __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>& tk, float te) {
   // four votes issued back to back (computed against the bound at group entry: a superset of what
   // the tightening bound would admit), then the branch-free network only where some lane qualifies
-  const bool e0 = __any_sync(0xffffffffu, w[0] < te);
-  const bool e1 = __any_sync(0xffffffffu, w[1] < te);
-  const bool e2 = __any_sync(0xffffffffu, w[2] < te);
-  const bool e3 = __any_sync(0xffffffffu, w[3] < te);
+  const bool e0 = any_lane(w[0] < te);
+  const bool e1 = any_lane(w[1] < te);
+  const bool e2 = any_lane(w[2] < te);
+  const bool e3 = any_lane(w[3] < te);
   if (e0) tk.insert(w[0], enc_index<J0>(tp));
   if (e1) tk.insert(w[1], enc_index<J0 + 1>(tp));
   if (e2) tk.insert(w[2], enc_index<J0 + 2>(tp));
@@ -185,10 +197,10 @@ __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>
 template <int KTOP, int H>
 __device__ __forceinline__ void consume16(const float* w, int tp, TopK<KTOP>& tk, float pb_up) {
   const float te = fminf(tk.thr(), pb_up);
-  const bool t0 = __any_sync(0xffffffffu, fminf(fmin3(w[0], w[1], w[2]), w[3]) < te);
-  const bool t1 = __any_sync(0xffffffffu, fminf(fmin3(w[4], w[5], w[6]), w[7]) < te);
-  const bool t2 = __any_sync(0xffffffffu, fminf(fmin3(w[8], w[9], w[10]), w[11]) < te);
-  const bool t3 = __any_sync(0xffffffffu, fminf(fmin3(w[12], w[13], w[14]), w[15]) < te);
+  const bool t0 = any_lane(fminf(fmin3(w[0], w[1], w[2]), w[3]) < te);
+  const bool t1 = any_lane(fminf(fmin3(w[4], w[5], w[6]), w[7]) < te);
+  const bool t2 = any_lane(fminf(fmin3(w[8], w[9], w[10]), w[11]) < te);
+  const bool t3 = any_lane(fminf(fmin3(w[12], w[13], w[14]), w[15]) < te);
   if (t0) consume_group<KTOP, H * 16>(w, tp, tk, fminf(tk.thr(), pb_up));
   if (t1) consume_group<KTOP, H * 16 + 4>(w + 4, tp, tk, fminf(tk.thr(), pb_up));
   if (t2) consume_group<KTOP, H * 16 + 8>(w + 8, tp, tk, fminf(tk.thr(), pb_up));
@@ -201,10 +213,10 @@ __device__ __forceinline__ void consume32(const float (&v)[32], int tp, TopK<KTO
   consume16<KTOP, 1>(&v[16], tp, tk, pb_up);
 }
 
-template <Kind kKind, int KTOP, bool kATmem, bool kCluster>
+template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
-                int* __restrict__ out_idx, float* __restrict__ out_d2, int dbg_flags) {
+                int* __restrict__ out_idx, float* __restrict__ out_d2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kSmemA;
@@ -291,70 +303,102 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc(128, kBRows, 0, 0);
-      const uint32_t a_addr = smem_u32(smem_a);
-      const uint32_t b_addr = smem_u32(smem_b);
-      uint32_t it = 0, uit = 0;
-      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
-        const int u = pu * kCtas + cta_rank;
-        const KnnUnit unit = units[u];
-        const ImgDev t = imgs[unit.t_slot];
-        const int n_tb = (t.n + kBRows - 1) / kBRows;
-        // query tiles: shared-memory staging -> tensor memory (tcgen05.cp), then the staging is free again.
-        // tcgen05 operations of one thread execute in issue order, so these copies run after every MMA of
-        // the previous unit that still reads the old A tiles.
-        for (int a = 0; a < kATiles; ++a) {
-          mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
-          tc_fence_after();
-          if (kATmem) {
+    // The whole warp walks the loops with warp-uniform values (made provably uniform by a shuffle, so the
+    // descriptor arithmetic lives in the uniform datapath instead of vector registers + R2UR); one elected lane
+    // issues the tcgen05 instructions.  The issue stream of this warp is on the critical path: it shares its
+    // scheduler with six ALU-bound epilogue warps.
+    constexpr uint32_t idesc = make_idesc(128, kBRows, 0, 0);
+    const uint32_t a_addr = smem_u32(smem_a);
+    const uint32_t b_addr = smem_u32(smem_b);
+    const uint32_t bars_addr = smem_u32(bars);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t tm_a = tm + kTmemA;
+    const uint32_t b_lo0 = smem_desc_lo(b_addr, kLBO);
+    uint32_t stage = 0, bpar = 0;   // B ring position
+    uint32_t slot = 0, tpar = 1;    // accumulator ring position; parity to wait for on t_empty (fresh barrier: 1)
+    uint32_t uit = 0;
+    for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
+      const int u = pu * kCtas + cta_rank;
+      const int n_t = __shfl_sync(0xffffffffu, imgs[units[u].t_slot].n, 0);
+      const int n_tb = (n_t + kBRows - 1) / kBRows;
+      // query tiles: shared-memory staging -> tensor memory (tcgen05.cp), then the staging is free again.
+      // tcgen05 operations of one thread execute in issue order, so these copies run after every MMA of
+      // the previous unit that still reads the old A tiles.
+      for (int a = 0; a < kATiles; ++a) {
+        mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
+        tc_fence_after();
+        if (kATmem) {
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks)
-              tmem_cp_128x256b(tmem_base + kTmemA + a * kTmemAColsPerTile + ks * 8,
+              tmem_cp_128x256b(tm + kTmemA + a * kTmemAColsPerTile + ks * 8,
                                make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO));
             umma_commit(&bars->a_empty[a]);
           }
+          __syncwarp();
         }
-        for (int tb = 0; tb < n_tb; ++tb, ++it) {
-          const uint32_t stage = it % kBStages;
-          const uint32_t par = (it / kBStages) & 1;
-          mbar_wait(&bars->b_full[stage], par, 30);
+      }
+      for (int tb = 0; tb < n_tb; ++tb) {
+        mbar_wait_a(bars_addr + offsetof(Barriers, b_full) + stage * 8, bpar, 30);
+        const uint32_t b_lo = b_lo0 + stage * (kBTileBytes >> 4);
 #pragma unroll
-          for (int a = 0; a < kATiles; ++a) {
-            const uint32_t sq = it * kATiles + a;          // running (B tile, A tile) product counter
-            const uint32_t slot = sq % kSlots;
-            mbar_wait(&bars->t_empty[slot], ((sq / kSlots) & 1) ^ 1, 31);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + slot * kBRows;
+        for (int a = 0; a < kATiles; ++a) {
+          mbar_wait_a(bars_addr + offsetof(Barriers, t_empty) + slot * 8, tpar, 31);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t taddr = tm + slot * kBRows;
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks) {
-              const uint64_t bdesc = make_smem_desc(b_addr + stage * kBTileBytes + ks * kKStepBytes, kLBO, kSBO);
+              const uint64_t bdesc = pack_desc(b_lo + ks * (kKStepBytes >> 4), smem_desc_hi(kSBO));
               if (kATmem) {
-                umma_ts<kKind>(taddr, tmem_base + kTmemA + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+                umma_ts<kKind>(taddr, tm_a + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
               } else {
                 const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
                 umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
               }
             }
             if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
-            umma_commit(&bars->t_full[slot]);
+            umma_commit_a(bars_addr + offsetof(Barriers, t_full) + slot * 8);
           }
+          __syncwarp();
+          if (++slot == kSlots) {
+            slot = 0;
+            tpar ^= 1;
+          }
+        }
+        if (elect_one()) {
           if (kCluster)
             umma_commit_multicast(&bars->b_empty[stage], 0x3);
           else
             umma_commit(&bars->b_empty[stage]);
         }
+        __syncwarp();
+        if (++stage == kBStages) {
+          stage = 0;
+          bpar ^= 1;
+        }
       }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
+    // The per-tile loop is ALU-pipe bound (profiles/): everything loop-invariant lives in pinned registers as
+    // ready-made shared-memory / tensor-memory addresses, and the slot / phase of the accumulator ring advance
+    // incrementally instead of by division.
     const int e = (warp - 4) >> 2;      // 0 .. kATiles*kParts-1
     const int a = e / kParts;           // which A tile
     const int part = e % kParts;        // which 32 of the B tile's columns
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int urow = a * kTileRows + quad * 32 + lane;  // row within the unit
+    constexpr uint32_t kPartStride = kSuperRows * 4;            // bytes between the parts' bound slots of one row
+    constexpr uint32_t kParityStride = kParts * kPartStride;    // bytes between the two unit-parity buffers
+    const uint32_t share_row = smem_u32(share) + urow * 4;
+    const uint32_t bar_full0 = pin_reg(smem_u32(&bars->t_full[0]));
+    constexpr uint32_t kEmptyOff = kSlots * 8;                  // t_empty[] follows t_full[] in Barriers
+    const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
+    const bool lane0 = lane == 0;
     TopK<KTOP> tk;
-    uint32_t it = 0;
+    uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kATiles + a, slot = sq % kSlots
+    static_assert(kATiles <= kSlots, "one wrap per step at most");
     int uit = 0;
     for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
       const int u = pu * kCtas + cta_rank;
@@ -367,37 +411,37 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       // Bounds live in a buffer selected by the unit's parity.  At the start of unit u every thread resets its
       // slot in the OTHER buffer (the one unit u+1 will use); the end-of-unit barrier orders that reset before
       // any partner reads it, so a slot only ever holds +inf or values of the unit being processed.
-      float* my_share = share + (uit & 1) * kParts * kSuperRows + urow;
-      sts_volatile_f32(share + ((uit + 1) & 1) * kParts * kSuperRows + part * kSuperRows + urow, kInf);
-      for (int tb = 0; tb < n_tb; ++tb, ++it) {
-        const uint32_t sq = it * kATiles + a;
-        const uint32_t slot = sq % kSlots;
-        // Bound from the threads that own the other column parts of this row: the k-th best of the union of
-        // all lists (stale values are still valid bounds).  Ties with it are admitted; the final merge orders
-        // them by index.
-        // Bound from the threads that own the other column parts of this row: nothing worse than the smallest
-        // of their k-th bests can end up in the merged list (ties are admitted; the final merge orders them by
-        // index).  Stale values are still valid bounds, so plain volatile shared-memory traffic suffices.
-        if ((tb & (kShareEvery - 1)) == 0 && kParts > 1) {
-          const float g1 = lds_volatile_f32(&my_share[((part + 1) % kParts) * kSuperRows]);
-          const float g2 = kParts > 2 ? lds_volatile_f32(&my_share[((part + 2) % kParts) * kSuperRows]) : kInf;
-          const float merged = fminf(g1, g2);
-          if (merged < kInf) pb_up = fminf(pb_up, next_up(merged));
+      const uint32_t rd = pin_reg(share_row + (uit & 1) * kParityStride);
+      const uint32_t wr = pin_reg(rd + part * kPartStride);
+      sts_volatile_f32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, kInf);
+      const int tp_end = n_tb * kParts + part;
+      for (int tp = part; tp < tp_end; tp += kParts) {  // tp numbers the 32-column slices of the train image
+        // Bound from the threads that own the column parts of this row (own slot included, it is harmless):
+        // nothing worse than the smallest of the k-th bests can end up in the merged list.  Ties are admitted
+        // (next_up; the final merge orders them by index); next_up(+inf) is a NaN, which fminf ignores.  Stale
+        // values are still valid bounds, so plain volatile shared-memory traffic suffices.
+        if (kParts > 1) {
+          float g = lds_volatile_f32_a(rd);
+#pragma unroll
+          for (int pp = 1; pp < kParts; ++pp) g = fminf(g, lds_volatile_f32_a(rd + pp * kPartStride));
+          pb_up = fminf(pb_up, __int_as_float(__float_as_int(g) + 1));
         }
-        mbar_wait_bare(&bars->t_full[slot], (sq / kSlots) & 1);
+        const uint32_t bar = bar_full0 + slot * 8;
+        mbar_wait_bare_a(bar, par);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * kBRows + part * 32;
-        if (dbg_flags != 1) {
+        if (kDbg != 1) {
           float v[32];
           __syncwarp();
-          tmem_ld32(taddr, v);
+          tmem_ld32(tm_warp + slot * kBRows, v);
           tmem_ld_wait(v);
           // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
           __syncwarp();
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
-          if (dbg_flags == 0) {
-            consume32<KTOP>(v, tb * kParts + part, tk, pb_up);
+          if (lane0) mbar_arrive_a(bar + kEmptyOff);
+          if (kDbg == 0) {
+            consume32<KTOP>(v, tp, tk, pb_up);
+          } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
+            tk.d[0] = fminf(tk.d[0], v[lane]);
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v[0];
 #pragma unroll
@@ -407,9 +451,14 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
           __syncwarp();
           tc_fence_before();
-          if (lane == 0) mbar_arrive(&bars->t_empty[slot]);
+          if (lane0) mbar_arrive_a(bar + kEmptyOff);
         }
-        if ((tb & (kShareEvery - 1)) == kShareEvery - 1 && kParts > 1) sts_volatile_f32(&my_share[part * kSuperRows], tk.d[KTOP - 1]);
+        if (kParts > 1) sts_volatile_f32_a(wr, tk.d[KTOP - 1]);
+        slot += kATiles;
+        if (slot >= kSlots) {
+          slot -= kSlots;
+          par ^= 1;
+        }
       }
       // end of unit: parts 1.. hand their lists to part 0's thread of the same row
       if (part > 0) {
@@ -522,16 +571,22 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     return !(e && atoi(e) == 1);
   }();
   static const int flags = [] {
-    const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only
+    const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only, 3 = accumulator read-out only
     return e ? atoi(e) : 0;
   }();
-  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, int);
-  KernT kern;
-  if (cluster && (n_units % 2 == 0))
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true> : knn_umma_kernel<kKind, KTOP, false, true>;
-  else
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false> : knn_umma_kernel<kKind, KTOP, false, false>;
+  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*);
   const bool use_cluster = cluster && (n_units % 2 == 0);
+  KernT kern;
+  if (flags != 0) {  // profiling variants exist for the production configuration only
+    if (!use_cluster || !a_tmem || flags < 0 || flags > 3) return cudaErrorInvalidValue;
+    kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1>
+           : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2>
+                        : knn_umma_kernel<kKind, KTOP, true, true, 3>;
+  } else if (use_cluster) {
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0> : knn_umma_kernel<kKind, KTOP, false, true, 0>;
+  } else {
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0> : knn_umma_kernel<kKind, KTOP, false, false, 0>;
+  }
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
   int grid = n_units < num_sms ? n_units : num_sms;
@@ -551,7 +606,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     cfg.numAttrs = 1;
   }
   cfg.gridDim = dim3(grid);
-  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, flags);
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2);
 }
 
 }  // namespace

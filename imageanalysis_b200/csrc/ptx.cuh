@@ -76,6 +76,92 @@ __device__ __forceinline__ void mbar_wait_bare(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Address-based variants for hot loops that keep shared-memory addresses in registers (no per-use
+// generic -> shared conversion, offsets fold into the instruction's immediate).
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+// try_wait with the implementation-defined (short) time limit: the warp is parked and woken by the barrier
+__device__ __forceinline__ bool mbar_try_wait_nohint_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking poll
+__device__ __forceinline__ bool mbar_test_wait_a(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifndef IAM_EPI_WAIT
+#define IAM_EPI_WAIT 0
+#endif
+#ifndef IAM_MMA_WAIT
+#define IAM_MMA_WAIT 0
+#endif
+__device__ __forceinline__ void mbar_wait_bare_a(uint32_t bar_addr, uint32_t parity) {
+#if IAM_EPI_WAIT == 0
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+  }
+#elif IAM_EPI_WAIT == 1
+  while (!mbar_try_wait_nohint_a(bar_addr, parity)) {
+  }
+#else
+  while (!mbar_test_wait_a(bar_addr, parity)) {
+  }
+#endif
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity, int tag = 0) {
+  uint32_t spins = 0;
+#if IAM_MMA_WAIT == 0
+  while (!mbar_try_wait_a(bar_addr, parity)) {
+#else
+  while (!mbar_try_wait_nohint_a(bar_addr, parity)) {
+#endif
+    if (++spins == IAM_SPIN_LIMIT) {
+      printf("iamatch: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+             (int)threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ float lds_volatile_f32_a(uint32_t addr) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_f32_a(uint32_t addr, float v) {
+  asm volatile("st.volatile.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// Opaque to the optimiser: the value is kept in a register instead of being recomputed at every use.
+__device__ __forceinline__ uint32_t pin_reg(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+
 // ------------------------------------------------------- bulk copy (TMA 1-D)
 // global -> shared, completion reported on an mbarrier in bytes.
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -129,6 +215,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr)
+               : "memory");
+}
+
 // same, arriving on the barrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
@@ -147,6 +238,21 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (sm_100)
   // base_offset = 0, lbo_mode = 0, layout_type (bits 61..63) = 0: SWIZZLE_NONE
+  return d;
+}
+
+// The same descriptor in two 32-bit halves, for issue loops that step the start address: the low word of
+// a tile at byte offset `o` from a base is  desc_lo(base) + (o >> 4)  as long as the sum stays inside the
+// 14-bit address field (always true for shared-memory addresses), the high word never changes.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14);
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 
