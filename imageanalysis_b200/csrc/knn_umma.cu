@@ -441,7 +441,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           if (kDbg == 0) {
             consume32<KTOP>(v, tp, tk, pb_up);
           } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
-            tk.d[0] = fminf(tk.d[0], v[lane]);
+            tk.d[0] = fminf(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
             float m = v[0];
 #pragma unroll

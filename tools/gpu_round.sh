@@ -15,10 +15,13 @@ echo "== bench all-pairs (124750 pairs/step)"; timeout 900 python bench.py --ste
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tee gpurun_out/bench_reference.log | tail -1 | cut -c1-600
 echo "== bench no-epilogue (MMA+TMA only), cluster"; IAM_UMMA_DEBUG=1 $B 2>&1 | tee gpurun_out/bench_dbg1.log | tail -1 | python -c "$P"
 echo "== bench fast-path only"; IAM_UMMA_DEBUG=2 $B 2>&1 | tee gpurun_out/bench_dbg2.log | tail -1 | python -c "$P"
+echo "== bench read-out only"; IAM_UMMA_DEBUG=3 $B 2>&1 | tee gpurun_out/bench_dbg3.log | tail -1 | python -c "$P"
 echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1
 echo "== bench ORB"; timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e 2>&1 | tee gpurun_out/bench_orb.log | tail -1
 echo "== ncu launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"knn_umma_kernel|knn_simt_kernel|metric_reduce_kernel|dedupe_kernel|crosscheck_kernel|finish_dist_kernel|convert_l2_kernel|convert_hamming_kernel|pack_knn_kernel" -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --frames 40 --no-cpu > gpurun_out/ncu_list.log 2>&1
+echo "== ncu dram traffic of one bench-sized launch"
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:knn_umma -s 1 -c 1 --csv --log-file gpurun_out/traffic.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_traffic.log 2>&1
 echo "== ncu full (knn kernel)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:knn_umma -s 1 -c 1 -o gpurun_out/knn_umma python bench.py --steps 1 --warmup 1 --frames 60 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:knn_umma -s 1 -c 1 -f -o gpurun_out/knn_umma python bench.py --steps 1 --warmup 1 --frames 60 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
