@@ -327,9 +327,13 @@ def main():
         ids = np.arange(args.frames, dtype=np.int32)
         frames_host = [host_np[f] for f in range(args.frames)]
 
+        # result buffers a pipeline would keep around: page-locked, so each wave's tables come back asynchronously
+        out_table = torch.empty((P, prm.cap, 2), dtype=torch.int32, pin_memory=True).numpy()
+        out_count = torch.zeros((P,), dtype=torch.int32, pin_memory=True).numpy()
+
         def step_e2e():
             # the public one-call API: host descriptors in, host match tables out (H2D + conversion + matching + D2H)
-            return eng.match_images(ids, frames_host, pairs, prm)
+            return eng.match_images(ids, frames_host, pairs, prm, out=(out_table, out_count))
         step_e2e()
         torch.cuda.synchronize()
         if world > 1:

@@ -254,10 +254,12 @@ class Engine:
             return table, count, rtable, rcount
         return table, count
 
-    def match_images(self, image_ids, arrays, pairs, params: MatchParams, keys=None):
+    def match_images(self, image_ids, arrays, pairs, params: MatchParams, keys=None, out=None):
         """Upload + match in one call with PCIe/compute overlap (iam_match_images).
         arrays[i]: [N_i, D] float32 or uint8 descriptors of image image_ids[i] (all the same dtype);
-        keys[i]: optional int32 [N_i] keypoint position ids."""
+        keys[i]: optional int32 [N_i] keypoint position ids;
+        out: optional (table [P, cap, 2] int32, count [P] int32) C-contiguous arrays to receive the result --
+        page-locked ones make the wave-by-wave download truly asynchronous."""
         ids = np.ascontiguousarray(image_ids, np.int32)
         arrs = [np.ascontiguousarray(a) for a in arrays]
         if len(arrs) != len(ids):
@@ -279,8 +281,14 @@ class Engine:
             kptrs = (C.c_void_p * max(n, 1))(*[None if k is None else k.ctypes.data for k in karrs])
         pr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
         P = pr.shape[0]
-        table = np.empty((P, params.cap, 2), np.int32)
-        count = np.zeros((P,), np.int32)
+        if out is not None:
+            table, count = out
+            if (table.dtype != np.int32 or count.dtype != np.int32 or table.shape != (P, params.cap, 2)
+                    or count.shape != (P,) or not table.flags.c_contiguous or not count.flags.c_contiguous):
+                raise IamError("out must be (int32 [P, cap, 2], int32 [P]) C-contiguous arrays")
+        else:
+            table = np.empty((P, params.cap, 2), np.int32)
+            count = np.zeros((P,), np.int32)
         self._check(self._lib.iam_match_images(self._h, n, _ptr(ids), ptrs, _ptr(counts), dt, kptrs, _ptr(pr), P,
                                                C.byref(params), _ptr(table), _ptr(count)), "iam_match_images")
         return table, count

@@ -108,6 +108,8 @@ struct iam_ctx {
                                      // copy of one image overlaps the conversion of the previous one)
   Buffer stage2;
   cudaEvent_t lane2_ev = nullptr;
+  cudaStream_t dl_stream = nullptr;  // iam_match_images: a wave's tables go back to the host while later waves still compute
+  std::vector<cudaEvent_t> done_ev;  // one per wave: its rows of out_table / out_count are final
   unsigned up_rr = 0;
   cudaEvent_t compute_done = nullptr;
   bool compute_pending = false;
@@ -389,6 +391,7 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
   e = cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->up_stream2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2_ev, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->dl_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->compute_done, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete c;
@@ -415,6 +418,12 @@ int iam_destroy(iam_ctx* c) {
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
   if (c->up_stream2) cudaStreamDestroy(c->up_stream2);
   if (c->lane2_ev) cudaEventDestroy(c->lane2_ev);
+  if (c->dl_stream) {
+    cudaStreamSynchronize(c->dl_stream);
+    cudaStreamDestroy(c->dl_stream);
+  }
+  for (cudaEvent_t ev : c->done_ev)
+    if (ev) cudaEventDestroy(ev);
   c->stage2.release();
   Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
                     &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
@@ -714,6 +723,7 @@ struct UploadFeed {  // host-side sources for iam_match_images: enqueue an image
   int dtype = 0;
   std::vector<int> slot_of_id;   // image id -> index into ptrs
   std::vector<char> done;
+  std::vector<std::pair<int, int>> waves_done;  // pair ranges whose done_ev was recorded, in order
 };
 
 int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
@@ -758,7 +768,11 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
     c->images[image_ids[i]].seq = 0;  // contents are stale until this call uploads them
   }
   // enough waves that the first kernels start after a few per cent of the bytes have crossed PCIe
-  const int waves = std::max(1, std::min(16, n_pairs / 96));
+  // (measured: 16 / 32 / 41 waves give 29.9 / 30.9 / 30.8 ms for 1990 pairs -- past 16 the matching itself is the
+  // critical path, more waves only add launches)
+  int max_waves = 16;
+  if (const char* env = getenv("IAM_MAX_WAVES")) max_waves = std::max(1, atoi(env));  // A/B aid
+  const int waves = std::max(1, std::min(max_waves, n_pairs / 96));
   const auto h0 = std::chrono::steady_clock::now();
   if (c->compute_pending) {
     CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
@@ -785,7 +799,19 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   c->timing.host_enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - h0).count();
   c->timing.waves = waves;
   c->span_pending = true;
-  return iam_fetch_tables(c, out_table, out_count);
+  // Results travel back wave by wave on their own stream: only the last wave's rows are copied after the last
+  // kernel.  (With a pageable destination each copy blocks this thread, not the GPU: everything is enqueued.)
+  const size_t row = size_t(prm->cap) * 2;
+  for (size_t w = 0; w < feed.waves_done.size(); ++w) {
+    const int p0 = feed.waves_done[w].first, p1 = feed.waves_done[w].second;
+    CU(cudaStreamWaitEvent(c->dl_stream, c->done_ev[w], 0));
+    CU(cudaMemcpyAsync(out_count + p0, c->out_count.as<int>() + p0, size_t(p1 - p0) * sizeof(int), cudaMemcpyDeviceToHost, c->dl_stream));
+    CU(cudaMemcpyAsync(out_table + size_t(p0) * row, c->out_table.as<int>() + size_t(p0) * row, size_t(p1 - p0) * row * sizeof(int),
+                       cudaMemcpyDeviceToHost, c->dl_stream));
+  }
+  CU(cudaStreamSynchronize(c->dl_stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
 }
 
 }  // extern "C"
@@ -901,6 +927,15 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "cross-check launch: %s", cudaGetErrorString(e));
     c->timing.total_launches += 3;
     if (prof) CU(cudaEventRecord(c->ev[2], c->stream));
+    if (feed) {
+      const size_t w = feed->waves_done.size();
+      if (c->done_ev.size() <= w) {
+        c->done_ev.resize(w + 1, nullptr);
+        CU(cudaEventCreateWithFlags(&c->done_ev[w], cudaEventDisableTiming));
+      }
+      CU(cudaEventRecord(c->done_ev[w], c->stream));
+      feed->waves_done.emplace_back(p0, p1);
+    }
   }
   c->timing_pending = c->profiling && n_chunks == 1 && n_pairs > 0;  // resolved lazily in iam_get_timing
   if ((rc = mark_compute(c)) != IAM_OK) return rc;

@@ -6,20 +6,22 @@
 // One work unit = 256 query descriptors (two 128-row A tiles, copied once per
 // unit from a shared-memory staging buffer into TENSOR MEMORY with tcgen05.cp,
 // so the MMAs read only the B operand from shared memory) against every
-// descriptor of the train image (64-row B tiles streamed by cp.async.bulk
-// through a 6-deep mbarrier ring).  The augmented
-// K-step makes every accumulator element the exact squared L2 distance
-// (integer valued < 2^23, exact in fp32) or the exact Hamming distance, so
-// the N x M distance matrix never leaves the SM: eight epilogue warps read
-// it from TMEM and keep a per-row running top-k in registers.
+// descriptor of the train image (96-row B tiles streamed by cp.async.bulk
+// through a 4-deep mbarrier ring; in a 2-CTA cluster each CTA fetches half of
+// every tile and multicasts it to both).  The augmented K-step makes every
+// accumulator element the exact squared L2 distance (integer valued < 2^23,
+// exact in fp32) or the exact Hamming distance, so the N x M distance matrix
+// never leaves the SM: 24 epilogue warps read it from TMEM and keep a per-row
+// running top-k in registers.
 //
-// Warp roles (640 threads, 1 CTA / SM, persistent over units):
+// Warp roles (896 threads, 1 CTA / SM, persistent over units):
 //   warp 0      : B-tile producer  (bulk copy  -> b_full[stage])
-//   warp 1      : MMA issuer       (one elected lane: 18 tcgen05.cp per unit, 18 tcgen05.mma M128xN64xK16 per B tile)
+//   warp 1      : MMA issuer       (warp-uniform loop, one elected lane issues: 18 tcgen05.cp per unit,
+//                 18 TS-form tcgen05.mma M128xN96xK16 per B tile into a ring of three 96-column accumulator slots)
 //   warp 2      : TMEM allocator / deallocator
-//   warp 3      : A-tile producer  (bulk copy  -> a_full[half])
-//   warps 4..19 : epilogue (4 per SM sub-partition): warp -> (A tile, 32-column half of each
-//                 64-column accumulator tile, TMEM lane quadrant = warp_id % 4); the two threads
+//   warp 3      : A-tile producer  (bulk copy  -> a_full[tile])
+//   warps 4..27 : epilogue (6 per SM sub-partition): warp -> (A tile, 32-column part of each
+//                 96-column accumulator tile, TMEM lane quadrant = warp_id % 4); the three threads
 //                 that share a row exchange their running bounds through shared memory every
 //                 tile (stale bounds are still valid) and merge their lists once per unit
 #include <cuda_runtime.h>
@@ -175,15 +177,39 @@ __device__ __forceinline__ bool any_lane(bool p) {
   return p;
 #endif
 }
+// "does any lane have x < te": x and te are non-negative floats, so their bit patterns order like integers.
+// IAM_REDUX routes the test through one warp-wide integer minimum (REDUX, result in a uniform register, the
+// branch is then a uniform-datapath compare) instead of FSETP + VOTE on the ALU pipe.
+// level 1: group tests of the fast path; level 2: also the per-element tests of a triggered group.
+#ifndef IAM_REDUX
+#define IAM_REDUX 0
+#endif
+template <int kLevel>
+__device__ __forceinline__ bool any_below(float x, float te) {
+  if (IAM_REDUX >= kLevel) {
+    return __reduce_min_sync(0xffffffffu, __float_as_int(x) - __float_as_int(te)) < 0;
+  } else {
+    return any_lane(x < te);
+  }
+}
 
-template <int KTOP, int J0>
+template <int KTOP, int J0, bool kFixed = false>
 __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>& tk, float te) {
+  if (kFixed) {  // profiling aid: every warp does the same slow-path work (4 element tests, 2 insertions)
+    const bool f0 = any_below<2>(w[0], 3.0e38f), f1 = any_below<2>(w[1], -1.0f);
+    const bool f2 = any_below<2>(w[2], 3.0e38f), f3 = any_below<2>(w[3], -1.0f);
+    if (f0) tk.insert(w[0], enc_index<J0>(tp));
+    if (f1) tk.insert(w[1], enc_index<J0 + 1>(tp));
+    if (f2) tk.insert(w[2], enc_index<J0 + 2>(tp));
+    if (f3) tk.insert(w[3], enc_index<J0 + 3>(tp));
+    return;
+  }
   // four votes issued back to back (computed against the bound at group entry: a superset of what
   // the tightening bound would admit), then the branch-free network only where some lane qualifies
-  const bool e0 = any_lane(w[0] < te);
-  const bool e1 = any_lane(w[1] < te);
-  const bool e2 = any_lane(w[2] < te);
-  const bool e3 = any_lane(w[3] < te);
+  const bool e0 = any_below<2>(w[0], te);
+  const bool e1 = any_below<2>(w[1], te);
+  const bool e2 = any_below<2>(w[2], te);
+  const bool e3 = any_below<2>(w[3], te);
   if (e0) tk.insert(w[0], enc_index<J0>(tp));
   if (e1) tk.insert(w[1], enc_index<J0 + 1>(tp));
   if (e2) tk.insert(w[2], enc_index<J0 + 2>(tp));
@@ -194,23 +220,23 @@ __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>
 // entry (it only tightens, so the votes stay conservative): independent FMNMX3/FSETP/VOTE chains
 // instead of serialised vote->branch round trips.  (Moving the tests to the idle FMA pipe with
 // IMAD/IMAD.HI sign accumulation was measured and is slower: IMAD.HI is not a full-rate instruction.)
-template <int KTOP, int H>
+template <int KTOP, int H, bool kFixed = false>
 __device__ __forceinline__ void consume16(const float* w, int tp, TopK<KTOP>& tk, float pb_up) {
-  const float te = fminf(tk.thr(), pb_up);
-  const bool t0 = any_lane(fminf(fmin3(w[0], w[1], w[2]), w[3]) < te);
-  const bool t1 = any_lane(fminf(fmin3(w[4], w[5], w[6]), w[7]) < te);
-  const bool t2 = any_lane(fminf(fmin3(w[8], w[9], w[10]), w[11]) < te);
-  const bool t3 = any_lane(fminf(fmin3(w[12], w[13], w[14]), w[15]) < te);
+  const float te = kFixed ? -1.0f : fminf(tk.thr(), pb_up);
+  const bool t0 = any_below<1>(fminf(fmin3(w[0], w[1], w[2]), w[3]), te);
+  const bool t1 = any_below<1>(fminf(fmin3(w[4], w[5], w[6]), w[7]), te);
+  const bool t2 = any_below<1>(fminf(fmin3(w[8], w[9], w[10]), w[11]), te);
+  const bool t3 = any_below<1>(fminf(fmin3(w[12], w[13], w[14]), w[15]), te);
   if (t0) consume_group<KTOP, H * 16>(w, tp, tk, fminf(tk.thr(), pb_up));
-  if (t1) consume_group<KTOP, H * 16 + 4>(w + 4, tp, tk, fminf(tk.thr(), pb_up));
+  if (t1 || kFixed) consume_group<KTOP, H * 16 + 4, kFixed>(w + 4, tp, tk, fminf(tk.thr(), pb_up));
   if (t2) consume_group<KTOP, H * 16 + 8>(w + 8, tp, tk, fminf(tk.thr(), pb_up));
   if (t3) consume_group<KTOP, H * 16 + 12>(w + 12, tp, tk, fminf(tk.thr(), pb_up));
 }
 
-template <int KTOP>
+template <int KTOP, bool kFixed = false>
 __device__ __forceinline__ void consume32(const float (&v)[32], int tp, TopK<KTOP>& tk, float pb_up) {
-  consume16<KTOP, 0>(&v[0], tp, tk, pb_up);
-  consume16<KTOP, 1>(&v[16], tp, tk, pb_up);
+  consume16<KTOP, 0, kFixed>(&v[0], tp, tk, pb_up);
+  consume16<KTOP, 1, kFixed>(&v[16], tp, tk, pb_up);
 }
 
 template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg>
@@ -440,6 +466,10 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           if (lane0) mbar_arrive_a(bar + kEmptyOff);
           if (kDbg == 0) {
             consume32<KTOP>(v, tp, tk, pb_up);
+          } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
+            consume32<KTOP, true>(v, tp, tk, pb_up);
+          } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): group tests + votes + branches, never taken
+            consume32<KTOP>(v, tp, tk, -1.0f);
           } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
             tk.d[0] = fminf(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
@@ -571,17 +601,19 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     return !(e && atoi(e) == 1);
   }();
   static const int flags = [] {
-    const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only, 3 = accumulator read-out only
+    const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only, 3 = accumulator read-out only, 4 = group tests never taken, 5 = fixed slow-path work
     return e ? atoi(e) : 0;
   }();
   using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*);
   const bool use_cluster = cluster && (n_units % 2 == 0);
   KernT kern;
   if (flags != 0) {  // profiling variants exist for the production configuration only
-    if (!use_cluster || !a_tmem || flags < 0 || flags > 3) return cudaErrorInvalidValue;
+    if (!use_cluster || !a_tmem || flags < 0 || flags > 5) return cudaErrorInvalidValue;
     kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1>
            : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2>
-                        : knn_umma_kernel<kKind, KTOP, true, true, 3>;
+           : flags == 3 ? knn_umma_kernel<kKind, KTOP, true, true, 3>
+           : flags == 4 ? knn_umma_kernel<kKind, KTOP, true, true, 4>
+                        : knn_umma_kernel<kKind, KTOP, true, true, 5>;
   } else if (use_cluster) {
     kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0> : knn_umma_kernel<kKind, KTOP, false, true, 0>;
   } else {
