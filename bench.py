@@ -275,13 +275,24 @@ def main():
         for f in range(args.frames):
             eng.upload(f, host_np[f], pinned=True)
 
-    def step_device():
+    gather_out = None
+    gather_ev = []
+    if world > 1:  # every rank ends a step holding all ranks' tables
+        gather_out = (torch.empty((P * world, prm.cap, 2), dtype=torch.int32, device=dev),
+                      torch.empty((P * world,), dtype=torch.int32, device=dev))
+
+    def step_device(timed=False):
         dt, dc = eng.match_pairs_device(pairs, prm)
         if world > 1:
             t = dist.as_tensor(dt, (P, prm.cap, 2), local)
             c = dist.as_tensor(dc, (P,), local)
-            loc, b, e = dist.shard_pairs(np.zeros((P * world, 2), np.int32), rank, world)
-            dist.allgather_tables(t, c, P * world, rank, world)
+            if timed:
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record(stream)
+            dist.allgather_tables(t, c, P * world, rank, world, out=gather_out)
+            if timed:
+                g1.record(stream)
+                gather_ev.append((g0, g1))
 
     upload_all()
     eng.synchronize()
@@ -299,7 +310,7 @@ def main():
     torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(args.steps):
-        step_device()
+        step_device(timed=True)
         knn_ms.append(None)
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -307,6 +318,7 @@ def main():
         torch.distributed.barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
+    gather_ms = sum(a.elapsed_time(b) for a, b in gather_ev) / max(1, len(gather_ev)) if gather_ev else 0.0
     tm = eng.timing()
     launches = tm.total_launches - launches0
     # per-kernel time of the dominant kernel (events recorded by the library on the same stream)
@@ -363,6 +375,9 @@ def main():
                                "waves": eng.timing().waves},
                "bare_h2d_gb_per_s": h2d / h2d_ms / 1e6}
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     peaks = {}
@@ -385,7 +400,7 @@ def main():
                 "frac_of_burst": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
                 "kernel": "knn_umma_kernel (tcgen05 %s)" % ("kind::f16" if args.detector == "SIFT" else "kind::f8f6f4"),
                 "kernel_ms_per_launch": knn_kernel_ms, "reduce_ms_per_step": reduce_ms,
-                "algorithmic_work_per_pair": work,
+                "algorithmic_work_per_pair": work, "allgather_ms_per_step": gather_ms,
                 "engine": {1: "umma", 2: "simt"}.get(tm.engine_used)}
     cpu = None
     if not args.no_cpu and world == 1:

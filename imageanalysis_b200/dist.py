@@ -54,16 +54,30 @@ def as_tensor(ptr: int, shape, device: int) -> torch.Tensor:
     return torch.as_tensor(DevicePtr(ptr, shape), device=torch.device("cuda", device))
 
 
-def allgather_tables(table: torch.Tensor, count: torch.Tensor, n_total: int, rank: int, world: int):
+def allgather_tables(table: torch.Tensor, count: torch.Tensor, n_total: int, rank: int, world: int, out=None):
     """table [P_local, cap, 2] int32, count [P_local] int32 on every rank (the
     rank's contiguous shard) -> (table [n_total, cap, 2], count [n_total]) on
-    every rank.  One collective: counts ride in an extra table row so a single
-    all_gather moves everything (padded to the largest shard)."""
+    every rank; `out` = optional preallocated pair of result tensors.
+
+    Equal shards (the benchmark's weak-scaling layout, and any pair count
+    divisible by the world size): the shards are gathered straight into their
+    final place -- one all-gather of the tables and one of the 4-byte counts,
+    no staging copies.  Ragged shards: counts ride in an extra table row so a
+    single all-gather (padded to the largest shard) moves everything."""
     if world == 1:
         return table, count
     cap = table.shape[1]
     sizes = [_pairs.shard(n_total, r, world) for r in range(world)]
     p_max = max(e - b for b, e in sizes)
+    if out is not None:
+        out_t, out_c = out
+    else:
+        out_t = torch.empty((n_total, cap, 2), dtype=torch.int32, device=table.device)
+        out_c = torch.empty((n_total,), dtype=torch.int32, device=table.device)
+    if all(e - b == p_max for b, e in sizes):
+        td.all_gather_into_tensor(out_t, table.contiguous())   # THE collective of this path
+        td.all_gather_into_tensor(out_c, count.contiguous())
+        return out_t, out_c
     send = torch.zeros((p_max, cap + 1, 2), dtype=torch.int32, device=table.device)
     p_loc = table.shape[0]
     send[:p_loc, :cap] = table
@@ -71,8 +85,6 @@ def allgather_tables(table: torch.Tensor, count: torch.Tensor, n_total: int, ran
     recv = torch.empty((world * p_max, cap + 1, 2), dtype=torch.int32, device=table.device)
     td.all_gather_into_tensor(recv, send)      # THE collective of this path
     recv = recv.view(world, p_max, cap + 1, 2)
-    out_t = torch.empty((n_total, cap, 2), dtype=torch.int32, device=table.device)
-    out_c = torch.empty((n_total,), dtype=torch.int32, device=table.device)
     for r, (b, e) in enumerate(sizes):
         out_t[b:e] = recv[r, :e - b, :cap]
         out_c[b:e] = recv[r, :e - b, cap, 0]

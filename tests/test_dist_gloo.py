@@ -55,6 +55,19 @@ def test_allgather_tables_world2(tmp_path):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])   # byte-identical on all ranks
 
 
+def test_allgather_tables_world2_equal_shards(tmp_path):
+    # pair count divisible by the world size: shards are gathered in place (no staging copies)
+    world, n_total, cap = 2, 12, 5
+    mp.spawn(_worker, args=(world, _free_port(), n_total, cap, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(tmp_path, "r%d.pt" % r)) for r in range(world)]
+    for t, c in res:
+        assert t.shape == (n_total, cap, 2) and c.tolist() == [p % cap for p in range(n_total)]
+        for p in range(n_total):
+            for k in range(p % cap):
+                assert t[p, k].tolist() == [p, k]
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_allgather_single_rank_is_identity():
     sys.path.insert(0, ROOT)
     from imageanalysis_b200 import dist
