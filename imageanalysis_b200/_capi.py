@@ -19,7 +19,8 @@ LIB_PATH = os.environ.get("IAMATCH_LIB") or os.path.join(_HERE, "lib", "libiamat
 
 NORM_L2, NORM_HAMMING = 0, 1
 DTYPE_U8, DTYPE_F32 = 0, 1
-ENGINE_AUTO, ENGINE_UMMA, ENGINE_SIMT = 0, 1, 2
+ENGINE_AUTO, ENGINE_UMMA, ENGINE_SIMT, ENGINE_UMMA_F16 = 0, 1, 2, 3
+KIND_F16, KIND_F8, KIND_I8 = 0, 1, 2
 REDUCE_LOWE, REDUCE_REF_METRIC = 0, 1
 MODEL_ESSENTIAL, MODEL_HOMOGRAPHY = 0, 1
 
@@ -56,7 +57,7 @@ class Timing(C.Structure):
         ("total_launches", C.c_int),
         ("engine_used", C.c_int),
         ("waves", C.c_int),
-        ("reserved", C.c_int),
+        ("mma_kind", C.c_int),
         ("host_enqueue_ms", C.c_float),
         ("upload_span_ms", C.c_float),
         ("compute_span_ms", C.c_float),

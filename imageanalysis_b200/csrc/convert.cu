@@ -8,6 +8,9 @@
 // in the tiled layout of layout.h, so that A'.B' = ||q||^2 + ||t||^2 - 2 q.t
 // = the exact squared distance.  For Hamming the 256 bits become e4m3
 // {0,1} / {0,-2} bytes and the popcounts ride in the augmentation step.
+// Integer-valued L2 descriptors additionally (or only) get the BYTE layout of
+// layout.h for tcgen05 kind::i8 (convert_i8_kernel): one form for both roles,
+// rows stably partitioned by the parity of their squared norm.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -45,10 +48,12 @@ __device__ __forceinline__ void split_norm(float n, __half (&x)[4]) {
 template <typename SrcT>
 __global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict__ src, int dim, int n, int n_pad,
                                                          uint8_t* __restrict__ raw, uint8_t* __restrict__ a_form,
-                                                         uint8_t* __restrict__ b_form, int* __restrict__ exact_flag) {
+                                                         uint8_t* __restrict__ b_form, int* __restrict__ meta,
+                                                         int* __restrict__ nrm_out, uint8_t* __restrict__ even_mask,
+                                                         int* __restrict__ ctx_flag) {
+  __shared__ int s_even[8];
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (r >= n_pad) return;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);  // n_pad is a multiple of 8: whole blocks only
   const bool valid = r < n;
 
   float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -77,11 +82,32 @@ __global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict_
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
-  if (!__all_sync(0xffffffffu, exact) && lane == 0) atomicAnd(exact_flag, 0);
+  const bool row_exact = __all_sync(0xffffffffu, exact);
+  if (!row_exact && lane == 0) atomicAnd(meta + kMetaExact, 0);
+  if (nrm_out) {  // inputs of the byte-layout pass: squared norm, its parity, eligibility (layout.h)
+    const bool ok = row_exact && nrm <= static_cast<float>(kI8MaxNorm);
+    const int inrm = ok ? static_cast<int>(nrm) : 0;
+    if (lane == 0) {
+      nrm_out[r] = inrm;
+      s_even[threadIdx.x >> 5] = (valid && !(inrm & 1)) ? 1 : 0;
+      if (!ok) {
+        atomicAnd(meta + kMetaI8Ok, 0);
+        if (ctx_flag) atomicAnd(ctx_flag, 0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int m = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) m |= s_even[w] << w;
+      even_mask[blockIdx.x] = static_cast<uint8_t>(m);
+    }
+  }
 
   // raw u8 row (dim bytes, word `lane`)
   if (lane * 4 < dim) reinterpret_cast<uint32_t*>(raw + static_cast<size_t>(r) * dim)[lane] = rawword;
 
+  if (!a_form) return;  // wide forms not wanted (byte layout only)
   // data chunks: lane -> chunk lane/2, half-chunk lane%2 (8 bytes = 4 halfs)
   const size_t base = row_base(r) + static_cast<size_t>(lane >> 1) * 128 + static_cast<size_t>(lane & 1) * 8;
   {
@@ -123,6 +149,82 @@ __global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict_
     const size_t abase = row_base(r) + static_cast<size_t>(16 + (lane >> 3)) * 128 + static_cast<size_t>(lane & 7) * 2;
     *reinterpret_cast<__half*>(a_form + abase) = av;
     *reinterpret_cast<__half*>(b_form + abase) = bv;
+  }
+}
+
+
+// Byte layout (layout.h): 32 rows per block (one word of the even-norm mask), one warp per 4 rows.
+// rank(r) = #even rows before r                      (||r||^2 even)
+//         = #even rows in all + #odd rows before r   (odd)          -> stable partition, padding rows stay in place.
+__global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restrict__ raw, int dim, int n, int n_pad,
+                                                         const int* __restrict__ nrm, const uint32_t* __restrict__ even_mask,
+                                                         uint8_t* __restrict__ form, int* __restrict__ perm,
+                                                         int* __restrict__ rowc, int* __restrict__ meta) {
+  __shared__ int s_before[8], s_total[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_words = n_pad >> 5;
+  int before = 0, total = 0;
+  for (int w = threadIdx.x; w < n_words; w += 256) {
+    const int c = __popc(even_mask[w]);
+    total += c;
+    if (w < static_cast<int>(blockIdx.x)) before += c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+  }
+  if (lane == 0) {
+    s_before[warp] = before;
+    s_total[warp] = total;
+  }
+  __syncthreads();
+  before = total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    before += s_before[w];
+    total += s_total[w];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) meta[kMetaNEven] = total;
+  const uint32_t word = even_mask[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int bit = warp * 4 + i;
+    const int r = blockIdx.x * 32 + bit;
+    const bool valid = r < n;
+    const int ev_before = before + __popc(word & ((1u << bit) - 1u));
+    const bool even = (word >> bit) & 1u;
+    const int rank = !valid ? r : (even ? ev_before : total + (r - ev_before));
+    uint32_t data = 0;
+    if (valid && lane * 4 < dim) data = reinterpret_cast<const uint32_t*>(raw + static_cast<size_t>(r) * dim)[lane];
+    const size_t base = static_cast<size_t>(rank >> 3) * kI8GroupBytes + static_cast<size_t>(rank & 7) * 16;
+    *reinterpret_cast<uint32_t*>(form + base + static_cast<size_t>(lane >> 2) * 128 + (lane & 3) * 4) = data;
+    if (lane < 16) {
+      uint32_t aug = 0;
+      if (valid) {
+        if (lane < 8) {  // query role: weights {1, 255, 255 x30}
+          aug = lane == 0 ? 0xFFFFFF01u : 0xFFFFFFFFu;
+        } else {         // train role: digits of G = CAP - floor(norm/2)
+          int g = kI8Cap - (nrm[r] >> 1);
+          g = g < 0 ? 0 : g;
+          const int g2 = g / 65025;
+          const int rem = g - g2 * 65025;
+          const int g1 = rem / 255;
+          const int g0 = rem - g1 * 255;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int slot = (lane - 8) * 4 + b;
+            const int v = slot == 0 ? g0 : (slot == 1 ? g1 : ((slot - 2) < g2 ? 255 : 0));
+            aug |= static_cast<uint32_t>(v) << (8 * b);
+          }
+        }
+      }
+      *reinterpret_cast<uint32_t*>(form + base + static_cast<size_t>(8 + (lane >> 2)) * 128 + (lane & 3) * 4) = aug;
+    }
+    if (lane == 0) {
+      perm[rank] = valid ? r : -1;
+      rowc[rank] = valid ? nrm[r] + 2 * kI8Cap : 0;
+    }
   }
 }
 
@@ -195,17 +297,23 @@ __global__ void finish_dist_kernel(int norm, float* __restrict__ d, int* __restr
 }  // namespace
 
 cudaError_t launch_convert(int norm, int raw_bytes, const void* src, int src_dtype, int n, int n_pad, uint8_t* raw,
-                           uint8_t* a_form, uint8_t* b_form, int* exact_flag, cudaStream_t stream) {
+                           uint8_t* a_form, uint8_t* b_form, int* meta, const I8Out* i8, cudaStream_t stream) {
   const int blocks = n_pad / 8;
   if (blocks <= 0) return cudaSuccess;
   if (norm == 0) {
     if (raw_bytes > 128 || (raw_bytes & 3)) return cudaErrorInvalidValue;
+    int* nrm = i8 ? i8->nrm : nullptr;
+    uint8_t* mask = i8 ? reinterpret_cast<uint8_t*>(i8->even_mask) : nullptr;
+    int* ctx_flag = i8 ? i8->ctx_flag : nullptr;
     if (src_dtype == 0)
       convert_l2_kernel<uint8_t><<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(src), raw_bytes, n, n_pad,
-                                                             raw, a_form, b_form, exact_flag);
+                                                             raw, a_form, b_form, meta, nrm, mask, ctx_flag);
     else
       convert_l2_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(src), raw_bytes, n, n_pad, raw,
-                                                           a_form, b_form, exact_flag);
+                                                           a_form, b_form, meta, nrm, mask, ctx_flag);
+    if (i8 && i8->form)
+      convert_i8_kernel<<<n_pad / 32, 256, 0, stream>>>(raw, raw_bytes, n, n_pad, nrm, i8->even_mask, i8->form, i8->perm,
+                                                        i8->rowc, meta);
   } else {
     if (raw_bytes > 32 || src_dtype != 0) return cudaErrorInvalidValue;
     convert_hamming_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(src), raw_bytes, n, n_pad, raw,

@@ -73,11 +73,14 @@ struct Buffer {
 
 struct Image {
   int* keys = nullptr;
-  uint8_t* block = nullptr;   // [256 B flag word][raw][a_form][b_form]
+  uint8_t* block = nullptr;   // [256 B meta words][raw][a_form][b_form] (+ L2: [byte form][perm][rowc][norms][even mask])
   size_t block_bytes = 0;
   int n = -1;
   int n_pad = 0;
   int exact = 1;              // -1: not read back from the device yet
+  int i8ok = 0;               // byte layout usable (integer valued, norms within capacity); -1: not read back yet
+  bool has_wide = false;      // a_form / b_form hold this descriptor set
+  bool has_i8 = false;        // i8_form / perm / rowc hold this descriptor set
   cudaEvent_t ready = nullptr;  // recorded on the upload stream after the layout conversion
   uint64_t seq = 0;           // upload order; a later seq completing implies every earlier one did
   iam::ImgDev dev{};
@@ -130,6 +133,10 @@ struct iam_ctx {
   std::vector<cudaEvent_t> wave_ev;   // one event per wave of uploads in iam_match_images
   int reserve_sms = 0;                // SMs left free for conversion kernels while uploads are in flight
   bool feed_mode = false;             // inside iam_match_images: no per-image memset / event
+  bool feed_wide = false;             // ... and its uploads build the wide (fp16) forms instead of the byte layout
+  bool l2_wide_sticky = false;        // a feed-mode call met descriptors the byte layout cannot hold: stay on fp16 operands
+  int* d_ctx_flag = nullptr;          // device word, cleared by a conversion that met such descriptors
+  int last_kind = -1;
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -170,17 +177,45 @@ int check_image(const iam_ctx* c, int id) {
   return IAM_OK;
 }
 
-// Read an image's exactness flag back from the device on first use.
-int resolve_exact(iam_ctx* c, int id) {
+// Offsets of the parts of an image's device block.
+struct BlockLayout {
+  size_t raw, a_form, b_form, i8_form, perm, rowc, nrm, mask, total;
+};
+BlockLayout block_layout(const iam_ctx* c, int n_pad) {
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  BlockLayout b{};
+  b.raw = 256;
+  b.a_form = b.raw + up(size_t(n_pad) * c->desc_bytes);
+  b.b_form = b.a_form + iam::form_bytes(n_pad);
+  b.i8_form = b.b_form + iam::form_bytes(n_pad);
+  if (c->norm == IAM_NORM_L2) {
+    b.perm = b.i8_form + iam::i8_form_bytes(n_pad);
+    b.rowc = b.perm + up(size_t(n_pad) * 4);
+    b.nrm = b.rowc + up(size_t(n_pad) * 4);
+    b.mask = b.nrm + up(size_t(n_pad) * 4);
+    b.total = b.mask + up(size_t(n_pad) / 8);
+  } else {
+    b.perm = b.rowc = b.nrm = b.mask = b.total = b.i8_form;
+  }
+  return b;
+}
+
+// Read an image's flags (integer valued? byte layout usable?) back from the device on first use.
+int resolve_flags(iam_ctx* c, int id) {
   Image& im = c->images[id];
-  if (im.exact < 0) {
-    int flag = 0;
-    if (cudaMemcpyAsync(&flag, im.block, sizeof(int), cudaMemcpyDeviceToHost, c->up_stream) != cudaSuccess ||
+  if (im.exact < 0 || im.i8ok < 0) {
+    int flag[2] = {0, 0};
+    if (cudaMemcpyAsync(flag, im.block, sizeof flag, cudaMemcpyDeviceToHost, c->up_stream) != cudaSuccess ||
         cudaStreamSynchronize(c->up_stream) != cudaSuccess)
       return -1;
-    im.exact = flag != 0;
+    if (im.exact < 0) im.exact = flag[iam::kMetaExact] != 0;
+    if (im.i8ok < 0) im.i8ok = flag[iam::kMetaI8Ok] != 0;
   }
-  return im.exact;
+  return 0;
+}
+int resolve_exact(iam_ctx* c, int id) {
+  if (resolve_flags(c, id) != 0) return -1;
+  return c->images[id].exact;
 }
 
 // Make the compute stream wait for the uploads of every image a chunk of pairs touches.
@@ -205,9 +240,37 @@ int mark_compute(iam_ctx* c) {
   return IAM_OK;
 }
 
+// Which tensor-core operand kind serves this pair list.  L2: the byte layout (kind::i8) when every image involved
+// holds one; fp16 operands otherwise.  Inside iam_match_images the images are not uploaded yet: the call's own
+// decision (feed_wide) says what its uploads build.
+int pick_kind(iam_ctx* c, const int32_t* pairs, int n_pairs, int* kind) {
+  if (c->norm == IAM_NORM_HAMMING) {
+    *kind = iam::kKindF8;
+    return IAM_OK;
+  }
+  bool i8 = c->engine != IAM_ENGINE_UMMA_F16;
+  if (c->feed_mode) {
+    i8 = !c->feed_wide;
+  } else {
+    for (int p = 0; p < n_pairs * 2 && i8; ++p) {
+      Image& im = c->images[pairs[p]];
+      if (!im.has_i8) i8 = false;
+      else if (resolve_flags(c, pairs[p]) != 0) return fail(IAM_E_CUDA, "flag read-back failed");
+      else if (im.i8ok != 1) i8 = false;
+    }
+    if (!i8)
+      for (int p = 0; p < n_pairs * 2; ++p)
+        if (!c->images[pairs[p]].has_wide)
+          return fail(IAM_E_STATE, "image %d holds only the byte layout but this pair list needs fp16 operands: upload it again", pairs[p]);
+  }
+  *kind = i8 ? iam::kKindI8 : iam::kKindF16;
+  return IAM_OK;
+}
+
 int pick_engine(const iam_ctx* c, const int32_t* pairs, int n_pairs, int* engine) {
   int e = c->engine;
   if (e == IAM_ENGINE_AUTO) e = umma_capable(c) ? IAM_ENGINE_UMMA : IAM_ENGINE_SIMT;
+  if (e == IAM_ENGINE_UMMA_F16) e = IAM_ENGINE_UMMA;
   if (e == IAM_ENGINE_UMMA && !umma_capable(c)) return fail(IAM_E_UNSUPPORTED, "descriptor size %d has no tensor-core layout", c->desc_bytes);
   if (e == IAM_ENGINE_SIMT) {
     if (!simt_capable(c)) return fail(IAM_E_UNSUPPORTED, "SIMT engine supports 32/64/128-byte descriptors, got %d", c->desc_bytes);
@@ -329,11 +392,12 @@ int upload_plan(iam_ctx* c, const Plan& pl) {
   return IAM_OK;
 }
 
-int launch_knn(iam_ctx* c, int engine, int k, int unit_begin, int n_units) {
+int launch_knn(iam_ctx* c, int engine, int kind, int k, int unit_begin, int n_units) {
   const iam::KnnUnit* u = c->units.as<iam::KnnUnit>() + unit_begin;
   cudaError_t e;
+  c->timing.mma_kind = engine == IAM_ENGINE_UMMA ? kind : -1;
   if (engine == IAM_ENGINE_UMMA)
-    e = iam::launch_knn_umma(c->norm, k, c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), std::max(2, c->num_sms - c->reserve_sms), c->stream);
+    e = iam::launch_knn_umma(kind, k, c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), std::max(2, c->num_sms - c->reserve_sms), c->stream);
   else
     e = iam::launch_knn_simt(c->norm, k, raw_row_bytes(c), c->d_imgs.as<iam::ImgDev>(), u, n_units, c->knn_idx.as<int>(), c->knn_dist.as<float>(), c->stream);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "kNN launch failed: %s", cudaGetErrorString(e));
@@ -399,6 +463,11 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   for (auto& ev : c->span) cudaEventCreate(&ev);
+  if (cudaMalloc(reinterpret_cast<void**>(&c->d_ctx_flag), 256) != cudaSuccess ||
+      cudaMemset(c->d_ctx_flag, 1, 256) != cudaSuccess) {
+    iam_destroy(c);
+    return fail(IAM_E_NOMEM, "context flag allocation failed");
+  }
   *out = c;
   return IAM_OK;
 }
@@ -414,6 +483,7 @@ int iam_destroy(iam_ctx* c) {
     if (im.keys) cudaFree(im.keys);
     if (im.ready) cudaEventDestroy(im.ready);
   }
+  if (c->d_ctx_flag) cudaFree(c->d_ctx_flag);
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
   if (c->up_stream2) cudaStreamDestroy(c->up_stream2);
@@ -449,7 +519,7 @@ int iam_set_stream(iam_ctx* c, void* s) {
 
 int iam_set_engine(iam_ctx* c, int engine) {
   if (!c) return fail(IAM_E_ARG, "null context");
-  if (engine < IAM_ENGINE_AUTO || engine > IAM_ENGINE_SIMT) return fail(IAM_E_ARG, "unknown engine %d", engine);
+  if (engine < IAM_ENGINE_AUTO || engine > IAM_ENGINE_UMMA_F16) return fail(IAM_E_ARG, "unknown engine %d", engine);
   c->engine = engine;
   return IAM_OK;
 }
@@ -502,12 +572,12 @@ static int prepare_image(iam_ctx* c, int id, int n) {
   if ((int)c->images.size() <= id) c->images.resize(id + 1);
   Image& im = c->images[id];
   const int n_pad = std::max(iam::kSuperRows, iam::round_up(iam::round_up(n, iam::kBRows), iam::kSuperRows));  // whole B tiles and whole units
-  const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
-  const size_t form_b = iam::form_bytes(n_pad);
-  const size_t total = 256 + raw_b + 2 * form_b;
+  const BlockLayout bl = block_layout(c, n_pad);
+  const size_t total = bl.total;
   if (im.block_bytes < total) {
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->up_stream));
+    CU(cudaStreamSynchronize(c->up_stream2));
     if (im.block) CU(cudaFree(im.block));
     im.block = nullptr;
     im.block_bytes = 0;
@@ -518,9 +588,13 @@ static int prepare_image(iam_ctx* c, int id, int n) {
   if (im.n != n || im.n_pad != n_pad) c->shape_epoch++;
   im.n = n;
   im.n_pad = n_pad;
-  im.dev.raw = im.block + 256;
-  im.dev.a_form = im.block + 256 + raw_b;
-  im.dev.b_form = im.block + 256 + raw_b + form_b;
+  im.dev.raw = im.block + bl.raw;
+  im.dev.a_form = im.block + bl.a_form;
+  im.dev.b_form = im.block + bl.b_form;
+  im.dev.i8_form = im.block + bl.i8_form;
+  im.dev.perm = reinterpret_cast<const int*>(im.block + bl.perm);
+  im.dev.rowc = reinterpret_cast<const int*>(im.block + bl.rowc);
+  im.dev.meta = reinterpret_cast<const int*>(im.block);
   im.dev.n = n;
   im.dev.n_pad = n_pad;
   c->imgs_dirty = true;
@@ -531,8 +605,13 @@ static int prepare_image(iam_ctx* c, int id, int n) {
 static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host, int dtype, const int32_t* host_keys) {
   Image& im = c->images[id];
   const int n = im.n, n_pad = im.n_pad;
-  const size_t raw_b = (size_t(n_pad) * c->desc_bytes + 255) / 256 * 256;
-  const size_t form_b = iam::form_bytes(n_pad);
+  const BlockLayout bl = block_layout(c, n_pad);
+  // Which operand forms this upload builds.  Hamming: the wide (e4m3) forms.  L2: both the fp16 forms and the byte
+  // layout, except inside iam_match_images, whose uploads are on the critical path and build only the one its
+  // kernels will read.
+  const bool l2 = c->norm == IAM_NORM_L2;
+  const bool want_i8 = l2 && (c->feed_mode ? !c->feed_wide : true);
+  const bool want_wide = !l2 || (c->feed_mode ? c->feed_wide : true);
   if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
     CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
     CU(cudaStreamWaitEvent(c->up_stream2, c->compute_done, 0));
@@ -564,14 +643,26 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
     if (bytes) CU(cudaMemcpyAsync(stg.p, src, bytes, cudaMemcpyHostToDevice, us));
     dsrc = stg.p;
   }
-  // exactness flag: non-zero = exact.  u8 / Hamming sources are exact by construction: no flag traffic at all.
-  const bool need_flag = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32);
-  if (need_flag) CU(cudaMemsetAsync(im.block, 1, sizeof(int), us));
+  // flag words: non-zero = exact / byte layout usable.  Hamming sources are exact by construction: no flag traffic.
+  if (l2) CU(cudaMemsetAsync(im.block, 1, 2 * sizeof(int), us));
   if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[4], us));
-  cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block + 256, im.block + 256 + raw_b,
-                                      im.block + 256 + raw_b + form_b, reinterpret_cast<int*>(im.block), us);
+  iam::I8Out i8{};
+  if (want_i8) {
+    i8.form = im.block + bl.i8_form;
+    i8.perm = reinterpret_cast<int*>(im.block + bl.perm);
+    i8.rowc = reinterpret_cast<int*>(im.block + bl.rowc);
+    i8.nrm = reinterpret_cast<int*>(im.block + bl.nrm);
+    i8.even_mask = reinterpret_cast<uint32_t*>(im.block + bl.mask);
+    i8.ctx_flag = c->feed_mode ? c->d_ctx_flag : nullptr;
+  }
+  cudaError_t e = iam::launch_convert(c->norm, c->desc_bytes, dsrc, dtype, n, n_pad, im.block + bl.raw,
+                                      want_wide ? im.block + bl.a_form : nullptr, want_wide ? im.block + bl.b_form : nullptr,
+                                      reinterpret_cast<int*>(im.block), want_i8 ? &i8 : nullptr, us);
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "convert launch: %s", cudaGetErrorString(e));
-  c->timing.total_launches += 1;
+  c->timing.total_launches += want_i8 ? 2 : 1;
+  im.has_wide = want_wide;
+  im.has_i8 = want_i8;
+  im.i8ok = want_i8 ? -1 : 0;
   if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[5], us));
   if (!c->feed_mode) CU(cudaEventRecord(im.ready, us));  // feed mode: one event per wave instead
   im.seq = c->feed_mode ? 0 : ++c->up_seq;
@@ -670,6 +761,8 @@ int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_st
   const Plan& pl = c->plan;
   int engine;
   if ((rc = pick_engine(c, pairs, n_pairs, &engine)) != IAM_OK) return rc;
+  int kind = 0;
+  if (engine == IAM_ENGINE_UMMA && (rc = pick_kind(c, pairs, n_pairs, &kind)) != IAM_OK) return rc;
   if ((rc = sync_imgs(c)) != IAM_OK) return rc;
   CU(c->knn_idx.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(int)));
   CU(c->knn_dist.ensure(std::max<size_t>(1, pl.max_chunk_rows) * k * sizeof(float)));
@@ -684,7 +777,7 @@ int iam_knn_pairs(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, int n_st
     if (p1 == p0) continue;
     if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) return rc;
     if (c->profiling) CU(cudaEventRecord(c->ev[0], c->stream));
-    if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
+    if ((rc = launch_knn(c, engine, kind, k, u0, u1 - u0)) != IAM_OK) return rc;
     cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
     c->timing.total_launches += 1;
@@ -767,6 +860,25 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
     if ((rc = prepare_image(c, image_ids[i], counts[i])) != IAM_OK) return rc;
     c->images[image_ids[i]].seq = 0;  // contents are stale until this call uploads them
   }
+  // L2: which operand forms this call's uploads build and its kernels read.  The byte layout (kind::i8) unless
+  // the context already met descriptors it cannot hold, the caller forces fp16 operands, or a resident image
+  // (not part of this call's uploads) has no usable byte layout.
+  bool wide = c->norm != IAM_NORM_L2 || c->l2_wide_sticky || c->engine == IAM_ENGINE_UMMA_F16;
+  if (c->norm == IAM_NORM_L2) {
+    auto resident = [&](int id) { return id < 0 || id >= (int)feed.slot_of_id.size() || feed.slot_of_id[id] < 0; };
+    for (int i = 0; i < 2 * n_pairs && !wide; ++i) {
+      const int id = pairs[i];
+      if (!resident(id)) continue;
+      if ((rc = check_image(c, id)) != IAM_OK) return rc;
+      Image& im = c->images[id];
+      if (!im.has_i8 || resolve_flags(c, id) != 0 || im.i8ok != 1) wide = true;
+    }
+    if (wide)
+      for (int i = 0; i < 2 * n_pairs; ++i)
+        if (resident(pairs[i]) && check_image(c, pairs[i]) == IAM_OK && !c->images[pairs[i]].has_wide)
+          return fail(IAM_E_STATE, "image %d holds only the byte layout but this call needs fp16 operands: upload it again", pairs[i]);
+  }
+  c->feed_wide = wide;
   // enough waves that the first kernels start after a few per cent of the bytes have crossed PCIe
   // (measured: 16 / 32 / 41 waves give 29.9 / 30.9 / 30.8 ms for 1990 pairs -- past 16 the matching itself is the
   // critical path, more waves only add launches)
@@ -811,6 +923,17 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   }
   CU(cudaStreamSynchronize(c->dl_stream));
   CU(cudaStreamSynchronize(c->stream));
+  if (c->norm == IAM_NORM_L2 && !wide) {
+    // The uploads built the byte layout optimistically.  A conversion that met a non-integer component or a norm
+    // beyond the layout's capacity cleared the context word: those results are void, the call is repeated on
+    // fp16 operands and the context stays there (SURF / RootSIFT projects pay this once).
+    int ok = 1;
+    CU(cudaMemcpy(&ok, c->d_ctx_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!ok) {
+      c->l2_wide_sticky = true;
+      return iam_match_images(c, n_images, image_ids, host_ptrs, counts, dtype, key_ptrs, pairs, n_pairs, prm, out_table, out_count);
+    }
+  }
   return IAM_OK;
 }
 
@@ -829,6 +952,8 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
   const Plan& pl = c->plan;
   int engine;
   if ((rc = pick_engine(c, pairs, n_pairs, &engine)) != IAM_OK) return rc;
+  int kind = 0;
+  if (engine == IAM_ENGINE_UMMA && (rc = pick_kind(c, pairs, n_pairs, &kind)) != IAM_OK) return rc;
   if (feed && feed->keys) {  // device key pointers must be in the image table before it is made resident
     for (int i = 0; i < feed->n_images; ++i) {
       Image& im = c->images[feed->ids[i]];
@@ -908,7 +1033,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     }
     const bool prof = c->profiling && n_chunks == 1;
     if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
-    if ((rc = launch_knn(c, engine, k, u0, u1 - u0)) != IAM_OK) return rc;
+    if ((rc = launch_knn(c, engine, kind, k, u0, u1 - u0)) != IAM_OK) return rc;
     if (prof) CU(cudaEventRecord(c->ev[1], c->stream));
     cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
@@ -995,9 +1120,19 @@ int iam_debug_tile(iam_ctx* c, int q_id, int t_id, int q_tile, int t_tile, uint3
   if (q_tile < 0 || t_tile < 0 || (q_tile + 1) * iam::kTileRows > q.n_pad || (t_tile + 1) * iam::kTileRows > t.n_pad)
     return fail(IAM_E_ARG, "tile index out of range");
   CU(c->packed_d.ensure(128 * 128 * sizeof(float)));
-  cudaError_t e = iam::launch_umma_tile_debug(c->norm, q.dev.a_form + size_t(q_tile) * iam::kTileBytes,
-                                              t.dev.b_form + size_t(t_tile) * iam::kTileBytes, lbo, sbo, kstep_bytes,
-                                              ksteps, c->packed_d.as<float>(), c->stream);
+  cudaError_t e;
+  if (lbo == 0) {  // byte layout (kind::i8): the layout's own strides; only the sign of `ksteps` is used
+    if (!q.has_i8 || !t.has_i8) return fail(IAM_E_STATE, "no byte layout resident");
+    const size_t tb = iam::LayD<iam::Kind::I8>::kTileBytes;
+    e = iam::launch_umma_tile_debug(iam::kKindI8, q.dev.i8_form + size_t(q_tile) * tb, t.dev.i8_form + size_t(t_tile) * tb, 0, 0,
+                                    0, ksteps, c->packed_d.as<float>(), c->stream);
+  } else {
+    if (!q.has_wide || !t.has_wide) return fail(IAM_E_STATE, "no wide operand forms resident");
+    e = iam::launch_umma_tile_debug(c->norm == IAM_NORM_L2 ? iam::kKindF16 : iam::kKindF8,
+                                    q.dev.a_form + size_t(q_tile) * iam::kTileBytes,
+                                    t.dev.b_form + size_t(t_tile) * iam::kTileBytes, lbo, sbo, kstep_bytes, ksteps,
+                                    c->packed_d.as<float>(), c->stream);
+  }
   if (e != cudaSuccess) return fail(IAM_E_CUDA, "debug tile launch: %s", cudaGetErrorString(e));
   CU(cudaMemcpyAsync(out_host, c->packed_d.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));

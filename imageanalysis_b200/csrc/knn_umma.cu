@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "knn.h"
 #include "layout.h"
@@ -36,7 +37,6 @@ namespace iam {
 
 namespace {
 
-constexpr int kBStages = 4;
 #ifndef IAM_SHARE_EVERY
 #define IAM_SHARE_EVERY 1
 #endif
@@ -46,70 +46,120 @@ constexpr int kWarpsPerATile = 4 * kParts;
 constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
 constexpr int kThreads = 128 + 32 * kEpiWarps;   // 896
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kTmemAColsPerTile = kKSteps * 8;  // 72 columns: 128 rows x 144 fp16 (two K elements per 32-bit cell)
-// Accumulator slots of kBRows columns each, handed round-robin to successive (B tile, A tile) products.
-constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;  // 3 for 96-column tiles, 5 for 64
-constexpr uint32_t kTmemA = kSlots * kBRows;     // A operand region behind the accumulator slots
 
-struct __align__(8) Barriers {
-  uint64_t a_full[kATiles];
-  uint64_t a_empty[kATiles];
-  uint64_t b_full[kBStages];
-  uint64_t b_empty[kBStages];
-  uint64_t t_full[kSlots];
-  uint64_t t_empty[kSlots];
-  uint32_t tmem_base;
-  uint32_t pad;
+// Per-kind kernel configuration: operand layout (layout.h) + tensor-memory / shared-memory budget.
+template <Kind kKind>
+struct Cfg : LayD<kKind> {
+  using L = LayD<kKind>;
+  static constexpr int kBStages = L::kBStages;
+  static constexpr uint32_t kTmemAColsPerTile = L::kKSteps * 8;  // 128 rows x 32 bytes per K-step = 8 columns
+  // Accumulator slots of kBRows columns each, handed round-robin to successive (B tile, A tile) products:
+  // 3 with the wide layout (144 columns of query operand), 4 with the byte layout (80 columns).
+  static constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;
+  static constexpr uint32_t kTmemA = kSlots * kBRows;            // A operand region behind the accumulator slots
+  struct __align__(8) Barriers {
+    uint64_t a_full[kATiles];
+    uint64_t a_empty[kATiles];
+    uint64_t b_full[kBStages];
+    uint64_t b_empty[kBStages];
+    uint64_t t_full[kSlots];
+    uint64_t t_empty[kSlots];
+    uint32_t tmem_base;
+    uint32_t pad;
+  };
+  static constexpr size_t kSmemA = kATiles * L::kTileBytes;       // staging for the next unit's query tiles
+  static constexpr size_t kSmemB = kBStages * L::kBTileBytes;     // streamed train tiles
+  static constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
+  static constexpr size_t kSmemShare = 2 * kParts * kSuperRows * 4;   // running k-th bests exchanged between the column parts of a row
+  static constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kSuperRows * 3 * 8;  // end-of-unit hand-over of the other parts' lists
+  static constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
+  static_assert(kSmemTotal <= 232448, "shared memory budget");
+  static_assert(kTmemA + kATiles * kTmemAColsPerTile <= 512, "tensor memory budget");
+  static_assert(kATiles <= kSlots, "one wrap per step at most");
 };
-
-constexpr size_t kSmemA = kATiles * kTileBytes;         //  73728: staging for the next unit's query tiles
-constexpr size_t kSmemB = kBStages * kBTileBytes;       // 110592: streamed train tiles
-constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
-constexpr size_t kSmemShare = 2 * kParts * kSuperRows * 4;   //  6144: running k-th bests exchanged between the column parts of a row
-constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kSuperRows * 3 * 8;  // end-of-unit hand-over of the other parts' lists
-constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
-static_assert(kSmemTotal <= 232448, "shared memory budget");
-static_assert(kTmemA + kATiles * kTmemAColsPerTile <= 512, "tensor memory budget");
 
 constexpr float kInf = 3.0e38f;
 
-template <int KTOP>
+// Ordering of accumulator values.  Wide layouts: the accumulator IS the distance (float, smaller = nearer).
+// Byte layout: acc = q.t + CAP - floor(||t||^2/2) (int, LARGER = nearer), see layout.h.
+template <Kind kKind>
+struct Ord {
+  using T = float;
+  __device__ static constexpr T worst() { return kInf; }
+  __device__ static constexpr T never() { return -1.0f; }   // a bound no value beats
+  __device__ static __forceinline__ bool better(T x, T y) { return x < y; }
+  __device__ static __forceinline__ T best(T a, T b) { return fminf(a, b); }
+  __device__ static __forceinline__ T best3(T a, T b, T c) { return fmin3(a, b, c); }
+  // first value NOT admissible when a partner's k-th best is g (ties are admitted: the merge orders them by index)
+  __device__ static __forceinline__ T loosen(T g) { return __int_as_float(__float_as_int(g) + 1); }
+  __device__ static __forceinline__ uint32_t bits(T x) { return __float_as_uint(x); }
+  __device__ static __forceinline__ T from_bits(uint32_t b) { return __uint_as_float(b); }
+};
+template <>
+struct Ord<Kind::I8> {
+  using T = int;
+  __device__ static constexpr T worst() { return -1; }
+  __device__ static constexpr T never() { return 0x7fffffff; }
+  __device__ static __forceinline__ bool better(T x, T y) { return x > y; }
+  __device__ static __forceinline__ T best(T a, T b) { return max(a, b); }
+  __device__ static __forceinline__ T best3(T a, T b, T c) { return imax3(a, b, c); }
+  __device__ static __forceinline__ T loosen(T g) { return g - 1; }
+  __device__ static __forceinline__ uint32_t bits(T x) { return static_cast<uint32_t>(x); }
+  __device__ static __forceinline__ T from_bits(uint32_t b) { return static_cast<int>(b); }
+};
+
+template <int KTOP, typename O>
 struct TopK {
-  float d[KTOP];
+  using T = typename O::T;
+  T d[KTOP];
   int i[KTOP];
   __device__ __forceinline__ void reset() {
 #pragma unroll
     for (int s = 0; s < KTOP; ++s) {
-      d[s] = kInf;
+      d[s] = O::worst();
       i[s] = 0x7fffffff;
     }
   }
-  __device__ __forceinline__ float thr() const { return d[KTOP - 1]; }
-  // Branch-free insertion network; a no-op when x >= thr().  A thread sees its
+  __device__ __forceinline__ T thr() const { return d[KTOP - 1]; }
+  // Branch-free insertion network; a no-op when x is not better than thr().  A thread sees its
   // columns in ascending order and every comparison is strict, so among equal
-  // distances the earliest (lowest) column stays first: the order
+  // values the earliest (lowest) column stays first: the order
   // cv2.BFMatcher reports ties in.
-  __device__ __forceinline__ void insert(float x, int col) {
+  __device__ __forceinline__ void insert(T x, int col) {
     if constexpr (KTOP == 2) {
-      // Same network as below, written with predicated moves: two compares on the ALU pipe, the six
+      // Written with predicated moves: two compares on the ALU pipe, the six
       // moves can issue as IMAD.MOV on the FMA pipe, which the (ALU-pipe-bound) epilogue leaves idle.
-      asm("{\n\t.reg .pred p0, p1;\n\t"
-          "setp.lt.f32 p0, %4, %0;\n\t"
-          "setp.lt.and.f32 p1, %4, %1, !p0;\n\t"
-          "@p1 mov.f32 %1, %4;\n\t"
-          "@p1 mov.b32 %3, %5;\n\t"
-          "@p0 mov.f32 %1, %0;\n\t"
-          "@p0 mov.b32 %3, %2;\n\t"
-          "@p0 mov.f32 %0, %4;\n\t"
-          "@p0 mov.b32 %2, %5;\n\t}"
-          : "+f"(d[0]), "+f"(d[1]), "+r"(i[0]), "+r"(i[1])
-          : "f"(x), "r"(col));
+      if constexpr (std::is_same<T, float>::value) {  // float, smaller is better
+        asm("{\n\t.reg .pred p0, p1;\n\t"
+            "setp.lt.f32 p0, %4, %0;\n\t"
+            "setp.lt.and.f32 p1, %4, %1, !p0;\n\t"
+            "@p1 mov.f32 %1, %4;\n\t"
+            "@p1 mov.b32 %3, %5;\n\t"
+            "@p0 mov.f32 %1, %0;\n\t"
+            "@p0 mov.b32 %3, %2;\n\t"
+            "@p0 mov.f32 %0, %4;\n\t"
+            "@p0 mov.b32 %2, %5;\n\t}"
+            : "+f"(d[0]), "+f"(d[1]), "+r"(i[0]), "+r"(i[1])
+            : "f"(x), "r"(col));
+      } else {  // int, larger is better
+        asm("{\n\t.reg .pred p0, p1;\n\t"
+            "setp.gt.s32 p0, %4, %0;\n\t"
+            "setp.gt.and.s32 p1, %4, %1, !p0;\n\t"
+            "@p1 mov.b32 %1, %4;\n\t"
+            "@p1 mov.b32 %3, %5;\n\t"
+            "@p0 mov.b32 %1, %0;\n\t"
+            "@p0 mov.b32 %3, %2;\n\t"
+            "@p0 mov.b32 %0, %4;\n\t"
+            "@p0 mov.b32 %2, %5;\n\t}"
+            : "+r"(d[0]), "+r"(d[1]), "+r"(i[0]), "+r"(i[1])
+            : "r"(x), "r"(col));
+      }
       return;
     }
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
-      const bool lt_prev = (s > 0) ? (x < d[s > 0 ? s - 1 : 0]) : false;
-      const bool lt_cur = x < d[s];
+      const bool lt_prev = (s > 0) ? O::better(x, d[s > 0 ? s - 1 : 0]) : false;
+      const bool lt_cur = O::better(x, d[s]);
       if (s > 0) {
         d[s] = lt_prev ? d[s - 1] : (lt_cur ? x : d[s]);
         i[s] = lt_prev ? i[s - 1] : (lt_cur ? col : i[s]);
@@ -119,8 +169,13 @@ struct TopK {
       }
     }
   }
-  // Order-independent insert ((distance, index) lexicographic): merges the list of
-  // the other column half at the end of a unit.
+};
+
+// (distance, index)-lexicographic list: the end-of-unit merge of the column parts of a row
+template <int KTOP>
+struct Final {
+  float d[KTOP];
+  int i[KTOP];
   __device__ __forceinline__ void insert_lex(float x, int col) {
 #pragma unroll
     for (int s = KTOP - 1; s >= 0; --s) {
@@ -138,18 +193,14 @@ struct TopK {
   }
 };
 
-__device__ __forceinline__ float next_up(float x) {  // x >= 0
-  return __int_as_float(__float_as_int(x) + 1);
-}
-
-// 32 accumulator columns of one row.  Fast path: one FMNMX3-based minimum per
+// 32 accumulator columns of one row.  Fast path: one 3-input min/max based extremum per
 // group of 4 columns and a warp vote; the insertion network runs (for the whole
 // warp, uniformly: no divergence) only for columns where some lane can beat its
-// bound.  `pb_up` is the smallest value NOT admissible according to the partner
-// thread that owns the other 32 columns of this row (ties with the partner's
+// bound.  `pb` is the first value NOT admissible according to the partner
+// threads that own the other columns of this row (ties with the partner's
 // bound are admitted; the final merge orders them by index).  Expected
 // insertions per row over M columns are ~k*ln(M/k), so almost every group takes
-// the 5-instruction fast path.
+// the short fast path.
 // The running lists carry an ENCODED column index e = tp * 33 + j, where tp = tile * kParts + part numbers
 // the 32-column slices of the train image and j < 32 is the column inside the slice.  e is monotone in the real
 // column (tp * 32 + j), so ties order identically, and it is formed by ONE IMAD with an immediate addend: the
@@ -177,27 +228,12 @@ __device__ __forceinline__ bool any_lane(bool p) {
   return p;
 #endif
 }
-// "does any lane have x < te": x and te are non-negative floats, so their bit patterns order like integers.
-// IAM_REDUX routes the test through one warp-wide integer minimum (REDUX, result in a uniform register, the
-// branch is then a uniform-datapath compare) instead of FSETP + VOTE on the ALU pipe.
-// level 1: group tests of the fast path; level 2: also the per-element tests of a triggered group.
-#ifndef IAM_REDUX
-#define IAM_REDUX 0
-#endif
-template <int kLevel>
-__device__ __forceinline__ bool any_below(float x, float te) {
-  if (IAM_REDUX >= kLevel) {
-    return __reduce_min_sync(0xffffffffu, __float_as_int(x) - __float_as_int(te)) < 0;
-  } else {
-    return any_lane(x < te);
-  }
-}
 
-template <int KTOP, int J0, bool kFixed = false>
-__device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>& tk, float te) {
+template <int KTOP, typename O, int J0, bool kFixed = false>
+__device__ __forceinline__ void consume_group(const typename O::T* w, int tp, TopK<KTOP, O>& tk, typename O::T te) {
   if (kFixed) {  // profiling aid: every warp does the same slow-path work (4 element tests, 2 insertions)
-    const bool f0 = any_below<2>(w[0], 3.0e38f), f1 = any_below<2>(w[1], -1.0f);
-    const bool f2 = any_below<2>(w[2], 3.0e38f), f3 = any_below<2>(w[3], -1.0f);
+    const bool f0 = any_lane(O::better(w[0], O::worst())), f1 = any_lane(O::better(w[1], O::never()));
+    const bool f2 = any_lane(O::better(w[2], O::worst())), f3 = any_lane(O::better(w[3], O::never()));
     if (f0) tk.insert(w[0], enc_index<J0>(tp));
     if (f1) tk.insert(w[1], enc_index<J0 + 1>(tp));
     if (f2) tk.insert(w[2], enc_index<J0 + 2>(tp));
@@ -206,10 +242,10 @@ __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>
   }
   // four votes issued back to back (computed against the bound at group entry: a superset of what
   // the tightening bound would admit), then the branch-free network only where some lane qualifies
-  const bool e0 = any_below<2>(w[0], te);
-  const bool e1 = any_below<2>(w[1], te);
-  const bool e2 = any_below<2>(w[2], te);
-  const bool e3 = any_below<2>(w[3], te);
+  const bool e0 = any_lane(O::better(w[0], te));
+  const bool e1 = any_lane(O::better(w[1], te));
+  const bool e2 = any_lane(O::better(w[2], te));
+  const bool e3 = any_lane(O::better(w[3], te));
   if (e0) tk.insert(w[0], enc_index<J0>(tp));
   if (e1) tk.insert(w[1], enc_index<J0 + 1>(tp));
   if (e2) tk.insert(w[2], enc_index<J0 + 2>(tp));
@@ -217,38 +253,56 @@ __device__ __forceinline__ void consume_group(const float* w, int tp, TopK<KTOP>
 }
 
 // Per 16-column batch the four group tests are formed and voted on up front against the bound at
-// entry (it only tightens, so the votes stay conservative): independent FMNMX3/FSETP/VOTE chains
-// instead of serialised vote->branch round trips.  (Moving the tests to the idle FMA pipe with
-// IMAD/IMAD.HI sign accumulation was measured and is slower: IMAD.HI is not a full-rate instruction.)
-template <int KTOP, int H, bool kFixed = false>
-__device__ __forceinline__ void consume16(const float* w, int tp, TopK<KTOP>& tk, float pb_up) {
-  const float te = kFixed ? -1.0f : fminf(tk.thr(), pb_up);
-  const bool t0 = any_below<1>(fminf(fmin3(w[0], w[1], w[2]), w[3]), te);
-  const bool t1 = any_below<1>(fminf(fmin3(w[4], w[5], w[6]), w[7]), te);
-  const bool t2 = any_below<1>(fminf(fmin3(w[8], w[9], w[10]), w[11]), te);
-  const bool t3 = any_below<1>(fminf(fmin3(w[12], w[13], w[14]), w[15]), te);
-  if (t0) consume_group<KTOP, H * 16>(w, tp, tk, fminf(tk.thr(), pb_up));
-  if (t1 || kFixed) consume_group<KTOP, H * 16 + 4, kFixed>(w + 4, tp, tk, fminf(tk.thr(), pb_up));
-  if (t2) consume_group<KTOP, H * 16 + 8>(w + 8, tp, tk, fminf(tk.thr(), pb_up));
-  if (t3) consume_group<KTOP, H * 16 + 12>(w + 12, tp, tk, fminf(tk.thr(), pb_up));
+// entry (it only tightens, so the votes stay conservative): independent min3/setp/vote chains
+// instead of serialised vote->branch round trips.
+template <int KTOP, typename O, int H, bool kFixed = false>
+__device__ __forceinline__ void consume16(const typename O::T* w, int tp, TopK<KTOP, O>& tk, typename O::T pb) {
+  using T = typename O::T;
+  const T te = kFixed ? O::never() : O::best(tk.thr(), pb);
+  const bool t0 = any_lane(O::better(O::best(O::best3(w[0], w[1], w[2]), w[3]), te));
+  const bool t1 = any_lane(O::better(O::best(O::best3(w[4], w[5], w[6]), w[7]), te));
+  const bool t2 = any_lane(O::better(O::best(O::best3(w[8], w[9], w[10]), w[11]), te));
+  const bool t3 = any_lane(O::better(O::best(O::best3(w[12], w[13], w[14]), w[15]), te));
+  if (t0) consume_group<KTOP, O, H * 16>(w, tp, tk, O::best(tk.thr(), pb));
+  if (t1 || kFixed) consume_group<KTOP, O, H * 16 + 4, kFixed>(w + 4, tp, tk, O::best(tk.thr(), pb));
+  if (t2) consume_group<KTOP, O, H * 16 + 8>(w + 8, tp, tk, O::best(tk.thr(), pb));
+  if (t3) consume_group<KTOP, O, H * 16 + 12>(w + 12, tp, tk, O::best(tk.thr(), pb));
 }
 
-template <int KTOP, bool kFixed = false>
-__device__ __forceinline__ void consume32(const float (&v)[32], int tp, TopK<KTOP>& tk, float pb_up) {
-  consume16<KTOP, 0, kFixed>(&v[0], tp, tk, pb_up);
-  consume16<KTOP, 1, kFixed>(&v[16], tp, tk, pb_up);
+template <int KTOP, typename O, bool kFixed = false>
+__device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, TopK<KTOP, O>& tk, typename O::T pb) {
+  consume16<KTOP, O, 0, kFixed>(&v[0], tp, tk, pb);
+  consume16<KTOP, O, 1, kFixed>(&v[16], tp, tk, pb);
 }
+
+template <Kind kKind>
+__device__ __forceinline__ const uint8_t* a_src(const ImgDev& im) { return kKind == Kind::I8 ? im.i8_form : im.a_form; }
+template <Kind kKind>
+__device__ __forceinline__ const uint8_t* b_src(const ImgDev& im) { return kKind == Kind::I8 ? im.i8_form : im.b_form; }
 
 template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  using C = Cfg<kKind>;
+  using O = Ord<kKind>;
+  using T = typename O::T;
+  using Barriers = typename C::Barriers;
+  constexpr int kBStages = C::kBStages;
+  constexpr int kSlots = C::kSlots;
+  constexpr int kKSteps = C::kKSteps;
+  constexpr uint32_t kTileBytes = C::kTileBytes;
+  constexpr uint32_t kBTileBytes = C::kBTileBytes;
+  constexpr uint32_t kRowBytes = C::kRowBytes;
+  constexpr uint32_t kSBO = C::kSBO;
+  constexpr uint32_t kTmemA = C::kTmemA;
+  constexpr uint32_t kTmemAColsPerTile = C::kTmemAColsPerTile;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kSmemA;
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + kSmemA + kSmemB);
-  float* share = reinterpret_cast<float*>(smem + kSmemA + kSmemB + kSmemBars);               // [unit parity][part][row]
-  float2* merge = reinterpret_cast<float2*>(smem + kSmemA + kSmemB + kSmemBars + kSmemShare);  // [part-1][row][k]
+  uint8_t* smem_b = smem + C::kSmemA;
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + C::kSmemA + C::kSmemB);
+  uint32_t* share = reinterpret_cast<uint32_t*>(smem + C::kSmemA + C::kSmemB + C::kSmemBars);               // [unit parity][part][row]
+  float2* merge = reinterpret_cast<float2*>(smem + C::kSmemA + C::kSmemB + C::kSmemBars + C::kSmemShare);  // [part-1][row][k]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -260,7 +314,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   const int first_pu = blockIdx.x / kCtas;
   const int pu_stride = gridDim.x / kCtas;
 
-  for (int i = threadIdx.x; i < 2 * kParts * kSuperRows; i += blockDim.x) share[i] = kInf;
+  for (int i = threadIdx.x; i < 2 * kParts * kSuperRows; i += blockDim.x) share[i] = O::bits(O::worst());
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < kATiles; ++i) {
       mbar_init(&bars->a_full[i], 1);
@@ -292,6 +346,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         const int u = pu * kCtas + cta_rank;
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
+        const uint8_t* tsrc = b_src<kKind>(t);
         const int n_tb = (t.n + kBRows - 1) / kBRows;
         for (int tb = 0; tb < n_tb; ++tb, ++it) {
           const uint32_t stage = it % kBStages;
@@ -299,12 +354,12 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           mbar_wait(&bars->b_empty[stage], par ^ 1, 10);
           mbar_arrive_expect_tx(&bars->b_full[stage], kBTileBytes);
           if (kCluster) {
-            constexpr uint32_t kHalf = kBTileBytes / 2;  // 32 train rows = 4 core-matrix groups, contiguous
+            constexpr uint32_t kHalf = kBTileBytes / 2;  // half the train rows = whole core-matrix groups, contiguous
             bulk_g2s_multicast(smem_b + stage * kBTileBytes + cta_rank * kHalf,
-                               t.b_form + static_cast<size_t>(tb) * kBTileBytes + cta_rank * kHalf, kHalf,
+                               tsrc + static_cast<size_t>(tb) * kBTileBytes + cta_rank * kHalf, kHalf,
                                &bars->b_full[stage], 0x3);
           } else {
-            bulk_g2s(smem_b + stage * kBTileBytes, t.b_form + static_cast<size_t>(tb) * kBTileBytes, kBTileBytes,
+            bulk_g2s(smem_b + stage * kBTileBytes, tsrc + static_cast<size_t>(tb) * kBTileBytes, kBTileBytes,
                      &bars->b_full[stage]);
           }
         }
@@ -318,7 +373,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         const int u = pu * kCtas + cta_rank;
         const KnnUnit unit = units[u];
         const ImgDev q = imgs[unit.q_slot];
-        const uint8_t* src = q.a_form + static_cast<size_t>(unit.super) * kSuperRows * kRowBytes;
+        const uint8_t* src = a_src<kKind>(q) + static_cast<size_t>(unit.super) * kSuperRows * kRowBytes;
         const uint32_t par = it & 1;
         for (int a = 0; a < kATiles; ++a) {
           mbar_wait(&bars->a_empty[a], par ^ 1, 20 + a);
@@ -333,7 +388,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // descriptor arithmetic lives in the uniform datapath instead of vector registers + R2UR); one elected lane
     // issues the tcgen05 instructions.  The issue stream of this warp is on the critical path: it shares its
     // scheduler with six ALU-bound epilogue warps.
-    constexpr uint32_t idesc = make_idesc(128, kBRows, 0, 0);
+    constexpr uint32_t idesc = make_idesc_kind<kKind>(128, kBRows);
     const uint32_t a_addr = smem_u32(smem_a);
     const uint32_t b_addr = smem_u32(smem_b);
     const uint32_t bars_addr = smem_u32(bars);
@@ -358,7 +413,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks)
               tmem_cp_128x256b(tm + kTmemA + a * kTmemAColsPerTile + ks * 8,
-                               make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO));
+                               make_smem_desc(a_addr + a * kTileBytes + C::a_koff(ks), kLBO, kSBO));
             umma_commit(&bars->a_empty[a]);
           }
           __syncwarp();
@@ -375,11 +430,11 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             const uint32_t taddr = tm + slot * kBRows;
 #pragma unroll
             for (int ks = 0; ks < kKSteps; ++ks) {
-              const uint64_t bdesc = pack_desc(b_lo + ks * (kKStepBytes >> 4), smem_desc_hi(kSBO));
+              const uint64_t bdesc = pack_desc(b_lo + (C::b_koff(ks) >> 4), smem_desc_hi(kSBO));
               if (kATmem) {
                 umma_ts<kKind>(taddr, tm_a + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
               } else {
-                const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + ks * kKStepBytes, kLBO, kSBO);
+                const uint64_t adesc = make_smem_desc(a_addr + a * kTileBytes + C::a_koff(ks), kLBO, kSBO);
                 umma<kKind>(taddr, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
               }
             }
@@ -422,9 +477,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     constexpr uint32_t kEmptyOff = kSlots * 8;                  // t_empty[] follows t_full[] in Barriers
     const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
     const bool lane0 = lane == 0;
-    TopK<KTOP> tk;
+    TopK<KTOP, O> tk;
     uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kATiles + a, slot = sq % kSlots
-    static_assert(kATiles <= kSlots, "one wrap per step at most");
     int uit = 0;
     for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
       const int u = pu * kCtas + cta_rank;
@@ -433,30 +487,30 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const ImgDev t = imgs[unit.t_slot];
       const int n_tb = (t.n + kBRows - 1) / kBRows;
       tk.reset();
-      float pb_up = kInf;  // smallest value NOT admissible according to the other column parts of this row
+      T pb = O::worst();  // first value NOT admissible according to the other column parts of this row
       // Bounds live in a buffer selected by the unit's parity.  At the start of unit u every thread resets its
       // slot in the OTHER buffer (the one unit u+1 will use); the end-of-unit barrier orders that reset before
-      // any partner reads it, so a slot only ever holds +inf or values of the unit being processed.
+      // any partner reads it, so a slot only ever holds the worst value or values of the unit being processed.
       const uint32_t rd = pin_reg(share_row + (uit & 1) * kParityStride);
       const uint32_t wr = pin_reg(rd + part * kPartStride);
-      sts_volatile_f32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, kInf);
+      sts_volatile_b32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, O::bits(O::worst()));
       const int tp_end = n_tb * kParts + part;
       for (int tp = part; tp < tp_end; tp += kParts) {  // tp numbers the 32-column slices of the train image
         // Bound from the threads that own the column parts of this row (own slot included, it is harmless):
-        // nothing worse than the smallest of the k-th bests can end up in the merged list.  Ties are admitted
-        // (next_up; the final merge orders them by index); next_up(+inf) is a NaN, which fminf ignores.  Stale
+        // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted
+        // (loosen; the final merge orders them by index).  Stale
         // values are still valid bounds, so plain volatile shared-memory traffic suffices.
         if (kParts > 1) {
-          float g = lds_volatile_f32_a(rd);
+          T g = O::from_bits(lds_volatile_b32_a(rd));
 #pragma unroll
-          for (int pp = 1; pp < kParts; ++pp) g = fminf(g, lds_volatile_f32_a(rd + pp * kPartStride));
-          pb_up = fminf(pb_up, __int_as_float(__float_as_int(g) + 1));
+          for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
+          pb = O::best(pb, O::loosen(g));
         }
         const uint32_t bar = bar_full0 + slot * 8;
         mbar_wait_bare_a(bar, par);
         tc_fence_after();
         if (kDbg != 1) {
-          float v[32];
+          T v[32];
           __syncwarp();
           tmem_ld32(tm_warp + slot * kBRows, v);
           tmem_ld_wait(v);
@@ -465,54 +519,81 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_before();
           if (lane0) mbar_arrive_a(bar + kEmptyOff);
           if (kDbg == 0) {
-            consume32<KTOP>(v, tp, tk, pb_up);
+            consume32<KTOP, O>(v, tp, tk, pb);
           } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
-            consume32<KTOP, true>(v, tp, tk, pb_up);
+            consume32<KTOP, O, true>(v, tp, tk, pb);
           } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): group tests + votes + branches, never taken
-            consume32<KTOP>(v, tp, tk, -1.0f);
+            consume32<KTOP, O>(v, tp, tk, O::never());
           } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
-            tk.d[0] = fminf(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
+            tk.d[0] = O::best(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
           } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
-            float m = v[0];
+            T m = v[0];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) m = fminf(m, fminf(fmin3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
-            tk.d[0] = fminf(tk.d[0], m);
+            for (int j = 0; j < 8; ++j) m = O::best(m, O::best(O::best3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
+            tk.d[0] = O::best(tk.d[0], m);
           }
         } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
           __syncwarp();
           tc_fence_before();
           if (lane0) mbar_arrive_a(bar + kEmptyOff);
         }
-        if (kParts > 1) sts_volatile_f32_a(wr, tk.d[KTOP - 1]);
+        if (kParts > 1) sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
         slot += kATiles;
         if (slot >= kSlots) {
           slot -= kSlots;
           par ^= 1;
         }
       }
-      // end of unit: parts 1.. hand their lists to part 0's thread of the same row
+      // end of unit: every list becomes (squared distance, train row); parts 1.. hand theirs to part 0's thread
+      // of the same row, which merges (distance, index)-lexicographically
+      const int row = unit.super * kSuperRows + urow;  // wide layouts: the query row; byte layout: its rank
+      Final<KTOP> fin;
+      {
+        int rowc = 0, n_even = 0;
+        if (kKind == Kind::I8) {
+          rowc = q.rowc[row];
+          n_even = t.meta[kMetaNEven];
+        }
+#pragma unroll
+        for (int s = 0; s < KTOP; ++s) {
+          const int enc = tk.i[s];
+          if (kKind == Kind::I8) {
+            const int rank = enc == 0x7fffffff ? 0x7fffffff : dec_index(enc);
+            if (rank < t.n) {  // d^2 = ||q||^2 + 2 CAP + (||t||^2 & 1) - 2 acc, exact (layout.h)
+              fin.d[s] = static_cast<float>(rowc + (rank >= n_even ? 1 : 0) - 2 * static_cast<int>(tk.d[s]));
+              fin.i[s] = t.perm[rank];
+            } else {
+              fin.d[s] = kInf;
+              fin.i[s] = -1;
+            }
+          } else {
+            fin.d[s] = static_cast<float>(tk.d[s]);
+            fin.i[s] = enc == 0x7fffffff ? -1 : dec_index(enc);
+          }
+        }
+      }
       if (part > 0) {
 #pragma unroll
         for (int s = 0; s < KTOP; ++s)
-          merge[((part - 1) * kSuperRows + urow) * KTOP + s] = make_float2(tk.d[s], __int_as_float(tk.i[s]));
+          merge[((part - 1) * kSuperRows + urow) * KTOP + s] = make_float2(fin.d[s], __int_as_float(fin.i[s]));
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      const int row = unit.super * kSuperRows + urow;
       if (part == 0) {
 #pragma unroll
         for (int pp = 0; pp < kParts - 1; ++pp) {
 #pragma unroll
           for (int s = 0; s < KTOP; ++s) {
             const float2 m = merge[(pp * kSuperRows + urow) * KTOP + s];
-            tk.insert_lex(m.x, __float_as_int(m.y));
+            fin.insert_lex(m.x, __float_as_int(m.y));
           }
         }
         if (row < q.n) {
-          const size_t o = (static_cast<size_t>(unit.out_base) + row) * KTOP;
+          const int orow = kKind == Kind::I8 ? q.perm[row] : row;
+          const size_t o = (static_cast<size_t>(unit.out_base) + orow) * KTOP;
 #pragma unroll
           for (int s = 0; s < KTOP; ++s) {
-            out_idx[o + s] = tk.i[s] == 0x7fffffff ? -1 : dec_index(tk.i[s]);
-            out_d2[o + s] = tk.d[s];
+            out_idx[o + s] = fin.i[s];
+            out_d2[o + s] = fin.d[s];
           }
         }
       }
@@ -529,12 +610,14 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   }
 }
 
-// Debug aid: one 128x128 distance tile (first A tile of `q` x first B tile of `t`)
-// with the descriptor strides given at run time, accumulators dumped to global.
+// Debug aid: one 128x128 accumulator tile (first A tile of `q` x first B tile of `t`)
+// with the descriptor strides given at run time, accumulators dumped to global as floats.
+// The last K-step of each role sits at aug_a / aug_b (byte offsets) when those are >= 0.
 template <Kind kKind>
 __global__ void __launch_bounds__(128, 1)
-umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __restrict__ b_tile, uint32_t lbo,
-                       uint32_t sbo, uint32_t kstep_bytes, int ksteps_in, float* __restrict__ out) {
+umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __restrict__ b_tile, uint32_t tile_bytes,
+                       uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, int ksteps_in, int aug_a, int aug_b,
+                       float* __restrict__ out) {
   const bool a_in_tmem = ksteps_in < 0;  // negative K-step count selects the TS form (A staged through tcgen05.cp)
   const int ksteps = a_in_tmem ? -ksteps_in : ksteps_in;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -552,18 +635,20 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   tc_fence_after();
   const uint32_t tmem = s_tmem;
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar_full, 2 * kTileBytes);
-    bulk_g2s(smem, a_tile, kTileBytes, &bar_full);
-    bulk_g2s(smem + kTileBytes, b_tile, kTileBytes, &bar_full);
+    mbar_arrive_expect_tx(&bar_full, 2 * tile_bytes);
+    bulk_g2s(smem, a_tile, tile_bytes, &bar_full);
+    bulk_g2s(smem + tile_bytes, b_tile, tile_bytes, &bar_full);
     mbar_wait(&bar_full, 0, 90);
     tc_fence_after();
-    constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+    constexpr uint32_t idesc = make_idesc_kind<kKind>(128, 128);
+    auto a_off = [&](int ks) { return (ks == ksteps - 1 && aug_a >= 0) ? uint32_t(aug_a) : ks * kstep_bytes; };
+    auto b_off = [&](int ks) { return (ks == ksteps - 1 && aug_b >= 0) ? uint32_t(aug_b) : ks * kstep_bytes; };
     if (a_in_tmem)
       for (int ks = 0; ks < ksteps; ++ks)
-        tmem_cp_128x256b(tmem + 128 + ks * 8, make_smem_desc(smem_u32(smem) + ks * kstep_bytes, lbo, sbo));
+        tmem_cp_128x256b(tmem + 128 + ks * 8, make_smem_desc(smem_u32(smem) + a_off(ks), lbo, sbo));
     for (int ks = 0; ks < ksteps; ++ks) {
-      const uint64_t ad = make_smem_desc(smem_u32(smem) + ks * kstep_bytes, lbo, sbo);
-      const uint64_t bd = make_smem_desc(smem_u32(smem + kTileBytes) + ks * kstep_bytes, lbo, sbo);
+      const uint64_t ad = make_smem_desc(smem_u32(smem) + a_off(ks), lbo, sbo);
+      const uint64_t bd = make_smem_desc(smem_u32(smem + tile_bytes) + b_off(ks), lbo, sbo);
       if (a_in_tmem)
         umma_ts<kKind>(tmem, tmem + 128 + ks * 8, bd, idesc, ks > 0 ? 1u : 0u);
       else
@@ -574,12 +659,12 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   mbar_wait(&bar_done, 0, 91);
   tc_fence_after();
   for (int c = 0; c < 4; ++c) {
-    float v[32];
+    typename Ord<kKind>::T v[32];
     __syncwarp();
     tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
     tmem_ld_wait(v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 128 + c * 32 + j] = v[j];
+    for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 128 + c * 32 + j] = static_cast<float>(v[j]);
   }
   tc_fence_before();
   __syncthreads();
@@ -619,6 +704,7 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
   } else {
     kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0> : knn_umma_kernel<kKind, KTOP, false, false, 0>;
   }
+  constexpr size_t kSmemTotal = Cfg<kKind>::kSmemTotal;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
   int grid = n_units < num_sms ? n_units : num_sms;
@@ -641,34 +727,46 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
   return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2);
 }
 
-}  // namespace
-
-cudaError_t launch_umma_tile_debug(int norm, const uint8_t* a_tile, const uint8_t* b_tile, uint32_t lbo, uint32_t sbo,
-                                   uint32_t kstep_bytes, int ksteps, float* out, cudaStream_t stream) {
-  const size_t smem = 2 * kTileBytes + 1024;
-  if (norm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(umma_tile_debug_kernel<Kind::F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    umma_tile_debug_kernel<Kind::F16><<<1, 128, smem, stream>>>(a_tile, b_tile, lbo, sbo, kstep_bytes, ksteps, out);
-  } else {
-    cudaError_t e = cudaFuncSetAttribute(umma_tile_debug_kernel<Kind::F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    umma_tile_debug_kernel<Kind::F8><<<1, 128, smem, stream>>>(a_tile, b_tile, lbo, sbo, kstep_bytes, ksteps, out);
-  }
+template <Kind kKind>
+cudaError_t launch_debug_t(const uint8_t* a_tile, const uint8_t* b_tile, uint32_t tile_bytes, uint32_t lbo, uint32_t sbo,
+                           uint32_t kstep_bytes, int ksteps, int aug_a, int aug_b, float* out, cudaStream_t stream) {
+  const size_t smem = 2 * tile_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(umma_tile_debug_kernel<kKind>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  umma_tile_debug_kernel<kKind><<<1, 128, smem, stream>>>(a_tile, b_tile, tile_bytes, lbo, sbo, kstep_bytes, ksteps, aug_a,
+                                                          aug_b, out);
   return cudaGetLastError();
 }
 
-cudaError_t launch_knn_umma(int norm, int k, const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx,
+}  // namespace
+
+cudaError_t launch_umma_tile_debug(int kind, const uint8_t* a_tile, const uint8_t* b_tile, uint32_t lbo, uint32_t sbo,
+                                   uint32_t kstep_bytes, int ksteps, float* out, cudaStream_t stream) {
+  if (kind == kKindF16) return launch_debug_t<Kind::F16>(a_tile, b_tile, kTileBytes, lbo, sbo, kstep_bytes, ksteps, -1, -1, out, stream);
+  if (kind == kKindF8) return launch_debug_t<Kind::F8>(a_tile, b_tile, kTileBytes, lbo, sbo, kstep_bytes, ksteps, -1, -1, out, stream);
+  if (kind == kKindI8) {
+    using L = LayD<Kind::I8>;
+    const int ks = ksteps < 0 ? -L::kKSteps : L::kKSteps;  // only the sign (SS / TS form) is taken from the caller
+    return launch_debug_t<Kind::I8>(a_tile, b_tile, L::kTileBytes, kLBO, L::kSBO, kKStepBytes, ks, L::kAugA, L::kAugB, out, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_knn_umma(int kind, int k, const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx,
                             float* out_d2, int num_sms, cudaStream_t stream) {
   if (n_units <= 0) return cudaSuccess;
-  if (norm == 0) {
+  if (kind == kKindF16) {
     if (k == 1) return launch_t<Kind::F16, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
     if (k == 2) return launch_t<Kind::F16, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
     if (k == 3) return launch_t<Kind::F16, 3>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
-  } else {
+  } else if (kind == kKindF8) {
     if (k == 1) return launch_t<Kind::F8, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
     if (k == 2) return launch_t<Kind::F8, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
     if (k == 3) return launch_t<Kind::F8, 3>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
+  } else if (kind == kKindI8) {
+    if (k == 1) return launch_t<Kind::I8, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
+    if (k == 2) return launch_t<Kind::I8, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
+    if (k == 3) return launch_t<Kind::I8, 3>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "layout.h"
+
 namespace iam {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -262,7 +264,14 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t m, uint32_t n, uint32
   return (1u << 4) /* D = F32 */ | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
-enum class Kind { F16, F8 };
+// kind::i8: unsigned 8-bit operands (format 0), s32 accumulate (D format 2)
+__host__ __device__ constexpr uint32_t make_idesc_i8(uint32_t m, uint32_t n) {
+  return (2u << 4) /* D = S32 */ | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+template <Kind kKind>
+__host__ __device__ constexpr uint32_t make_idesc_kind(uint32_t m, uint32_t n) {
+  return kKind == Kind::I8 ? make_idesc_i8(m, n) : make_idesc(m, n, 0, 0);
+}
 
 template <Kind kKind>
 __device__ __forceinline__ void umma(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -273,11 +282,18 @@ __device__ __forceinline__ void umma(uint32_t taddr, uint64_t adesc, uint64_t bd
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
-  } else {
+  } else if constexpr (kKind == Kind::F8) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(taddr),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
@@ -294,11 +310,18 @@ __device__ __forceinline__ void umma_ts(uint32_t taddr, uint32_t a_taddr, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(taddr),
         "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
-  } else {
+  } else if constexpr (kKind == Kind::F8) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(taddr),
+        "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(taddr),
         "r"(a_taddr), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
@@ -311,7 +334,9 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc)
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+template <typename T>
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, T (&v)[32]) {
+  static_assert(sizeof(T) == 4, "32-bit accumulator cells");
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -327,7 +352,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // Wait for outstanding tcgen05.ld; the loaded registers are threaded through
 // as in/out operands so the compiler cannot hoist their uses above the wait.
-__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+template <typename T>
+__device__ __forceinline__ void tmem_ld_wait(T (&v)[32]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -364,5 +390,14 @@ __device__ __forceinline__ void sts_volatile_f32(void* p, float v) {
 }
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }  // -> FMNMX3
+__device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }                // -> VIMNMX3
+__device__ __forceinline__ uint32_t lds_volatile_b32_a(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_b32_a(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 }  // namespace iam

@@ -39,10 +39,20 @@ extern "C" {
 
 /* kNN engine selection (debug / validation aid; IAM_ENGINE_AUTO in
  * production).  UMMA = tcgen05 tensor-core kernel, SIMT = exact CUDA-core
- * kernel used as the on-device cross-check. */
-#define IAM_ENGINE_AUTO  0
-#define IAM_ENGINE_UMMA  1
-#define IAM_ENGINE_SIMT  2
+ * kernel used as the on-device cross-check.  For L2 the tensor-core kernel
+ * has two operand kinds: integer-valued descriptors (what cv2.SIFT produces,
+ * image.py:324) run on byte operands (kind::i8, s32 accumulate, exact);
+ * anything else (SURF, RootSIFT, norms beyond the byte layout's capacity)
+ * on fp16 operands (kind::f16).  UMMA_F16 forces the latter. */
+#define IAM_ENGINE_AUTO      0
+#define IAM_ENGINE_UMMA      1
+#define IAM_ENGINE_SIMT      2
+#define IAM_ENGINE_UMMA_F16  3
+
+/* tensor-core operand kind reported in iam_timing.mma_kind */
+#define IAM_KIND_F16  0
+#define IAM_KIND_F8   1
+#define IAM_KIND_I8   2
 
 /* Reduction applied to the k=2 neighbour lists of one direction. */
 #define IAM_REDUCE_LOWE        0  /* keep d0 <= d1*ratio          (find_obj.py:50-60, matcher.py:227) */
@@ -204,7 +214,7 @@ typedef struct iam_timing {
   int   total_launches;/* all kernel launches since context creation         */
   int   engine_used;   /* IAM_ENGINE_UMMA or IAM_ENGINE_SIMT                 */
   int   waves;         /* pair-list chunks of the last match call            */
-  int   reserved;
+  int   mma_kind;      /* IAM_KIND_* of the last tensor-core launch, -1: SIMT */
   /* last iam_match_images call (device timeline from CUDA events, host time from a monotonic clock) */
   float host_enqueue_ms;  /* host time spent enqueueing uploads + kernels          */
   float upload_span_ms;   /* first H2D copy start -> last conversion end           */
@@ -217,7 +227,9 @@ int iam_get_timing(iam_ctx* ctx, iam_timing* out);
  * tensor-core distance tile (query tile `q_tile` of image q_id x train tile
  * `t_tile` of image t_id) with explicit UMMA descriptor strides, into
  * out_host[128*128].  Production values: lbo=128, sbo=2304, kstep_bytes=256,
- * ksteps=9. */
+ * ksteps=9 (negative: A operand through tensor memory).  lbo=0 selects the
+ * byte layout (kind::i8) of an L2 context with its own strides; the tile is
+ * then s32 accumulators (converted to float) of RANK-ordered rows. */
 int iam_debug_tile(iam_ctx* ctx, int q_id, int t_id, int q_tile, int t_tile,
                    uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes, int ksteps,
                    float* out_host);

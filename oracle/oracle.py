@@ -228,3 +228,97 @@ def worklist(neds: np.ndarray, mode: str = "sequential", min_dist: float = 0.0, 
             elif abs(i - j) <= seq_k:
                 work.append([int(round(dist / interval)) * interval, i, j])
     return work
+
+
+# --------------------------------------------------------------------------
+# GMS grid-motion-statistics filter  (matcher.py:285 cv2.xfeatures2d.matchGMS;
+# restated from the reference's own scripts/lib/archive/gms_matcher.py, which
+# its header says reproduces the OpenCV C++ output)
+# --------------------------------------------------------------------------
+# Which right-cell neighbour faces left-cell neighbour j under each of the 8 rotations
+# (gms_matcher.py:29-60; 1-based there, 0-based here).
+GMS_ROTATIONS = [
+    [0, 1, 2, 3, 4, 5, 6, 7, 8], [3, 0, 1, 6, 4, 2, 7, 8, 5], [6, 3, 0, 7, 4, 1, 8, 5, 2], [7, 6, 3, 8, 4, 0, 5, 2, 1],
+    [8, 7, 6, 5, 4, 3, 2, 1, 0], [5, 8, 7, 2, 4, 6, 1, 0, 3], [2, 5, 8, 1, 4, 7, 0, 3, 6], [1, 2, 5, 0, 4, 8, 3, 6, 7]]
+GMS_SCALES = [1.0, 0.5, 1.0 / np.sqrt(2.0), np.sqrt(2.0), 2.0]   # gms_matcher.py:63
+GMS_GRID = 20                                                    # gms_matcher.py:83
+
+
+def _gms_nb9(cell: int, gw: int, gh: int):
+    """3x3 neighbourhood of a cell, -1 outside the grid (gms_matcher.py:112-127)."""
+    cx, cy = cell % gw, cell // gw
+    out = []
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            x, y = cx + dx, cy + dy
+            out.append(x + y * gw if 0 <= x < gw and 0 <= y < gh else -1)
+    return out
+
+
+def _gms_run(lcell, rcell, n_right, gw_r, gh_r, rot, factor):
+    """One GmsMatcher.run(RotationType) (gms_matcher.py:187-209): the four half-cell shifted left grids,
+    each with its own statistics, cell pairing and verification; a match is an inlier if any of the four accepts it.
+    lcell: [4][n] left cell per grid type (-1 = outside); rcell: [n] right cell."""
+    n = len(rcell)
+    n_left = GMS_GRID * GMS_GRID
+    mask = np.zeros(n, bool)
+    for g in range(4):
+        stats = np.zeros((n_left, n_right), np.int64)
+        per_left = np.zeros(n_left, np.int64)
+        for i in range(n):                                        # AssignMatchPairs :211-226
+            lg, rg = lcell[g][i], rcell[i]
+            if lg < 0 or rg < 0:
+                continue
+            stats[lg, rg] += 1
+            per_left[lg] += 1
+        pair = np.full(n_left, -1, np.int64)
+        for i in range(n_left):                                   # VerifyCellPairs :253-285
+            if stats[i].sum() == 0:
+                continue
+            j = int(np.argmax(stats[i]))                          # first maximum, as the strict '>' scan :261-265
+            nl = _gms_nb9(i, GMS_GRID, GMS_GRID)
+            nr = _gms_nb9(j, gw_r, gh_r)
+            score = thresh = numpair = 0
+            for s in range(9):
+                ll, rr = nl[s], nr[GMS_ROTATIONS[rot][s]]
+                if ll == -1 or rr == -1:
+                    continue
+                score += stats[ll, rr]
+                thresh += per_left[ll]
+                numpair += 1
+            pair[i] = j if score >= factor * np.sqrt(thresh / numpair) else -2
+        for i in range(n):                                        # mark inliers :203-207
+            if lcell[g][i] >= 0 and pair[lcell[g][i]] == rcell[i]:
+                mask[i] = True
+    return mask
+
+
+def gms_mask(pts1, pts2, size1, size2, matches, with_rotation: bool = True, with_scale: bool = False,
+             threshold_factor: float = 5.0) -> np.ndarray:
+    """Inlier mask over `matches` ([[queryIdx, trainIdx], ...]) as GmsMatcher.GetInlierMask returns it
+    (gms_matcher.py:129-176): the rotation (and scale) hypothesis with the most inliers, first one on ties;
+    the reference calls it with withRotation=True, withScale=False, thresholdFactor=5.0 (matcher.py:285).
+    pts are pixel coordinates, size = (width, height) (gms_matcher.py:91-97)."""
+    matches = np.asarray(matches, np.int64).reshape(-1, 2)
+    n = len(matches)
+    if n == 0:
+        return np.zeros(0, bool)
+    p1 = np.asarray(pts1, np.float64)[matches[:, 0]] / np.array(size1, np.float64)
+    p2 = np.asarray(pts2, np.float64)[matches[:, 1]] / np.array(size2, np.float64)
+    lcell = []
+    for sx, sy in ((0.0, 0.0), (0.5, 0.0), (0.0, 0.5), (0.5, 0.5)):      # GetGridIndexLeft :228-246
+        x = np.floor(p1[:, 0] * GMS_GRID + sx).astype(np.int64)
+        y = np.floor(p1[:, 1] * GMS_GRID + sy).astype(np.int64)
+        lcell.append(np.where((x >= GMS_GRID) | (y >= GMS_GRID), -1, x + y * GMS_GRID))
+    best_mask, best = None, 0
+    last = np.zeros(n, bool)
+    for sc in (range(5) if with_scale else (0,)):
+        gw = int(GMS_GRID * GMS_SCALES[sc])                              # SetScale :178-185
+        gh = int(GMS_GRID * GMS_SCALES[sc])
+        rcell = np.floor(p2[:, 0] * gw).astype(np.int64) + np.floor(p2[:, 1] * gh).astype(np.int64) * gw  # :248-251
+        for rot in (range(8) if with_rotation else (0,)):
+            last = _gms_run(lcell, rcell, gw * gh, gw, gh, rot, threshold_factor)
+            c = int(last.sum())
+            if c > best:
+                best, best_mask = c, last
+    return best_mask if best_mask is not None else last

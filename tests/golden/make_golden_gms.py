@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Golden fixtures for the GMS grid filter (matcher.py:285).
+
+cv2.xfeatures2d (contrib) is absent from this image, so the pin is the
+reference's own restatement of that algorithm, scripts/lib/archive/gms_matcher.py,
+imported UNMODIFIED from /root/reference and run with the threshold factor the
+reference's call site passes (thresholdFactor=5.0; the module constant is 6).
+
+Key points are kept inside the first 97 % of the image: for a point in the last
+half cell the archive module indexes mCellPairs[-1] (Python wrap-around to cell
+399) where the C++ original skips the match; the oracle and the CUDA kernel follow
+the C++ behaviour and tests/test_gms.py covers that edge separately.
+
+usage: python tests/golden/make_golden_gms.py      (from the repo root; needs /root/reference)
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, "/root/reference/scripts/lib/archive")
+import gms_matcher as ref  # noqa: E402
+
+ref.THRESHOLD_FACTOR = 5.0          # matcher.py:285 thresholdFactor=5.0
+
+
+def scene(n, inlier_frac, angle_deg, scale, seed, w=5472, h=3648, clustered=False):
+    rng = np.random.default_rng(seed)
+    if clustered:   # matches concentrated in a few cells: large per-cell counts
+        centres = rng.uniform(0.2, 0.75, (6, 2))
+        p1 = centres[rng.integers(0, 6, n)] + rng.normal(0, 0.02, (n, 2))
+        p1 = np.clip(p1, 0.01, 0.96)
+    else:
+        p1 = rng.uniform(0.0, 0.97, (n, 2))
+    a = np.deg2rad(angle_deg)
+    R = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+    p2 = (p1 - 0.5) @ R.T * scale + 0.5 + rng.normal(0, 0.002, (n, 2))
+    out = rng.random(n) > inlier_frac
+    p2[out] = rng.uniform(0.0, 0.97, (int(out.sum()), 2))
+    ok = (p2 >= 0).all(1) & (p2 < 0.97).all(1)
+    p1, p2 = p1[ok], p2[ok]
+    n = len(p1)
+    # key-point tables are larger than the match list and shuffled, as in the reference (matches index into them)
+    n1, n2 = n + 37, n + 11
+    pts1 = rng.uniform(0, 0.97, (n1, 2))
+    pts2 = rng.uniform(0, 0.97, (n2, 2))
+    qi = rng.permutation(n1)[:n]
+    ti = rng.permutation(n2)[:n]
+    pts1[qi] = p1
+    pts2[ti] = p2
+    pts1 = (pts1 * [w, h]).astype(np.float32)     # cv2.KeyPoint.pt is float32
+    pts2 = (pts2 * [w, h]).astype(np.float32)
+    return pts1, pts2, np.stack([qi, ti], 1).astype(np.int32), (w, h)
+
+
+def run_ref(pts1, pts2, matches, size, with_scale, with_rotation):
+    dm = [types.SimpleNamespace(queryIdx=int(q), trainIdx=int(t)) for q, t in matches]
+    s = ref.Size(size[0], size[1])
+    with contextlib.redirect_stdout(io.StringIO()):
+        g = ref.GmsMatcher([tuple(map(float, p)) for p in pts1], s, [tuple(map(float, p)) for p in pts2], s, dm)
+        mask, n_in = g.GetInlierMask(with_scale, with_rotation)
+    return np.array(mask, bool), int(n_in)
+
+
+def main():
+    cases = {
+        "rot0": dict(n=1200, inlier_frac=0.6, angle_deg=0, scale=1.0, seed=1),
+        "rot90": dict(n=2000, inlier_frac=0.5, angle_deg=90, scale=0.9, seed=2),
+        "rot180": dict(n=800, inlier_frac=0.7, angle_deg=180, scale=1.0, seed=3),
+        "rot45": dict(n=1500, inlier_frac=0.6, angle_deg=45, scale=0.8, seed=4),
+        "rot225_small": dict(n=120, inlier_frac=0.8, angle_deg=225, scale=1.0, seed=5),
+        "outliers_only": dict(n=400, inlier_frac=0.0, angle_deg=0, scale=1.0, seed=6),
+        "clustered": dict(n=2000, inlier_frac=0.8, angle_deg=10, scale=1.0, seed=7, clustered=True),
+    }
+    out = {}
+    for name, kw in cases.items():
+        pts1, pts2, matches, size = scene(**kw)
+        mask, n_in = run_ref(pts1, pts2, matches, size, False, True)     # the reference's flags (matcher.py:285)
+        print(name, len(matches), "matches ->", n_in, "inliers")
+        out[name + "_pts1"], out[name + "_pts2"], out[name + "_matches"] = pts1, pts2, matches
+        out[name + "_size"] = np.array(size, np.int32)
+        out[name + "_mask"] = mask
+    # the other flag combinations on one scene
+    pts1, pts2, matches, size = scene(n=900, inlier_frac=0.6, angle_deg=0, scale=0.55, seed=8)
+    for ws, wr in ((False, False), (True, False), (True, True)):
+        mask, n_in = run_ref(pts1, pts2, matches, size, ws, wr)
+        print("flags", ws, wr, "->", n_in)
+        out["flags_s%d_r%d_mask" % (ws, wr)] = mask
+    out["flags_pts1"], out["flags_pts2"], out["flags_matches"], out["flags_size"] = pts1, pts2, matches, np.array(size, np.int32)
+    out["names"] = np.array(sorted(cases))
+    np.savez_compressed(os.path.join(HERE, "gms_reference.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,7 +13,9 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
-ENGINES = [(_capi.ENGINE_UMMA, "umma"), (_capi.ENGINE_SIMT, "simt")]
+# UMMA: the tcgen05 kernel with the operand kind the library picks (byte operands / kind::i8 for integer-valued L2,
+# e4m3 for Hamming); UMMA_F16: the same kernel forced onto fp16 operands; SIMT: the CUDA-core cross-check engine.
+ENGINES = [(_capi.ENGINE_UMMA, "umma"), (_capi.ENGINE_UMMA_F16, "umma_f16"), (_capi.ENGINE_SIMT, "simt")]
 KNN_CASES = [("knn_l2_synth.npz", _capi.NORM_L2), ("knn_hamming_synth.npz", _capi.NORM_HAMMING),
              ("knn_sift_real.npz", _capi.NORM_L2), ("knn_orb_real.npz", _capi.NORM_HAMMING)]
 
@@ -25,9 +27,11 @@ def run_knn(norm, q, t, k, engine, reverse=True):
     eng.upload(1, t)
     n = max(q.shape[0], t.shape[0])
     out = eng.knn_pairs([(0, 1)], k, n, reverse=reverse)
-    used = eng.timing().engine_used
+    tm = eng.timing()
     eng.close()
-    assert used == engine
+    assert tm.engine_used == (_capi.ENGINE_SIMT if engine == _capi.ENGINE_SIMT else _capi.ENGINE_UMMA)
+    if engine == _capi.ENGINE_UMMA_F16 and norm == _capi.NORM_L2:
+        assert tm.mma_kind == _capi.KIND_F16
     return out
 
 
@@ -113,6 +117,94 @@ def test_full_size_5000_umma_equals_simt_and_oracle_rows(norm, gen, nb):
     rows = rng.permutation(5000)[:300]
     oi, od = oracle.knn(q[rows], t, 2, norm, threads=8)
     assert (a[0][0, rows] == oi).all() and (a[1][0, rows] == od).all()
+
+
+def test_operand_kind_selection():
+    """Integer-valued L2 descriptors run on byte operands (kind::i8); rows whose squared norm exceeds the byte
+    layout's capacity, non-integer descriptors and forced fp16 fall back to fp16 operands; Hamming is e4m3."""
+    def kind_of(norm, q, t, engine=_capi.ENGINE_AUTO):
+        eng = _capi.Engine(norm, q.shape[1], 0)
+        eng.set_engine(engine)
+        eng.upload(0, q)
+        eng.upload(1, t)
+        idx, dist, _, _ = eng.knn_pairs([(0, 1)], 2, len(q), reverse=False)
+        k = eng.timing().mma_kind
+        eng.close()
+        return k, idx, dist
+    q, t = synth.sift_like(300, seed=1), synth.sift_like(400, seed=2)
+    k, idx, dist = kind_of(_capi.NORM_L2, q, t)
+    assert k == _capi.KIND_I8
+    k2, idx2, dist2 = kind_of(_capi.NORM_L2, q.astype(np.float32), t.astype(np.float32))
+    assert k2 == _capi.KIND_I8 and (idx2 == idx).all() and (dist2 == dist).all()
+    k3, idx3, dist3 = kind_of(_capi.NORM_L2, q, t, _capi.ENGINE_UMMA_F16)
+    assert k3 == _capi.KIND_F16 and (idx3 == idx).all() and (dist3 == dist).all()
+    t_big = t.copy()
+    t_big[7] = 255                                  # squared norm 8 323 200 > capacity 4 031 547
+    k4, idx4, dist4 = kind_of(_capi.NORM_L2, q, t_big)
+    oi, od = oracle.knn(q, t_big, 2, oracle.NORM_L2, threads=4)
+    assert k4 == _capi.KIND_F16 and (idx4[0] == oi).all() and (dist4[0] == od).all()
+    k5, _, _ = kind_of(_capi.NORM_L2, q.astype(np.float32) + 0.25, t.astype(np.float32))
+    assert k5 == _capi.KIND_F16
+    k6, _, _ = kind_of(_capi.NORM_HAMMING, synth.orb_like(300, seed=1), synth.orb_like(300, seed=2))
+    assert k6 == _capi.KIND_F8
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_byte_layout_norm_parity_and_ties(k):
+    """The byte layout orders train rows by the parity of their squared norm and compares q.t - floor(|t|^2/2):
+    small-valued descriptors give many exactly equal distances within and across the two parity classes, the
+    largest eligible norms sit at the capacity limit -- results must still be cv2's (distance, then lowest index)."""
+    rng = np.random.default_rng(44)
+    q = rng.integers(0, 3, (700, 128)).astype(np.uint8)
+    t = rng.integers(0, 3, (900, 128)).astype(np.uint8)
+    t[100:160] = q[:60]                      # exact duplicates (distance 0) ...
+    t[500:560] = q[:60]                      # ... twice: ties on the best AND second best
+    t[300] = t[301] = t[0]
+    q[650:] = 0                              # all-zero queries: distance = |t|^2, every parity mix
+    big = np.zeros((4, 128), np.uint8)
+    big[:, :61] = 255
+    big[:, 61:67] = [254, 22, 4, 2, 1, 1]    # squared norm 4 031 547: the largest the byte layout holds (odd)
+    big[1, 66] = 0                           # ... and its even neighbour 4 031 546
+    big[2, :] = big[2, ::-1].copy()
+    assert int((big[0].astype(np.int64) ** 2).sum()) == 4031547
+    t[600:604] = big
+    q[600:604] = big
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.upload(0, q)
+    eng.upload(1, t)
+    idx, dist, ridx, rdist = eng.knn_pairs([(0, 1)], k, 900)
+    assert eng.timing().mma_kind == _capi.KIND_I8
+    eng.close()
+    oi, od = oracle.knn(q, t, k, oracle.NORM_L2, threads=4)
+    ri, rd = oracle.knn(t, q, k, oracle.NORM_L2, threads=4)
+    assert (idx[0, :700] == oi).all() and (dist[0, :700] == od).all()
+    assert (ridx[0, :900] == ri).all() and (rdist[0, :900] == rd).all()
+
+
+def test_match_images_falls_back_to_fp16_operands_once():
+    """iam_match_images builds the byte layout optimistically; a descriptor set it cannot hold voids the run,
+    the call repeats itself on fp16 operands and the context stays there."""
+    des, _, _ = synth.sift_project(6, 600, seed=33)
+    des = [d.copy() for d in des]
+    des[4][17] = 255                          # one row beyond the byte layout's capacity
+    pairs = [(i, j) for i in range(6) for j in range(i + 1, 6)]
+    prm = _capi.Engine.make_params(cross_check=True)
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for rep in range(2):
+        table, count = eng.match_images(list(range(6)), des, pairs, prm)
+        assert eng.timing().mma_kind == _capi.KIND_F16
+        for p, (a, b) in enumerate(pairs):
+            f, _ = oracle.bidirectional(des[a], des[b], oracle.NORM_L2, 0.75, 270.0, threads=4)
+            assert table[p, :count[p]].tolist() == f
+    eng.close()
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)   # the same project without the offending row stays on byte operands
+    des[4][17] = des[4][16]
+    table, count = eng.match_images(list(range(6)), des, pairs, prm)
+    assert eng.timing().mma_kind == _capi.KIND_I8
+    for p, (a, b) in enumerate(pairs):
+        f, _ = oracle.bidirectional(des[a], des[b], oracle.NORM_L2, 0.75, 270.0, threads=4)
+        assert table[p, :count[p]].tolist() == f
+    eng.close()
 
 
 def test_many_pairs_and_chunking(monkeypatch):

@@ -37,6 +37,28 @@ def main():
                 name, tag, diff.max(), int((diff == 0).sum()), got[0, :4].tolist(), ref[0, :4].tolist()))
             out["%s_%s" % (name, tag)] = got
         out[name + "_exp"] = exp
+        if norm == _capi.NORM_L2:
+            # byte layout (kind::i8): rows in rank order (even squared norms first), acc = q.t + CAP - floor(|t|^2/2)
+            CAP = 254 + 255 * 254 + 30 * 65025
+
+            def ranked(x):
+                nrm = (x.astype(np.int64) ** 2).sum(1)
+                order = np.concatenate([np.flatnonzero(nrm % 2 == 0), np.flatnonzero(nrm % 2 == 1)])
+                return x[order].astype(np.int64), nrm[order]
+            qr, _ = ranked(q)
+            tr, tn = ranked(t)
+            ref8 = qr[:128] @ tr[:128].T + CAP - tn[None, :128] // 2
+            for tag, kw in (("i8_A_in_tmem", dict(lbo=0, ksteps=-5)), ("i8_A_in_smem", dict(lbo=0, ksteps=5))):
+                try:
+                    got = eng.debug_tile(0, 1, **kw)
+                except Exception as e:  # noqa: BLE001
+                    print(name, tag, "FAILED:", e)
+                    continue
+                diff = np.abs(got.astype(np.float64) - ref8)
+                print("%s %-11s max|diff|=%g  exact=%d/16384  got[0,:4]=%s ref[0,:4]=%s" % (
+                    name, tag, diff.max(), int((diff == 0).sum()), got[0, :4].tolist(), ref8[0, :4].tolist()))
+                out["%s_%s" % (name, tag)] = got
+            out["l2_i8_exp"] = ref8
         eng.close()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     np.savez_compressed(os.path.join(ROOT, "gpurun_out", "debug_tile.npz"), **out)
