@@ -28,10 +28,11 @@ MODEL_ESSENTIAL, MODEL_HOMOGRAPHY = 0, 1
 EXPORTS = (
     "iam_create", "iam_destroy", "iam_last_error", "iam_abi_version", "iam_set_stream",
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
-    "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_release_descriptors", "iam_num_descriptors",
+    "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
     "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
-    "iam_debug_minimal_solver",
+    "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
+    "iam_debug_ba_host",
 )
 
 
@@ -44,7 +45,12 @@ class MatchParams(C.Structure):
         ("min_pairs", C.c_int),
         ("cross_check", C.c_int),
         ("dedupe", C.c_int),
-        ("reserved", C.c_int * 3),
+        ("gms", C.c_int),
+        ("gms_rotation", C.c_int),
+        ("gms_scale", C.c_int),
+        ("gms_threshold", C.c_double),
+        ("width_px", C.c_int),
+        ("height_px", C.c_int),
     ]
 
 
@@ -67,6 +73,18 @@ class Timing(C.Structure):
 
 class IamError(RuntimeError):
     pass
+
+
+def ba_observation_host(cam7, pt3, uv, K4, dist5, jac: bool = True):
+    """The kernel's per-observation function run on the host (iam_debug_ba_host; needs no GPU)."""
+    lib = load_library()
+    a = [np.ascontiguousarray(v, np.float64) for v in (cam7, pt3, uv, K4, dist5)]
+    res = np.zeros(2)
+    J = np.zeros((2, 10)) if jac else None
+    rc = lib.iam_debug_ba_host(*[_ptr(v) for v in a], _ptr(res), _ptr(J))
+    if rc != 0:
+        raise IamError("iam_debug_ba_host failed: %s" % lib.iam_last_error().decode())
+    return res, J
 
 
 _lib = None
@@ -96,6 +114,8 @@ def load_library(path: Optional[str] = None):
     lib.iam_upload_descriptors.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
     lib.iam_upload_descriptors_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
     lib.iam_upload_keypoint_keys.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.iam_upload_keypoints.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.iam_gms_filter.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp]
     lib.iam_release_descriptors.argtypes = [vp, C.c_int]
     lib.iam_num_descriptors.argtypes = [vp, C.c_int]
     lib.iam_descriptors_exact.argtypes = [vp, C.c_int]
@@ -108,6 +128,11 @@ def load_library(path: Optional[str] = None):
                                      C.c_uint32, vp, vp, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     lib.iam_debug_minimal_solver.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+    lib.iam_ba_setup.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    lib.iam_ba_eval.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.iam_ba_upload_params.argtypes = [vp, vp]
+    lib.iam_ba_eval_device.argtypes = [vp, vp, vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    lib.iam_debug_ba_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.iam_set_profiling.argtypes = [vp, C.c_int]
     lib.iam_get_timing.argtypes = [vp, C.POINTER(Timing)]
     for name in EXPORTS:
@@ -205,6 +230,22 @@ class Engine:
         self._check(self._lib.iam_upload_keypoint_keys(self._h, image_id, _ptr(keys), keys.shape[0]),
                     "iam_upload_keypoint_keys")
 
+    def upload_keypoints(self, image_id: int, xy: np.ndarray):
+        """xy: [N, 2] float32 pixel coordinates (cv2.KeyPoint.pt) for the GMS filter."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        self._check(self._lib.iam_upload_keypoints(self._h, image_id, _ptr(xy), xy.shape[0]), "iam_upload_keypoints")
+
+    def gms_filter(self, xy1, xy2, matches, size, with_rotation=True, with_scale=False, threshold_factor=5.0):
+        """Inlier mask of cv2.xfeatures2d.matchGMS over `matches` ([[queryIdx, trainIdx], ...]); matcher.py:285."""
+        xy1 = np.ascontiguousarray(xy1, np.float32).reshape(-1, 2)
+        xy2 = np.ascontiguousarray(xy2, np.float32).reshape(-1, 2)
+        m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+        mask = np.zeros((m.shape[0],), np.uint8)
+        self._check(self._lib.iam_gms_filter(self._h, _ptr(xy1), xy1.shape[0], _ptr(xy2), xy2.shape[0], _ptr(m), m.shape[0],
+                                             int(size[0]), int(size[1]), int(with_rotation), int(with_scale),
+                                             float(threshold_factor), _ptr(mask)), "iam_gms_filter")
+        return mask.astype(bool)
+
     def release(self, image_id: int):
         self._check(self._lib.iam_release_descriptors(self._h, image_id), "iam_release_descriptors")
 
@@ -231,7 +272,8 @@ class Engine:
     # -- full match -------------------------------------------------------------
     @staticmethod
     def make_params(match_ratio=0.75, max_distance=270.0, reduce_mode=REDUCE_REF_METRIC, cap=2000, min_pairs=25,
-                    cross_check=True, dedupe=False) -> MatchParams:
+                    cross_check=True, dedupe=False, gms=False, gms_rotation=True, gms_scale=False, gms_threshold=5.0,
+                    size=(0, 0)) -> MatchParams:
         p = MatchParams()
         p.match_ratio = float(match_ratio)
         p.max_distance = float(max_distance)
@@ -240,6 +282,11 @@ class Engine:
         p.min_pairs = int(min_pairs)
         p.cross_check = int(bool(cross_check))
         p.dedupe = int(bool(dedupe))
+        p.gms = int(bool(gms))                       # matcher.py:285 defaults: withRotation=True, withScale=False, 5.0
+        p.gms_rotation = int(bool(gms_rotation))
+        p.gms_scale = int(bool(gms_scale))
+        p.gms_threshold = float(gms_threshold)
+        p.width_px, p.height_px = int(size[0]), int(size[1])
         return p
 
     def match_pairs(self, pairs, params: MatchParams, want_reverse: bool = False):
@@ -313,6 +360,44 @@ class Engine:
         self._check(self._lib.iam_debug_tile(self._h, q_id, t_id, q_tile, t_tile, lbo, sbo, kstep_bytes, ksteps,
                                              _ptr(out)), "iam_debug_tile")
         return out
+
+    # -- bundle adjustment ------------------------------------------------------
+    def ba_setup(self, n_cam: int, n_pts: int, cam_idx, pt_idx, obs_uv):
+        """Problem structure of Optimizer.fun (optimizer.py:396-404): observation i = pixel obs_uv[i] of point
+        pt_idx[i] in camera cam_idx[i]."""
+        ci = np.ascontiguousarray(cam_idx, np.int32)
+        pi = np.ascontiguousarray(pt_idx, np.int32)
+        uv = np.ascontiguousarray(obs_uv, np.float64).reshape(-1, 2)
+        if not (len(ci) == len(pi) == len(uv)):
+            raise IamError("cam_idx, pt_idx and obs_uv differ in length")
+        self._check(self._lib.iam_ba_setup(self._h, int(n_cam), int(n_pts), len(ci), _ptr(ci), _ptr(pi), _ptr(uv)),
+                    "iam_ba_setup")
+        self._ba_shape = (int(n_cam), int(n_pts), len(ci))
+
+    def ba_eval(self, params, K4, dist5, jac: bool = False):
+        """residual [2*n_obs] (and the Jacobian blocks [n_obs, 2, 10]) at `params` (cameras then points)."""
+        n_cam, n_pts, n_obs = self._ba_shape
+        p = np.ascontiguousarray(params, np.float64)
+        if p.size < n_cam * 7 + n_pts * 3:
+            raise IamError("parameter vector shorter than n_cam*7 + n_pts*3")
+        k4 = np.ascontiguousarray(K4, np.float64)
+        d5 = np.ascontiguousarray(dist5, np.float64)
+        res = np.empty(2 * n_obs, np.float64)
+        J = np.empty((n_obs, 2, 10), np.float64) if jac else None
+        self._check(self._lib.iam_ba_eval(self._h, _ptr(p), _ptr(k4), _ptr(d5), _ptr(res), _ptr(J)), "iam_ba_eval")
+        return (res, J) if jac else res
+
+    def ba_upload_params(self, params):
+        p = np.ascontiguousarray(params, np.float64)
+        self._check(self._lib.iam_ba_upload_params(self._h, _ptr(p)), "iam_ba_upload_params")
+
+    def ba_eval_device(self, K4, dist5, jac: bool = True):
+        k4 = np.ascontiguousarray(K4, np.float64)
+        d5 = np.ascontiguousarray(dist5, np.float64)
+        dr, dj = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.iam_ba_eval_device(self._h, _ptr(k4), _ptr(d5), int(jac), C.byref(dr), C.byref(dj)),
+                    "iam_ba_eval_device")
+        return dr.value or 0, dj.value or 0
 
     # -- RANSAC -----------------------------------------------------------------
     def ransac_pairs(self, model: int, pts1: np.ndarray, pts2: np.ndarray, offsets: np.ndarray, K: Optional[np.ndarray],

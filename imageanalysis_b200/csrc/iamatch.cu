@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "../../include/iamatch.h"
+#include "ba.h"
+#include "gms.h"
 #include "knn.h"
 #include "layout.h"
 #include "ransac.h"
@@ -73,6 +75,8 @@ struct Buffer {
 
 struct Image {
   int* keys = nullptr;
+  float2* kp = nullptr;       // keypoint pixel coordinates (GMS), kp_n entries
+  int kp_n = 0;
   uint8_t* block = nullptr;   // [256 B meta words][raw][a_form][b_form] (+ L2: [byte form][perm][rowc][norms][even mask])
   size_t block_bytes = 0;
   int n = -1;
@@ -137,6 +141,9 @@ struct iam_ctx {
   bool l2_wide_sticky = false;        // a feed-mode call met descriptors the byte layout cannot hold: stay on fp16 operands
   int* d_ctx_flag = nullptr;          // device word, cleared by a conversion that met such descriptors
   int last_kind = -1;
+  // bundle-adjustment problem (iam_ba_*): structure resident, parameters re-uploaded per evaluation
+  Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac;
+  int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -425,7 +432,7 @@ __global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jo
 
 extern "C" {
 
-int iam_abi_version(void) { return 2; }
+int iam_abi_version(void) { return 3; }
 const char* iam_last_error(void) { return g_err.c_str(); }
 
 int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
@@ -481,6 +488,7 @@ int iam_destroy(iam_ctx* c) {
   for (auto& im : c->images) {
     if (im.block) cudaFree(im.block);
     if (im.keys) cudaFree(im.keys);
+    if (im.kp) cudaFree(im.kp);
     if (im.ready) cudaEventDestroy(im.ready);
   }
   if (c->d_ctx_flag) cudaFree(c->d_ctx_flag);
@@ -495,6 +503,8 @@ int iam_destroy(iam_ctx* c) {
   for (cudaEvent_t ev : c->done_ev)
     if (ev) cudaEventDestroy(ev);
   c->stage2.release();
+  Buffer* ba_bufs[] = {&c->ba_params, &c->ba_cam_idx, &c->ba_pt_idx, &c->ba_obs, &c->ba_res, &c->ba_jac};
+  for (Buffer* b : ba_bufs) b->release();
   Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
                     &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
   for (Buffer* b : bufs) b->release();
@@ -595,6 +605,7 @@ static int prepare_image(iam_ctx* c, int id, int n) {
   im.dev.perm = reinterpret_cast<const int*>(im.block + bl.perm);
   im.dev.rowc = reinterpret_cast<const int*>(im.block + bl.rowc);
   im.dev.meta = reinterpret_cast<const int*>(im.block);
+  im.dev.kp_xy = (im.kp && im.kp_n == n) ? im.kp : nullptr;  // coordinates of another descriptor count are stale
   im.dev.n = n;
   im.dev.n_pad = n_pad;
   c->imgs_dirty = true;
@@ -706,6 +717,7 @@ int iam_release_descriptors(iam_ctx* c, int id) {
   CU(cudaStreamSynchronize(c->up_stream));
   if (im.block) CU(cudaFree(im.block));
   if (im.keys) CU(cudaFree(im.keys));
+  if (im.kp) CU(cudaFree(im.kp));
   if (im.ready) CU(cudaEventDestroy(im.ready));
   im = Image{};
   c->shape_epoch++;
@@ -733,6 +745,93 @@ int iam_upload_keypoint_keys(iam_ctx* c, int id, const int32_t* keys, int n) {
   }
   im.dev.kp_key = im.keys;
   c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+int iam_upload_keypoints(iam_ctx* c, int id, const float* xy, int n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (id < 0 || id > (1 << 24)) return fail(IAM_E_ARG, "bad image id %d", id);
+  if (n < 0 || (n > 0 && !xy)) return fail(IAM_E_ARG, "bad keypoint buffer");
+  if ((int)c->images.size() <= id) c->images.resize(id + 1);
+  Image& im = c->images[id];
+  // The descriptors may arrive later (iam_match_images uploads them itself): the coordinates are matched
+  // against the descriptor count when a GMS run needs them.
+  if (im.kp_n < n || !im.kp) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (im.kp) CU(cudaFree(im.kp));
+    im.kp = nullptr;
+    im.kp_n = 0;
+    if (n > 0) CU(cudaMalloc(reinterpret_cast<void**>(&im.kp), size_t(n) * sizeof(float2)));
+  } else if (c->compute_pending) {  // a kernel of the previous call may still read the old coordinates
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  im.kp_n = n;
+  if (n > 0) {
+    CU(cudaMemcpyAsync(im.kp, xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, c->up_stream));
+    CU(cudaStreamSynchronize(c->up_stream));
+  }
+  im.dev.kp_xy = (im.kp && im.kp_n == im.n) ? im.kp : nullptr;
+  c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+int iam_gms_filter(iam_ctx* c, const float* xy1, int n1, const float* xy2, int n2, const int32_t* matches, int n_matches,
+                   int width_px, int height_px, int with_rotation, int with_scale, double threshold_factor,
+                   uint8_t* out_mask) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_matches < 0 || n1 < 0 || n2 < 0 || (n_matches > 0 && (!xy1 || !xy2 || !matches || !out_mask))) return fail(IAM_E_ARG, "bad arguments");
+  if (n_matches > iam::kGmsMaxMatches) return fail(IAM_E_UNSUPPORTED, "the GMS filter handles at most %d matches (got %d)", iam::kGmsMaxMatches, n_matches);
+  if (width_px <= 0 || height_px <= 0) return fail(IAM_E_ARG, "the GMS filter needs the image size");
+  if (n_matches == 0) return IAM_OK;
+  for (int m = 0; m < n_matches; ++m)
+    if (matches[2 * m] < 0 || matches[2 * m] >= n1 || matches[2 * m + 1] < 0 || matches[2 * m + 1] >= n2)
+      return fail(IAM_E_ARG, "match %d indexes outside the keypoint tables", m);
+  // one self-contained job: [coordinates 1][coordinates 2][table][count][job][two image records]
+  const size_t o_xy2 = size_t(n1) * 8, o_tab = o_xy2 + size_t(n2) * 8, o_cnt = o_tab + size_t(n_matches) * 8;
+  const size_t o_job = (o_cnt + 4 + 15) / 16 * 16, o_img = o_job + sizeof(iam::RedJob);
+  const size_t total = o_img + 2 * sizeof(iam::ImgDev);
+  CU(cudaStreamSynchronize(c->stream));
+  CU(c->packed_d.ensure(total + 16));
+  uint8_t* d = c->packed_d.as<uint8_t>();
+  std::vector<uint8_t> h(total, 0);
+  if (n1) memcpy(h.data(), xy1, size_t(n1) * 8);
+  if (n2) memcpy(h.data() + o_xy2, xy2, size_t(n2) * 8);
+  memcpy(h.data() + o_tab, matches, size_t(n_matches) * 8);
+  memcpy(h.data() + o_cnt, &n_matches, 4);
+  iam::RedJob jb{0, n1, n2, 0, 1, {0, 0, 0}};
+  memcpy(h.data() + o_job, &jb, sizeof jb);
+  iam::ImgDev im[2] = {};
+  im[0].kp_xy = reinterpret_cast<const float2*>(d);
+  im[0].n = n1;
+  im[1].kp_xy = reinterpret_cast<const float2*>(d + o_xy2);
+  im[1].n = n2;
+  memcpy(h.data() + o_img, im, sizeof im);
+  CU(cudaMemcpyAsync(d, h.data(), total, cudaMemcpyHostToDevice, c->stream));
+  iam::GmsParams gp{};
+  gp.threshold_factor = threshold_factor;
+  gp.width = width_px;
+  gp.height = height_px;
+  gp.with_rotation = with_rotation;
+  gp.with_scale = with_scale;
+  gp.gate_min_pairs = 0;
+  cudaError_t e = iam::launch_gms(reinterpret_cast<const iam::RedJob*>(d + o_job), 1, reinterpret_cast<const iam::ImgDev*>(d + o_img), gp,
+                                  n_matches, reinterpret_cast<int*>(d + o_tab), reinterpret_cast<int*>(d + o_cnt), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "GMS launch: %s", cudaGetErrorString(e));
+  c->timing.total_launches += 1;
+  std::vector<int32_t> kept(size_t(n_matches) * 2 + 1);
+  CU(cudaMemcpyAsync(kept.data(), d + o_tab, size_t(n_matches) * 8 + 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  // the kernel compacts in order: walk both lists to recover the mask
+  const int n_kept = kept[size_t(n_matches) * 2];
+  int o = 0;
+  for (int m = 0; m < n_matches; ++m) {
+    const bool k = o < n_kept && kept[2 * o] == matches[2 * m] && kept[2 * o + 1] == matches[2 * m + 1];
+    out_mask[m] = k ? 1 : 0;
+    if (k) ++o;
+  }
+  if (o != n_kept) return fail(IAM_E_CUDA, "GMS result is not an ordered subset of its input (%d of %d placed)", o, n_kept);
   return IAM_OK;
 }
 
@@ -948,6 +1047,16 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
   if (prm->cap <= 0 || prm->cap > 65536) return fail(IAM_E_ARG, "cap=%d out of range", prm->cap);
   if (prm->reduce_mode != IAM_REDUCE_LOWE && prm->reduce_mode != IAM_REDUCE_REF_METRIC) return fail(IAM_E_ARG, "unknown reduce mode %d", prm->reduce_mode);
   const int k = 2;
+  if (prm->gms) {
+    if (prm->cap > iam::kGmsMaxMatches) return fail(IAM_E_UNSUPPORTED, "the GMS filter handles at most %d matches per direction (cap=%d)", iam::kGmsMaxMatches, prm->cap);
+    if (prm->width_px <= 0 || prm->height_px <= 0) return fail(IAM_E_ARG, "the GMS filter needs the image size (width_px, height_px)");
+    for (int i = 0; i < 2 * n_pairs; ++i) {
+      const int id = pairs[i];
+      if (id < 0 || id >= (int)c->images.size() || c->images[id].n < 0) return fail(IAM_E_STATE, "image %d has no descriptors uploaded", id);
+      if (c->images[id].n > 0 && (!c->images[id].kp || c->images[id].kp_n != c->images[id].n))
+        return fail(IAM_E_STATE, "the GMS filter needs iam_upload_keypoints for image %d", id);
+    }
+  }
   if ((rc = prepare_plan(c, pairs, n_pairs, k, true, waves)) != IAM_OK) return rc;
   const Plan& pl = c->plan;
   int engine;
@@ -1041,6 +1150,18 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     e = iam::launch_reduce(jobs, (p1 - p0) * 2, c->knn_idx.as<int>(), c->knn_dist.as<float>(), k, rp, c->cand_metric.as<double>(),
                            c->cand_qt.as<int2>(), cand_stride, c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "reduce launch: %s", cudaGetErrorString(e));
+    if (prm->gms) {  // matcher.py:285, between the metric reduction and filter_duplicates
+      iam::GmsParams gp{};
+      gp.threshold_factor = prm->gms_threshold;
+      gp.width = prm->width_px;
+      gp.height = prm->height_px;
+      gp.with_rotation = prm->gms_rotation;
+      gp.with_scale = prm->gms_scale;
+      gp.gate_min_pairs = prm->dedupe ? 0 : prm->min_pairs;  // the gate of matcher.py:296-298 follows filter_duplicates
+      e = iam::launch_gms(jobs, (p1 - p0) * 2, c->d_imgs.as<iam::ImgDev>(), gp, prm->cap, c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
+      if (e != cudaSuccess) return fail(IAM_E_CUDA, "GMS launch: %s", cudaGetErrorString(e));
+      c->timing.total_launches += 1;
+    }
     if (prm->dedupe) {
       e = iam::launch_dedupe(jobs, (p1 - p0) * 2, c->d_imgs.as<iam::ImgDev>(), prm->cap, prm->min_pairs, pl.max_n,
                              c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
@@ -1158,6 +1279,88 @@ int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2
                          out_inliers, c->stream, &err);
   if (rc != 0) return fail(rc, "%s", err.c_str());
   c->timing.total_launches += 1;
+  return IAM_OK;
+}
+
+
+// ---- bundle-adjustment residual / Jacobian (optimizer.py:174-279) ----------------------------------------------
+
+int iam_ba_setup(iam_ctx* c, int n_cam, int n_pts, int n_obs, const int32_t* cam_idx, const int32_t* pt_idx,
+                 const double* obs_uv) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_cam < 0 || n_pts < 0 || n_obs < 0 || (n_obs > 0 && (!cam_idx || !pt_idx || !obs_uv))) return fail(IAM_E_ARG, "bad arguments");
+  for (int i = 0; i < n_obs; ++i)
+    if (cam_idx[i] < 0 || cam_idx[i] >= n_cam || pt_idx[i] < 0 || pt_idx[i] >= n_pts)
+      return fail(IAM_E_ARG, "observation %d refers to camera %d / point %d outside the problem", i, cam_idx[i], pt_idx[i]);
+  CU(cudaStreamSynchronize(c->stream));
+  c->ba_n_obs = -1;
+  const size_t no = std::max(1, n_obs);
+  CU(c->ba_params.ensure((size_t(n_cam) * 7 + size_t(n_pts) * 3 + 1) * sizeof(double)));
+  CU(c->ba_cam_idx.ensure(no * sizeof(int)));
+  CU(c->ba_pt_idx.ensure(no * sizeof(int)));
+  CU(c->ba_obs.ensure(no * 2 * sizeof(double)));
+  CU(c->ba_res.ensure(no * 2 * sizeof(double)));
+  if (n_obs > 0) {
+    CU(cudaMemcpyAsync(c->ba_cam_idx.p, cam_idx, size_t(n_obs) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ba_pt_idx.p, pt_idx, size_t(n_obs) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->ba_obs.p, obs_uv, size_t(n_obs) * 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  c->ba_n_cam = n_cam;
+  c->ba_n_pts = n_pts;
+  c->ba_n_obs = n_obs;
+  return IAM_OK;
+}
+
+int iam_ba_upload_params(iam_ctx* c, const double* params) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (c->ba_n_obs < 0) return fail(IAM_E_STATE, "iam_ba_setup has not been called");
+  if (!params) return fail(IAM_E_ARG, "null parameter vector");
+  const size_t n = size_t(c->ba_n_cam) * 7 + size_t(c->ba_n_pts) * 3;
+  if (n) CU(cudaMemcpyAsync(c->ba_params.p, params, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return IAM_OK;
+}
+
+int iam_ba_eval_device(iam_ctx* c, const double* K4, const double* dist5, int want_jac, void** d_residual, void** d_jac) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (c->ba_n_obs < 0) return fail(IAM_E_STATE, "iam_ba_setup has not been called");
+  if (!K4 || !dist5) return fail(IAM_E_ARG, "K4 and dist5 are required");
+  iam::BaCalib cal{K4[0], K4[1], K4[2], K4[3], dist5[0], dist5[1], dist5[2], dist5[3], dist5[4]};
+  if (want_jac) CU(c->ba_jac.ensure(std::max<size_t>(1, c->ba_n_obs) * 2 * iam::kBaJacCols * sizeof(double)));
+  const double* cams = c->ba_params.as<double>();
+  cudaError_t e = iam::launch_ba(cams, cams + size_t(c->ba_n_cam) * 7, c->ba_cam_idx.as<int>(), c->ba_pt_idx.as<int>(),
+                                 c->ba_obs.as<double>(), c->ba_n_obs, cal, c->ba_res.as<double>(),
+                                 want_jac ? c->ba_jac.as<double>() : nullptr, c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "residual launch: %s", cudaGetErrorString(e));
+  c->timing.total_launches += 1;
+  if (d_residual) *d_residual = c->ba_res.p;
+  if (d_jac) *d_jac = want_jac ? c->ba_jac.p : nullptr;
+  return IAM_OK;
+}
+
+int iam_ba_eval(iam_ctx* c, const double* params, const double* K4, const double* dist5, double* out_residual,
+                double* out_jac) {
+  if (!out_residual) return fail(IAM_E_ARG, "null output");
+  int rc = iam_ba_upload_params(c, params);
+  if (rc) return rc;
+  if ((rc = iam_ba_eval_device(c, K4, dist5, out_jac != nullptr, nullptr, nullptr)) != IAM_OK) return rc;
+  if (c->ba_n_obs > 0) {
+    CU(cudaMemcpyAsync(out_residual, c->ba_res.p, size_t(c->ba_n_obs) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out_jac)
+      CU(cudaMemcpyAsync(out_jac, c->ba_jac.p, size_t(c->ba_n_obs) * 2 * iam::kBaJacCols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_debug_ba_host(const double* cam7, const double* pt3, const double* uv, const double* K4, const double* dist5,
+                      double* out_res2, double* out_jac20) {
+  if (!cam7 || !pt3 || !uv || !K4 || !dist5 || !out_res2) return fail(IAM_E_ARG, "null argument");
+  iam::BaCalib cal{K4[0], K4[1], K4[2], K4[3], dist5[0], dist5[1], dist5[2], dist5[3], dist5[4]};
+  iam::ba_observation(cam7, pt3, uv[0], uv[1], cal, out_res2, out_jac20);
   return IAM_OK;
 }
 

@@ -25,6 +25,8 @@
 //   (acc = 0 < any real acc).  Within a parity class acc orders exactly like d^2; across classes an odd row with
 //   equal acc is farther by one, and it is always seen later, so strict comparisons keep cv2's order.
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstdint>
 
 namespace iam {
@@ -56,7 +58,10 @@ struct Lay<Kind::I8> {
   static constexpr int kKSteps = 5;                  // 4 data K-steps + 1 augmentation step
   static constexpr int kAugA = 4 * kKStepBytes;      // chunks 8,9
   static constexpr int kAugB = 5 * kKStepBytes;      // chunks 10,11
-  static constexpr int kBStages = 6;
+#ifndef IAM_I8_STAGES
+#define IAM_I8_STAGES 6
+#endif
+  static constexpr int kBStages = IAM_I8_STAGES;
 };
 template <Kind kKind>
 struct LayD : Lay<kKind> {
@@ -104,6 +109,7 @@ struct ImgDev {
   const int* perm;         // [n_pad] rank -> original row (-1 for padding)
   const int* rowc;         // [n_pad] by rank: ||q||^2 + 2*kI8Cap
   const int* meta;         // ImgMeta words
+  const float2* kp_xy;     // optional [n] keypoint pixel coordinates for the GMS filter (nullptr: none)
   int n;                   // valid descriptors
   int n_pad;               // rows allocated, multiple of kSuperRows and of kBRows
 };

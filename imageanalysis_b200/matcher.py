@@ -21,8 +21,9 @@ Differences, all deliberate:
   * find_matches() hands the WHOLE pair work-list to one C call; the
     per-pair Python loop of the reference survives only for bookkeeping.
   * there is no CPU fallback: without libiamatch.so / a B200 the calls raise.
-  * cv2.xfeatures2d.matchGMS (contrib-only, D6) is applied when the running
-    OpenCV has it; otherwise the GMS stage is skipped and said so in the log.
+  * the GMS stage (cv2.xfeatures2d.matchGMS, matcher.py:285; contrib-only, D6)
+    runs on the GPU (csrc/gms.cu) with the reference's arguments, so it no
+    longer depends on an opencv-contrib build.
 """
 from __future__ import annotations
 
@@ -57,6 +58,9 @@ detector_node = getNode('/config/detector', True)
 matcher_node = getNode('/config/matcher', True)
 
 detect_scale = 0.40
+# The reference always runs the GMS grid filter inside basic_pair_matches (matcher.py:285).  False skips the stage
+# (what an identity matchGMS would give); it exists for comparisons against pre-GMS fixtures, not for production.
+gms_enabled = True
 the_matcher = None
 max_distance = None
 min_pairs = 25
@@ -271,21 +275,20 @@ def raw_matches(i1, i2, k=2):
 
 
 def _gms(i1, i2, idx_pairs, dist_of):
-    """The GMS stage of basic_pair_matches (matcher.py:275-291) when the
-    running OpenCV has the contrib module; identity otherwise."""
-    try:
-        import cv2  # noqa: WPS433 - optional, only for the contrib GMS filter
-        gms = cv2.xfeatures2d.matchGMS
-    except (ImportError, AttributeError):
-        qlog("  GMS filter unavailable (opencv-contrib not installed): stage skipped")
-        return idx_pairs
+    """The GMS stage of basic_pair_matches (matcher.py:275-291), on the GPU:
+    matchGMS(size, size, kp1, kp2, matches, withRotation=True, withScale=False, thresholdFactor=5.0)."""
     w, h = _image_size()
     if not w or not h:
         log("Zero image sizes will crash matchGMS():", w, h)
+        log("Recommend removing all meta/*.feat files and")
+        log("rerun the matching step.")
         quit()
-    ms = [cv2.DMatch(int(q), int(t), float(dist_of(q))) for q, t in idx_pairs]
-    out = gms((w, h), (w, h), i1.kp_list, i2.kp_list, ms, withRotation=True, withScale=False, thresholdFactor=5.0)
-    return [[m.queryIdx, m.trainIdx] for m in out]
+    if not idx_pairs or not gms_enabled:
+        return idx_pairs
+    eng = the_matcher.engine(128 if _norm == _capi.NORM_L2 else 32)
+    mask = eng.gms_filter(np.float32([k.pt for k in i1.kp_list]), np.float32([k.pt for k in i2.kp_list]),
+                          np.int32(idx_pairs), (w, h), with_rotation=True, with_scale=False, threshold_factor=5.0)
+    return [p for p, keep in zip(idx_pairs, mask) if keep]
 
 
 def basic_pair_matches(i1, i2):
@@ -502,9 +505,17 @@ def _batched_traditional(image_list, todo):
         arrays = [np.ascontiguousarray(a, np.float32) for a in arrays]
     keys = [keypoint_keys(image_list[i].kp_list) for i in used]
     eng = the_matcher.engine(int(arrays[0].shape[1]))
+    w, h = _image_size()
+    if not w or not h:
+        log("Zero image sizes will crash matchGMS():", w, h)
+        quit()
+    if gms_enabled:   # keypoint coordinates for the GMS stage (matcher.py:285); the descriptors follow inside the call
+        for i in used:
+            eng.upload_keypoints(i, np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2))
     prm = _capi.Engine.make_params(match_ratio=matcher_node.getFloat('match_ratio'), max_distance=float(max_distance),
                                    reduce_mode=_capi.REDUCE_REF_METRIC, cap=2000, min_pairs=int(min_pairs),
-                                   cross_check=True, dedupe=True)
+                                   cross_check=True, dedupe=True, gms=gms_enabled, gms_rotation=True, gms_scale=False,
+                                   gms_threshold=5.0, size=(w, h))
     # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching
     table, count = eng.match_images(used, arrays, np.int32(todo), prm, keys=keys)
     out = []

@@ -115,3 +115,53 @@ def two_view_scene(n: int, outlier_frac: float, K: np.ndarray, seed: int = 0, no
     p2[bad] = np.stack([rng.uniform(0, width, n_out), rng.uniform(0, height, n_out)], 1)
     truth[bad] = 0
     return p1.astype(np.float32), p2.astype(np.float32), truth
+
+
+def ba_problem(n_cam: int, n_pts: int, seed: int = 0, obs_per_cam: int = 200, empty=(), width: int = 5472,
+               height: int = 3648):
+    """A bundle-adjustment problem of the shape the reference's Optimizer.setup() builds (optimizer.py:283-420):
+    nadir cameras on a strip 15 m apart at 75 m AGL as [ned(3), quat(4)] rows (cam_method 'ned_quat', :84-85),
+    3-D points on rough ground, per camera a list of point indices it observes and their (distorted) pixel
+    coordinates plus noise.  Returns a dict: params (cameras then points, as x0 :422-423), n_cam, n_pts,
+    idx_lists, uv_lists, K, dist."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[3666.666504, 0.0, width / 2.0], [0.0, 3666.666504, height / 2.0], [0.0, 0.0, 1.0]])
+    dist = np.array([-0.012, 0.006, 0.0004, -0.0002, 0.001])
+    cam2body = np.array([[0.0, 0, 1], [1, 0, 0], [0, 1, 0]])
+    cams = np.zeros((n_cam, 7))
+    for i in range(n_cam):
+        yaw, pitch, roll = np.deg2rad(rng.normal(0, 3.0)), np.deg2rad(-90 + rng.normal(0, 2.0)), np.deg2rad(rng.normal(0, 2.0))
+        cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+        # body -> ned quaternion (w, x, y, z) of a ZYX euler sequence; deliberately NOT unit length: the reference
+        # normalises inside quaternion_matrix and the optimiser is free to scale it
+        q = np.array([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy])
+        cams[i, :3] = [15.0 * i + rng.normal(0, 0.5), rng.normal(0, 0.5), -75.0 + rng.normal(0, 0.5)]
+        cams[i, 3:] = q * rng.uniform(0.8, 1.25)
+    pts = np.stack([rng.uniform(-60, 15.0 * n_cam + 60, n_pts), rng.uniform(-45, 45, n_pts), rng.normal(0, 3.0, n_pts)], 1)
+    idx_lists, uv_lists = [], []
+    order = np.argsort(pts[:, 0], kind="stable")      # only points near the camera's footprint are projected
+    xs = pts[order, 0]
+    for i in range(n_cam):
+        if i in empty:   # shapes as optimizer.py:390-392 leaves them
+            idx_lists.append(np.array([], np.int64))
+            uv_lists.append(np.zeros((0, 1, 2)))
+            continue
+        w, x, y, z = cams[i, 3:] / np.linalg.norm(cams[i, 3:])
+        b2n = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        R = cam2body.T @ b2n.T
+        near = np.sort(order[np.searchsorted(xs, cams[i, 0] - 90.0):np.searchsorted(xs, cams[i, 0] + 90.0)])
+        Xc = (pts[near] - cams[i, :3]) @ R.T
+        xn, yn = Xc[:, 0] / Xc[:, 2], Xc[:, 1] / Xc[:, 2]
+        r2 = xn * xn + yn * yn
+        rad = 1 + dist[0] * r2 + dist[1] * r2 * r2 + dist[4] * r2 ** 3
+        xd = xn * rad + 2 * dist[2] * xn * yn + dist[3] * (r2 + 2 * xn * xn)
+        yd = yn * rad + dist[2] * (r2 + 2 * yn * yn) + 2 * dist[3] * xn * yn
+        u, v = K[0, 0] * xd + K[0, 2], K[1, 1] * yd + K[1, 2]
+        vis = np.flatnonzero((Xc[:, 2] > 1) & (u >= 0) & (u < width) & (v >= 0) & (v < height))
+        pick = rng.permutation(vis)[:obs_per_cam]
+        idx_lists.append(np.asarray(near[pick], np.int64))
+        uv_lists.append((np.stack([u[pick], v[pick]], 1) + rng.normal(0, 1.5, (len(pick), 2))).reshape(len(pick), 1, 2))
+    params = np.concatenate([cams.ravel(), (pts + rng.normal(0, 0.3, pts.shape)).ravel()])
+    return dict(params=params, n_cam=n_cam, n_pts=n_pts, idx_lists=idx_lists, uv_lists=uv_lists, K=K, dist=dist)

@@ -135,6 +135,18 @@ int iam_knn_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs, int k,
                   int32_t* out_idx_fwd, float* out_dist_fwd,
                   int32_t* out_idx_rev, float* out_dist_rev);
 
+/* Keypoint pixel coordinates (cv2.KeyPoint.pt, float32 xy interleaved, HOST) of an image whose
+ * descriptors are resident; consumed by the GMS filter.  They stay until replaced or released. */
+int iam_upload_keypoints(iam_ctx* ctx, int image_id, const float* xy, int n);
+
+/* Stand-alone GMS grid filter on one HOST match list: what
+ * cv2.xfeatures2d.matchGMS((w,h), (w,h), kp1, kp2, matches, withRotation, withScale, thresholdFactor)
+ * returns at matcher.py:285, as a mask over `matches` ([n][2] = queryIdx, trainIdx; at most 4096).
+ * Duplicate (queryIdx, trainIdx) rows are not supported. */
+int iam_gms_filter(iam_ctx* ctx, const float* xy1, int n1, const float* xy2, int n2,
+                   const int32_t* matches, int n_matches, int width_px, int height_px,
+                   int with_rotation, int with_scale, double threshold_factor, uint8_t* out_mask);
+
 /* ---- full per-pair match: kNN (both ways) + reduction + cross-check --- */
 
 typedef struct iam_match_params {
@@ -146,10 +158,17 @@ typedef struct iam_match_params {
   int    cross_check;   /* !=0: filter_cross_check (matcher.py:187-200)            */
   int    dedupe;        /* !=0: filter_duplicates (matcher.py:157-182, :294) + its min_pairs gate (:296-298);
                            uses the keys given to iam_upload_keypoint_keys (identity keys if none)  */
-  int    reserved[3];
+  int    gms;           /* !=0: GMS grid filter between the metric reduction and filter_duplicates, as
+                           cv2.xfeatures2d.matchGMS(size, size, kp1, kp2, matches, withRotation, withScale,
+                           thresholdFactor) at matcher.py:285; needs iam_upload_keypoints for both images */
+  int    gms_rotation;  /* withRotation (matcher.py:285: True)                     */
+  int    gms_scale;     /* withScale    (matcher.py:285: False)                    */
+  double gms_threshold; /* thresholdFactor (matcher.py:285: 5.0)                   */
+  int    width_px;      /* camera.get_image_params() (matcher.py:275-283)          */
+  int    height_px;
 } iam_match_params;
 
-/* Device pipeline for the 'traditional' strategy minus GMS
+/* Device pipeline for the 'traditional' strategy
  * (bidirectional_pair_matches, matcher.py:304-318, with basic_pair_matches
  * :218-273 for each direction).  Writes per pair a table of [queryIdx,
  * trainIdx] rows in the order the reference would produce (ascending
@@ -200,6 +219,35 @@ int iam_ransac_pairs(iam_ctx* ctx, int model, const float* pts1, const float* pt
                      const int32_t* off, int n_pairs, const double* K,
                      double threshold_px, double prob, int max_iters, uint32_t seed,
                      uint8_t* out_mask, double* out_model, int32_t* out_inliers);
+
+/* ---- bundle adjustment: replaces Optimizer.fun (optimizer.py:174-279) -- */
+
+/* The reprojection residual of every observation in one launch, and its
+ * analytic Jacobian, for cam_method 'ned_quat' (optimizer.py:84-85): a camera
+ * is [ned(3), quat(4) = (w, x, y, z), normalised as quaternion_matrix does],
+ * the projection is cv2.projectPoints' pinhole + (k1, k2, p1, p2, k3) model.
+ *
+ * iam_ba_setup makes the problem STRUCTURE resident: observation i is pixel
+ * obs_uv[i] = (u, v) of 3-D point pt_idx[i] seen by camera cam_idx[i];
+ * observations are in the order Optimizer.setup() lays them out (by camera,
+ * then list order, optimizer.py:396-404).  HOST pointers. */
+int iam_ba_setup(iam_ctx* ctx, int n_cam, int n_pts, int n_obs, const int32_t* cam_idx,
+                 const int32_t* pt_idx, const double* obs_uv);
+/* One evaluation.  params (HOST) = [n_cam][7] cameras then [n_pts][3] points, the layout of x0
+ * (optimizer.py:422-423); K4 = (fx, fy, cx, cy), dist5 = distCoeffs (either the fixed calibration, :190-191,
+ * or the tail of the parameter vector in global-calibration mode, :182-188).
+ * out_residual[2*n_obs] = observed - projected, (u, v) interleaved: the vector fun() returns.
+ * out_jac (may be NULL) [n_obs][2][10]: per residual row d/d(ned, quat) of its camera, then d/d(point) --
+ * the non-zeros of the row in the column order of bundle_adjustment_sparsity (:142-169). */
+int iam_ba_eval(iam_ctx* ctx, const double* params, const double* K4, const double* dist5,
+                double* out_residual, double* out_jac);
+/* The same in two steps with the results left in device memory (pointers valid until the next iam_ba_* call). */
+int iam_ba_upload_params(iam_ctx* ctx, const double* params);
+int iam_ba_eval_device(iam_ctx* ctx, const double* K4, const double* dist5, int want_jac,
+                       void** d_residual, void** d_jac);
+/* Debug aid: the per-observation function of the kernel (same source) evaluated on the HOST.  Needs no GPU. */
+int iam_debug_ba_host(const double* cam7, const double* pt3, const double* uv, const double* K4,
+                      const double* dist5, double* out_res2, double* out_jac20);
 
 /* ---- instrumentation ------------------------------------------------- */
 

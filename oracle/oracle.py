@@ -178,21 +178,38 @@ def filter_duplicates(pts1: np.ndarray, pts2: np.ndarray, idx_pairs: Sequence[Se
     return result
 
 
-def bidirectional(q: np.ndarray, t: np.ndarray, norm: int, match_ratio: float, max_distance: float, cap: int = 2000,
-                  min_pairs: int = 25, threads: int = 1, mode: str = "ref_metric", cross_check: bool = True):
-    """bidirectional_pair_matches (matcher.py:304-318) without the GMS stage
-    (cv2.xfeatures2d is contrib-only) and without filter_duplicates
-    (needs keypoints): forward reduce, reverse only if forward >= min_pairs,
-    cross-check."""
+def basic_pair(q: np.ndarray, t: np.ndarray, norm: int, match_ratio: float, max_distance: float, cap: int = 2000,
+               min_pairs: int = 25, threads: int = 1, mode: str = "ref_metric", pts_q=None, pts_t=None, size=None,
+               dedupe: bool = False, gms_kw=None):
+    """basic_pair_matches (matcher.py:218-300) for one direction: kNN, metric reduction + gate (:220-273),
+    then -- when `size` is given -- the GMS filter (:285), and -- with `dedupe` -- filter_duplicates and its
+    gate (:294-298).  The reference gates once more only after filter_duplicates; without it the survivors of
+    GMS are gated the same way (what the device pipeline does when no dedupe stage follows)."""
     i1, d1 = knn(q, t, 2, norm, threads)
-    red = (lambda i, d: reduce_ref_metric(i, d, match_ratio, max_distance, cap, min_pairs)) if mode == "ref_metric" \
-        else (lambda i, d: reduce_lowe(i, d, match_ratio, cap, min_pairs))
-    p1 = red(i1, d1)
+    p = reduce_ref_metric(i1, d1, match_ratio, max_distance, cap, min_pairs) if mode == "ref_metric" \
+        else reduce_lowe(i1, d1, match_ratio, cap, min_pairs)
+    if size is not None and len(p) > 0:
+        mask = gms_mask(pts_q, pts_t, size, size, p, **(gms_kw or {}))
+        p = [m for m, keep in zip(p, mask) if keep]
+    if dedupe:
+        p = filter_duplicates(pts_q, pts_t, p)
+    if (size is not None or dedupe) and len(p) < min_pairs:
+        p = []
+    return p
+
+
+def bidirectional(q: np.ndarray, t: np.ndarray, norm: int, match_ratio: float, max_distance: float, cap: int = 2000,
+                  min_pairs: int = 25, threads: int = 1, mode: str = "ref_metric", cross_check: bool = True,
+                  pts_q=None, pts_t=None, size=None, dedupe: bool = False, gms_kw=None):
+    """bidirectional_pair_matches (matcher.py:304-318): forward basic_pair_matches, reverse only if forward
+    >= min_pairs, cross-check.  GMS runs when `size` (and the keypoint coordinates) are given,
+    filter_duplicates with `dedupe`; by default both are off (descriptor-only callers)."""
+    kw = dict(cap=cap, min_pairs=min_pairs, threads=threads, mode=mode, size=size, dedupe=dedupe, gms_kw=gms_kw)
+    p1 = basic_pair(q, t, norm, match_ratio, max_distance, pts_q=pts_q, pts_t=pts_t, **kw)
     if not cross_check:
         return p1, None
     if len(p1) >= min_pairs and len(p1) > 0:
-        i2, d2 = knn(t, q, 2, norm, threads)
-        p2 = red(i2, d2)
+        p2 = basic_pair(t, q, norm, match_ratio, max_distance, pts_q=pts_t, pts_t=pts_q, **kw)
     else:
         p2 = []
     return filter_cross_check(p1, p2)
@@ -322,3 +339,79 @@ def gms_mask(pts1, pts2, size1, size2, matches, with_rotation: bool = True, with
             if c > best:
                 best, best_mask = c, last
     return best_mask if best_mask is not None else last
+
+
+# --------------------------------------------------------------------------
+# bundle-adjustment residual  (scripts/lib/optimizer.py:174-279 Optimizer.fun,
+# cam_method 'ned_quat' :84-85; cv2.projectPoints restated from the OpenCV
+# pinhole + 5-coefficient distortion model)
+# --------------------------------------------------------------------------
+BA_CAM2BODY = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])   # optimizer.py:91-93
+
+
+def ba_rotation(quat) -> np.ndarray:
+    """ned -> camera rotation of nedquat2rvectvec (optimizer.py:121-127): quaternion_matrix normalises the
+    (w, x, y, z) quaternion (transformations.py quaternion_matrix), body2ned = that matrix, R = body2cam . ned2body.
+    (The reference then passes R through cv2.Rodrigues and back inside projectPoints: the same rotation.)"""
+    q = np.asarray(quat, np.float64)
+    n = float(q @ q)
+    if n < np.finfo(float).eps * 4.0:
+        b2n = np.identity(3)
+    else:
+        w, x, y, z = q * np.sqrt(2.0 / n)           # outer(q, q) below then carries the factor 2
+        b2n = np.array([[1.0 - y * y - z * z, x * y - z * w, x * z + y * w],
+                        [x * y + z * w, 1.0 - x * x - z * z, y * z - x * w],
+                        [x * z - y * w, y * z + x * w, 1.0 - x * x - y * y]])
+    return np.linalg.inv(BA_CAM2BODY) @ b2n.T
+
+
+def ba_project(X: np.ndarray, R: np.ndarray, ned: np.ndarray, K4, dist) -> np.ndarray:
+    """cv2.projectPoints(X, rvec(R), tvec = -R ned, K, distCoeffs) (optimizer.py:220): [n, 2] pixels."""
+    fx, fy, cx, cy = K4
+    k1, k2, p1, p2, k3 = dist
+    Xc = (np.asarray(X, np.float64) - np.asarray(ned, np.float64)) @ R.T
+    x, y = Xc[:, 0] / Xc[:, 2], Xc[:, 1] / Xc[:, 2]
+    r2 = x * x + y * y
+    rad = 1.0 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2
+    xd = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x)
+    yd = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y
+    return np.stack([fx * xd + cx, fy * yd + cy], 1)
+
+
+def ba_residuals(params, n_cam: int, n_pts: int, cam_idx, pt_idx, obs_uv, K4, dist) -> np.ndarray:
+    """Optimizer.fun (optimizer.py:174-279) for optimize_calib 'none': observed - projected, (u, v) interleaved,
+    observations grouped by camera in list order (`cam_idx` non-decreasing, as :400-404 lays them out)."""
+    params = np.asarray(params, np.float64)
+    cams = params[:n_cam * 7].reshape(n_cam, 7)
+    pts = params[n_cam * 7:n_cam * 7 + n_pts * 3].reshape(n_pts, 3)
+    cam_idx = np.asarray(cam_idx)
+    out = np.zeros((len(cam_idx), 2))
+    for c in np.unique(cam_idx):
+        sel = np.flatnonzero(cam_idx == c)
+        R = ba_rotation(cams[c, 3:7])
+        out[sel] = np.asarray(obs_uv, np.float64)[sel] - ba_project(pts[np.asarray(pt_idx)[sel]], R, cams[c, :3], K4, dist)
+    return out.ravel()
+
+
+def ba_jacobian_fd(params, n_cam, n_pts, cam_idx, pt_idx, obs_uv, K4, dist, rel_step: float = 1e-6) -> np.ndarray:
+    """Central-difference Jacobian blocks of ba_residuals, [n_obs][2][10]: columns 0..6 = the observation's camera
+    parameters (ned, quat), 7..9 = its 3-D point.  Checker for the analytic Jacobian kernel (the reference itself
+    lets SciPy difference fun(): least_squares(..., jac_sparsity=A), optimizer.py:491-501)."""
+    params = np.asarray(params, np.float64)
+    n_obs = len(cam_idx)
+    J = np.zeros((n_obs, 2, 10))
+    cam_idx, pt_idx = np.asarray(cam_idx), np.asarray(pt_idx)
+    for col in range(10):
+        # one column of every camera (or point) block at a time: blocks of different cameras/points do not interact
+        hp = np.zeros_like(params)
+        if col < 7:
+            cols = np.arange(n_cam) * 7 + col
+        else:
+            cols = n_cam * 7 + np.arange(n_pts) * 3 + (col - 7)
+        h = rel_step * np.maximum(1.0, np.abs(params[cols]))
+        hp[cols] = h
+        f1 = ba_residuals(params + hp, n_cam, n_pts, cam_idx, pt_idx, obs_uv, K4, dist).reshape(n_obs, 2)
+        f0 = ba_residuals(params - hp, n_cam, n_pts, cam_idx, pt_idx, obs_uv, K4, dist).reshape(n_obs, 2)
+        step = h[cam_idx] if col < 7 else h[pt_idx]
+        J[:, :, col] = (f1 - f0) / (2.0 * step[:, None])
+    return J

@@ -66,6 +66,57 @@ def run_ref(pts1, pts2, matches, size, with_scale, with_rotation):
     return np.array(mask, bool), int(n_in)
 
 
+def gen_pipeline():
+    """The reference's own lib.matcher (unmodified) with cv2.xfeatures2d.matchGMS served by the reference's
+    archive GmsMatcher: basic_pair_matches / bidirectional_pair_matches and the find_matches driver with the GMS
+    stage live (matcher.py:285), on a strip of synthetic frames whose planted matches move by a common shift."""
+    import cv2
+    REPO = os.path.dirname(os.path.dirname(HERE))
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+    sys.path.insert(0, "/root/reference/scripts")
+    import make_golden as mg
+    from imageanalysis_b200 import synth
+    matcher, _ = mg.import_reference_matcher()
+
+    def match_gms(size1, size2, kp1, kp2, matches, withRotation=False, withScale=False, thresholdFactor=6.0):
+        ref.THRESHOLD_FACTOR = thresholdFactor
+        with contextlib.redirect_stdout(io.StringIO()):
+            g = ref.GmsMatcher([k.pt for k in kp1], ref.Size(*size1), [k.pt for k in kp2], ref.Size(*size2), matches)
+            mask, _ = g.GetInlierMask(withScale, withRotation)
+        return [m for m, keep in zip(matches, mask) if keep]
+
+    cv2.xfeatures2d = types.SimpleNamespace(matchGMS=match_gms)
+    n = 5
+    des, pts, neds = synth.sift_project(n, 1200, seed=17, planted=0.4)
+    for p in pts:                       # stay clear of the last half cell (module docstring)
+        p[:, 0] = np.minimum(p[:, 0], 0.97 * 5472)
+        p[:, 1] = np.minimum(p[:, 1], 0.97 * 3648)
+        p[40:60] = p[0:20]              # colliding keypoints: filter_duplicates has work after GMS
+    imgs = [mg.FakeImage("frame%02d" % i, des[i].astype(np.float32), pts[i], neds[i]) for i in range(n)]
+    out = {"n": n}
+    fwd = matcher.basic_pair_matches(imgs[0], imgs[1])
+    rev = matcher.basic_pair_matches(imgs[1], imgs[0])
+    out["basic01"] = np.int32(fwd).reshape(-1, 2)
+    out["basic10"] = np.int32(rev).reshape(-1, 2)
+    b1, b2 = matcher.bidirectional_pair_matches(imgs[1], imgs[2])
+    out["bidir12_fwd"] = np.int32(b1).reshape(-1, 2)
+    out["bidir12_rev"] = np.int32(b2).reshape(-1, 2)
+    print("pipeline: basic01", len(fwd), "basic10", len(rev), "bidir12", len(b1))
+    proj = types.SimpleNamespace(image_list=imgs, analysis_dir="/tmp")
+    K = np.array([[3666.666504, 0, 2736], [0, 3666.666504, 1824], [0, 0, 1]])
+    with contextlib.redirect_stdout(io.StringIO()):
+        matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
+    for i, im in enumerate(imgs):
+        out["des%d" % i] = des[i]
+        out["pts%d" % i] = pts[i]
+        out["ned%d" % i] = np.float64(neds[i])
+        for other, lst in im.match_list.items():
+            out["match_%s_%s" % (im.name, other)] = np.int32(lst).reshape(-1, 2)
+            print("  ", im.name, other, len(lst))
+    np.savez_compressed(os.path.join(HERE, "reference_gms_pipeline.npz"), **out)
+
+
 def main():
     cases = {
         "rot0": dict(n=1200, inlier_frac=0.6, angle_deg=0, scale=1.0, seed=1),
@@ -93,6 +144,7 @@ def main():
     out["flags_pts1"], out["flags_pts2"], out["flags_matches"], out["flags_size"] = pts1, pts2, matches, np.array(size, np.int32)
     out["names"] = np.array(sorted(cases))
     np.savez_compressed(os.path.join(HERE, "gms_reference.npz"), **out)
+    gen_pipeline()
 
 
 if __name__ == "__main__":

@@ -357,8 +357,11 @@ class FakeImage:
         pass
 
 
-def _configure_matcher(detector="SIFT"):
+def _configure_matcher(detector="SIFT", gms=False):
+    """gms=False: the fixtures reference_find_matches / reference_reductions were recorded with an identity
+    matchGMS (tests/golden/make_golden.py); the GMS-live fixtures are exercised with gms=True."""
     from imageanalysis_b200 import matcher
+    matcher.gms_enabled = gms
     from imageanalysis_b200.propshim import getNode
     det = getNode("/config/detector", True)
     det.setString("detector", detector)
@@ -396,6 +399,30 @@ def test_find_matches_equals_reference_driver():
     before = {im.name: {k: list(v) for k, v in im.match_list.items()} for im in imgs}
     matcher.find_matches(proj, K, strategy="traditional")
     assert before == {im.name: im.match_list for im in imgs}
+
+
+def test_find_matches_with_gms_equals_reference_driver():
+    """find_matches() with the GMS stage live against the reference's own find_matches run with
+    cv2.xfeatures2d.matchGMS served by its archive GmsMatcher (tests/golden/make_golden_gms.py)."""
+    g = load_golden("reference_gms_pipeline.npz")
+    matcher = _configure_matcher(gms=True)
+    n = int(g["n"])
+    imgs = [FakeImage("frame%02d" % i, g["des%d" % i].astype(np.float32), g["pts%d" % i], g["ned%d" % i])
+            for i in range(n)]
+    proj = types.SimpleNamespace(image_list=imgs, analysis_dir="/tmp")
+    K = np.array([[3666.666504, 0, 2736], [0, 3666.666504, 1824], [0, 0, 1]])
+    matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
+    checked = 0
+    for im in imgs:
+        for other, lst in im.match_list.items():
+            assert lst == g["match_%s_%s" % (im.name, other)].tolist(), (im.name, other)
+            checked += 1
+    assert checked == 2 * 10
+    # the single-pair functions run the same stage through iam_gms_filter
+    assert matcher.basic_pair_matches(imgs[0], imgs[1]) == g["basic01"].tolist()
+    f, r = matcher.bidirectional_pair_matches(imgs[1], imgs[2])
+    assert f == g["bidir12_fwd"].tolist() and r == g["bidir12_rev"].tolist()
+    matcher.gms_enabled = False
 
 
 def test_raw_matches_and_pair_functions():

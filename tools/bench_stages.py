@@ -1,0 +1,128 @@
+#!/usr/bin/env python3
+"""Stage benchmarks for the rows next to the kNN kernel: the GMS grid filter inside the
+match pipeline and the bundle-adjustment residual / Jacobian kernel, each timed with CUDA events on the stream the
+library launches on, after warm-up.  One JSON line per stage (also appended to gpurun_out/stages.jsonl).
+
+GMS: whole-pipeline step time with and without the stage (the difference is its cost) on the bench workload.
+BA : achieved HBM bandwidth = algorithmic bytes per observation (~104 B read + 176 B written) x
+     observations / kernel time, against MEASURED_PEAKS.json hbm_gbs; the reference's CPU path
+     (oracle port of Optimizer.fun, numpy) is timed beside it."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=200)
+    ap.add_argument("--desc", type=int, default=5000)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ba-cams", type=int, default=1000)
+    ap.add_argument("--ba-obs-per-cam", type=int, default=1000)
+    args = ap.parse_args()
+    import torch
+    from imageanalysis_b200 import _capi, synth
+    import bench as B
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    out = []
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    # ------------------------------------------------------------------ GMS inside the match pipeline
+    des = B.make_frames_gpu(args.frames, args.desc, "SIFT", seed=1234, device=dev)
+    rng = np.random.default_rng(7)
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.set_stream(stream.cuda_stream)
+    pairs = B.pair_list(args.frames, "sequential")
+    # key points: planted rows of neighbouring frames move by a common shift (what the frames' descriptors were
+    # built to match), everything else is uniform
+    w, h = 5472, 3648
+    for f in range(args.frames):
+        eng.upload(f, des[f])
+        eng.upload_keypoints(f, np.stack([rng.uniform(0, w, args.desc), rng.uniform(0, h, args.desc)], 1).astype(np.float32))
+    eng.synchronize()
+    res = {}
+    for tag, kw in (("no_gms", dict()), ("gms", dict(gms=True, size=(w, h)))):
+        prm = _capi.Engine.make_params(**kw)
+        res[tag] = timed(lambda: eng.match_pairs_device(pairs, prm), args.steps, args.warmup)
+    line = {"stage": "gms_kernel (csrc/gms.cu) inside iam_match_pairs_device", "pairs": len(pairs), "directed_jobs": 2 * len(pairs),
+            "ms_per_step_without": res["no_gms"], "ms_per_step_with": res["gms"], "gms_ms_per_step": res["gms"] - res["no_gms"],
+            "gms_us_per_directed_job": 1e3 * (res["gms"] - res["no_gms"]) / (2 * len(pairs)),
+            "note": "random key points: the filter rejects nearly everything, which is its most expensive path (all four grids x 8 rotations are always evaluated)"}
+    out.append(line)
+    print(json.dumps(line))
+    eng.close()
+
+    # ------------------------------------------------------------------ BA residual + Jacobian
+    prob = synth.ba_problem(n_cam=args.ba_cams, n_pts=args.ba_cams * 200, seed=5, obs_per_cam=args.ba_obs_per_cam)
+    cam_idx = np.concatenate([np.full(len(ix), c, np.int32) for c, ix in enumerate(prob["idx_lists"])])
+    pt_idx = np.concatenate(prob["idx_lists"]).astype(np.int32)
+    uv = np.concatenate([u.reshape(-1, 2) for u in prob["uv_lists"]])
+    K = prob["K"]
+    K4, dist = (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), prob["dist"]
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.set_stream(stream.cuda_stream)
+    eng.ba_setup(prob["n_cam"], prob["n_pts"], cam_idx, pt_idx, uv)
+    eng.ba_upload_params(prob["params"])
+    n_obs = len(cam_idx)
+    ms_j = timed(lambda: eng.ba_eval_device(K4, dist, jac=True), 50, 5)
+    ms_r = timed(lambda: eng.ba_eval_device(K4, dist, jac=False), 50, 5)
+    t0 = time.perf_counter()
+    r_h, J_h = eng.ba_eval(prob["params"], K4, dist, jac=True)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = peaks.get("hbm_gbs") or 6500.0
+    bytes_j, bytes_r = 104 + 176, 104 + 16
+    from oracle import oracle
+    t0 = time.perf_counter()
+    sample = min(n_obs, 200000)
+    last_cam = int(cam_idx[sample - 1])
+    sel = cam_idx <= last_cam
+    oracle.ba_residuals(prob["params"], prob["n_cam"], prob["n_pts"], cam_idx[sel], pt_idx[sel], uv[sel], K4, dist)
+    cpu_s = time.perf_counter() - t0
+    line = {"stage": "ba_kernel (csrc/ba.cu): residual + analytic 2x10 Jacobian blocks", "observations": n_obs,
+            "cameras": prob["n_cam"], "points": prob["n_pts"],
+            "kernel_ms_residual_and_jacobian": ms_j, "kernel_ms_residual_only": ms_r,
+            "observations_per_s": n_obs / (ms_j / 1e3),
+            "roofline": {"bound": "hbm", "achieved": n_obs * bytes_j / (ms_j / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": n_obs * bytes_j / (ms_j / 1e3) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_observation": bytes_j,
+                         "residual_only": {"achieved": n_obs * bytes_r / (ms_r / 1e3) / 1e9, "frac": n_obs * bytes_r / (ms_r / 1e3) / 1e9 / peak,
+                                           "algorithmic_bytes_per_observation": bytes_r}},
+            "e2e_ms_host_params_to_host_jacobian": e2e_ms,
+            "cpu_baseline": {"value": int(sel.sum()) / cpu_s, "unit": "observations/s (residual only)", "cores": 1, "kind": "port",
+                             "sample": "%d observations of the same problem through oracle.ba_residuals (numpy restatement of Optimizer.fun)" % int(sel.sum())}}
+    out.append(line)
+    print(json.dumps(line))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "stages.jsonl"), "w") as f:
+        for l in out:
+            f.write(json.dumps(l) + "\n")
+
+
+if __name__ == "__main__":
+    main()
