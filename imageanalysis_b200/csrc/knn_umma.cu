@@ -134,30 +134,27 @@ struct TopK {
   // cv2.BFMatcher reports ties in.
   __device__ __forceinline__ void insert(T x, int col) {
     if constexpr (KTOP == 2) {
-      // Written with predicated moves: two compares on the ALU pipe, the six
-      // moves can issue as IMAD.MOV on the FMA pipe, which the (ALU-pipe-bound) epilogue leaves idle.
+      // Six ALU-pipe instructions, all guarded by "x beats the second best": the new second best is the worse of
+      // (old best, x), the new best the better of them; only the two index moves need the second compare.
+      // (A compare-twice / select-six network costs eight; the epilogue is ALU-pipe bound.)
       if constexpr (std::is_same<T, float>::value) {  // float, smaller is better
         asm("{\n\t.reg .pred p0, p1;\n\t"
-            "setp.lt.f32 p0, %4, %0;\n\t"
-            "setp.lt.and.f32 p1, %4, %1, !p0;\n\t"
-            "@p1 mov.f32 %1, %4;\n\t"
-            "@p1 mov.b32 %3, %5;\n\t"
-            "@p0 mov.f32 %1, %0;\n\t"
-            "@p0 mov.b32 %3, %2;\n\t"
-            "@p0 mov.f32 %0, %4;\n\t"
-            "@p0 mov.b32 %2, %5;\n\t}"
+            "setp.lt.f32 p1, %4, %1;\n\t"
+            "@p1 max.f32 %1, %0, %4;\n\t"
+            "setp.lt.and.f32 p0, %4, %0, p1;\n\t"
+            "@p1 selp.b32 %3, %2, %5, p0;\n\t"
+            "@p0 mov.b32 %2, %5;\n\t"
+            "@p1 min.f32 %0, %0, %4;\n\t}"
             : "+f"(d[0]), "+f"(d[1]), "+r"(i[0]), "+r"(i[1])
             : "f"(x), "r"(col));
       } else {  // int, larger is better
         asm("{\n\t.reg .pred p0, p1;\n\t"
-            "setp.gt.s32 p0, %4, %0;\n\t"
-            "setp.gt.and.s32 p1, %4, %1, !p0;\n\t"
-            "@p1 mov.b32 %1, %4;\n\t"
-            "@p1 mov.b32 %3, %5;\n\t"
-            "@p0 mov.b32 %1, %0;\n\t"
-            "@p0 mov.b32 %3, %2;\n\t"
-            "@p0 mov.b32 %0, %4;\n\t"
-            "@p0 mov.b32 %2, %5;\n\t}"
+            "setp.gt.s32 p1, %4, %1;\n\t"
+            "@p1 min.s32 %1, %0, %4;\n\t"
+            "setp.gt.and.s32 p0, %4, %0, p1;\n\t"
+            "@p1 selp.b32 %3, %2, %5, p0;\n\t"
+            "@p0 mov.b32 %2, %5;\n\t"
+            "@p1 max.s32 %0, %0, %4;\n\t}"
             : "+r"(d[0]), "+r"(d[1]), "+r"(i[0]), "+r"(i[1])
             : "r"(x), "r"(col));
       }
