@@ -44,10 +44,13 @@ namespace {
 #ifndef IAM_ROLES_LAST
 #define IAM_ROLES_LAST 1
 #endif
-#ifndef IAM_SHARE_EVERY
-#define IAM_SHARE_EVERY 1
+//   IAM_DUAL_ISSUE   1: one MMA-issuing warp PER QUERY TILE (the TMEM allocator warp becomes the second issuer) when the
+//                       accumulator slots split evenly between the tiles: each tile's products then advance on their own,
+//                       so a slow epilogue warp of one tile no longer stalls the other tile's twelve warps, and the
+//                       per-product issue latency (barrier waits, descriptor set-up) is paid by two warps in parallel
+#ifndef IAM_DUAL_ISSUE
+#define IAM_DUAL_ISSUE 1
 #endif
-constexpr int kShareEvery = IAM_SHARE_EVERY;                   // tiles between exchanges of running bounds (power of two)
 constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
 constexpr int kWarpsPerATile = 4 * kParts;
 constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
@@ -64,6 +67,7 @@ struct Cfg : LayD<kKind> {
   // 3 with the wide layout (144 columns of query operand), 4 with the byte layout (80 columns).
   static constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;
   static constexpr uint32_t kTmemA = kSlots * kBRows;            // A operand region behind the accumulator slots
+  static constexpr bool kDual = IAM_DUAL_ISSUE && kATiles == 2 && kSlots % kATiles == 0;
   struct __align__(8) Barriers {
     uint64_t a_full[kATiles];
     uint64_t a_empty[kATiles];
@@ -294,6 +298,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   using Barriers = typename C::Barriers;
   constexpr int kBStages = C::kBStages;
   constexpr int kSlots = C::kSlots;
+  constexpr bool kDual = C::kDual && kATmem;
   constexpr int kKSteps = C::kKSteps;
   constexpr uint32_t kTileBytes = C::kTileBytes;
   constexpr uint32_t kBTileBytes = C::kBTileBytes;
@@ -328,7 +333,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     }
     for (int i = 0; i < kBStages; ++i) {
       mbar_init(&bars->b_full[i], 1);
-      mbar_init(&bars->b_empty[i], kCtas);  // every CTA that received the tile must be done with it
+      mbar_init(&bars->b_empty[i], kCtas * (kDual ? kATiles : 1));  // every consumer of every CTA that received the tile
     }
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&bars->t_full[i], 1);
@@ -388,13 +393,16 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         }
       }
     }
-  } else if (role == 1) {
-    // ------------------------------------------------ MMA issuer
+  } else if (role == 1 || (kDual && role == 2)) {
+    // ------------------------------------------------ MMA issuer(s)
     // The whole warp walks the loops with warp-uniform values (made provably uniform by a shuffle, so the
     // descriptor arithmetic lives in the uniform datapath instead of vector registers + R2UR); one elected lane
-    // issues the tcgen05 instructions.  The issue stream of this warp is on the critical path: it shares its
-    // scheduler with six ALU-bound epilogue warps.
+    // issues the tcgen05 instructions.  With kDual each query tile has its own issuer (roles 1 and 2) with its own
+    // half of the accumulator slots; otherwise one warp issues the products of both tiles in turn.
     constexpr uint32_t idesc = make_idesc_kind<kKind>(128, kBRows);
+    constexpr int kMyTiles = kDual ? 1 : kATiles;             // query tiles this warp issues for
+    constexpr int kSlotStep = kDual ? kATiles : 1;            // distance between successive slots of this warp
+    const int a0 = kDual ? role - 1 : 0;
     const uint32_t a_addr = smem_u32(smem_a);
     const uint32_t b_addr = smem_u32(smem_b);
     const uint32_t bars_addr = smem_u32(bars);
@@ -402,7 +410,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const uint32_t tm_a = tm + kTmemA;
     const uint32_t b_lo0 = smem_desc_lo(b_addr, kLBO);
     uint32_t stage = 0, bpar = 0;   // B ring position
-    uint32_t slot = 0, tpar = 1;    // accumulator ring position; parity to wait for on t_empty (fresh barrier: 1)
+    uint32_t slot = a0, tpar = 1;   // accumulator ring position; parity to wait for on t_empty (fresh barrier: 1)
     uint32_t uit = 0;
     for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
       const int u = pu * kCtas + cta_rank;
@@ -411,7 +419,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       // query tiles: shared-memory staging -> tensor memory (tcgen05.cp), then the staging is free again.
       // tcgen05 operations of one thread execute in issue order, so these copies run after every MMA of
       // the previous unit that still reads the old A tiles.
-      for (int a = 0; a < kATiles; ++a) {
+      for (int a = a0; a < a0 + kMyTiles; ++a) {
         mbar_wait(&bars->a_full[a], uit & 1, 32 + a);
         tc_fence_after();
         if (kATmem) {
@@ -429,7 +437,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         mbar_wait_a(bars_addr + offsetof(Barriers, b_full) + stage * 8, bpar, 30);
         const uint32_t b_lo = b_lo0 + stage * (kBTileBytes >> 4);
 #pragma unroll
-        for (int a = 0; a < kATiles; ++a) {
+        for (int am = 0; am < kMyTiles; ++am) {
+          const int a = a0 + am;
           mbar_wait_a(bars_addr + offsetof(Barriers, t_empty) + slot * 8, tpar, 31);
           tc_fence_after();
           if (elect_one()) {
@@ -448,8 +457,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             umma_commit_a(bars_addr + offsetof(Barriers, t_full) + slot * 8);
           }
           __syncwarp();
-          if (++slot == kSlots) {
-            slot = 0;
+          slot += kSlotStep;
+          if (slot >= static_cast<uint32_t>(kSlots)) {
+            slot -= kSlots;
             tpar ^= 1;
           }
         }
