@@ -48,29 +48,41 @@ namespace {
 //                       accumulator slots split evenly between the tiles: each tile's products then advance on their own,
 //                       so a slow epilogue warp of one tile no longer stalls the other tile's twelve warps, and the
 //                       per-product issue latency (barrier waits, descriptor set-up) is paid by two warps in parallel
+#ifndef IAM_GROUP_UNCOND
+#define IAM_GROUP_UNCOND 0
+#endif
 #ifndef IAM_DUAL_ISSUE
 #define IAM_DUAL_ISSUE 1
 #endif
 constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
 constexpr int kWarpsPerATile = 4 * kParts;
-constexpr int kEpiWarps = kATiles * kWarpsPerATile;  // 24 = 6 per SM sub-partition
-constexpr int kThreads = 128 + 32 * kEpiWarps;   // 896
-constexpr uint32_t kTmemCols = 512;
 
-// Per-kind kernel configuration: operand layout (layout.h) + tensor-memory / shared-memory budget.
-template <Kind kKind>
+// Per-kind, per-shape kernel configuration: operand layout (layout.h) + tensor-memory / shared-memory budget.
+// kT = query tiles (128 rows each) resident per CTA:
+//   2: one CTA per SM owns a whole 256-row work unit (896 threads, all 512 tensor-memory columns);
+//   1: a CTA owns HALF a unit (512 threads, 256 columns) and two CTAs share an SM.  The insertion work of a unit is
+//      front-loaded (every row starts with empty lists: the first eight of ~53 train tiles carry 60 % of all
+//      insertions), so one CTA alternates between an ALU-bound phase with an idle tensor pipe and an MMA-bound phase
+//      with idle ALUs; two co-resident CTAs drift out of phase and fill each other's gaps.
+template <Kind kKind, int kT>
 struct Cfg : LayD<kKind> {
   using L = LayD<kKind>;
-  static constexpr int kBStages = L::kBStages;
+  static constexpr int kEpiWarps = kT * kWarpsPerATile;          // 24 (6 per SM sub-partition) / 12
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;          // 896 / 512
+  static constexpr int kCtasPerSm = kT == 1 ? 2 : 1;
+  static constexpr int kRows = kT * kTileRows;                   // query rows per CTA pass
+  static constexpr int kItems = kATiles / kT;                    // CTA passes ("items") per 256-row work unit
+  static constexpr uint32_t kTmemCols = kT == 1 ? 256 : 512;
+  static constexpr int kBStages = kT == 1 ? 4 : L::kBStages;
   static constexpr uint32_t kTmemAColsPerTile = L::kKSteps * 8;  // 128 rows x 32 bytes per K-step = 8 columns
   // Accumulator slots of kBRows columns each, handed round-robin to successive (B tile, A tile) products:
-  // 3 with the wide layout (144 columns of query operand), 4 with the byte layout (80 columns).
-  static constexpr int kSlots = (512 - kATiles * static_cast<int>(kTmemAColsPerTile)) / kBRows;
+  // kT = 2: 3 with the wide layout (144 columns of query operand), 4 with the byte layout (80 columns).
+  static constexpr int kSlots = (static_cast<int>(kTmemCols) - kT * static_cast<int>(kTmemAColsPerTile)) / kBRows;
   static constexpr uint32_t kTmemA = kSlots * kBRows;            // A operand region behind the accumulator slots
-  static constexpr bool kDual = IAM_DUAL_ISSUE && kATiles == 2 && kSlots % kATiles == 0;
+  static constexpr bool kDual = IAM_DUAL_ISSUE && kT == 2 && kSlots % kT == 0;
   struct __align__(8) Barriers {
-    uint64_t a_full[kATiles];
-    uint64_t a_empty[kATiles];
+    uint64_t a_full[kT];
+    uint64_t a_empty[kT];
     uint64_t b_full[kBStages];
     uint64_t b_empty[kBStages];
     uint64_t t_full[kSlots];
@@ -78,15 +90,16 @@ struct Cfg : LayD<kKind> {
     uint32_t tmem_base;
     uint32_t pad;
   };
-  static constexpr size_t kSmemA = kATiles * L::kTileBytes;       // staging for the next unit's query tiles
+  static constexpr size_t kSmemA = kT * L::kTileBytes;            // staging for the next item's query tiles
   static constexpr size_t kSmemB = kBStages * L::kBTileBytes;     // streamed train tiles
   static constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
-  static constexpr size_t kSmemShare = 2 * kParts * kSuperRows * 4;   // running k-th bests exchanged between the column parts of a row
-  static constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kSuperRows * 3 * 8;  // end-of-unit hand-over of the other parts' lists
+  static constexpr size_t kSmemShare = 2 * kParts * kRows * 4;    // running k-th bests exchanged between the column parts of a row
+  static constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kRows * 3 * 8;  // end-of-item hand-over of the other parts' lists
   static constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
-  static_assert(kSmemTotal <= 232448, "shared memory budget");
-  static_assert(kTmemA + kATiles * kTmemAColsPerTile <= 512, "tensor memory budget");
-  static_assert(kATiles <= kSlots, "one wrap per step at most");
+  static_assert(kCtasPerSm * (kSmemTotal + 1024) <= 233472, "shared memory budget");
+  static_assert(kTmemA + kT * kTmemAColsPerTile <= kTmemCols, "tensor memory budget");
+  static_assert(kT <= kSlots, "one wrap per step at most");
+  static_assert(kATiles % kT == 0, "whole CTA passes per work unit");
 };
 
 constexpr float kInf = 3.0e38f;
@@ -248,6 +261,15 @@ __device__ __forceinline__ void consume_group(const typename O::T* w, int tp, To
     if (f3) tk.insert(w[3], enc_index<J0 + 3>(tp));
     return;
   }
+#if IAM_GROUP_UNCOND
+  // A/B aid: no per-column tests; the (self-guarded) insertion network runs for all four columns of a triggered group
+  (void)te;
+  tk.insert(w[0], enc_index<J0>(tp));
+  tk.insert(w[1], enc_index<J0 + 1>(tp));
+  tk.insert(w[2], enc_index<J0 + 2>(tp));
+  tk.insert(w[3], enc_index<J0 + 3>(tp));
+  return;
+#endif
   // four votes issued back to back (computed against the bound at group entry: a superset of what
   // the tightening bound would admit), then the branch-free network only where some lane qualifies
   const bool e0 = any_lane(O::better(w[0], te));
@@ -288,11 +310,16 @@ __device__ __forceinline__ const uint8_t* a_src(const ImgDev& im) { return kKind
 template <Kind kKind>
 __device__ __forceinline__ const uint8_t* b_src(const ImgDev& im) { return kKind == Kind::I8 ? im.i8_form : im.b_form; }
 
-template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg>
-__global__ void __launch_bounds__(kThreads, 1)
+template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg, int kT>
+__global__ void __launch_bounds__((Cfg<kKind, kT>::kThreads), (Cfg<kKind, kT>::kCtasPerSm))
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2) {
-  using C = Cfg<kKind>;
+  using C = Cfg<kKind, kT>;
+  constexpr int kEpiWarps = C::kEpiWarps;
+  constexpr int kRows = C::kRows;
+  constexpr int kItems = C::kItems;
+  constexpr uint32_t kTmemCols = C::kTmemCols;
+  const int n_items = n_units * kItems;   // a work item = kRows query rows of one unit against its whole train image
   using O = Ord<kKind>;
   using T = typename O::T;
   using Barriers = typename C::Barriers;
@@ -325,15 +352,15 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   const int first_pu = blockIdx.x / kCtas;
   const int pu_stride = gridDim.x / kCtas;
 
-  for (int i = threadIdx.x; i < 2 * kParts * kSuperRows; i += blockDim.x) share[i] = O::bits(O::worst());
+  for (int i = threadIdx.x; i < 2 * kParts * kRows; i += blockDim.x) share[i] = O::bits(O::worst());
   if (role == 1 && elect_one()) {
-    for (int i = 0; i < kATiles; ++i) {
+    for (int i = 0; i < kT; ++i) {
       mbar_init(&bars->a_full[i], 1);
       mbar_init(&bars->a_empty[i], 1);
     }
     for (int i = 0; i < kBStages; ++i) {
       mbar_init(&bars->b_full[i], 1);
-      mbar_init(&bars->b_empty[i], kCtas * (kDual ? kATiles : 1));  // every consumer of every CTA that received the tile
+      mbar_init(&bars->b_empty[i], kCtas * (kDual ? kT : 1));  // every consumer of every CTA that received the tile
     }
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&bars->t_full[i], 1);
@@ -353,8 +380,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // ------------------------------------------------ B-tile producer
     if (elect_one()) {
       uint32_t it = 0;  // running B-tile counter across units
-      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride) {
-        const int u = pu * kCtas + cta_rank;
+      for (int pu = first_pu; pu * kCtas < n_items; pu += pu_stride) {
+        const int u = (pu * kCtas + cta_rank) / kItems;
         const KnnUnit unit = units[u];
         const ImgDev t = imgs[unit.t_slot];
         const uint8_t* tsrc = b_src<kKind>(t);
@@ -380,13 +407,13 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // ------------------------------------------------ A-tile producer
     if (elect_one()) {
       uint32_t it = 0;  // unit counter of this CTA
-      for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++it) {
-        const int u = pu * kCtas + cta_rank;
-        const KnnUnit unit = units[u];
+      for (int pu = first_pu; pu * kCtas < n_items; pu += pu_stride, ++it) {
+        const int w = pu * kCtas + cta_rank;
+        const KnnUnit unit = units[w / kItems];
         const ImgDev q = imgs[unit.q_slot];
-        const uint8_t* src = a_src<kKind>(q) + static_cast<size_t>(unit.super) * kSuperRows * kRowBytes;
+        const uint8_t* src = a_src<kKind>(q) + (static_cast<size_t>(unit.super) * kSuperRows + (w % kItems) * kRows) * kRowBytes;
         const uint32_t par = it & 1;
-        for (int a = 0; a < kATiles; ++a) {
+        for (int a = 0; a < kT; ++a) {
           mbar_wait(&bars->a_empty[a], par ^ 1, 20 + a);
           mbar_arrive_expect_tx(&bars->a_full[a], kTileBytes);
           bulk_g2s(smem_a + a * kTileBytes, src + static_cast<size_t>(a) * kTileBytes, kTileBytes, &bars->a_full[a]);
@@ -400,8 +427,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // issues the tcgen05 instructions.  With kDual each query tile has its own issuer (roles 1 and 2) with its own
     // half of the accumulator slots; otherwise one warp issues the products of both tiles in turn.
     constexpr uint32_t idesc = make_idesc_kind<kKind>(128, kBRows);
-    constexpr int kMyTiles = kDual ? 1 : kATiles;             // query tiles this warp issues for
-    constexpr int kSlotStep = kDual ? kATiles : 1;            // distance between successive slots of this warp
+    constexpr int kMyTiles = kDual ? 1 : kT;                  // query tiles this warp issues for
+    constexpr int kSlotStep = kDual ? kT : 1;                 // distance between successive slots of this warp
     const int a0 = kDual ? role - 1 : 0;
     const uint32_t a_addr = smem_u32(smem_a);
     const uint32_t b_addr = smem_u32(smem_b);
@@ -412,8 +439,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     uint32_t stage = 0, bpar = 0;   // B ring position
     uint32_t slot = a0, tpar = 1;   // accumulator ring position; parity to wait for on t_empty (fresh barrier: 1)
     uint32_t uit = 0;
-    for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
-      const int u = pu * kCtas + cta_rank;
+    for (int pu = first_pu; pu * kCtas < n_items; pu += pu_stride, ++uit) {
+      const int u = (pu * kCtas + cta_rank) / kItems;
       const int n_t = __shfl_sync(0xffffffffu, imgs[units[u].t_slot].n, 0);
       const int n_tb = (n_t + kBRows - 1) / kBRows;
       // query tiles: shared-memory staging -> tensor memory (tcgen05.cp), then the staging is free again.
@@ -481,12 +508,12 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // The per-tile loop is ALU-pipe bound (profiles/): everything loop-invariant lives in pinned registers as
     // ready-made shared-memory / tensor-memory addresses, and the slot / phase of the accumulator ring advance
     // incrementally instead of by division.
-    const int e = (role - 4) >> 2;      // 0 .. kATiles*kParts-1
+    const int e = (role - 4) >> 2;      // 0 .. kT*kParts-1
     const int a = e / kParts;           // which A tile
     const int part = e % kParts;        // which 32 of the B tile's columns
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int urow = a * kTileRows + quad * 32 + lane;  // row within the unit
-    constexpr uint32_t kPartStride = kSuperRows * 4;            // bytes between the parts' bound slots of one row
+    constexpr uint32_t kPartStride = kRows * 4;                 // bytes between the parts' bound slots of one row
     constexpr uint32_t kParityStride = kParts * kPartStride;    // bytes between the two unit-parity buffers
     const uint32_t share_row = smem_u32(share) + urow * 4;
     const uint32_t bar_full0 = pin_reg(smem_u32(&bars->t_full[0]));
@@ -494,11 +521,12 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
     const bool lane0 = lane == 0;
     TopK<KTOP, O> tk;
-    uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kATiles + a, slot = sq % kSlots
+    uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kT + a, slot = sq % kSlots
+    const int group_bar = 1 + a * 4 + quad;   // named barrier of the kParts warps that share these 32 rows
     int uit = 0;
-    for (int pu = first_pu; pu * kCtas < n_units; pu += pu_stride, ++uit) {
-      const int u = pu * kCtas + cta_rank;
-      const KnnUnit unit = units[u];
+    for (int pu = first_pu; pu * kCtas < n_items; pu += pu_stride, ++uit) {
+      const int w = pu * kCtas + cta_rank;
+      const KnnUnit unit = units[w / kItems];
       const ImgDev q = imgs[unit.q_slot];
       const ImgDev t = imgs[unit.t_slot];
       const int n_tb = (t.n + kBRows - 1) / kBRows;
@@ -554,7 +582,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           if (lane0) mbar_arrive_a(bar + kEmptyOff);
         }
         if (kParts > 1) sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
-        slot += kATiles;
+        slot += kT;
         if (slot >= kSlots) {
           slot -= kSlots;
           par ^= 1;
@@ -562,7 +590,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       }
       // end of unit: every list becomes (squared distance, train row); parts 1.. hand theirs to part 0's thread
       // of the same row, which merges (distance, index)-lexicographically
-      const int row = unit.super * kSuperRows + urow;  // wide layouts: the query row; byte layout: its rank
+      const int row = unit.super * kSuperRows + (w % kItems) * kRows + urow;  // wide layouts: the query row; byte layout: its rank
       Final<KTOP> fin;
       {
         int rowc = 0, n_even = 0;
@@ -591,15 +619,16 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       if (part > 0) {
 #pragma unroll
         for (int s = 0; s < KTOP; ++s)
-          merge[((part - 1) * kSuperRows + urow) * KTOP + s] = make_float2(fin.d[s], __int_as_float(fin.i[s]));
+          merge[((part - 1) * kRows + urow) * KTOP + s] = make_float2(fin.d[s], __int_as_float(fin.i[s]));
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      // only the kParts warps that own these 32 rows meet here: the other row groups run on
+      asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");
       if (part == 0) {
 #pragma unroll
         for (int pp = 0; pp < kParts - 1; ++pp) {
 #pragma unroll
           for (int s = 0; s < KTOP; ++s) {
-            const float2 m = merge[(pp * kSuperRows + urow) * KTOP + s];
+            const float2 m = merge[(pp * kRows + urow) * KTOP + s];
             fin.insert_lex(m.x, __float_as_int(m.y));
           }
         }
@@ -613,7 +642,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           }
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");  // merge area is free again
+      asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");  // merge area is free again
     }
   }
 
@@ -690,9 +719,9 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   }
 }
 
-template <Kind kKind, int KTOP>
-cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
-                     cudaStream_t stream) {
+template <Kind kKind, int KTOP, int kT>
+cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
+                         cudaStream_t stream) {
   static const bool a_tmem = [] {
     const char* e = getenv("IAM_UMMA_A_SMEM");  // A/B aid: 1 = keep the A operand in shared memory (SS form)
     return !(e && atoi(e) == 1);
@@ -705,27 +734,34 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only, 3 = accumulator read-out only, 4 = group tests never taken, 5 = fixed slow-path work
     return e ? atoi(e) : 0;
   }();
+  using C = Cfg<kKind, kT>;
   using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*);
-  const bool use_cluster = cluster && (n_units % 2 == 0);
+  const int n_items = n_units * C::kItems;
+  const bool use_cluster = cluster && (n_items % 2 == 0);
   KernT kern;
   if (flags != 0) {  // profiling variants exist for the production configuration only
     if (!use_cluster || !a_tmem || flags < 0 || flags > 5) return cudaErrorInvalidValue;
-    kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1>
-           : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2>
-           : flags == 3 ? knn_umma_kernel<kKind, KTOP, true, true, 3>
-           : flags == 4 ? knn_umma_kernel<kKind, KTOP, true, true, 4>
-                        : knn_umma_kernel<kKind, KTOP, true, true, 5>;
+    kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1, kT>
+           : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2, kT>
+           : flags == 3 ? knn_umma_kernel<kKind, KTOP, true, true, 3, kT>
+           : flags == 4 ? knn_umma_kernel<kKind, KTOP, true, true, 4, kT>
+                        : knn_umma_kernel<kKind, KTOP, true, true, 5, kT>;
   } else if (use_cluster) {
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0> : knn_umma_kernel<kKind, KTOP, false, true, 0>;
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0, kT> : knn_umma_kernel<kKind, KTOP, false, true, 0, kT>;
   } else {
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0> : knn_umma_kernel<kKind, KTOP, false, false, 0>;
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0, kT> : knn_umma_kernel<kKind, KTOP, false, false, 0, kT>;
   }
-  constexpr size_t kSmemTotal = Cfg<kKind>::kSmemTotal;
+  constexpr size_t kSmemTotal = C::kSmemTotal;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
   if (err != cudaSuccess) return err;
-  int grid = n_units < num_sms ? n_units : num_sms;
+  if (C::kCtasPerSm > 1) {  // both CTAs of an SM must fit: all of the unified L1 as shared memory
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return err;
+  }
+  const int slots = num_sms * C::kCtasPerSm;
+  int grid = n_items < slots ? n_items : slots;
   cudaLaunchConfig_t cfg{};
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::kThreads);
   cfg.dynamicSmemBytes = kSmemTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -741,6 +777,21 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
   }
   cfg.gridDim = dim3(grid);
   return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2);
+}
+
+template <Kind kKind, int KTOP>
+cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
+                     cudaStream_t stream) {
+  if constexpr (kKind == Kind::I8) {
+    // A/B aid: IAM_UMMA_CTA_TILES=1 runs two half-unit CTAs per SM (Cfg).  Measured slower than one whole-unit CTA
+    // (22.1 vs 19.6 ms per 1990 pairs): co-resident CTAs start their units together and stay in phase.
+    static const int tiles = [] {
+      const char* e = getenv("IAM_UMMA_CTA_TILES");
+      return e ? atoi(e) : 2;
+    }();
+    if (tiles == 1) return launch_shape<kKind, KTOP, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
+  }
+  return launch_shape<kKind, KTOP, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
 }
 
 template <Kind kKind>
