@@ -28,6 +28,7 @@
 
 #include <cstdlib>
 #include <type_traits>
+#include <utility>
 
 #include "knn.h"
 #include "layout.h"
@@ -305,6 +306,101 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
   consume16<KTOP, O, 1, kFixed>(&v[16], tp, tk, pb);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Packed-key path (byte layout, k = 2).  The s32 accumulators are < 2^24 (layout.h), so
+//     key_j = acc_j * 32 + (31 - j)
+// is an order-preserving, UNIQUE 29-bit key of the 32 columns a thread holds: larger key = nearer descriptor, and
+// among equal distances the lower column (the order cv2.BFMatcher reports ties in).  With unique keys the two best
+// columns of the slice need no compare/select network and no per-column votes:
+//     m1 = max_j key_j                                   16 three-input max (ALU pipe)
+//     u_j = key_j - m1  (mod 2^32)                       the winner becomes 0, every other column a huge unsigned
+//     m2 = m1 + umax_j u_j                               number that still orders like its key: 16 three-input umax
+// The 32 packing multiply-adds and half of the subtractions are IMADs (FMA pipe, idle in this kernel); the
+// epilogue is ALU-pipe bound.  Only the warp vote "some lane's m1 beats its bound" guards the second half, and
+// the two winners enter the running list through the ordinary six-instruction insertion.
+// The cost per slice no longer depends on how many columns qualify, which is what made the first tiles of every
+// unit (empty lists, everything qualifies) cost seven times a late tile.
+#ifndef IAM_PACKED
+#define IAM_PACKED 1
+#endif
+#ifndef IAM_PACK_IMAD
+#define IAM_PACK_IMAD 1          // A/B aid: 0 = literal multipliers (ptxas emits LEA / IADD on the ALU pipe)
+#endif
+#ifndef IAM_PACKED_FMA_SUBS
+#define IAM_PACKED_FMA_SUBS 16   // 32: all knock-out subtractions as IMAD + one tree; 16: half as fused add-max chains
+#endif
+template <int J>
+__device__ __forceinline__ int pack_key(int acc, uint32_t mul32) {
+  int k;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(k) : "r"(acc), "r"(mul32), "n"(31 - J));
+  return k;
+}
+template <int J>
+__device__ __forceinline__ uint32_t knock(int key, int m1, int neg_m1, uint32_t one) {
+  (void)m1;
+  uint32_t u;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(u) : "r"(key), "r"(one), "r"(neg_m1));
+  return u;
+}
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+template <typename F, int... Js>
+__device__ __forceinline__ void static_for32(F&& f, std::integer_sequence<int, Js...>) {
+  (f(std::integral_constant<int, Js>{}), ...);
+}
+// kMode 0: production; 1: profiling aid, second half never taken; 2: profiling aid, second half always taken.
+// The running lists carry the index  e = tp32 | (31 - j)  (tp32 = 32 * slice number): the low five bits come
+// straight out of the key (one LOP3 per winner), and the real column is  e ^ 31.
+template <int kMode = 0>
+__device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, TopK<2, Ord<Kind::I8>>& tk, int pb,
+                                                 uint32_t mul32, uint32_t one) {
+  int k[32];
+  static_for32([&](auto j) { k[j] = pack_key<j>(v[j], mul32); }, std::make_integer_sequence<int, 32>{});
+  int a[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = imax3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+  const int b0 = imax3(a[0], a[1], a[2]), b1 = imax3(a[3], a[4], a[5]), b2 = imax3(a[6], a[7], a[8]);
+  const int b3 = imax3(a[9], k[30], k[31]);
+  const int m1 = max(imax3(b0, b1, b2), b3);
+  // admissible: acc > te  <=>  key > te * 32 + 31
+  const int te = max(tk.d[1], pb);
+  int te_key;
+  asm("mad.lo.s32 %0, %1, %2, 31;" : "=r"(te_key) : "r"(te), "r"(mul32));
+  const bool hit = kMode == 2 ? any_lane(m1 > -1) : any_lane(m1 > te_key);
+  if (hit && kMode != 1) {
+    const int neg_m1 = -m1;
+    uint32_t best;
+    if constexpr (IAM_PACKED_FMA_SUBS >= 32) {  // every subtraction an IMAD, one three-input tree
+      uint32_t u[32];
+      static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, 32>{});
+      uint32_t c[10];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) c[i] = umax3(u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+      const uint32_t d0 = umax3(c[0], c[1], c[2]), d1 = umax3(c[3], c[4], c[5]), d2 = umax3(c[6], c[7], c[8]);
+      const uint32_t d3 = umax3(c[9], u[30], u[31]);
+      best = max(umax3(d0, d1, d2), d3);
+    } else {
+      // Issue slots are the scarce resource once both pipes are loaded: columns 0..15 take the IMAD + three-input
+      // tree route (16 + 7 instructions), columns 16..31 two chains of fused add-max (VIADDMNMX.U32, one ALU-pipe
+      // instruction per column).
+      uint32_t u[16];
+      static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, 16>{});
+      uint32_t c[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) c[i] = umax3(u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+      uint32_t s0 = umax3(c[0], c[1], c[2]), s1 = umax3(c[3], c[4], u[15]);
+      const uint32_t nm = static_cast<uint32_t>(neg_m1);
+#pragma unroll
+      for (int j = 16; j < 24; ++j) s0 = max(s0, static_cast<uint32_t>(k[j]) + nm);
+#pragma unroll
+      for (int j = 24; j < 32; ++j) s1 = max(s1, static_cast<uint32_t>(k[j]) + nm);
+      best = max(s0, s1);
+    }
+    const int m2 = m1 + static_cast<int>(best);
+    tk.insert(m1 >> 5, (m1 & 31) | tp32);
+    tk.insert(m2 >> 5, (m2 & 31) | tp32);
+  }
+}
+
 template <Kind kKind>
 __device__ __forceinline__ const uint8_t* a_src(const ImgDev& im) { return kKind == Kind::I8 ? im.i8_form : im.a_form; }
 template <Kind kKind>
@@ -521,7 +617,22 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
     const bool lane0 = lane == 0;
     TopK<KTOP, O> tk;
+    constexpr bool kPacked = IAM_PACKED && kKind == Kind::I8 && KTOP == 2;
+    // Multipliers ptxas cannot fold (n_units >= 0): with a literal 32 the packing multiply-adds are strength-reduced
+    // to LEA, an ALU-pipe instruction; as register operands they stay IMADs on the otherwise idle FMA pipe.
+    const uint32_t opaque0 = static_cast<uint32_t>(n_units) >> 31;
+    const uint32_t mul32 = IAM_PACK_IMAD ? 32u + opaque0 : 32u, one = IAM_PACK_IMAD ? 1u + opaque0 : 1u;
+    (void)mul32;
+    (void)one;
     uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kT + a, slot = sq % kSlots
+    constexpr bool kPair = kPacked && kDual && kSlots == 2 * kT && kParts > 1 && (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5);
+    const uint32_t bar_a = pin_reg(bar_full0 + a * 8);       // kPair: t_full of this tile's first slot (second: + kT * 8)
+    const uint32_t tm_a = pin_reg(tm_warp + a * kBRows);     // kPair: its accumulator columns (second slot: + kT * kBRows)
+    int phase = 0;
+    (void)bar_a;
+    (void)tm_a;
+    (void)phase;
+    (void)slot;
     const int group_bar = 1 + a * 4 + quad;   // named barrier of the kParts warps that share these 32 rows
     int uit = 0;
     for (int pu = first_pu; pu * kCtas < n_items; pu += pu_stride, ++uit) {
@@ -538,54 +649,102 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       const uint32_t rd = pin_reg(share_row + (uit & 1) * kParityStride);
       const uint32_t wr = pin_reg(rd + part * kPartStride);
       sts_volatile_b32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, O::bits(O::worst()));
-      const int tp_end = n_tb * kParts + part;
-      for (int tp = part; tp < tp_end; tp += kParts) {  // tp numbers the 32-column slices of the train image
-        // Bound from the threads that own the column parts of this row (own slot included, it is harmless):
-        // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted
-        // (loosen; the final merge orders them by index).  Stale
-        // values are still valid bounds, so plain volatile shared-memory traffic suffices.
-        if (kParts > 1) {
+      if constexpr (kPair) {
+        // Production shape: this query tile owns the accumulator slots a and a + 2 and uses them alternately, so the
+        // tiles are walked in PAIRS with every barrier / tensor-memory address a constant offset from a pinned base,
+        // one parity flip and one exchange of bounds per pair.  `phase` says which slot the unit's first tile sits in
+        // (the ring runs on across units; an odd tile count flips it).
+        // Bound from the threads that own the other column parts of this row (own slot included, it is harmless):
+        // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted (loosen;
+        // the final merge orders them by index).  Stale values are still valid bounds: plain volatile traffic.
+        auto tile = [&](auto sl, int tp32) {
+          constexpr uint32_t kSl = decltype(sl)::value;
+          const uint32_t bar = bar_a + kSl * (kT * 8);
+          mbar_wait_bare_a(bar, par);
+          tc_fence_after();
+          if constexpr (kDbg != 1) {
+            int v[32];
+            __syncwarp();
+            tmem_ld32(tm_a + kSl * (kT * kBRows), v);
+            tmem_ld_wait(v);
+            // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
+            __syncwarp();
+            tc_fence_before();
+            if (lane0) mbar_arrive_a(bar + kEmptyOff);
+            consume32_packed<kDbg == 5 ? 2 : kDbg == 4 ? 1 : 0>(v, tp32, tk, pb, mul32, one);
+          } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
+            __syncwarp();
+            tc_fence_before();
+            if (lane0) mbar_arrive_a(bar + kEmptyOff);
+          }
+        };
+        int tp32 = part * 32 - phase * (kBRows);  // 32 * (tile * kParts + part) of the pair's first tile
+        for (int tb = -phase; tb < n_tb; tb += 2, tp32 += 2 * kBRows) {
           T g = O::from_bits(lds_volatile_b32_a(rd));
 #pragma unroll
           for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
           pb = O::best(pb, O::loosen(g));
-        }
-        const uint32_t bar = bar_full0 + slot * 8;
-        mbar_wait_bare_a(bar, par);
-        tc_fence_after();
-        if (kDbg != 1) {
-          T v[32];
-          __syncwarp();
-          tmem_ld32(tm_warp + slot * kBRows, v);
-          tmem_ld_wait(v);
-          // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
-          __syncwarp();
-          tc_fence_before();
-          if (lane0) mbar_arrive_a(bar + kEmptyOff);
-          if (kDbg == 0) {
-            consume32<KTOP, O>(v, tp, tk, pb);
-          } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
-            consume32<KTOP, O, true>(v, tp, tk, pb);
-          } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): group tests + votes + branches, never taken
-            consume32<KTOP, O>(v, tp, tk, O::never());
-          } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
-            tk.d[0] = O::best(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
-          } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
-            T m = v[0];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m = O::best(m, O::best(O::best3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
-            tk.d[0] = O::best(tk.d[0], m);
+          if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tp32);
+          if (tb + 1 < n_tb) {
+            tile(std::integral_constant<uint32_t, 1>{}, tp32 + kBRows);
+            par ^= 1;
           }
-        } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
-          __syncwarp();
-          tc_fence_before();
-          if (lane0) mbar_arrive_a(bar + kEmptyOff);
+          sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
         }
-        if (kParts > 1) sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
-        slot += kT;
-        if (slot >= kSlots) {
-          slot -= kSlots;
-          par ^= 1;
+        phase = (phase + n_tb) & 1;
+      } else {
+        const int tp_end = n_tb * kParts + part;
+        for (int tp = part; tp < tp_end; tp += kParts) {  // tp numbers the 32-column slices of the train image
+          // Bound from the threads that own the column parts of this row (own slot included, it is harmless):
+          // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted
+          // (loosen; the final merge orders them by index).  Stale
+          // values are still valid bounds, so plain volatile shared-memory traffic suffices.
+          if (kParts > 1) {
+            T g = O::from_bits(lds_volatile_b32_a(rd));
+  #pragma unroll
+            for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
+            pb = O::best(pb, O::loosen(g));
+          }
+          const uint32_t bar = bar_full0 + slot * 8;
+          mbar_wait_bare_a(bar, par);
+          tc_fence_after();
+          if (kDbg != 1) {
+            T v[32];
+            __syncwarp();
+            tmem_ld32(tm_warp + slot * kBRows, v);
+            tmem_ld_wait(v);
+            // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
+            __syncwarp();
+            tc_fence_before();
+            if (lane0) mbar_arrive_a(bar + kEmptyOff);
+            if (kDbg == 0) {
+              if constexpr (kPacked) consume32_packed<0>(v, tp * 32, tk, pb, mul32, one);
+              else consume32<KTOP, O>(v, tp, tk, pb);
+            } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
+              if constexpr (kPacked) consume32_packed<2>(v, tp * 32, tk, pb, mul32, one);
+              else consume32<KTOP, O, true>(v, tp, tk, pb);
+            } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): tests + votes + branches, never taken
+              if constexpr (kPacked) consume32_packed<1>(v, tp * 32, tk, pb, mul32, one);
+              else consume32<KTOP, O>(v, tp, tk, O::never());
+            } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
+              tk.d[0] = O::best(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
+            } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
+              T m = v[0];
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) m = O::best(m, O::best(O::best3(v[j * 4], v[j * 4 + 1], v[j * 4 + 2]), v[j * 4 + 3]));
+              tk.d[0] = O::best(tk.d[0], m);
+            }
+          } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
+            __syncwarp();
+            tc_fence_before();
+            if (lane0) mbar_arrive_a(bar + kEmptyOff);
+          }
+          if (kParts > 1) sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
+          slot += kT;
+          if (slot >= kSlots) {
+            slot -= kSlots;
+            par ^= 1;
+          }
         }
       }
       // end of unit: every list becomes (squared distance, train row); parts 1.. hand theirs to part 0's thread
@@ -602,7 +761,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         for (int s = 0; s < KTOP; ++s) {
           const int enc = tk.i[s];
           if (kKind == Kind::I8) {
-            const int rank = enc == 0x7fffffff ? 0x7fffffff : dec_index(enc);
+            const int rank = enc == 0x7fffffff ? 0x7fffffff : (kPacked ? (enc ^ 31) : dec_index(enc));
             if (rank < t.n) {  // d^2 = ||q||^2 + 2 CAP + (||t||^2 & 1) - 2 acc, exact (layout.h)
               fin.d[s] = static_cast<float>(rowc + (rank >= n_even ? 1 : 0) - 2 * static_cast<int>(tk.d[s]));
               fin.i[s] = t.perm[rank];
