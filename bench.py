@@ -368,8 +368,13 @@ def main():
         torch.cuda.synchronize()
         h2d_ms = (time.perf_counter() - c0) * 1e3
         del dst
+        # bytes that actually crossed PCIe in the last step: float32 frames the library's worker threads narrowed to
+        # uint8 on the host (integer-valued SIFT descriptors, transport only) count as bytes
+        tme = eng.timing()
         e2e = {"value": P * world * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e_ms.item()) / n_e,
+               "h2d_bytes_per_step": int(tme.h2d_bytes) or h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e_ms.item()) / n_e,
+               "host_input_bytes_per_step": h2d, "frames_narrowed_on_host": int(tme.narrowed_images),
+               "host_threads": int(os.environ.get("IAM_HOST_THREADS", "0")) or None,
                "mean_matches_per_pair": float(count.mean()), "bare_h2d_ms_same_bytes": h2d_ms,
                "timeline_ms": {"host_enqueue": eng.timing().host_enqueue_ms, "upload_span": eng.timing().upload_span_ms,
                                "compute_span": eng.timing().compute_span_ms, "total_span": eng.timing().total_span_ms,

@@ -32,7 +32,7 @@ EXPORTS = (
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
     "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
-    "iam_debug_ba_host",
+    "iam_debug_ba_host", "iam_debug_narrow",
 )
 
 
@@ -68,11 +68,25 @@ class Timing(C.Structure):
         ("upload_span_ms", C.c_float),
         ("compute_span_ms", C.c_float),
         ("total_span_ms", C.c_float),
+        ("h2d_bytes", C.c_ulonglong),
+        ("narrowed_images", C.c_int),
     ]
 
 
 class IamError(RuntimeError):
     pass
+
+
+def narrow_host(src):
+    """The host-side float32 -> uint8 narrowing of iam_match_images (iam_debug_narrow; needs no GPU).
+    Returns (bytes, ok): ok is False when some component is not an integer in 0..255."""
+    lib = load_library()
+    a = np.ascontiguousarray(src, np.float32)
+    out = np.zeros(a.shape, np.uint8)
+    bad = lib.iam_debug_narrow(_ptr(a), _ptr(out), a.size)
+    if bad < 0:
+        raise IamError("iam_debug_narrow failed: %s" % lib.iam_last_error().decode())
+    return out, bad == 0
 
 
 def ba_observation_host(cam7, pt3, uv, K4, dist5, jac: bool = True):
@@ -128,6 +142,7 @@ def load_library(path: Optional[str] = None):
                                      C.c_uint32, vp, vp, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     lib.iam_debug_minimal_solver.argtypes = [C.c_int, vp, vp, vp, vp, vp]
+    lib.iam_debug_narrow.argtypes = [vp, vp, C.c_size_t]
     lib.iam_ba_setup.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_ba_eval.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.iam_ba_upload_params.argtypes = [vp, vp]

@@ -18,6 +18,10 @@
 #include "../../include/iamatch.h"
 #include "ba.h"
 #include "gms.h"
+#include <memory>
+#include <thread>
+
+#include "host_narrow.h"
 #include "knn.h"
 #include "layout.h"
 #include "ransac.h"
@@ -144,6 +148,15 @@ struct iam_ctx {
   // bundle-adjustment problem (iam_ba_*): structure resident, parameters re-uploaded per evaluation
   Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac;
   int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
+  // iam_match_images, float32 L2 descriptors: worker threads narrow them to bytes (host_narrow.h) into a pinned arena
+  std::unique_ptr<iam::NarrowPool> narrow_pool;
+  bool narrow_pool_tried = false;
+  uint8_t* narrow_arena = nullptr;
+  size_t narrow_cap = 0;
+  std::unique_ptr<iam::NarrowJob[]> narrow_jobs;
+  int narrow_jobs_cap = 0;
+  unsigned long long h2d_bytes = 0;   // descriptor bytes copied host -> device by the current iam_match_images call
+  int narrowed_images = 0;
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -432,7 +445,7 @@ __global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jo
 
 extern "C" {
 
-int iam_abi_version(void) { return 3; }
+int iam_abi_version(void) { return 4; }
 const char* iam_last_error(void) { return g_err.c_str(); }
 
 int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
@@ -491,6 +504,8 @@ int iam_destroy(iam_ctx* c) {
     if (im.kp) cudaFree(im.kp);
     if (im.ready) cudaEventDestroy(im.ready);
   }
+  c->narrow_pool.reset();
+  if (c->narrow_arena) cudaFreeHost(c->narrow_arena);
   if (c->d_ctx_flag) cudaFree(c->d_ctx_flag);
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
@@ -652,6 +667,7 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
       CU(stg.ensure(std::max<size_t>(bytes, 256)));
     }
     if (bytes) CU(cudaMemcpyAsync(stg.p, src, bytes, cudaMemcpyHostToDevice, us));
+    c->h2d_bytes += bytes;
     dsrc = stg.p;
   }
   // flag words: non-zero = exact / byte layout usable.  Hamming sources are exact by construction: no flag traffic.
@@ -916,6 +932,12 @@ struct UploadFeed {  // host-side sources for iam_match_images: enqueue an image
   std::vector<int> slot_of_id;   // image id -> index into ptrs
   std::vector<char> done;
   std::vector<std::pair<int, int>> waves_done;  // pair ranges whose done_ev was recorded, in order
+  // float32 -> byte narrowing on the host (host_narrow.h): job index per slot (-1: none), in order of first use
+  bool narrow = false;
+  bool narrow_always = false;  // IAM_HOST_NARROW=2 (tests): never fall back to a float32 upload of a narrowable image
+  iam::NarrowJob* jobs = nullptr;
+  std::vector<int> job_of_slot;
+  std::vector<cudaEvent_t> upload_waves;  // wave events of this call, in order (pacing of the enqueueing thread)
 };
 
 int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
@@ -994,11 +1016,39 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   CU(cudaEventRecord(c->span[2], c->stream));
   // The matching kernel fills every SM it is given (registers, shared memory); leave a few SMs to the layout
   // conversion kernels of later waves so that uploads really overlap the matching of earlier waves.
+  // float32 descriptors bound for the byte layout are integers in 0..255 (or the call is repeated on fp16 operands
+  // anyway): worker threads narrow them to bytes while earlier waves upload and match (host_narrow.h)
+  int narrow_mode = 1;  // 0: off, 1: adaptive (default), 2: always
+  if (const char* env = getenv("IAM_HOST_NARROW")) narrow_mode = atoi(env);
+  feed.narrow = narrow_mode != 0 && c->norm == IAM_NORM_L2 && !wide && dtype == IAM_DTYPE_F32;
+  feed.narrow_always = narrow_mode == 2;
+  if (feed.narrow && !c->narrow_pool_tried) {
+    c->narrow_pool_tried = true;
+    const int threads = iam::narrow_default_threads();
+    if (threads > 0) c->narrow_pool.reset(new iam::NarrowPool(threads));
+  }
+  if (feed.narrow && c->narrow_pool) {  // the arena of the previous call must have left the host
+    CU(cudaStreamSynchronize(c->up_stream));
+    CU(cudaStreamSynchronize(c->up_stream2));
+  }
+  c->h2d_bytes = 0;
+  c->narrowed_images = 0;
+  // Workers that outrun the bus walk the images in order and this thread never sends float32 rows (it narrows
+  // an image itself if it gets there first); otherwise the adaptive scheme of NarrowPool::run().
+  if (feed.narrow && c->narrow_pool && !c->narrow_pool->backward()) feed.narrow_always = true;
   c->feed_mode = true;
   c->reserve_sms = waves > 1 ? 8 : 0;
+  if (const char* env = getenv("IAM_RESERVE_SMS")) c->reserve_sms = waves > 1 ? std::max(0, atoi(env)) : 0;  // A/B aid
   rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr);
   c->feed_mode = false;
   c->reserve_sms = 0;
+  if (c->narrow_pool && feed.jobs) {  // no worker may touch the job list (or this call's buffers) past this point
+    for (int k = 0; k < feed.n_images && k < c->narrow_jobs_cap; ++k) {
+      int expect = iam::NarrowJob::kFree;  // images nobody needed any more: not worth narrowing
+      c->narrow_jobs[k].state.compare_exchange_strong(expect, iam::NarrowJob::kTaken, std::memory_order_acq_rel);
+    }
+    c->narrow_pool->finish();
+  }
   if (rc != IAM_OK) return rc;
   for (int i = 0; i < n_images; ++i)  // images no pair referenced are still part of the resident set
     if (!feed.done[i] && (rc = enqueue_upload(c, image_ids[i], host_ptrs[i], true, dtype, key_ptrs ? key_ptrs[i] : nullptr)) != IAM_OK)
@@ -1009,6 +1059,8 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   CU(cudaEventRecord(c->span[3], c->stream));
   c->timing.host_enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - h0).count();
   c->timing.waves = waves;
+  c->timing.h2d_bytes = c->h2d_bytes;
+  c->timing.narrowed_images = c->narrowed_images;
   c->span_pending = true;
   // Results travel back wave by wave on their own stream: only the last wave's rows are copied after the last
   // kernel.  (With a pageable destination each copy blocks this thread, not the GPU: everything is enqueued.)
@@ -1039,6 +1091,58 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
 }  // extern "C"
 
 namespace {
+
+// Hand every float32 image of this call to the narrowing workers, in the order the waves will need them.
+int start_narrowing(iam_ctx* c, const Plan& pl, const int32_t* pairs, UploadFeed* feed) {
+  feed->job_of_slot.assign(feed->n_images, -1);
+  if (!c->narrow_pool) {
+    feed->narrow = false;
+    return IAM_OK;
+  }
+  std::vector<int> order;
+  order.reserve(feed->n_images);
+  size_t bytes = 0;
+  for (size_t ch = 0; ch + 1 < pl.chunk_pair_begin.size(); ++ch)
+    for (int i = 2 * pl.chunk_pair_begin[ch]; i < 2 * pl.chunk_pair_begin[ch + 1]; ++i) {
+      const int id = pairs[i];
+      const int slot = id < (int)feed->slot_of_id.size() ? feed->slot_of_id[id] : -1;
+      if (slot < 0 || feed->job_of_slot[slot] >= 0 || c->images[id].n <= 0) continue;
+      feed->job_of_slot[slot] = (int)order.size();
+      order.push_back(slot);
+      bytes += size_t(c->images[id].n) * c->desc_bytes;
+    }
+  if (order.empty()) {
+    feed->narrow = false;
+    return IAM_OK;
+  }
+  if (c->narrow_cap < bytes) {  // page-locked: the H2D copies out of it are asynchronous
+    CU(cudaStreamSynchronize(c->up_stream));
+    CU(cudaStreamSynchronize(c->up_stream2));
+    if (c->narrow_arena) CU(cudaFreeHost(c->narrow_arena));
+    c->narrow_arena = nullptr;
+    c->narrow_cap = 0;
+    CU(cudaHostAlloc(reinterpret_cast<void**>(&c->narrow_arena), bytes + bytes / 8, cudaHostAllocDefault));
+    c->narrow_cap = bytes + bytes / 8;
+  }
+  if (c->narrow_jobs_cap < (int)order.size()) {
+    c->narrow_jobs.reset(new iam::NarrowJob[order.size()]);
+    c->narrow_jobs_cap = (int)order.size();
+  }
+  size_t off = 0;
+  for (size_t k = 0; k < order.size(); ++k) {
+    const int slot = order[k];
+    const Image& im = c->images[feed->ids[slot]];
+    iam::NarrowJob& job = c->narrow_jobs[k];
+    job.src = static_cast<const float*>(feed->ptrs[slot]);
+    job.dst = c->narrow_arena + off;
+    job.n = size_t(im.n) * c->desc_bytes;
+    job.state.store(iam::NarrowJob::kFree, std::memory_order_relaxed);
+    off += job.n;
+  }
+  feed->jobs = c->narrow_jobs.get();
+  c->narrow_pool->start(feed->jobs, (int)order.size());
+  return IAM_OK;
+}
 
 int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
                void** d_table, void** d_count) {
@@ -1077,6 +1181,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     }
   }
   if ((rc = sync_imgs(c)) != IAM_OK) return rc;
+  if (feed && feed->narrow && (rc = start_narrowing(c, pl, pairs, feed)) != IAM_OK) return rc;
 
   const size_t cap = prm->cap;
   int max_chunk_pairs = 1;
@@ -1110,6 +1215,9 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     if (p1 == p0) continue;
     if (feed) {  // enqueue the uploads this chunk is the first to need (upload stream; overlaps earlier chunks' kernels)
       bool any_upload = false;
+      // With narrowing the enqueueing thread paces itself on the upload stream (at most two waves ahead): an image
+      // is claimed for a float32 upload only when PCIe is about to run dry, which gives the workers time to get ahead.
+      if (feed->narrow && !feed->narrow_always && feed->upload_waves.size() >= 2) CU(cudaEventSynchronize(feed->upload_waves[feed->upload_waves.size() - 2]));
       for (int i = 2 * p0; i < 2 * p1; ++i) {
         const int id = pairs[i];
         const int slot = id < (int)feed->slot_of_id.size() ? feed->slot_of_id[id] : -1;
@@ -1119,7 +1227,33 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
           const int32_t* hk = feed->keys ? feed->keys[slot] : nullptr;
           int* keep = im.keys;  // allocated above; enqueue_upload must reuse it, not free it
           im.keys = nullptr;
-          if ((rc = enqueue_upload(c, id, feed->ptrs[slot], true, feed->dtype, nullptr)) != IAM_OK) return rc;
+          const void* usrc = feed->ptrs[slot];
+          int udtype = feed->dtype;
+          if (feed->narrow && feed->job_of_slot[slot] >= 0) {
+            // Bytes when a worker has narrowed (or is narrowing) this image; the float32 rows when no worker has
+            // reached it yet -- PCIe then carries them while the workers go on with later images.
+            iam::NarrowJob& job = feed->jobs[feed->job_of_slot[slot]];
+            int st = job.state.load(std::memory_order_acquire);
+            if (st == iam::NarrowJob::kFree) {
+              int expect = iam::NarrowJob::kFree;
+              const int claim = feed->narrow_always ? iam::NarrowJob::kBusy : iam::NarrowJob::kTaken;
+              st = job.state.compare_exchange_strong(expect, claim, std::memory_order_acq_rel) ? claim : expect;
+              if (st == iam::NarrowJob::kBusy && feed->narrow_always) {  // IAM_HOST_NARROW=2: this thread does it itself
+                st = iam::narrow_f32_to_u8(job.src, job.dst, job.n) ? iam::NarrowJob::kBad : iam::NarrowJob::kDone;
+                job.state.store(st, std::memory_order_release);
+              }
+            }
+            while (st == iam::NarrowJob::kBusy) {
+              std::this_thread::yield();
+              st = job.state.load(std::memory_order_acquire);
+            }
+            if (st == iam::NarrowJob::kDone) {
+              usrc = job.dst;
+              udtype = IAM_DTYPE_U8;
+              c->narrowed_images++;
+            }
+          }
+          if ((rc = enqueue_upload(c, id, usrc, true, udtype, nullptr)) != IAM_OK) return rc;
           im.keys = keep;
           im.dev.kp_key = keep;
           if (hk && keep) CU(cudaMemcpyAsync(keep, hk, size_t(im.n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
@@ -1136,6 +1270,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
         CU(cudaStreamWaitEvent(c->up_stream, c->lane2_ev, 0));
         CU(cudaEventRecord(c->wave_ev[ch], c->up_stream));
         CU(cudaStreamWaitEvent(c->stream, c->wave_ev[ch], 0));
+        feed->upload_waves.push_back(c->wave_ev[ch]);
       }
     } else if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) {
       return rc;
@@ -1258,6 +1393,11 @@ int iam_debug_tile(iam_ctx* c, int q_id, int t_id, int q_tile, int t_tile, uint3
   CU(cudaMemcpyAsync(out_host, c->packed_d.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return IAM_OK;
+}
+
+int iam_debug_narrow(const float* src, uint8_t* dst, size_t n) {
+  if (n && (!src || !dst)) return fail(IAM_E_ARG, "null buffer");
+  return iam::narrow_f32_to_u8(src, dst, n);
 }
 
 int iam_debug_minimal_solver(int model, const float* x1, const float* y1, const float* x2, const float* y2,

@@ -268,6 +268,9 @@ typedef struct iam_timing {
   float upload_span_ms;   /* first H2D copy start -> last conversion end           */
   float compute_span_ms;  /* first kernel start -> last kernel end                 */
   float total_span_ms;    /* first H2D copy start -> last kernel end               */
+  unsigned long long h2d_bytes; /* descriptor bytes copied host -> device (float32 images that worker threads
+                                   narrowed to bytes on the host count as bytes)       */
+  int   narrowed_images;  /* images uploaded as host-narrowed bytes                */
 } iam_timing;
 int iam_get_timing(iam_ctx* ctx, iam_timing* out);
 
@@ -288,6 +291,11 @@ int iam_debug_tile(iam_ctx* ctx, int q_id, int t_id, int q_tile, int t_tile,
  * written to out_models[10][9] (row-major), or <0.  Needs no GPU. */
 int iam_debug_minimal_solver(int model, const float* x1, const float* y1,
                              const float* x2, const float* y2, float* out_models);
+
+/* Debug aid: the host-side float32 -> uint8 narrowing iam_match_images applies to integer-valued L2 descriptors
+ * before they cross PCIe (transport only; the reference holds SIFT descriptors as float32, image.py:160-180).
+ * Returns 0 when every src[i] is an integer in 0..255 (dst[i] = that value), 1 otherwise.  Needs no GPU. */
+int iam_debug_narrow(const float* src, uint8_t* dst, size_t n);
 
 #ifdef __cplusplus
 }

@@ -331,6 +331,45 @@ def test_match_images_one_call_equals_two_phase():
     assert (c2 == c3).all()
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_match_images_host_narrowing(monkeypatch, mode):
+    """float32 descriptors are narrowed to bytes on the host for transport (IAM_HOST_NARROW: 0 off, 1 adaptive,
+    2 always): identical tables in every mode; a non-integer component is never narrowed away -- the call falls back
+    to fp16 operands as it does without narrowing."""
+    monkeypatch.setenv("IAM_HOST_NARROW", mode)
+    des, _, _ = synth.sift_project(24, 700, seed=5)
+    pairs = [(i, j) for i in range(24) for j in range(i + 1, min(24, i + 5))]
+    prm = _capi.Engine.make_params(cross_check=True)
+    ref = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i, d in enumerate(des):
+        ref.upload(i, d)
+    t0, c0 = ref.match_pairs(pairs, prm)
+    ref.close()
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for rep in range(2):
+        t1, c1 = eng.match_images(list(range(24)), [d.astype(np.float32) for d in des], pairs, prm)
+        assert eng.timing().mma_kind == _capi.KIND_I8
+        assert (c0 == c1).all() and c0.max() > 100
+        for p in range(len(pairs)):
+            assert (t0[p, :c0[p]] == t1[p, :c1[p]]).all()
+        if mode == "2":
+            assert eng.timing().narrowed_images == 24 and eng.timing().h2d_bytes == 24 * 700 * 128
+        if mode == "0":
+            assert eng.timing().narrowed_images == 0 and eng.timing().h2d_bytes == 24 * 700 * 128 * 4
+    eng.close()
+    fl = [d.astype(np.float32) for d in des]
+    fl[7][33, 5] += 0.5                       # not an integer: bytes cannot carry it
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    table, count = eng.match_images(list(range(24)), fl, pairs, prm)
+    assert eng.timing().mma_kind == _capi.KIND_F16
+    chk = [p for p, (a, b) in enumerate(pairs) if 7 in (a, b)][:3]
+    for p in chk:
+        a, b = pairs[p]
+        f, _ = oracle.bidirectional(fl[a], fl[b], oracle.NORM_L2, 0.75, 270.0, threads=4)
+        assert table[p, :count[p]].tolist() == f
+    eng.close()
+
+
 class FakeImage:
     def __init__(self, name, des, pts, ned):
         self.name = name
