@@ -7,23 +7,25 @@
 // unit from a shared-memory staging buffer into TENSOR MEMORY with tcgen05.cp,
 // so the MMAs read only the B operand from shared memory) against every
 // descriptor of the train image (96-row B tiles streamed by cp.async.bulk
-// through a 4-deep mbarrier ring; in a 2-CTA cluster each CTA fetches half of
+// through an mbarrier ring; in a 2-CTA cluster each CTA fetches half of
 // every tile and multicasts it to both).  The augmented K-step makes every
-// accumulator element the exact squared L2 distance (integer valued < 2^23,
-// exact in fp32) or the exact Hamming distance, so the N x M distance matrix
-// never leaves the SM: 24 epilogue warps read it from TMEM and keep a per-row
-// running top-k in registers.
+// accumulator element an exact function of the squared L2 distance (byte layout:
+// s32, larger = nearer; wide layouts: the distance itself in fp32) or the exact
+// Hamming distance, so the N x M distance matrix never leaves the SM: 24 epilogue
+// warps read it from TMEM and keep a per-row running top-k in registers.
 //
-// Warp roles (896 threads, 1 CTA / SM, persistent over units):
-//   warp 0      : B-tile producer  (bulk copy  -> b_full[stage])
-//   warp 1      : MMA issuer       (warp-uniform loop, one elected lane issues: 18 tcgen05.cp per unit,
-//                 18 TS-form tcgen05.mma M128xN96xK16 per B tile into a ring of three 96-column accumulator slots)
-//   warp 2      : TMEM allocator / deallocator
-//   warp 3      : A-tile producer  (bulk copy  -> a_full[tile])
-//   warps 4..27 : epilogue (6 per SM sub-partition): warp -> (A tile, 32-column part of each
-//                 96-column accumulator tile, TMEM lane quadrant = warp_id % 4); the three threads
-//                 that share a row exchange their running bounds through shared memory every
-//                 tile (stale bounds are still valid) and merge their lists once per unit
+// Warp roles (896 threads, 1 CTA / SM, persistent over units; the role warps carry the highest warp ids):
+//   B-tile producer  (bulk copy -> b_full[stage])
+//   MMA issuer(s)    (warp-uniform loop, one elected lane issues: per unit kKSteps tcgen05.cp per query tile,
+//                     per B tile kKSteps TS-form tcgen05.mma M128 x N96 into the accumulator slots; byte layout:
+//                     one issuer per query tile, each with its own pair of slots)
+//   TMEM allocator   (second MMA issuer in the byte layout)
+//   A-tile producer  (bulk copy -> a_full[tile])
+//   warps 0..23      epilogue (6 per SM sub-partition): warp -> (A tile, 32-column part of each 96-column
+//                    accumulator tile, TMEM lane quadrant = warp_id % 4); the three threads that share a row
+//                    exchange their running bounds through shared memory (stale bounds are still valid) and
+//                    merge their lists once per unit.  Byte layout, k = 2: packed-key top-2 (consume32_packed);
+//                    other kinds / k: group extrema + warp votes + insertion network (consume32)
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -323,11 +325,14 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_PACKED
 #define IAM_PACKED 1
 #endif
+#ifndef IAM_EPI_NOSYNC
+#define IAM_EPI_NOSYNC 0           // A/B aid: 1 = no __syncwarp around the tensor-memory load of the pair loop
+#endif
 #ifndef IAM_PACK_IMAD
 #define IAM_PACK_IMAD 1          // A/B aid: 0 = literal multipliers (ptxas emits LEA / IADD on the ALU pipe)
 #endif
 #ifndef IAM_PACKED_FMA_SUBS
-#define IAM_PACKED_FMA_SUBS 16   // 32: all knock-out subtractions as IMAD + one tree; 16: half as fused add-max chains
+#define IAM_PACKED_FMA_SUBS 8    // columns whose knock-out subtraction is an IMAD + tree (FMA pipe); the others: fused add-max chains. 32: all IMAD
 #endif
 template <int J>
 __device__ __forceinline__ int pack_key(int acc, uint32_t mul32) {
@@ -343,6 +348,25 @@ __device__ __forceinline__ uint32_t knock(int key, int m1, int neg_m1, uint32_t 
   return u;
 }
 __device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+// maximum of N unsigned values by three-input maxima
+template <int N>
+__device__ __forceinline__ uint32_t umax_tree(const uint32_t* x) {
+  if constexpr (N == 1) {
+    return x[0];
+  } else if constexpr (N == 2) {
+    return max(x[0], x[1]);
+  } else if constexpr (N == 3) {
+    return umax3(x[0], x[1], x[2]);
+  } else {
+    constexpr int kM = (N + 2) / 3;
+    uint32_t y[kM];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) y[i] = umax3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+    if constexpr (N % 3 == 1) y[kM - 1] = x[N - 1];
+    if constexpr (N % 3 == 2) y[kM - 1] = max(x[N - 2], x[N - 1]);
+    return umax_tree<kM>(y);
+  }
+}
 template <typename F, int... Js>
 __device__ __forceinline__ void static_for32(F&& f, std::integer_sequence<int, Js...>) {
   (f(std::integral_constant<int, Js>{}), ...);
@@ -379,20 +403,20 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
       const uint32_t d3 = umax3(c[9], u[30], u[31]);
       best = max(umax3(d0, d1, d2), d3);
     } else {
-      // Issue slots are the scarce resource once both pipes are loaded: columns 0..15 take the IMAD + three-input
-      // tree route (16 + 7 instructions), columns 16..31 two chains of fused add-max (VIADDMNMX.U32, one ALU-pipe
-      // instruction per column).
-      uint32_t u[16];
-      static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, 16>{});
-      uint32_t c[5];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) c[i] = umax3(u[3 * i], u[3 * i + 1], u[3 * i + 2]);
-      uint32_t s0 = umax3(c[0], c[1], c[2]), s1 = umax3(c[3], c[4], u[15]);
+      // Issue slots are the scarce resource once both pipes are loaded: the first kNF columns take the IMAD +
+      // three-input tree route (kNF + kNF/2 instructions), the others two chains of fused add-max
+      // (VIADDMNMX.U32, one ALU-pipe instruction per column).
+      constexpr int kNF = IAM_PACKED_FMA_SUBS;
+      static_assert(kNF >= 2 && kNF <= 30 && kNF % 2 == 0, "IAM_PACKED_FMA_SUBS");
+      uint32_t u[kNF];
+      static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, kNF>{});
+      uint32_t s0 = umax_tree<kNF / 2>(u), s1 = umax_tree<kNF / 2>(u + kNF / 2);
       const uint32_t nm = static_cast<uint32_t>(neg_m1);
+      constexpr int kMid = kNF + (32 - kNF) / 2;
 #pragma unroll
-      for (int j = 16; j < 24; ++j) s0 = max(s0, static_cast<uint32_t>(k[j]) + nm);
+      for (int j = kNF; j < kMid; ++j) s0 = max(s0, static_cast<uint32_t>(k[j]) + nm);
 #pragma unroll
-      for (int j = 24; j < 32; ++j) s1 = max(s1, static_cast<uint32_t>(k[j]) + nm);
+      for (int j = kMid; j < 32; ++j) s1 = max(s1, static_cast<uint32_t>(k[j]) + nm);
       best = max(s0, s1);
     }
     const int m2 = m1 + static_cast<int>(best);
@@ -664,11 +688,15 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           tc_fence_after();
           if constexpr (kDbg != 1) {
             int v[32];
+#if !IAM_EPI_NOSYNC
             __syncwarp();
+#endif
             tmem_ld32(tm_a + kSl * (kT * kBRows), v);
             tmem_ld_wait(v);
             // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
+#if !IAM_EPI_NOSYNC
             __syncwarp();
+#endif
             tc_fence_before();
             if (lane0) mbar_arrive_a(bar + kEmptyOff);
             consume32_packed<kDbg == 5 ? 2 : kDbg == 4 ? 1 : 0>(v, tp32, tk, pb, mul32, one);

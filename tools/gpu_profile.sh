@@ -6,6 +6,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > g
 echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1 | cut -c1-3000
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tee gpurun_out/bench_reference.log | tail -1 | cut -c1-800
 echo "== bench ORB"; timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e --no-cpu 2>&1 | tee gpurun_out/bench_orb.log | tail -1 | cut -c1-1500
+echo "== bench ORB, MMA/TMA pipeline only"; IAM_UMMA_DEBUG=1 timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e --no-cpu 2>&1 | tail -1 | cut -c1-400
+for lib in imageanalysis_b200/lib/ab_*.so; do [ -f "$lib" ] && { echo "== bench $lib"; IAMATCH_LIB=$PWD/$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1 | cut -c1-400; }; done
 echo "== bench fp16 operands"; timeout 600 python bench.py --steps 10 --warmup 3 --engine umma_f16 --no-e2e --no-cpu 2>&1 | tee gpurun_out/bench_f16.log | tail -1 | cut -c1-1500
 echo "== stage benchmarks"; timeout 900 python tools/bench_stages.py 2>&1 | tail -2 | cut -c1-1500
 echo "== ncu launch list"
