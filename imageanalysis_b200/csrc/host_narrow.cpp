@@ -68,7 +68,11 @@ int narrow_default_threads() {
 }
 
 NarrowPool::NarrowPool(int threads) {
-  backward_ = threads < 7;
+  // in order only when this process has the host to itself: several ranks narrowing at once share the memory
+  // bandwidth, and the from-the-end scheme is the one that cannot lose against the plain float32 upload
+  int ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+  backward_ = threads < 7 || ranks > 2;
   if (const char* e = getenv("IAM_NARROW_ORDER")) backward_ = e[0] == 'b';  // A/B aid: "fwd" / "bwd"
   for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { run(); });
 }

@@ -157,6 +157,7 @@ struct iam_ctx {
   int narrow_jobs_cap = 0;
   unsigned long long h2d_bytes = 0;   // descriptor bytes copied host -> device by the current iam_match_images call
   int narrowed_images = 0;
+  cudaEvent_t probe_ev[2] = {};  // last upload enqueued on each lane by iam_match_images
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -483,6 +484,7 @@ int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
   }
   for (auto& ev : c->ev) cudaEventCreate(&ev);
   for (auto& ev : c->span) cudaEventCreate(&ev);
+  for (auto& ev : c->probe_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   if (cudaMalloc(reinterpret_cast<void**>(&c->d_ctx_flag), 256) != cudaSuccess ||
       cudaMemset(c->d_ctx_flag, 1, 256) != cudaSuccess) {
     iam_destroy(c);
@@ -526,6 +528,8 @@ int iam_destroy(iam_ctx* c) {
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->span)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->probe_ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->wave_ev)
     if (ev) cudaEventDestroy(ev);
@@ -692,6 +696,7 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
   im.i8ok = want_i8 ? -1 : 0;
   if (c->profiling && !c->feed_mode) CU(cudaEventRecord(c->ev[5], us));
   if (!c->feed_mode) CU(cudaEventRecord(im.ready, us));  // feed mode: one event per wave instead
+  if (c->feed_mode) CU(cudaEventRecord(c->probe_ev[lane2 ? 1 : 0], us));  // "has this lane run dry?" (host narrowing)
   im.seq = c->feed_mode ? 0 : ++c->up_seq;
   im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
   return IAM_OK;
@@ -934,6 +939,7 @@ struct UploadFeed {  // host-side sources for iam_match_images: enqueue an image
   std::vector<std::pair<int, int>> waves_done;  // pair ranges whose done_ev was recorded, in order
   // float32 -> byte narrowing on the host (host_narrow.h): job index per slot (-1: none), in order of first use
   bool narrow = false;
+  bool narrow_backward = false;  // the workers walk the images from the last one (few workers: NarrowPool::run)
   bool narrow_always = false;  // IAM_HOST_NARROW=2 (tests): never fall back to a float32 upload of a narrowable image
   iam::NarrowJob* jobs = nullptr;
   std::vector<int> job_of_slot;
@@ -1033,9 +1039,7 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   }
   c->h2d_bytes = 0;
   c->narrowed_images = 0;
-  // Workers that outrun the bus walk the images in order and this thread never sends float32 rows (it narrows
-  // an image itself if it gets there first); otherwise the adaptive scheme of NarrowPool::run().
-  if (feed.narrow && c->narrow_pool && !c->narrow_pool->backward()) feed.narrow_always = true;
+  feed.narrow_backward = c->narrow_pool && c->narrow_pool->backward();
   c->feed_mode = true;
   c->reserve_sms = waves > 1 ? 8 : 0;
   if (const char* env = getenv("IAM_RESERVE_SMS")) c->reserve_sms = waves > 1 ? std::max(0, atoi(env)) : 0;  // A/B aid
@@ -1217,7 +1221,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
       bool any_upload = false;
       // With narrowing the enqueueing thread paces itself on the upload stream (at most two waves ahead): an image
       // is claimed for a float32 upload only when PCIe is about to run dry, which gives the workers time to get ahead.
-      if (feed->narrow && !feed->narrow_always && feed->upload_waves.size() >= 2) CU(cudaEventSynchronize(feed->upload_waves[feed->upload_waves.size() - 2]));
+      if (feed->narrow && feed->narrow_backward && !feed->narrow_always && feed->upload_waves.size() >= 2) CU(cudaEventSynchronize(feed->upload_waves[feed->upload_waves.size() - 2]));
       for (int i = 2 * p0; i < 2 * p1; ++i) {
         const int id = pairs[i];
         const int slot = id < (int)feed->slot_of_id.size() ? feed->slot_of_id[id] : -1;
@@ -1234,7 +1238,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
             // reached it yet -- PCIe then carries them while the workers go on with later images.
             iam::NarrowJob& job = feed->jobs[feed->job_of_slot[slot]];
             int st = job.state.load(std::memory_order_acquire);
-            if (st == iam::NarrowJob::kFree) {
+            if (st == iam::NarrowJob::kFree && (feed->narrow_always || feed->narrow_backward)) {
               int expect = iam::NarrowJob::kFree;
               const int claim = feed->narrow_always ? iam::NarrowJob::kBusy : iam::NarrowJob::kTaken;
               st = job.state.compare_exchange_strong(expect, claim, std::memory_order_acq_rel) ? claim : expect;
@@ -1243,7 +1247,14 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
                 job.state.store(st, std::memory_order_release);
               }
             }
-            while (st == iam::NarrowJob::kBusy) {
+            while (st == iam::NarrowJob::kBusy || st == iam::NarrowJob::kFree) {
+              // kFree is only still seen in forward order (the workers are about to reach this image): wait for
+              // them while the bus has work queued, send the float32 rows as soon as it would run dry
+              if (st == iam::NarrowJob::kFree && cudaEventQuery(c->probe_ev[0]) == cudaSuccess &&
+                  cudaEventQuery(c->probe_ev[1]) == cudaSuccess) {
+                int expect = iam::NarrowJob::kFree;
+                if (job.state.compare_exchange_strong(expect, iam::NarrowJob::kTaken, std::memory_order_acq_rel)) break;
+              }
               std::this_thread::yield();
               st = job.state.load(std::memory_order_acquire);
             }
