@@ -249,32 +249,35 @@ __global__ void __launch_bounds__(256) convert_hamming_kernel(const uint8_t* __r
   for (int b = 0; b < 4; ++b) {
     if (byte & (1u << b)) {
       a_lo |= 0x38u << (8 * b);  // 1.0
-      b_lo |= 0xC0u << (8 * b);  // -2.0
+      b_lo |= 0xE8u << (8 * b);  // -64.0 = -2 * 32 (the accumulator is a KEY: 32 * distance + column, see below)
     }
     if (byte & (1u << (b + 4))) {
       a_hi |= 0x38u << (8 * b);
-      b_hi |= 0xC0u << (8 * b);
+      b_hi |= 0xE8u << (8 * b);
     }
   }
   const size_t base = row_base(r) + static_cast<size_t>(lane >> 1) * 128 + static_cast<size_t>(lane & 1) * 8;
   *reinterpret_cast<uint2*>(a_form + base) = make_uint2(a_lo, a_hi);
   *reinterpret_cast<uint2*>(b_form + base) = make_uint2(b_lo, b_hi);
 
-  // augmentation: 32 e4m3 elements in chunks 16,17; one byte per lane
-  const int d0 = pc & 15, d1 = pc >> 4;  // pc = d0 + 16*d1, d1 <= 16
+  // augmentation: 32 e4m3 elements in chunks 16,17; one byte per lane.  The accumulator of (query q, train t) is
+  //     32 * (|q| + |t| - 2 q.t) + (t's row index mod 32)  =  32 * Hamming distance + column inside the 32-column
+  // slice an epilogue thread holds: an exact, unique key that orders like (distance, column) -- the packing that
+  // the byte layout does with 32 IMADs per slice comes out of the tensor core for free (knn_umma.cu).
+  // pc = d0 + 16*d1, d1 <= 16;  32*pc = 32*d0 + 256*(2*d1), every factor an e4m3 integer.
+  const int d0 = pc & 15, d1 = pc >> 4;
+  const uint8_t two_d1 = d1 ? static_cast<uint8_t>(e4m3_small(d1) + 0x08) : 0;  // exponent + 1
   uint8_t av = 0, bv = 0;
-  if (valid) {
-    // A: [1, 16, p0, p1, 16, ...]   B: [p0, p1, 1, 16, 0, ...]
-    switch (lane) {
-      case 0: av = 0x38; bv = e4m3_small(d0); break;
-      case 1: av = 0x58; bv = e4m3_small(d1); break;
-      case 2: av = e4m3_small(d0); bv = 0x38; break;
-      case 3: av = e4m3_small(d1); bv = 0x58; break;
-      case 4: av = 0x58; bv = 0x00; break;
-      default: break;
-    }
-  } else {
-    if (lane == 4) bv = 0x78;  // 16 * 256 = 4096 > any Hamming distance
+  // A: [32, 256, p0, 2*p1, 256, 1, 1, ...]   B: [p0, 2*p1, 32, 256, pad, j & 15, j & 16, ...]
+  switch (lane) {
+    case 0: av = 0x60; bv = valid ? e4m3_small(d0) : 0; break;
+    case 1: av = 0x78; bv = valid ? two_d1 : 0; break;
+    case 2: av = valid ? e4m3_small(d0) : 0; bv = 0x60; break;
+    case 3: av = valid ? two_d1 : 0; bv = 0x78; break;
+    case 4: av = 0x78; bv = valid ? 0x00 : 0x78; break;  // padding train rows: 256 * 256 = 65536 > any key
+    case 5: av = 0x38; bv = e4m3_small(r & 15); break;
+    case 6: av = 0x38; bv = (r & 16) ? 0x58 : 0x00; break;
+    default: break;
   }
   const size_t abase = row_base(r) + static_cast<size_t>(16 + (lane >> 4)) * 128 + static_cast<size_t>(lane & 15);
   a_form[abase] = av;

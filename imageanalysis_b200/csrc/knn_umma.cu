@@ -253,24 +253,38 @@ __device__ __forceinline__ bool any_lane(bool p) {
 #endif
 }
 
-template <int KTOP, typename O, int J0, bool kFixed = false>
-__device__ __forceinline__ void consume_group(const typename O::T* w, int tp, TopK<KTOP, O>& tk, typename O::T te) {
+// kKey (Hamming): the accumulators are keys 32 * distance + column-in-slice (convert_hamming_kernel) while bounds and
+// lists hold distances: tests compare against 32 * bound, an inserted value is decoded with one FFMA (the column is a
+// compile-time constant here).
+template <int J, bool kKey, typename T>
+__device__ __forceinline__ T key_value(T w) {
+  if constexpr (kKey) return fmaf(w, 0.03125f, -static_cast<float>(J) * 0.03125f);
+  else return w;
+}
+template <bool kKey, typename T>
+__device__ __forceinline__ T key_bound(T te) {
+  if constexpr (kKey) return te * 32.0f;
+  else return te;
+}
+template <int KTOP, typename O, int J0, bool kFixed = false, bool kKey = false>
+__device__ __forceinline__ void consume_group(const typename O::T* w, int tp, TopK<KTOP, O>& tk, typename O::T te_in) {
+  const typename O::T te = key_bound<kKey>(te_in);
   if (kFixed) {  // profiling aid: every warp does the same slow-path work (4 element tests, 2 insertions)
     const bool f0 = any_lane(O::better(w[0], O::worst())), f1 = any_lane(O::better(w[1], O::never()));
     const bool f2 = any_lane(O::better(w[2], O::worst())), f3 = any_lane(O::better(w[3], O::never()));
-    if (f0) tk.insert(w[0], enc_index<J0>(tp));
-    if (f1) tk.insert(w[1], enc_index<J0 + 1>(tp));
-    if (f2) tk.insert(w[2], enc_index<J0 + 2>(tp));
-    if (f3) tk.insert(w[3], enc_index<J0 + 3>(tp));
+    if (f0) tk.insert(key_value<J0, kKey>(w[0]), enc_index<J0>(tp));
+    if (f1) tk.insert(key_value<J0 + 1, kKey>(w[1]), enc_index<J0 + 1>(tp));
+    if (f2) tk.insert(key_value<J0 + 2, kKey>(w[2]), enc_index<J0 + 2>(tp));
+    if (f3) tk.insert(key_value<J0 + 3, kKey>(w[3]), enc_index<J0 + 3>(tp));
     return;
   }
 #if IAM_GROUP_UNCOND
   // A/B aid: no per-column tests; the (self-guarded) insertion network runs for all four columns of a triggered group
   (void)te;
-  tk.insert(w[0], enc_index<J0>(tp));
-  tk.insert(w[1], enc_index<J0 + 1>(tp));
-  tk.insert(w[2], enc_index<J0 + 2>(tp));
-  tk.insert(w[3], enc_index<J0 + 3>(tp));
+  tk.insert(key_value<J0, kKey>(w[0]), enc_index<J0>(tp));
+  tk.insert(key_value<J0 + 1, kKey>(w[1]), enc_index<J0 + 1>(tp));
+  tk.insert(key_value<J0 + 2, kKey>(w[2]), enc_index<J0 + 2>(tp));
+  tk.insert(key_value<J0 + 3, kKey>(w[3]), enc_index<J0 + 3>(tp));
   return;
 #endif
   // four votes issued back to back (computed against the bound at group entry: a superset of what
@@ -279,33 +293,33 @@ __device__ __forceinline__ void consume_group(const typename O::T* w, int tp, To
   const bool e1 = any_lane(O::better(w[1], te));
   const bool e2 = any_lane(O::better(w[2], te));
   const bool e3 = any_lane(O::better(w[3], te));
-  if (e0) tk.insert(w[0], enc_index<J0>(tp));
-  if (e1) tk.insert(w[1], enc_index<J0 + 1>(tp));
-  if (e2) tk.insert(w[2], enc_index<J0 + 2>(tp));
-  if (e3) tk.insert(w[3], enc_index<J0 + 3>(tp));
+  if (e0) tk.insert(key_value<J0, kKey>(w[0]), enc_index<J0>(tp));
+  if (e1) tk.insert(key_value<J0 + 1, kKey>(w[1]), enc_index<J0 + 1>(tp));
+  if (e2) tk.insert(key_value<J0 + 2, kKey>(w[2]), enc_index<J0 + 2>(tp));
+  if (e3) tk.insert(key_value<J0 + 3, kKey>(w[3]), enc_index<J0 + 3>(tp));
 }
 
 // Per 16-column batch the four group tests are formed and voted on up front against the bound at
 // entry (it only tightens, so the votes stay conservative): independent min3/setp/vote chains
 // instead of serialised vote->branch round trips.
-template <int KTOP, typename O, int H, bool kFixed = false>
+template <int KTOP, typename O, int H, bool kFixed = false, bool kKey = false>
 __device__ __forceinline__ void consume16(const typename O::T* w, int tp, TopK<KTOP, O>& tk, typename O::T pb) {
   using T = typename O::T;
-  const T te = kFixed ? O::never() : O::best(tk.thr(), pb);
+  const T te = kFixed ? O::never() : key_bound<kKey>(O::best(tk.thr(), pb));
   const bool t0 = any_lane(O::better(O::best(O::best3(w[0], w[1], w[2]), w[3]), te));
   const bool t1 = any_lane(O::better(O::best(O::best3(w[4], w[5], w[6]), w[7]), te));
   const bool t2 = any_lane(O::better(O::best(O::best3(w[8], w[9], w[10]), w[11]), te));
   const bool t3 = any_lane(O::better(O::best(O::best3(w[12], w[13], w[14]), w[15]), te));
-  if (t0) consume_group<KTOP, O, H * 16>(w, tp, tk, O::best(tk.thr(), pb));
-  if (t1 || kFixed) consume_group<KTOP, O, H * 16 + 4, kFixed>(w + 4, tp, tk, O::best(tk.thr(), pb));
-  if (t2) consume_group<KTOP, O, H * 16 + 8>(w + 8, tp, tk, O::best(tk.thr(), pb));
-  if (t3) consume_group<KTOP, O, H * 16 + 12>(w + 12, tp, tk, O::best(tk.thr(), pb));
+  if (t0) consume_group<KTOP, O, H * 16, false, kKey>(w, tp, tk, O::best(tk.thr(), pb));
+  if (t1 || kFixed) consume_group<KTOP, O, H * 16 + 4, kFixed, kKey>(w + 4, tp, tk, O::best(tk.thr(), pb));
+  if (t2) consume_group<KTOP, O, H * 16 + 8, false, kKey>(w + 8, tp, tk, O::best(tk.thr(), pb));
+  if (t3) consume_group<KTOP, O, H * 16 + 12, false, kKey>(w + 12, tp, tk, O::best(tk.thr(), pb));
 }
 
-template <int KTOP, typename O, bool kFixed = false>
+template <int KTOP, typename O, bool kFixed = false, bool kKey = false>
 __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, TopK<KTOP, O>& tk, typename O::T pb) {
-  consume16<KTOP, O, 0, kFixed>(&v[0], tp, tk, pb);
-  consume16<KTOP, O, 1, kFixed>(&v[16], tp, tk, pb);
+  consume16<KTOP, O, 0, kFixed, kKey>(&v[0], tp, tk, pb);
+  consume16<KTOP, O, 1, kFixed, kKey>(&v[16], tp, tk, pb);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -324,6 +338,9 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 // unit (empty lists, everything qualifies) cost seven times a late tile.
 #ifndef IAM_PACKED
 #define IAM_PACKED 1
+#endif
+#ifndef IAM_PACKED_HAMMING
+#define IAM_PACKED_HAMMING 1        // packed-key epilogue for kind::f8f6f4 (Hamming), k = 2
 #endif
 #ifndef IAM_EPI_NOSYNC
 #define IAM_EPI_NOSYNC 0           // A/B aid: 1 = no __syncwarp around the tensor-memory load of the pair loop
@@ -348,6 +365,7 @@ __device__ __forceinline__ uint32_t knock(int key, int m1, int neg_m1, uint32_t 
   return u;
 }
 __device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return max(max(a, b), c); }
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 // maximum of N unsigned values by three-input maxima
 template <int N>
 __device__ __forceinline__ uint32_t umax_tree(const uint32_t* x) {
@@ -422,6 +440,46 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
     const int m2 = m1 + static_cast<int>(best);
     tk.insert(m1 >> 5, (m1 & 31) | tp32);
     tk.insert(m2 >> 5, (m2 & 31) | tp32);
+  }
+}
+
+// Packed-key path for Hamming (kind::f8f6f4, k = 2).  The operand layout makes every fp32 accumulator the exact
+// integer  key_j = 32 * distance + j  (convert_hamming_kernel; j = column inside the thread's 32-column slice),
+// unique, ordered like (distance, column): SMALLER = nearer, ties to the lower column.  m1 = min_j key_j by
+// three-input float minima; the runner-up by a knock-out on the raw bit patterns (below).
+// The running lists stay in the float domain of Ord<F8>; the index is  e = tp32 | j  (the real column).
+template <int kMode = 0>
+__device__ __forceinline__ void consume32_packed_f(const float (&v)[32], int tp32, TopK<2, Ord<Kind::F8>>& tk, float pb) {
+  const float (&k)[32] = v;  // the accumulators ARE the keys (convert_hamming_kernel)
+  float a[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = fmin3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+  const float b0 = fmin3(a[0], a[1], a[2]), b1 = fmin3(a[3], a[4], a[5]), b2 = fmin3(a[6], a[7], a[8]);
+  const float b3 = fmin3(a[9], k[30], k[31]);
+  const float m1 = fminf(fmin3(b0, b1, b2), b3);
+  // admissible: acc < te (te an integer or +big: own second best, or a partner's second best + 1)  <=>  key < te * 32
+  const float te_key = fminf(tk.d[1], pb) * 32.0f;
+  const bool hit = kMode == 2 ? any_lane(m1 > -1.0f) : any_lane(m1 < te_key);
+  if (hit && kMode != 1) {
+    // Knock-out: t_j = key_j - (m1 + 1/4) is -1/4 for the winner and n - 1/4 (n >= 1) for every other column.  Read
+    // as UNSIGNED integers, non-negative floats order like their values and the one negative float is larger than
+    // all of them, so the runner-up is an unsigned minimum over the raw bit patterns (three-input VIMNMX3.U32).
+    const float m1q = m1 + 0.25f;
+    uint32_t u[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = __float_as_uint(k[j] - m1q);
+    uint32_t c[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) c[i] = umin3(u[3 * i], u[3 * i + 1], u[3 * i + 2]);
+    const uint32_t d0 = umin3(c[0], c[1], c[2]), d1 = umin3(c[3], c[4], c[5]), d2 = umin3(c[6], c[7], c[8]);
+    const uint32_t d3 = umin3(c[9], u[30], u[31]);
+    const float m2 = __uint_as_float(min(umin3(d0, d1, d2), d3)) + m1q;
+    // key -> (distance, column): key + 2^23 carries the integer key in its mantissa, the column in its low five bits
+    const uint32_t q1 = __float_as_uint(m1 + 8388608.0f), q2 = __float_as_uint(m2 + 8388608.0f);
+    const float j1 = __uint_as_float((q1 & 31u) | 0x4b000000u) - 8388608.0f;
+    const float j2 = __uint_as_float((q2 & 31u) | 0x4b000000u) - 8388608.0f;
+    tk.insert((m1 - j1) * 0.03125f, static_cast<int>(q1 & 31u) | tp32);
+    tk.insert((m2 - j2) * 0.03125f, static_cast<int>(q2 & 31u) | tp32);
   }
 }
 
@@ -642,6 +700,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const bool lane0 = lane == 0;
     TopK<KTOP, O> tk;
     constexpr bool kPacked = IAM_PACKED && kKind == Kind::I8 && KTOP == 2;
+    constexpr bool kPackedF = IAM_PACKED && IAM_PACKED_HAMMING && kKind == Kind::F8 && KTOP == 2;
+    constexpr bool kKeyF = kKind == Kind::F8;  // accumulators are keys 32 * distance + column (convert_hamming_kernel)
     // Multipliers ptxas cannot fold (n_units >= 0): with a literal 32 the packing multiply-adds are strength-reduced
     // to LEA, an ALU-pipe instruction; as register operands they stay IMADs on the otherwise idle FMA pipe.
     const uint32_t opaque0 = static_cast<uint32_t>(n_units) >> 31;
@@ -731,7 +791,8 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             T g = O::from_bits(lds_volatile_b32_a(rd));
   #pragma unroll
             for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
-            pb = O::best(pb, O::loosen(g));
+            if constexpr (kKeyF) pb = O::best(pb, g + 1.0f);  // distances are integers: the first value NOT admissible
+            else pb = O::best(pb, O::loosen(g));
           }
           const uint32_t bar = bar_full0 + slot * 8;
           mbar_wait_bare_a(bar, par);
@@ -747,13 +808,16 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             if (lane0) mbar_arrive_a(bar + kEmptyOff);
             if (kDbg == 0) {
               if constexpr (kPacked) consume32_packed<0>(v, tp * 32, tk, pb, mul32, one);
-              else consume32<KTOP, O>(v, tp, tk, pb);
+              else if constexpr (kPackedF) consume32_packed_f<0>(v, tp * 32, tk, pb);
+              else consume32<KTOP, O, false, kKeyF>(v, tp, tk, pb);
             } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
               if constexpr (kPacked) consume32_packed<2>(v, tp * 32, tk, pb, mul32, one);
-              else consume32<KTOP, O, true>(v, tp, tk, pb);
+              else if constexpr (kPackedF) consume32_packed_f<2>(v, tp * 32, tk, pb);
+              else consume32<KTOP, O, true, kKeyF>(v, tp, tk, pb);
             } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): tests + votes + branches, never taken
               if constexpr (kPacked) consume32_packed<1>(v, tp * 32, tk, pb, mul32, one);
-              else consume32<KTOP, O>(v, tp, tk, O::never());
+              else if constexpr (kPackedF) consume32_packed_f<1>(v, tp * 32, tk, pb);
+              else consume32<KTOP, O, false, kKeyF>(v, tp, tk, O::never());
             } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
               tk.d[0] = O::best(tk.d[0], v[0]);  // the load itself is volatile: all 32 columns are still read
             } else {  // profiling aid (IAM_UMMA_DEBUG=2): fast path only, results NOT valid
@@ -799,7 +863,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             }
           } else {
             fin.d[s] = static_cast<float>(tk.d[s]);
-            fin.i[s] = enc == 0x7fffffff ? -1 : dec_index(enc);
+            fin.i[s] = enc == 0x7fffffff ? -1 : (kPackedF ? enc : dec_index(enc));
           }
         }
       }

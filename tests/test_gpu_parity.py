@@ -77,6 +77,27 @@ def test_knn_ragged_sizes(norm, gen, nb, nq, nt):
         assert (ridx[0, :nt] == ri).all() and (rdist[0, :nt] == rd).all()
 
 
+def test_hamming_extreme_popcounts_stay_exact():
+    """The Hamming operand layout makes the accumulator a key, 32 * distance + column (convert_hamming_kernel), out of
+    partial sums up to 32 * 512 = 16384 in magnitude: saturated, empty and nearly-saturated descriptors must still
+    give exact distances and cv2's tie order, for every k."""
+    rng = np.random.default_rng(7)
+    q = np.zeros((200, 32), np.uint8)
+    q[::3] = 255                                   # all ones
+    q[1::3] = rng.integers(0, 256, size=(67, 32), dtype=np.uint8) | rng.integers(0, 256, size=(67, 32), dtype=np.uint8) | 0xF0
+    t = np.full((333, 32), 255, np.uint8)
+    t[::4] = 0
+    t[1::4, :5] = rng.integers(0, 256, size=(83, 5), dtype=np.uint8)
+    t[2::4] = rng.integers(0, 256, size=(83, 32), dtype=np.uint8) | 0x0F
+    for k in (1, 2, 3):
+        for engine, _ in ENGINES:
+            idx, dist, ridx, rdist = run_knn(_capi.NORM_HAMMING, q, t, k, engine)
+            oi, od = oracle.knn(q, t, k, _capi.NORM_HAMMING, threads=4)
+            ri, rd = oracle.knn(t, q, k, _capi.NORM_HAMMING, threads=4)
+            assert (idx[0, :200] == oi).all() and (dist[0, :200] == od).all()
+            assert (ridx[0, :333] == ri).all() and (rdist[0, :333] == rd).all()
+
+
 def test_extreme_values_stay_exact():
     """all-255 vs all-0 rows: d^2 = 128*255^2 = 8 323 200, the largest value the
     fp32 accumulator must hold exactly."""

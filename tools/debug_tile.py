@@ -22,8 +22,9 @@ def main():
             exp = ((q[:128, None].astype(np.int64) - t[None, :128].astype(np.int64)) ** 2).sum(-1)
             dot = -2 * (q[:128].astype(np.int64) @ t[:128].astype(np.int64).T)
         else:
-            exp = np.unpackbits(q[:128, None] ^ t[None, :128], axis=-1).sum(-1)
-            dot = -2 * (np.unpackbits(q[:128], axis=-1).astype(np.int64) @ np.unpackbits(t[:128], axis=-1).astype(np.int64).T)
+            # the accumulator is the key 32 * distance + (train row mod 32); without the augmentation K-step: -64 q.t
+            exp = 32 * np.unpackbits(q[:128, None] ^ t[None, :128], axis=-1).sum(-1).astype(np.int64) + (np.arange(128) % 32)[None, :]
+            dot = -64 * (np.unpackbits(q[:128], axis=-1).astype(np.int64) @ np.unpackbits(t[:128], axis=-1).astype(np.int64).T)
         for tag, kw in (("prod", dict()), ("prod_A_in_tmem", dict(ksteps=-9)), ("data_only", dict(ksteps=8)),
                         ("data_only_A_in_tmem", dict(ksteps=-8))):
             try:
