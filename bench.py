@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--desc", type=int, default=5000)
     ap.add_argument("--detector", default="SIFT", choices=["SIFT", "ORB"])
     ap.add_argument("--pairs", default="sequential", choices=["sequential", "all"])
+    ap.add_argument("--workload", default="strip", choices=["strip", "bates"],
+                    help="strip: BASELINE configs[1] per GPU (weak scaling, the default); bates: configs[3], 2812 frames "
+                         "on a 38 x 74 serpentine survey grid, geotag-neighbour pair list sharded across the ranks")
     ap.add_argument("--engine", default="auto", choices=["auto", "umma", "umma_f16", "simt"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -229,7 +232,29 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bates_pairs(frames):
+    """BASELINE configs[3]: 38 flight lines x 74 frames, 15 m along-track, 25 m cross-track,
+    serpentine; pairs = the reference's camera-distance window (matcher.py:858-903, pairs.worklist 'geotag')."""
+    from imageanalysis_b200 import pairs as wl
+    per_line = 74
+    neds = []
+    for f in range(frames):
+        line, k = divmod(f, per_line)
+        along = k if line % 2 == 0 else per_line - 1 - k
+        neds.append([15.0 * along, 25.0 * line, -75.0])
+    return wl.pair_array(wl.worklist(neds, "geotag"))
+
+
 def workload_config(args, n_pairs, world):
+    if args.workload == "bates":
+        return {"workload": "%d frames (38 x 74 serpentine survey grid) x %d %s descriptors/frame, geotag-neighbour pair "
+                            "list (reference matcher.py:858-903), %d pairs in all, sharded across %d GPU(s)" % (
+                                args.frames, args.desc, args.detector, n_pairs, world),
+                "frames": args.frames, "desc_per_frame": args.desc, "pairs_total": n_pairs,
+                "pairs_per_gpu": -(-n_pairs // world), "match_ratio": 0.75, "cap": 2000, "min_pairs": 25,
+                "l2_hygiene": "inputs larger than L2 (byte forms %.2f GB per GPU, replicated)" % (
+                    args.frames * (-(-args.desc // 256) * 256) * 192 / 1e9),
+                "parallelism": "pair-sharded x%d + 1 NCCL all-gather of match tables" % world if world > 1 else "single GPU"}
     return {"workload": "%d frames x %d %s descriptors/frame, %s pair list (%d pairs) per GPU" % (
                 args.frames, args.desc, args.detector,
                 "|i-j|<=4 (reference matcher.py:899)" if args.pairs == "sequential" else "all-pairs", n_pairs),
@@ -254,11 +279,23 @@ def main():
     norm = _capi.NORM_L2 if args.detector == "SIFT" else _capi.NORM_HAMMING
     nbytes = 128 if args.detector == "SIFT" else 32
 
-    des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=1234 + rank, device=dev)
-    # host buffers exactly as the reference holds them: float32 [N,128] for SIFT (image.py:160-180), uint8 for ORB
-    host = torch.from_numpy(des_u8.astype(np.float32) if args.detector == "SIFT" else des_u8).pin_memory()
-    host_np = host.numpy()
-    pairs = pair_list(args.frames, args.pairs)
+    bates = args.workload == "bates"
+    if bates:  # every rank holds every frame (replicated descriptors), the pair list is sharded: strong scaling
+        if args.frames == 500:
+            args.frames = 2812
+        args.no_e2e = args.no_cpu = True
+        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=1234, device=dev)
+        host_np = des_u8
+        all_pairs = bates_pairs(args.frames)
+        pairs, _, _ = dist.shard_pairs(all_pairs, rank, world)
+        P_total = len(all_pairs)
+    else:
+        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=1234 + rank, device=dev)
+        # host buffers exactly as the reference holds them: float32 [N,128] for SIFT (image.py:160-180), uint8 for ORB
+        host = torch.from_numpy(des_u8.astype(np.float32) if args.detector == "SIFT" else des_u8).pin_memory()
+        host_np = host.numpy()
+        pairs = pair_list(args.frames, args.pairs)
+        P_total = len(pairs) * world
     P = len(pairs)
 
     eng = _capi.Engine(norm, nbytes, local)
@@ -279,8 +316,8 @@ def main():
     gather_out = None
     gather_ev = []
     if world > 1:  # every rank ends a step holding all ranks' tables
-        gather_out = (torch.empty((P * world, prm.cap, 2), dtype=torch.int32, device=dev),
-                      torch.empty((P * world,), dtype=torch.int32, device=dev))
+        gather_out = (torch.empty((P_total, prm.cap, 2), dtype=torch.int32, device=dev),
+                      torch.empty((P_total,), dtype=torch.int32, device=dev))
 
     def step_device(timed=False):
         dt, dc = eng.match_pairs_device(pairs, prm)
@@ -290,7 +327,7 @@ def main():
             if timed:
                 g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 g0.record(stream)
-            dist.allgather_tables(t, c, P * world, rank, world, out=gather_out)
+            dist.allgather_tables(t, c, P_total, rank, world, out=gather_out)
             if timed:
                 g1.record(stream)
                 gather_ev.append((g0, g1))
@@ -329,7 +366,7 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
     ms = float(t_ms.item())
-    value = P * world * args.steps / (ms / 1e3)
+    value = P_total * args.steps / (ms / 1e3)
 
     # ---- end to end through the public API with host buffers -----------------
     e2e = None
@@ -395,7 +432,7 @@ def main():
         if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
     work = FLOP_PER_PAIR_L2 if args.detector == "SIFT" else OP_PER_PAIR_HAMMING
     work *= (args.desc / 5000.0) ** 2
-    achieved = P * work / (knn_kernel_ms / 1e3) / 1e12 if knn_kernel_ms > 0 else None
+    achieved = P * work / (knn_kernel_ms / 1e3) / 1e12 if knn_kernel_ms > 0 else None  # rank 0's shard, rank 0's kernel time
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -419,9 +456,9 @@ def main():
         cpu = cpu_pairs_per_s(des_u8, pairs, args.detector, args.cpu_pairs, repeats=2)
     line = {"metric": "image-pairs matched/sec (5000 %s desc/img)" % args.detector, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if bates else "weak", "vs_baseline": None,
             "dtype": {0: "f16", 1: "e4m3", 2: "u8 (s32 accumulate)"}.get(tm.mma_kind, "u8"), "data": "synthetic",
-            "config": workload_config(args, P, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "config": workload_config(args, P_total if bates else P, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
 

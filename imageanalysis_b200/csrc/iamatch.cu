@@ -138,6 +138,8 @@ struct iam_ctx {
   bool timing_pending = false;
   bool profiling = false;
   cudaEvent_t ev[6] = {};
+  std::vector<cudaEvent_t> chunk_ev;  // profiling: (kNN start, kNN end, reductions end) per chunk of the last match call
+  int n_prof_chunks = 0;
   std::vector<cudaEvent_t> wave_ev;   // one event per wave of uploads in iam_match_images
   int reserve_sms = 0;                // SMs left free for conversion kernels while uploads are in flight
   bool feed_mode = false;             // inside iam_match_images: no per-image memset / event
@@ -533,6 +535,8 @@ int iam_destroy(iam_ctx* c) {
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->wave_ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->chunk_ev)
+    if (ev) cudaEventDestroy(ev);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return IAM_OK;
@@ -587,9 +591,16 @@ int iam_get_timing(iam_ctx* c, iam_timing* out) {
   }
   if (c->timing_pending) {
     CU(cudaSetDevice(c->device));
-    CU(cudaEventSynchronize(c->ev[2]));
-    CU(cudaEventElapsedTime(&c->timing.knn_ms, c->ev[0], c->ev[1]));
-    CU(cudaEventElapsedTime(&c->timing.reduce_ms, c->ev[1], c->ev[2]));
+    c->timing.knn_ms = 0.f;
+    c->timing.reduce_ms = 0.f;
+    for (int k = 0; k < c->n_prof_chunks; ++k) {
+      float a = 0.f, b = 0.f;
+      CU(cudaEventSynchronize(c->chunk_ev[3 * k + 2]));
+      CU(cudaEventElapsedTime(&a, c->chunk_ev[3 * k], c->chunk_ev[3 * k + 1]));
+      CU(cudaEventElapsedTime(&b, c->chunk_ev[3 * k + 1], c->chunk_ev[3 * k + 2]));
+      c->timing.knn_ms += a;
+      c->timing.reduce_ms += b;
+    }
     c->timing_pending = false;
   }
   *out = c->timing;
@@ -1212,6 +1223,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
   c->timing.knn_ms = 0.f;
   c->timing.reduce_ms = 0.f;
   const int n_chunks = (int)pl.chunk_rows.size();
+  int n_prof = 0;
   std::vector<std::pair<int, int>> ran;
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int p0 = pl.chunk_pair_begin[ch], p1 = pl.chunk_pair_begin[ch + 1];
@@ -1286,10 +1298,19 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     } else if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) {
       return rc;
     }
-    const bool prof = c->profiling && n_chunks == 1;
-    if (prof) CU(cudaEventRecord(c->ev[0], c->stream));
+    const bool prof = c->profiling && !feed;  // per-chunk event triples, summed in iam_get_timing
+    cudaEvent_t* pev = nullptr;
+    if (prof) {
+      while (c->chunk_ev.size() < size_t(3 * (n_prof + 1))) {
+        cudaEvent_t e = nullptr;
+        CU(cudaEventCreate(&e));
+        c->chunk_ev.push_back(e);
+      }
+      pev = &c->chunk_ev[3 * n_prof++];
+    }
+    if (prof) CU(cudaEventRecord(pev[0], c->stream));
     if ((rc = launch_knn(c, engine, kind, k, u0, u1 - u0)) != IAM_OK) return rc;
-    if (prof) CU(cudaEventRecord(c->ev[1], c->stream));
+    if (prof) CU(cudaEventRecord(pev[1], c->stream));
     cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
     const iam::RedJob* jobs = c->jobs.as<iam::RedJob>() + size_t(p0) * 2;
@@ -1318,7 +1339,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
                                c->out_table.as<int>() + size_t(p0) * cap * 2, c->out_count.as<int>() + p0, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "cross-check launch: %s", cudaGetErrorString(e));
     c->timing.total_launches += 3;
-    if (prof) CU(cudaEventRecord(c->ev[2], c->stream));
+    if (prof) CU(cudaEventRecord(pev[2], c->stream));
     if (feed) {
       const size_t w = feed->waves_done.size();
       if (c->done_ev.size() <= w) {
@@ -1329,7 +1350,8 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
       feed->waves_done.emplace_back(p0, p1);
     }
   }
-  c->timing_pending = c->profiling && n_chunks == 1 && n_pairs > 0;  // resolved lazily in iam_get_timing
+  c->timing_pending = n_prof > 0;  // resolved lazily in iam_get_timing
+  c->n_prof_chunks = n_prof;
   if ((rc = mark_compute(c)) != IAM_OK) return rc;
   c->last_pairs = n_pairs;
   c->last_cap = prm->cap;
