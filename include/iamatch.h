@@ -190,7 +190,15 @@ int iam_match_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs,
  * The pair list is cut into waves; each image's H2D copy + layout conversion
  * is enqueued on an upload stream right before the first wave that needs it,
  * so PCIe transfers overlap the matching of earlier waves.  Outputs as
- * iam_match_pairs.  The images stay resident afterwards. */
+ * iam_match_pairs.  The images stay resident afterwards.
+ * float32 L2 descriptors (the reference's SIFT arrays, image.py:160-180, are
+ * integers in 0..255): worker threads of the library narrow them to bytes in
+ * a page-locked arena while earlier waves upload and match, so a quarter of
+ * the bytes crosses PCIe; an image with a component that is not an integer in
+ * 0..255 is sent as float32 and the call repeats itself on fp16 operands.
+ * Transport only: every distance is computed on the GPU.  Environment:
+ * IAM_HOST_NARROW=0 switches it off, IAM_HOST_THREADS=n sets the worker count
+ * (default: hardware threads / LOCAL_WORLD_SIZE, at most 16, minus one). */
 int iam_match_images(iam_ctx* ctx, int n_images, const int32_t* image_ids,
                      const void* const* host_ptrs, const int32_t* counts, int dtype,
                      const int32_t* const* key_ptrs,

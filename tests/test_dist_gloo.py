@@ -75,3 +75,21 @@ def test_allgather_single_rank_is_identity():
     c = torch.tensor([1, 2, 3], dtype=torch.int32)
     t2, c2 = dist.allgather_tables(t, c, 3, 0, 1)
     assert t2 is t and c2 is c
+
+
+def test_bates_worklist_matches_survey_count():
+    """BASELINE configs[3]: 38 x 74 serpentine grid, the reference's camera-distance window (matcher.py:858-903):
+    32 neighbours per interior frame, ~4.3e4 pairs; shards tile the list without gaps."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from imageanalysis_b200 import pairs as wl
+    p = bench.bates_pairs(2812)
+    assert len(p) == 42694 and (p[:, 0] < p[:, 1]).all()
+    deg = np.bincount(p.ravel(), minlength=2812)
+    assert deg.max() == 32 and np.median(deg) == 32
+    assert (np.lexsort((p[:, 1], p[:, 0])) == np.arange(len(p))).all()      # (i, j)-sorted: contiguous shards share image i
+    cuts = [wl.shard(len(p), r, 8) for r in range(8)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == len(p) and all(cuts[r][1] == cuts[r + 1][0] for r in range(7))
