@@ -96,7 +96,7 @@ struct Cfg : LayD<kKind> {
   static constexpr size_t kSmemA = kT * L::kTileBytes;            // staging for the next item's query tiles
   static constexpr size_t kSmemB = kBStages * L::kBTileBytes;     // streamed train tiles
   static constexpr size_t kSmemBars = ((sizeof(Barriers) + 127) / 128) * 128;
-  static constexpr size_t kSmemShare = 2 * kParts * kRows * 4;    // running k-th bests exchanged between the column parts of a row
+  static constexpr size_t kSmemShare = 2 * kParts * kRows * 8;    // running bests exchanged between the column parts of a row: 8-byte slots (k-th best; the pair loop of the packed path also publishes the best)
   static constexpr size_t kSmemMerge = (kParts > 1 ? kParts - 1 : 1) * kRows * 3 * 8;  // end-of-item hand-over of the other parts' lists
   static constexpr size_t kSmemTotal = kSmemA + kSmemB + kSmemBars + kSmemShare + kSmemMerge + 128;
   static_assert(kCtasPerSm * (kSmemTotal + 1024) <= 233472, "shared memory budget");
@@ -339,6 +339,12 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_PACKED
 #define IAM_PACKED 1
 #endif
+#ifndef IAM_ROW_BOUND
+#define IAM_ROW_BOUND 1             // pair loop: bound = the row's true second best (parts publish best and second best)
+#endif
+#ifndef IAM_RAW_FIRST
+#define IAM_RAW_FIRST 0             // A/B aid: 1 = per-slice test on the raw accumulators, keys built only on a hit (measured 18.0 vs 16.4 ms: the second tree lands on the ALU pipe)
+#endif
 #ifndef IAM_PACKED_HAMMING
 #define IAM_PACKED_HAMMING 1        // packed-key epilogue for kind::f8f6f4 (Hamming), k = 2
 #endif
@@ -395,6 +401,24 @@ __device__ __forceinline__ void static_for32(F&& f, std::integer_sequence<int, J
 template <int kMode = 0>
 __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, TopK<2, Ord<Kind::I8>>& tk, int pb,
                                                  uint32_t mul32, uint32_t one) {
+  const int te = max(tk.d[1], pb);
+#if IAM_RAW_FIRST
+  // the test needs no keys: largest raw accumulator of the slice against the bound
+  int ra[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) ra[i] = imax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+  const int vmax = max(imax3(imax3(ra[0], ra[1], ra[2]), imax3(ra[3], ra[4], ra[5]), imax3(ra[6], ra[7], ra[8])),
+                       imax3(ra[9], v[30], v[31]));
+  const bool hit = kMode == 2 ? any_lane(vmax > -1) : any_lane(vmax > te);
+  if (hit && kMode != 1) {
+    int k[32];
+    static_for32([&](auto j) { k[j] = pack_key<j>(v[j], mul32); }, std::make_integer_sequence<int, 32>{});
+    int a[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) a[i] = imax3(k[3 * i], k[3 * i + 1], k[3 * i + 2]);
+    const int m1 = max(imax3(imax3(a[0], a[1], a[2]), imax3(a[3], a[4], a[5]), imax3(a[6], a[7], a[8])),
+                       imax3(a[9], k[30], k[31]));
+#else
   int k[32];
   static_for32([&](auto j) { k[j] = pack_key<j>(v[j], mul32); }, std::make_integer_sequence<int, 32>{});
   int a[10];
@@ -404,11 +428,11 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
   const int b3 = imax3(a[9], k[30], k[31]);
   const int m1 = max(imax3(b0, b1, b2), b3);
   // admissible: acc > te  <=>  key > te * 32 + 31
-  const int te = max(tk.d[1], pb);
   int te_key;
   asm("mad.lo.s32 %0, %1, %2, 31;" : "=r"(te_key) : "r"(te), "r"(mul32));
   const bool hit = kMode == 2 ? any_lane(m1 > -1) : any_lane(m1 > te_key);
   if (hit && kMode != 1) {
+#endif
     const int neg_m1 = -m1;
     uint32_t best;
     if constexpr (IAM_PACKED_FMA_SUBS >= 32) {  // every subtraction an IMAD, one three-input tree
@@ -530,7 +554,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   const int first_pu = blockIdx.x / kCtas;
   const int pu_stride = gridDim.x / kCtas;
 
-  for (int i = threadIdx.x; i < 2 * kParts * kRows; i += blockDim.x) share[i] = O::bits(O::worst());
+  for (int i = threadIdx.x; i < 2 * 2 * kParts * kRows; i += blockDim.x) share[i] = O::bits(O::worst());
   if (role == 1 && elect_one()) {
     for (int i = 0; i < kT; ++i) {
       mbar_init(&bars->a_full[i], 1);
@@ -691,9 +715,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const int part = e % kParts;        // which 32 of the B tile's columns
     const int quad = warp & 3;          // TMEM lane quadrant this warp may touch
     const int urow = a * kTileRows + quad * 32 + lane;  // row within the unit
-    constexpr uint32_t kPartStride = kRows * 4;                 // bytes between the parts' bound slots of one row
+    constexpr uint32_t kPartStride = kRows * 8;                 // bytes between the parts' bound slots of one row
     constexpr uint32_t kParityStride = kParts * kPartStride;    // bytes between the two unit-parity buffers
-    const uint32_t share_row = smem_u32(share) + urow * 4;
+    const uint32_t share_row = smem_u32(share) + urow * 8;
     const uint32_t bar_full0 = pin_reg(smem_u32(&bars->t_full[0]));
     constexpr uint32_t kEmptyOff = kSlots * 8;                  // t_empty[] follows t_full[] in Barriers
     const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
@@ -732,7 +756,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       // any partner reads it, so a slot only ever holds the worst value or values of the unit being processed.
       const uint32_t rd = pin_reg(share_row + (uit & 1) * kParityStride);
       const uint32_t wr = pin_reg(rd + part * kPartStride);
-      sts_volatile_b32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, O::bits(O::worst()));
+      sts_volatile_v2b32_a(share_row + ((uit + 1) & 1) * kParityStride + part * kPartStride, O::bits(O::worst()), O::bits(O::worst()));
       if constexpr (kPair) {
         // Production shape: this query tile owns the accumulator slots a and a + 2 and uses them alternately, so the
         // tiles are walked in PAIRS with every barrier / tensor-memory address a constant offset from a pinned base,
@@ -768,16 +792,35 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         };
         int tp32 = part * 32 - phase * (kBRows);  // 32 * (tile * kParts + part) of the pair's first tile
         for (int tb = -phase; tb < n_tb; tb += 2, tp32 += 2 * kBRows) {
-          T g = O::from_bits(lds_volatile_b32_a(rd));
+#if IAM_ROW_BOUND
+          {
+            // The row's true second best so far: every part publishes (second best, best); the second largest of the
+            // six values is  max(second largest of the three bests, largest of the three second bests).
+            static_assert(!IAM_ROW_BOUND || kParts == 3, "row-exact bound: three column parts");
+            const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride), e2 = lds_volatile_v2b32_a(rd + 2 * kPartStride);
+            const T h0 = O::from_bits(e0.y), h1 = O::from_bits(e1.y), h2 = O::from_bits(e2.y);
+            const T second_h = O::best3(min(h0, h1), min(h0, h2), min(h1, h2));
+            const T g = O::best(second_h, O::best3(O::from_bits(e0.x), O::from_bits(e1.x), O::from_bits(e2.x)));
+            pb = O::best(pb, O::loosen(g));
+          }
+#else
+          {
+            T g = O::from_bits(lds_volatile_b32_a(rd));
 #pragma unroll
-          for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
-          pb = O::best(pb, O::loosen(g));
+            for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
+            pb = O::best(pb, O::loosen(g));
+          }
+#endif
           if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tp32);
           if (tb + 1 < n_tb) {
             tile(std::integral_constant<uint32_t, 1>{}, tp32 + kBRows);
             par ^= 1;
           }
+#if IAM_ROW_BOUND
+          sts_volatile_v2b32_a(wr, O::bits(tk.d[KTOP - 1]), O::bits(tk.d[0]));
+#else
           sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
+#endif
         }
         phase = (phase + n_tb) & 1;
       } else {

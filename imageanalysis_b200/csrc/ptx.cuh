@@ -391,6 +391,14 @@ __device__ __forceinline__ void sts_volatile_f32(void* p, float v) {
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }  // -> FMNMX3
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }                // -> VIMNMX3
+__device__ __forceinline__ uint2 lds_volatile_v2b32_a(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile_v2b32_a(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_volatile_b32_a(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
