@@ -1042,7 +1042,13 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   if (feed.narrow && !c->narrow_pool_tried) {
     c->narrow_pool_tried = true;
     const int threads = iam::narrow_default_threads();
-    if (threads > 0) c->narrow_pool.reset(new iam::NarrowPool(threads));
+    if (threads > 0) {
+      try {
+        c->narrow_pool.reset(new iam::NarrowPool(threads));
+      } catch (...) {  // no threads to be had: the float32 rows cross the bus as they are
+        c->narrow_pool.reset();
+      }
+    }
   }
   if (feed.narrow && c->narrow_pool) {  // the arena of the previous call must have left the host
     CU(cudaStreamSynchronize(c->up_stream));
@@ -1136,7 +1142,13 @@ int start_narrowing(iam_ctx* c, const Plan& pl, const int32_t* pairs, UploadFeed
     if (c->narrow_arena) CU(cudaFreeHost(c->narrow_arena));
     c->narrow_arena = nullptr;
     c->narrow_cap = 0;
-    CU(cudaHostAlloc(reinterpret_cast<void**>(&c->narrow_arena), bytes + bytes / 8, cudaHostAllocDefault));
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->narrow_arena), bytes + bytes / 8, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();  // no page-locked memory for the arena: plain float32 uploads, not an error
+      c->narrow_arena = nullptr;
+      feed->narrow = false;
+      feed->job_of_slot.assign(feed->n_images, -1);
+      return IAM_OK;
+    }
     c->narrow_cap = bytes + bytes / 8;
   }
   if (c->narrow_jobs_cap < (int)order.size()) {

@@ -345,6 +345,9 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_RAW_FIRST
 #define IAM_RAW_FIRST 0             // A/B aid: 1 = per-slice test on the raw accumulators, keys built only on a hit (measured 18.0 vs 16.4 ms: the second tree lands on the ALU pipe)
 #endif
+#ifndef IAM_FMA_DECODE
+#define IAM_FMA_DECODE 0            // A/B aid: winners' (value, index) by IMAD.HI / IMAD instead of SHF / LOP3
+#endif
 #ifndef IAM_PACKED_HAMMING
 #define IAM_PACKED_HAMMING 1        // packed-key epilogue for kind::f8f6f4 (Hamming), k = 2
 #endif
@@ -402,6 +405,10 @@ template <int kMode = 0>
 __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, TopK<2, Ord<Kind::I8>>& tk, int pb,
                                                  uint32_t mul32, uint32_t one) {
   const int te = max(tk.d[1], pb);
+  const uint32_t two27 = mul32 << 22;                      // opaque like mul32: stays a register operand
+  const int neg32 = -static_cast<int>(mul32);
+  (void)two27;
+  (void)neg32;
 #if IAM_RAW_FIRST
   // the test needs no keys: largest raw accumulator of the slice against the bound
   int ra[10];
@@ -449,7 +456,7 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
       // three-input tree route (kNF + kNF/2 instructions), the others two chains of fused add-max
       // (VIADDMNMX.U32, one ALU-pipe instruction per column).
       constexpr int kNF = IAM_PACKED_FMA_SUBS;
-      static_assert(kNF >= 2 && kNF <= 30 && kNF % 2 == 0, "IAM_PACKED_FMA_SUBS");
+      static_assert(kNF >= 32 || (kNF >= 2 && kNF % 2 == 0), "IAM_PACKED_FMA_SUBS");
       uint32_t u[kNF];
       static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, kNF>{});
       uint32_t s0 = umax_tree<kNF / 2>(u), s1 = umax_tree<kNF / 2>(u + kNF / 2);
@@ -462,8 +469,19 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
       best = max(s0, s1);
     }
     const int m2 = m1 + static_cast<int>(best);
+#if IAM_FMA_DECODE
+    // value = key >> 5 as the high half of key * 2^27, index = key - 32 * value + tp32: multiply-adds (FMA pipe)
+    // instead of a shift and a LOP3 on the ALU pipe, which is the busier one
+    const int x1 = __umulhi(static_cast<uint32_t>(m1), two27), x2 = __umulhi(static_cast<uint32_t>(m2), two27);
+    int e1, e2;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(e1) : "r"(x1), "r"(neg32), "r"(m1 + tp32));
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(e2) : "r"(x2), "r"(neg32), "r"(m2 + tp32));
+    tk.insert(x1, e1);
+    tk.insert(x2, e2);
+#else
     tk.insert(m1 >> 5, (m1 & 31) | tp32);
     tk.insert(m2 >> 5, (m2 & 31) | tp32);
+#endif
   }
 }
 

@@ -3,6 +3,7 @@
 # bench-sized launch, one ncu --set full capture of the kNN kernel.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== pytest gpu (all)"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tee gpurun_out/pytest_gpu.log | tail -3
 echo "== bench full"; timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tee gpurun_out/bench_full.log | tail -1 | cut -c1-3000
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tee gpurun_out/bench_reference.log | tail -1 | cut -c1-800
 echo "== bench ORB"; timeout 600 python bench.py --steps 10 --warmup 3 --detector ORB --no-e2e --no-cpu 2>&1 | tee gpurun_out/bench_orb.log | tail -1 | cut -c1-1500
@@ -17,6 +18,8 @@ timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
 tail -3 gpurun_out/traffic.csv
 echo "== ncu full (knn kernel)"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:knn_umma -s 1 -c 1 -f -o gpurun_out/knn_umma python bench.py --steps 1 --warmup 1 --frames 60 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
+echo "== ncu full (knn kernel, ORB)"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:knn_umma -s 1 -c 1 -f -o gpurun_out/knn_umma_orb python bench.py --steps 1 --warmup 1 --frames 60 --detector ORB --no-e2e --no-cpu > gpurun_out/ncu_full_orb.log 2>&1
 echo "== ncu full (ba kernel)"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ba_kernel -s 2 -c 1 -f -o gpurun_out/ba_kernel python tools/bench_stages.py --frames 20 > gpurun_out/ncu_ba.log 2>&1
 ls -la gpurun_out | head -40
