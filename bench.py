@@ -235,13 +235,8 @@ def run_reference(args):
 def bates_pairs(frames):
     """BASELINE configs[3]: 38 flight lines x 74 frames, 15 m along-track, 25 m cross-track,
     serpentine; pairs = the reference's camera-distance window (matcher.py:858-903, pairs.worklist 'geotag')."""
-    from imageanalysis_b200 import pairs as wl
-    per_line = 74
-    neds = []
-    for f in range(frames):
-        line, k = divmod(f, per_line)
-        along = k if line % 2 == 0 else per_line - 1 - k
-        neds.append([15.0 * along, 25.0 * line, -75.0])
+    from imageanalysis_b200 import pairs as wl, synth
+    neds = synth.survey_grid_neds()[:frames]
     return wl.pair_array(wl.worklist(neds, "geotag"))
 
 

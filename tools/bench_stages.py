@@ -118,6 +118,59 @@ def main():
                              "sample": "%d observations of the same problem through oracle.ba_residuals (numpy restatement of Optimizer.fun)" % int(sel.sum())}}
     out.append(line)
     print(json.dumps(line))
+    eng.close()
+
+    # ------------------------------------------------------------------ essential-matrix RANSAC (matcher.py:126)
+    # BASELINE configs[4]: after matching, filter_by_transform(..., 'essential') per pair.  One two-view scene per
+    # pair: 800 matches, 30 % outliers, 0.5 px noise, DJI FC6310S intrinsics; host points in, host masks out.
+    Kc = np.array([[3666.5, 0, 2736.0], [0, 3666.5, 1824.0], [0, 0, 1.0]])
+    n_pairs, n_m = 1990, 800
+    rng = np.random.default_rng(11)
+    X = np.c_[rng.uniform(-60, 60, (n_pairs, n_m)).ravel(), rng.uniform(-40, 40, n_pairs * n_m), rng.uniform(60, 90, n_pairs * n_m)]
+    base = np.repeat(np.c_[rng.uniform(10, 20, n_pairs), rng.uniform(-3, 3, n_pairs), rng.uniform(-1, 1, n_pairs)], n_m, axis=0)
+    yaw = np.repeat(rng.uniform(-0.05, 0.05, n_pairs), n_m)
+    X2 = np.c_[np.cos(yaw) * X[:, 0] - np.sin(yaw) * X[:, 1], np.sin(yaw) * X[:, 0] + np.cos(yaw) * X[:, 1], X[:, 2]] - base
+
+    def proj(P):
+        return np.c_[Kc[0, 0] * P[:, 0] / P[:, 2] + Kc[0, 2], Kc[1, 1] * P[:, 1] / P[:, 2] + Kc[1, 2]]
+    p1 = proj(X) + rng.normal(0, 0.5, (n_pairs * n_m, 2))
+    p2 = proj(X2) + rng.normal(0, 0.5, (n_pairs * n_m, 2))
+    bad = rng.random(n_pairs * n_m) < 0.3
+    p2[bad] = np.c_[rng.uniform(0, 5472, bad.sum()), rng.uniform(0, 3648, bad.sum())]
+    off = (np.arange(n_pairs + 1) * n_m).astype(np.int32)
+    tol = 5472 ** 0.25
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.set_stream(stream.cuda_stream)
+    eng.ransac_pairs(_capi.MODEL_ESSENTIAL, p1, p2, off, Kc, tol)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        mask, E, ninl = eng.ransac_pairs(_capi.MODEL_ESSENTIAL, p1, p2, off, Kc, tol)
+    gpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    cpu = None
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+        t0 = time.perf_counter()
+        agree = []
+        n_cpu = 16
+        for s in range(n_cpu):
+            a, b = p1[off[s]:off[s + 1]].astype(np.float32), p2[off[s]:off[s + 1]].astype(np.float32)
+            _, m = cv2.findEssentialMat(a, b, Kc, cv2.RANSAC, threshold=tol)
+            m = m.ravel().astype(bool)
+            g = mask[off[s]:off[s + 1]].astype(bool)
+            agree.append((m & g).sum() / max(1, (m | g).sum()))
+        cpu_ms = (time.perf_counter() - t0) * 1e3 / n_cpu
+        cpu = {"value": 1e3 / cpu_ms, "unit": "pairs/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": "cv2.findEssentialMat(p1, p2, K, cv2.RANSAC, threshold=tol) on %d of the pairs" % n_cpu,
+               "inlier_iou_vs_gpu_min": float(min(agree)), "inlier_iou_vs_gpu_mean": float(np.mean(agree))}
+    except ImportError:
+        pass
+    line = {"stage": "ransac_kernel (csrc/ransac.cu): 5-point essential-matrix RANSAC, host points in -> host masks out",
+            "pairs": n_pairs, "matches_per_pair": n_m, "outlier_fraction": 0.3, "ms_per_call": gpu_ms,
+            "pairs_per_s": n_pairs / (gpu_ms / 1e3), "mean_inliers": float(ninl.mean()), "cpu_baseline": cpu}
+    out.append(line)
+    print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "stages.jsonl"), "w") as f:
         for l in out:
