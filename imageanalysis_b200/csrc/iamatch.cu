@@ -308,6 +308,8 @@ int pick_engine(const iam_ctx* c, const int32_t* pairs, int n_pairs, int* engine
 int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, int waves, Plan* pl) {
   const int max_pairs = waves > 1 ? std::max(64, (n_pairs + waves - 1) / waves) : (1 << 30);
   int in_chunk = 0;
+  bool ramp = waves >= 8;
+  if (const char* env = getenv("IAM_WAVE_RAMP")) ramp = ramp && atoi(env) != 0;  // A/B aid
   size_t budget_mb = 768;  // kNN output workspace per chunk; IAM_CHUNK_MB overrides (tests force many chunks)
   if (const char* env = getenv("IAM_CHUNK_MB")) budget_mb = std::max(1, atoi(env));
   const size_t budget_rows = (budget_mb << 20) / (size_t(k) * 8);
@@ -321,7 +323,12 @@ int build_plan(const iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool 
     const Image& a = c->images[i];
     const Image& b = c->images[j];
     const size_t need = size_t(a.n_pad) + (both ? size_t(b.n_pad) : 0);
-    if (rows > 0 && (rows + need > budget_rows || in_chunk >= max_pairs)) {
+    // Waves (uploads interleaved with matching): the first two are short, so that the first kernel starts after
+    // a handful of images has crossed the bus instead of a sixteenth of the project.
+    int limit = max_pairs;
+    if (ramp && pl->chunk_rows.size() == 0) limit = std::max(16, max_pairs / 8);
+    if (ramp && pl->chunk_rows.size() == 1) limit = std::max(32, max_pairs / 2);
+    if (rows > 0 && (rows + need > budget_rows || in_chunk >= limit)) {
       in_chunk = 0;
       pl->chunk_rows.push_back(rows);
       pl->max_chunk_rows = std::max(pl->max_chunk_rows, rows);
