@@ -533,7 +533,7 @@ __device__ __forceinline__ const uint8_t* b_src(const ImgDev& im) { return kKind
 template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg, int kT>
 __global__ void __launch_bounds__((Cfg<kKind, kT>::kThreads), (Cfg<kKind, kT>::kCtasPerSm))
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
-                int* __restrict__ out_idx, float* __restrict__ out_d2) {
+                int* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t pack_mul, uint32_t pack_one) {
   using C = Cfg<kKind, kT>;
   constexpr int kEpiWarps = C::kEpiWarps;
   constexpr int kRows = C::kRows;
@@ -744,10 +744,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     constexpr bool kPacked = IAM_PACKED && kKind == Kind::I8 && KTOP == 2;
     constexpr bool kPackedF = IAM_PACKED && IAM_PACKED_HAMMING && kKind == Kind::F8 && KTOP == 2;
     constexpr bool kKeyF = kKind == Kind::F8;  // accumulators are keys 32 * distance + column (convert_hamming_kernel)
-    // Multipliers ptxas cannot fold (n_units >= 0): with a literal 32 the packing multiply-adds are strength-reduced
+    // Multipliers ptxas cannot fold (kernel parameters 32 and 1): with a literal 32 the packing multiply-adds are strength-reduced
     // to LEA, an ALU-pipe instruction; as register operands they stay IMADs on the otherwise idle FMA pipe.
-    const uint32_t opaque0 = static_cast<uint32_t>(n_units) >> 31;
-    const uint32_t mul32 = IAM_PACK_IMAD ? 32u + opaque0 : 32u, one = IAM_PACK_IMAD ? 1u + opaque0 : 1u;
+    const uint32_t mul32 = IAM_PACK_IMAD ? pack_mul : 32u, one = IAM_PACK_IMAD ? pack_one : 1u;
     (void)mul32;
     (void)one;
     uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kT + a, slot = sq % kSlots
@@ -1047,7 +1046,7 @@ cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, 
     return e ? atoi(e) : 0;
   }();
   using C = Cfg<kKind, kT>;
-  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*);
+  using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, uint32_t, uint32_t);
   const int n_items = n_units * C::kItems;
   const bool use_cluster = cluster && (n_items % 2 == 0);
   KernT kern;
@@ -1088,7 +1087,7 @@ cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, 
     cfg.numAttrs = 1;
   }
   cfg.gridDim = dim3(grid);
-  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2);
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, 32u, 1u);  // the key-packing multipliers, as run-time values
 }
 
 template <Kind kKind, int KTOP>
