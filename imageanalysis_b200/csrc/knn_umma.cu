@@ -345,6 +345,12 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_RAW_FIRST
 #define IAM_RAW_FIRST 0             // A/B aid: 1 = per-slice test on the raw accumulators, keys built only on a hit (measured 18.0 vs 16.4 ms: the second tree lands on the ALU pipe)
 #endif
+#ifndef IAM_LAT_EX
+#define IAM_LAT_EX 0                // A/B aid: 1 = the exchange of bounds runs while the tensor-memory load is in flight
+#endif
+#ifndef IAM_LAT_CHAIN
+#define IAM_LAT_CHAIN 1             // four knock-out chains and literal subtractions (0: two chains, IMAD with a register multiplier)
+#endif
 #ifndef IAM_FMA_DECODE
 #define IAM_FMA_DECODE 0            // A/B aid: winners' (value, index) by IMAD.HI / IMAD instead of SHF / LOP3
 #endif
@@ -458,15 +464,34 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
       constexpr int kNF = IAM_PACKED_FMA_SUBS;
       static_assert(kNF >= 32 || (kNF >= 2 && kNF % 2 == 0), "IAM_PACKED_FMA_SUBS");
       uint32_t u[kNF];
+      const uint32_t nm = static_cast<uint32_t>(neg_m1);
+#if IAM_LAT_CHAIN
+      // plain subtractions (ptxas issues them as IMAD.IADD with a literal 1: no multiplier register to reload) and
+      // FOUR add-max chains: the second half sits on every warp's critical path, and the warps of a tile move in
+      // lock step with the MMAs, so dependent-chain length counts as much as instruction count
+#pragma unroll
+      for (int j = 0; j < kNF; ++j) u[j] = static_cast<uint32_t>(k[j]) - static_cast<uint32_t>(m1);
+      uint32_t s0 = umax_tree<kNF / 2>(u), s1 = umax_tree<kNF / 2>(u + kNF / 2), s2 = 0, s3 = 0;
+      constexpr int kQ = (32 - kNF) / 4;
+#pragma unroll
+      for (int j = 0; j < kQ; ++j) {
+        s0 = max(s0, static_cast<uint32_t>(k[kNF + j]) + nm);
+        s1 = max(s1, static_cast<uint32_t>(k[kNF + kQ + j]) + nm);
+        s2 = max(s2, static_cast<uint32_t>(k[kNF + 2 * kQ + j]) + nm);
+      }
+#pragma unroll
+      for (int j = kNF + 3 * kQ; j < 32; ++j) s3 = max(s3, static_cast<uint32_t>(k[j]) + nm);
+      best = max(umax3(s0, s1, s2), s3);
+#else
       static_for32([&](auto j) { u[j] = knock<j>(k[j], m1, neg_m1, one); }, std::make_integer_sequence<int, kNF>{});
       uint32_t s0 = umax_tree<kNF / 2>(u), s1 = umax_tree<kNF / 2>(u + kNF / 2);
-      const uint32_t nm = static_cast<uint32_t>(neg_m1);
       constexpr int kMid = kNF + (32 - kNF) / 2;
 #pragma unroll
       for (int j = kNF; j < kMid; ++j) s0 = max(s0, static_cast<uint32_t>(k[j]) + nm);
 #pragma unroll
       for (int j = kMid; j < 32; ++j) s1 = max(s1, static_cast<uint32_t>(k[j]) + nm);
       best = max(s0, s1);
+#endif
     }
     const int m2 = m1 + static_cast<int>(best);
 #if IAM_FMA_DECODE
@@ -782,7 +807,25 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         // Bound from the threads that own the other column parts of this row (own slot included, it is harmless):
         // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted (loosen;
         // the final merge orders them by index).  Stale values are still valid bounds: plain volatile traffic.
-        auto tile = [&](auto sl, int tp32) {
+        auto exchange = [&]() {
+#if IAM_ROW_BOUND
+          // The row's true second best so far: every part publishes (second best, best); the second largest of the
+          // six values is  max(second largest of the three bests, largest of the three second bests).
+          static_assert(!IAM_ROW_BOUND || kParts == 3, "row-exact bound: three column parts");
+          const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride), e2 = lds_volatile_v2b32_a(rd + 2 * kPartStride);
+          const T h0 = O::from_bits(e0.y), h1 = O::from_bits(e1.y), h2 = O::from_bits(e2.y);
+          const T second_h = O::best3(min(h0, h1), min(h0, h2), min(h1, h2));
+          const T g = O::best(second_h, O::best3(O::from_bits(e0.x), O::from_bits(e1.x), O::from_bits(e2.x)));
+          pb = O::best(pb, O::loosen(g));
+#else
+          T g = O::from_bits(lds_volatile_b32_a(rd));
+#pragma unroll
+          for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
+          pb = O::best(pb, O::loosen(g));
+#endif
+        };
+        // `ex`: this is the pair's first tile -- the exchange of bounds runs while the tensor-memory load is in flight
+        auto tile = [&](auto sl, int tp32, bool ex) {
           constexpr uint32_t kSl = decltype(sl)::value;
           const uint32_t bar = bar_a + kSl * (kT * 8);
           mbar_wait_bare_a(bar, par);
@@ -793,6 +836,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             __syncwarp();
 #endif
             tmem_ld32(tm_a + kSl * (kT * kBRows), v);
+            if (IAM_LAT_EX && ex) exchange();
             tmem_ld_wait(v);
             // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
 #if !IAM_EPI_NOSYNC
@@ -809,28 +853,10 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         };
         int tp32 = part * 32 - phase * (kBRows);  // 32 * (tile * kParts + part) of the pair's first tile
         for (int tb = -phase; tb < n_tb; tb += 2, tp32 += 2 * kBRows) {
-#if IAM_ROW_BOUND
-          {
-            // The row's true second best so far: every part publishes (second best, best); the second largest of the
-            // six values is  max(second largest of the three bests, largest of the three second bests).
-            static_assert(!IAM_ROW_BOUND || kParts == 3, "row-exact bound: three column parts");
-            const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride), e2 = lds_volatile_v2b32_a(rd + 2 * kPartStride);
-            const T h0 = O::from_bits(e0.y), h1 = O::from_bits(e1.y), h2 = O::from_bits(e2.y);
-            const T second_h = O::best3(min(h0, h1), min(h0, h2), min(h1, h2));
-            const T g = O::best(second_h, O::best3(O::from_bits(e0.x), O::from_bits(e1.x), O::from_bits(e2.x)));
-            pb = O::best(pb, O::loosen(g));
-          }
-#else
-          {
-            T g = O::from_bits(lds_volatile_b32_a(rd));
-#pragma unroll
-            for (int pp = 1; pp < kParts; ++pp) g = O::best(g, O::from_bits(lds_volatile_b32_a(rd + pp * kPartStride)));
-            pb = O::best(pb, O::loosen(g));
-          }
-#endif
-          if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tp32);
+          if (!IAM_LAT_EX || kDbg == 1) exchange();
+          if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tp32, true);
           if (tb + 1 < n_tb) {
-            tile(std::integral_constant<uint32_t, 1>{}, tp32 + kBRows);
+            tile(std::integral_constant<uint32_t, 1>{}, tp32 + kBRows, tb < 0);
             par ^= 1;
           }
 #if IAM_ROW_BOUND
