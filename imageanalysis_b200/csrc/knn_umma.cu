@@ -330,10 +330,13 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 // columns of the slice need no compare/select network and no per-column votes:
 //     m1 = max_j key_j                                   16 three-input max (ALU pipe)
 //     u_j = key_j - m1  (mod 2^32)                       the winner becomes 0, every other column a huge unsigned
-//     m2 = m1 + umax_j u_j                               number that still orders like its key: 16 three-input umax
-// The 32 packing multiply-adds and half of the subtractions are IMADs (FMA pipe, idle in this kernel); the
-// epilogue is ALU-pipe bound.  Only the warp vote "some lane's m1 beats its bound" guards the second half, and
-// the two winners enter the running list through the ordinary six-instruction insertion.
+//     m2 = m1 + umax_j u_j                               number that still orders like its key
+// The 32 packing multiply-adds are IMADs (FMA pipe, otherwise idle in this kernel; the multiplier is a kernel
+// parameter so that ptxas cannot turn them into ALU-pipe LEAs).  The knock-out takes IAM_PACKED_FMA_SUBS columns as
+// subtraction (IMAD.IADD) + three-input umax tree and the rest as four chains of fused add-max (VIADDMNMX.U32, one
+// ALU instruction per column): the measured optimum between issue slots, the two pipes and dependent-chain length
+// (DESIGN.md section 4).  Only the warp vote "some lane's m1 beats its bound" guards the second half, and the two
+// winners enter the running list through the ordinary six-instruction insertion.
 // The cost per slice no longer depends on how many columns qualify, which is what made the first tiles of every
 // unit (empty lists, everything qualifies) cost seven times a late tile.
 #ifndef IAM_PACKED
