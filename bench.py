@@ -152,7 +152,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference path
-def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1):
+def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1, context=False):
     """The reference's CPU path for `n_pairs` pairs: knnMatch both ways with the
     exact matcher (cv2.BFMatcher when cv2 is importable: kind 'reference';
     otherwise the C restatement oracle/oracle_knn.c: kind 'port') plus the
@@ -194,9 +194,33 @@ def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1):
             oracle.filter_cross_check(p1, p2)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return {"value": len(sample) / best, "unit": "pairs/s", "cores": cores_used, "kind": kind,
-            "sample": "%d of the %d pairs of this workload, both kNN directions + matcher.py:253-269 reduction + "
-                      "cross-check, best of %d" % (len(sample), len(pairs), repeats)}
+    out = {"value": len(sample) / best, "unit": "pairs/s", "cores": cores_used, "kind": kind,
+           "sample": "%d of the %d pairs of this workload, both kNN directions + matcher.py:253-269 reduction + "
+                     "cross-check, best of %d" % (len(sample), len(pairs), repeats)}
+    if context and kind == "reference":
+        # Context only: the same pair on ONE host thread, and the matcher the reference literally
+        # configures -- an approximate FLANN kd-tree search (matcher.py:62-79), kNN both directions without the reduction.
+        try:
+            import cv2
+            i, j = (int(x) for x in sample[0])
+            a, b = host[i], host[j]
+            cv2.setNumThreads(1)
+            t0 = time.perf_counter()
+            knn(a, b)
+            knn(b, a)
+            one = time.perf_counter() - t0
+            cv2.setNumThreads(cores)
+            ctx = {"one_thread_knn_pairs_per_s": 1.0 / one}
+            if detector == "SIFT":
+                fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+                t0 = time.perf_counter()
+                fl.knnMatch(a, b, k=2)
+                fl.knnMatch(b, a, k=2)
+                ctx["flann_kdtree_knn_pairs_per_s"] = 1.0 / (time.perf_counter() - t0)
+            out["context"] = ctx
+        except Exception as e:  # noqa: BLE001  (context figures must never break the bench line)
+            out["context"] = {"error": str(e)[:80]}
+    return out
 
 
 def run_reference(args):
@@ -217,7 +241,8 @@ def run_reference(args):
     steps = []
     base = None
     for s in range(args.warmup + args.steps):
-        base = cpu_pairs_per_s(des, pairs, args.detector, args.cpu_pairs, repeats=0 if s else 1)
+        base = cpu_pairs_per_s(des, pairs, args.detector, args.cpu_pairs, repeats=0 if s else 1,
+                               context=(s == args.warmup + args.steps - 1))
         if s >= args.warmup:
             steps.append(base["value"])
     v = statistics.median(steps)
@@ -448,7 +473,7 @@ def main():
                 "engine": {1: "umma", 2: "simt"}.get(tm.engine_used)}
     cpu = None
     if not args.no_cpu and world == 1:
-        cpu = cpu_pairs_per_s(des_u8, pairs, args.detector, args.cpu_pairs, repeats=2)
+        cpu = cpu_pairs_per_s(des_u8, pairs, args.detector, args.cpu_pairs, repeats=2, context=True)
     line = {"metric": "image-pairs matched/sec (5000 %s desc/img)" % args.detector, "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if bates else "weak", "vs_baseline": None,
