@@ -373,7 +373,7 @@ def test_match_images_host_narrowing(monkeypatch, mode):
         assert (c0 == c1).all() and c0.max() > 100
         for p in range(len(pairs)):
             assert (t0[p, :c0[p]] == t1[p, :c1[p]]).all()
-        if mode == "2":
+        if mode == "2" and (os.cpu_count() or 1) >= 2 and not os.environ.get("IAM_HOST_THREADS"):
             assert eng.timing().narrowed_images == 24 and eng.timing().h2d_bytes == 24 * 700 * 128
         if mode == "0":
             assert eng.timing().narrowed_images == 0 and eng.timing().h2d_bytes == 24 * 700 * 128 * 4
