@@ -1,23 +1,26 @@
 #!/usr/bin/env python3
-"""bench.py — image-pairs matched per second on BASELINE.json's config.
+"""bench.py — image-pairs matched per second on BASELINE.json's configs.
 
-A "step" is one pass of the hot path over one batch: every candidate pair of a
-500-frame strip with 5000 SIFT descriptors per frame (BASELINE configs[1];
-pair list = the reference's live generator, |i-j| <= 4 -> 1990 pairs; use
-`--pairs all` for the 124 750-pair upper triangle) goes through
+A "step" is one pass of the hot path over one batch: every candidate pair goes through
 kNN (both directions) -> metric reduction -> cross-check -> per-pair match table.
 
-  value : pairs/s with descriptors already resident in HBM (device timed, CUDA events)
-  e2e   : the same job through the public API with HOST buffers: H2D of every
-          frame's float32 descriptors from pinned memory + layout conversion +
-          matching + D2H of the match tables, every step
-  roofline : algorithmic 2*N*M*128 FLOP per pair / the kNN kernel's own time
-  cpu_baseline / --impl reference : the reference's CPU path (cv2.BFMatcher
-          both directions + the Python reduction of matcher.py:253-269) on the
-          box's host cores, on a bounded sample of the same pairs
+  --gpus 1 (default) : BASELINE configs[1] -- a 500-frame strip, 5000 SIFT descriptors per frame, the reference's
+                       live pair generator |i-j| <= 4 (matcher.py:899) -> 1990 pairs           (--workload strip)
+  --gpus N > 1       : BASELINE configs[3] -- 2812 frames on the 38 x 74 serpentine survey grid, the reference's
+                       camera-distance pair filter (matcher.py:858-903) -> 42 694 pairs, the pair list sharded in
+                       contiguous blocks across the ranks (strong scaling), every rank uploads only the frames its
+                       block touches, ONE compact all-gather collects the match tables        (--workload bates)
 
-Multi-GPU (torchrun, one rank per GPU): every rank matches its own 500-frame
-strip (weak scaling) and one NCCL all-gather collects all match tables.
+  value : pairs/s with descriptors already resident in HBM (device timed, CUDA events, max over ranks)
+  e2e   : the same job through the public one-call API with HOST buffers: H2D of every frame's float32
+          descriptors from pinned memory + layout conversion + matching + D2H of the match tables (+ the
+          gather for N > 1), every step
+  roofline : algorithmic 2*N*M*128 FLOP per pair / the kNN kernel's own time, against the measured peak of the
+          MMA kind the kernel issues
+  parity_spot : after the timed region, three pairs of the run are compared with the CPU oracle
+  cpu_baseline / --impl reference : the reference's CPU path (cv2.BFMatcher both directions + the Python
+          reduction of matcher.py:253-269 + cross-check) on the box's host cores, on a bounded sample of the
+          SAME frames and pair list
 """
 from __future__ import annotations
 
@@ -37,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR_L2 = 2.0 * 5000 * 5000 * 128      # one N x M product per pair
 OP_PER_PAIR_HAMMING = 2.0 * 5000 * 5000 * 256
+SEED = 1234
 
 
 def parse():
@@ -45,30 +49,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=500)
+    ap.add_argument("--frames", type=int, default=0, help="0: 500 (strip) / 2812 (bates)")
     ap.add_argument("--desc", type=int, default=5000)
     ap.add_argument("--detector", default="SIFT", choices=["SIFT", "ORB"])
     ap.add_argument("--pairs", default="sequential", choices=["sequential", "all"])
-    ap.add_argument("--workload", default="strip", choices=["strip", "bates"],
-                    help="strip: BASELINE configs[1] per GPU (weak scaling, the default); bates: configs[3], 2812 frames "
-                         "on a 38 x 74 serpentine survey grid, geotag-neighbour pair list sharded across the ranks")
+    ap.add_argument("--workload", default="auto", choices=["auto", "strip", "bates"],
+                    help="auto: strip (BASELINE configs[1]) on one GPU, bates (configs[3], pair-sharded) on several; "
+                         "strip with --gpus N > 1 = N independent replicas (weak scaling)")
     ap.add_argument("--engine", default="auto", choices=["auto", "umma", "umma_f16", "simt"])
+    ap.add_argument("--gather", default="packed", choices=["packed", "padded"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-orb", action="store_true", help="skip the short ORB (configs[2]) leg of the default line")
+    ap.add_argument("--no-spot", action="store_true")
     ap.add_argument("--cpu-pairs", type=int, default=4)
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------- data
-def make_frames_gpu(frames, n, detector, seed, device):
-    """Synthetic descriptors with OpenCV-SIFT statistics (see imageanalysis_b200/synth.py),
-    generated with torch for speed, returned as a HOST uint8 array [frames, n, D]."""
+def make_frames_gpu(frames, n, detector, seed, device, keep=None):
+    """Synthetic descriptors with OpenCV-SIFT statistics (see imageanalysis_b200/synth.py), generated with torch
+    (on `device`; the stream of frames is a chain -- 40 % of every frame's rows are noisy copies of rows of the
+    previous frame -- so frame f is the same whatever the total count).  Returns {frame: uint8 [n, D]} on the HOST
+    for the frames in `keep` (all when None)."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    out = []
+    out = {}
     prev = None
-    for f in range(frames):
+    last = frames - 1 if keep is None else max(keep)
+    for f in range(last + 1):
         if detector == "SIFT":
             v = torch._standard_gamma(torch.full((n, 128), 0.6, device=device), generator=g)
             v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-12)
@@ -94,14 +104,23 @@ def make_frames_gpu(frames, n, detector, seed, device):
                     flips[torch.arange(m, device=device), byte] ^= (1 << bit).to(torch.uint8)
                 d[dst] = prev[src] ^ flips
         prev = d
-        out.append(d.cpu())
-    return torch.stack(out).numpy()
+        if keep is None or f in keep:
+            out[f] = d.cpu().numpy()
+    return out
 
 
 def pair_list(frames, mode):
     if mode == "all":
         return np.asarray([(i, j) for i in range(frames) for j in range(i + 1, frames)], np.int32)
     return np.asarray([(i, j) for i in range(frames) for j in range(i + 1, min(frames, i + 5))], np.int32)
+
+
+def bates_pairs(frames):
+    """BASELINE configs[3] (SURVEY section 8d): 38 flight lines x 74 frames, 15 m along-track, 25 m cross-track,
+    serpentine; pairs = the reference's camera-distance window (matcher.py:858-903, pairs.worklist 'geotag')."""
+    from imageanalysis_b200 import pairs as wl, synth
+    neds = synth.survey_grid_neds()[:frames]
+    return wl.pair_array(wl.worklist(neds, "geotag"))
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -153,10 +172,10 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU reference path
 def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1, context=False):
-    """The reference's CPU path for `n_pairs` pairs: knnMatch both ways with the
-    exact matcher (cv2.BFMatcher when cv2 is importable: kind 'reference';
-    otherwise the C restatement oracle/oracle_knn.c: kind 'port') plus the
-    Python reduction of matcher.py:253-269 and the cross-check (:187-200)."""
+    """The reference's CPU path for the first `n_pairs` pairs of `pairs` on the frames `des_u8` ({frame: u8 rows},
+    the SAME frames the GPU arm matches): knnMatch both ways with the exact matcher (cv2.BFMatcher when cv2 is
+    importable: kind 'reference'; otherwise the C restatement oracle/oracle_knn.c: kind 'port') plus the Python
+    reduction of matcher.py:253-269 and the cross-check (:187-200)."""
     from oracle import oracle
     norm = oracle.NORM_L2 if detector == "SIFT" else oracle.NORM_HAMMING
     max_distance = 270.0 if detector == "SIFT" else 64.0
@@ -195,11 +214,14 @@ def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1, context=False):
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     out = {"value": len(sample) / best, "unit": "pairs/s", "cores": cores_used, "kind": kind,
-           "sample": "%d of the %d pairs of this workload, both kNN directions + matcher.py:253-269 reduction + "
-                     "cross-check, best of %d" % (len(sample), len(pairs), repeats)}
+           "sample": "the first %d of the %d pairs of this workload (same synthetic frames as the GPU arm; every pair "
+                     "costs the same on the CPU path, so the rate extrapolates), both kNN directions + matcher.py:253-269 "
+                     "reduction + cross-check, best of %d timed rounds after one warm-up round" % (
+                         len(sample), len(pairs), max(1, repeats))}
     if context and kind == "reference":
         # Context only: the same pair on ONE host thread, and the matcher the reference literally
-        # configures -- an approximate FLANN kd-tree search (matcher.py:62-79), kNN both directions without the reduction.
+        # configures -- an approximate FLANN kd-tree search (matcher.py:62-79, checks=100), kNN both directions
+        # without the reduction.
         try:
             import cv2
             i, j = (int(x) for x in sample[0])
@@ -212,77 +234,102 @@ def cpu_pairs_per_s(des_u8, pairs, detector, n_pairs, repeats=1, context=False):
             cv2.setNumThreads(cores)
             ctx = {"one_thread_knn_pairs_per_s": 1.0 / one}
             if detector == "SIFT":
-                fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+                fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=100))
                 t0 = time.perf_counter()
                 fl.knnMatch(a, b, k=2)
                 fl.knnMatch(b, a, k=2)
-                ctx["flann_kdtree_knn_pairs_per_s"] = 1.0 / (time.perf_counter() - t0)
+                ctx["flann_kdtree_checks100_knn_pairs_per_s"] = 1.0 / (time.perf_counter() - t0)
             out["context"] = ctx
         except Exception as e:  # noqa: BLE001  (context figures must never break the bench line)
             out["context"] = {"error": str(e)[:80]}
     return out
 
 
+def resolve_workload(args, world):
+    if args.workload == "auto":
+        args.workload = "strip" if world == 1 else "bates"
+    if not args.frames:
+        args.frames = 2812 if args.workload == "bates" else 500
+    return args.workload
+
+
+def workload_config(args, n_pairs_total, world, pairs_per_gpu=None, frames_per_gpu=None):
+    n_pad = -(-args.desc // 256) * 256
+    row_bytes = 192 if args.detector == "SIFT" else 288 * 2
+    if args.workload == "bates":
+        return {"workload": "%d frames (38 x 74 serpentine survey grid) x %d %s descriptors/frame, geotag-neighbour pair "
+                            "list (reference matcher.py:858-903), %d pairs in all, sharded across %d GPU(s)" % (
+                                args.frames, args.desc, args.detector, n_pairs_total, world),
+                "frames": args.frames, "desc_per_frame": args.desc, "pairs_total": n_pairs_total,
+                "pairs_per_gpu": pairs_per_gpu or -(-n_pairs_total // world), "frames_per_gpu": frames_per_gpu,
+                "match_ratio": 0.75, "cap": 2000, "min_pairs": 25,
+                "l2_hygiene": "inputs larger than L2 (operand forms %.2f GB per GPU)" % (
+                    (frames_per_gpu or args.frames) * n_pad * row_bytes / 1e9),
+                "parallelism": ("pair-sharded x%d (contiguous blocks of the (i, j)-sorted work list; a rank holds only the "
+                                "frames its block touches) + 1 NCCL all-gather of the compact match tables" % world)
+                if world > 1 else "single GPU"}
+    return {"workload": "%d frames x %d %s descriptors/frame, %s pair list (%d pairs) per GPU" % (
+                args.frames, args.desc, args.detector,
+                "|i-j|<=4 (reference matcher.py:899)" if args.pairs == "sequential" else "all-pairs",
+                n_pairs_total // world),
+            "frames_per_gpu": args.frames, "desc_per_frame": args.desc, "pairs_per_gpu": n_pairs_total // world,
+            "pairs_total": n_pairs_total, "match_ratio": 0.75, "cap": 2000, "min_pairs": 25,
+            "l2_hygiene": "inputs larger than L2 (operand forms %.2f GB per GPU)" % (args.frames * n_pad * row_bytes / 1e9),
+            "parallelism": "%d independent replicas + 1 NCCL all-gather of the match tables" % world if world > 1 else "single GPU"}
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (cv2.BFMatcher both directions + the
+    reduction and cross-check of scripts/lib/matcher.py), all host threads, on a bounded sample (the first
+    --cpu-pairs pairs) of the SAME frames and pair list the GPU arm runs.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from imageanalysis_b200 import synth
-    frames = min(args.frames, args.cpu_pairs // 4 + 6)
-    gen = synth.sift_like if args.detector == "SIFT" else synth.orb_like
-    rng = np.random.default_rng(0)
-    des = []
-    for f in range(frames):
-        d = gen(args.desc, seed=1000 + f)
-        if f > 0:
-            synth.plant(des[-1], d, 0.4, rng, "sift" if args.detector == "SIFT" else "orb")
-        des.append(d)
-    pairs = pair_list(frames, "sequential")
+    resolve_workload(args, world)
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))) if torch.cuda.is_available() else torch.device("cpu")
+    all_pairs = bates_pairs(args.frames) if args.workload == "bates" else pair_list(args.frames, args.pairs)
+    sample = all_pairs[:args.cpu_pairs]
+    keep = {int(i) for p in sample for i in p}
+    # the generator is a chain: the first frames are identical to the GPU arm's (same seed, same device kind)
+    des = make_frames_gpu(max(keep) + 1, args.desc, args.detector, seed=SEED, device=dev, keep=keep)
     steps = []
     base = None
     for s in range(args.warmup + args.steps):
-        base = cpu_pairs_per_s(des, pairs, args.detector, args.cpu_pairs, repeats=0 if s else 1,
+        base = cpu_pairs_per_s(des, all_pairs, args.detector, args.cpu_pairs, repeats=0 if s else 1,
                                context=(s == args.warmup + args.steps - 1))
         if s >= args.warmup:
             steps.append(base["value"])
     v = statistics.median(steps)
     base["value"] = v
+    P_total = len(all_pairs) * (world if args.workload == "strip" else 1)
     line = {"impl": "reference", "metric": "image-pairs matched/sec (5000 %s desc/img)" % args.detector, "value": v,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * args.cpu_pairs / v, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1000.0 * args.cpu_pairs / v, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "bates" else "weak",
             "vs_baseline": None, "dtype": "f32" if args.detector == "SIFT" else "u8", "data": "synthetic",
-            "config": workload_config(args, len(pair_list(args.frames, args.pairs)), 1),
+            "config": workload_config(args, P_total, world),
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def bates_pairs(frames):
-    """BASELINE configs[3] (SURVEY section 8d): 38 flight lines x 74 frames, 15 m along-track, 25 m cross-track,
-    serpentine; pairs = the reference's camera-distance window (matcher.py:858-903, pairs.worklist 'geotag')."""
-    from imageanalysis_b200 import pairs as wl, synth
-    neds = synth.survey_grid_neds()[:frames]
-    return wl.pair_array(wl.worklist(neds, "geotag"))
-
-
-def workload_config(args, n_pairs, world):
-    if args.workload == "bates":
-        return {"workload": "%d frames (38 x 74 serpentine survey grid) x %d %s descriptors/frame, geotag-neighbour pair "
-                            "list (reference matcher.py:858-903), %d pairs in all, sharded across %d GPU(s)" % (
-                                args.frames, args.desc, args.detector, n_pairs, world),
-                "frames": args.frames, "desc_per_frame": args.desc, "pairs_total": n_pairs,
-                "pairs_per_gpu": -(-n_pairs // world), "match_ratio": 0.75, "cap": 2000, "min_pairs": 25,
-                "l2_hygiene": "inputs larger than L2 (byte forms %.2f GB per GPU, replicated)" % (
-                    args.frames * (-(-args.desc // 256) * 256) * 192 / 1e9),
-                "parallelism": "pair-sharded x%d + 1 NCCL all-gather of match tables" % world if world > 1 else "single GPU"}
-    return {"workload": "%d frames x %d %s descriptors/frame, %s pair list (%d pairs) per GPU" % (
-                args.frames, args.desc, args.detector,
-                "|i-j|<=4 (reference matcher.py:899)" if args.pairs == "sequential" else "all-pairs", n_pairs),
-            "frames_per_gpu": args.frames, "desc_per_frame": args.desc, "pairs_per_gpu": n_pairs,
-            "pairs_total": n_pairs * world, "match_ratio": 0.75, "cap": 2000, "min_pairs": 25,
-            "l2_hygiene": "inputs larger than L2 (operand forms %.2f GB per GPU)" % (
-                args.frames * 2 * (-(-args.desc // 256) * 256) * 288 / 1e9),
-            "parallelism": "pair-sharded x%d + 1 NCCL all-gather of match tables" % world if world > 1 else "single GPU"}
+# ----------------------------------------------------------------------------- parity spot check
+def parity_spot(des_u8, pairs, table, count, detector, which):
+    """Untimed: the match tables of a few pairs of THIS run against the CPU oracle (bit-exact index lists)."""
+    from oracle import oracle
+    norm = oracle.NORM_L2 if detector == "SIFT" else oracle.NORM_HAMMING
+    maxd = 270.0 if detector == "SIFT" else 64.0
+    bad = []
+    for p in which:
+        a, b = int(pairs[p][0]), int(pairs[p][1])
+        f, _ = oracle.bidirectional(des_u8[a], des_u8[b], norm, 0.75, maxd, threads=os.cpu_count() or 4)
+        if table[p, :count[p]].tolist() != f:
+            bad.append(int(p))
+    return {"status": "ok" if not bad else "MISMATCH", "pairs_checked": [[int(pairs[p][0]), int(pairs[p][1])] for p in which],
+            "rows_checked": int(sum(int(count[p]) for p in which)), "mismatching_pairs": bad,
+            "checker": "oracle.bidirectional (CPU restatement of matcher.py:218-318), whole tables compared"}
 
 
 # ----------------------------------------------------------------------------- main
@@ -296,27 +343,29 @@ def main():
     rank, world, local = dist.init()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    resolve_workload(args, world)
     norm = _capi.NORM_L2 if args.detector == "SIFT" else _capi.NORM_HAMMING
     nbytes = 128 if args.detector == "SIFT" else 32
-
     bates = args.workload == "bates"
-    if bates:  # every rank holds every frame (replicated descriptors), the pair list is sharded: strong scaling
-        if args.frames == 500:
-            args.frames = 2812
-        args.no_e2e = args.no_cpu = True
-        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=1234, device=dev)
-        host_np = des_u8
+
+    if bates:   # one project, the pair list sharded: strong scaling.  A rank needs only the frames its block touches.
         all_pairs = bates_pairs(args.frames)
-        pairs, _, _ = dist.shard_pairs(all_pairs, rank, world)
+        pairs, p_begin, p_end = dist.shard_pairs(all_pairs, rank, world)
         P_total = len(all_pairs)
-    else:
-        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=1234 + rank, device=dev)
-        # host buffers exactly as the reference holds them: float32 [N,128] for SIFT (image.py:160-180), uint8 for ORB
-        host = torch.from_numpy(des_u8.astype(np.float32) if args.detector == "SIFT" else des_u8).pin_memory()
-        host_np = host.numpy()
+        touched = sorted({int(i) for p in pairs for i in p})
+        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=SEED, device=dev, keep=set(touched))
+    else:       # every rank its own strip (replicas; the default on one GPU)
         pairs = pair_list(args.frames, args.pairs)
         P_total = len(pairs) * world
+        touched = list(range(args.frames))
+        des_u8 = make_frames_gpu(args.frames, args.desc, args.detector, seed=SEED + rank, device=dev)
     P = len(pairs)
+    T = len(touched)
+    # host buffers exactly as the reference holds them: float32 [N,128] for SIFT (image.py:160-180), uint8 for ORB
+    host = torch.empty((T, args.desc, nbytes), dtype=torch.float32 if args.detector == "SIFT" else torch.uint8).pin_memory()
+    host_np = host.numpy()
+    for k, f in enumerate(touched):
+        host_np[k] = des_u8[f]
 
     eng = _capi.Engine(norm, nbytes, local)
     eng.set_engine({"auto": _capi.ENGINE_AUTO, "umma": _capi.ENGINE_UMMA, "umma_f16": _capi.ENGINE_UMMA_F16,
@@ -329,31 +378,41 @@ def main():
     eng.set_profiling(True)
     prm = _capi.Engine.make_params(max_distance=270.0 if args.detector == "SIFT" else 64.0)
 
-    def upload_all():
-        for f in range(args.frames):
-            eng.upload(f, host_np[f], pinned=True)
+    for k, f in enumerate(touched):
+        eng.upload(f, host_np[k], pinned=True)
+    eng.synchronize()
 
     gather_out = None
     gather_ev = []
-    if world > 1:  # every rank ends a step holding all ranks' tables
+    gathered = {}
+    if world > 1 and args.gather == "padded":
         gather_out = (torch.empty((P_total, prm.cap, 2), dtype=torch.int32, device=dev),
                       torch.empty((P_total,), dtype=torch.int32, device=dev))
 
+    def gather(dt, dc, timed=False):
+        """Every rank ends a step holding all ranks' match tables."""
+        if world == 1:
+            return
+        if timed:
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+        c = dist.as_tensor(dc, (P,), local)
+        if args.gather == "padded":
+            t = dist.as_tensor(dt, (P, prm.cap, 2), local)
+            dist.allgather_tables(t, c, P_total, rank, world, out=gather_out)
+        else:
+            d_rows, _d_off, total = eng.pack_tables_device()
+            rows = dist.as_tensor(d_rows, (max(total, 1), 2), local)[:total]
+            r_all, c_all = dist.allgather_packed(rows, c, P_total, rank, world)
+            gathered["rows"], gathered["count"] = int(r_all.shape[0]), int(c_all.shape[0])
+        if timed:
+            g1.record(stream)
+            gather_ev.append((g0, g1))
+
     def step_device(timed=False):
         dt, dc = eng.match_pairs_device(pairs, prm)
-        if world > 1:
-            t = dist.as_tensor(dt, (P, prm.cap, 2), local)
-            c = dist.as_tensor(dc, (P,), local)
-            if timed:
-                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                g0.record(stream)
-            dist.allgather_tables(t, c, P_total, rank, world, out=gather_out)
-            if timed:
-                g1.record(stream)
-                gather_ev.append((g0, g1))
+        gather(dt, dc, timed)
 
-    upload_all()
-    eng.synchronize()
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
@@ -364,12 +423,10 @@ def main():
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    knn_ms = []
     torch.cuda.synchronize()
     ev0.record(stream)
     for _ in range(args.steps):
         step_device(timed=True)
-        knn_ms.append(None)
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -388,34 +445,58 @@ def main():
     ms = float(t_ms.item())
     value = P_total * args.steps / (ms / 1e3)
 
+    # ---- untimed: a few tables of this run against the CPU oracle ----------------
+    spot = None
+    if not args.no_spot and rank == 0:
+        eng.match_pairs_device(pairs, prm)
+        table, count = eng.fetch_tables(P, prm.cap)
+        filled = np.nonzero(count > 0)[0]
+        which = sorted({0, int(filled[len(filled) // 2]) if len(filled) else P // 2, P - 1})
+        spot = parity_spot(des_u8, pairs, table, count, args.detector, which)
+        spot["mean_matches_per_pair"] = float(count.mean())
+        del table
+
     # ---- end to end through the public API with host buffers -----------------
     e2e = None
     if not args.no_e2e:
         h2d = int(host_np.nbytes)
         d2h = int(P * (prm.cap * 2 + 1) * 4)
-
-        ids = np.arange(args.frames, dtype=np.int32)
-        frames_host = [host_np[f] for f in range(args.frames)]
-
+        ids = np.asarray(touched, dtype=np.int32)
+        frames_host = [host_np[k] for k in range(T)]
         # result buffers a pipeline would keep around: page-locked, so each wave's tables come back asynchronously
         out_table = torch.empty((P, prm.cap, 2), dtype=torch.int32, pin_memory=True).numpy()
         out_count = torch.zeros((P,), dtype=torch.int32, pin_memory=True).numpy()
 
         def step_e2e():
-            # the public one-call API: host descriptors in, host match tables out (H2D + conversion + matching + D2H)
-            return eng.match_images(ids, frames_host, pairs, prm, out=(out_table, out_count))
+            # the public one-call API: host descriptors in, host match tables out (H2D + conversion + matching + D2H);
+            # several GPUs: plus the gather, so that every rank ends the step holding every table on its device
+            r = eng.match_images(ids, frames_host, pairs, prm, out=(out_table, out_count))
+            if world > 1:
+                d_rows, _d_off, total = eng.pack_tables_device()
+                rows = dist.as_tensor(d_rows, (max(total, 1), 2), local)[:total]
+                c = torch.from_numpy(out_count).to(dev, non_blocking=True)
+                dist.allgather_packed(rows, c, P_total, rank, world)
+            return r
+
         step_e2e()
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
+        n_e = max(1, args.steps // 2)
         t0 = time.perf_counter()
-        for _ in range(max(1, args.steps // 2)):
+        for _ in range(n_e):
             table, count = step_e2e()
         torch.cuda.synchronize()
         e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
         if world > 1:
             torch.distributed.all_reduce(e_ms, op=torch.distributed.ReduceOp.MAX)
-        n_e = max(1, args.steps // 2)
+        tme = eng.timing()
+        # bytes that actually crossed PCIe in the last step: float32 frames the library's worker threads narrowed to
+        # uint8 on the host (integer-valued SIFT descriptors, transport only) count as bytes
+        bytes_t = torch.tensor([float(int(tme.h2d_bytes) or h2d), float(d2h), float(h2d), float(tme.narrowed_images), float(T)],
+                               device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(bytes_t)
         # context for the e2e number: what a bare pinned-host -> device copy of the same bytes costs on this box
         dst = torch.empty_like(host, device=dev)
         dst.copy_(host, non_blocking=True)
@@ -425,18 +506,24 @@ def main():
         torch.cuda.synchronize()
         h2d_ms = (time.perf_counter() - c0) * 1e3
         del dst
-        # bytes that actually crossed PCIe in the last step: float32 frames the library's worker threads narrowed to
-        # uint8 on the host (integer-valued SIFT descriptors, transport only) count as bytes
-        tme = eng.timing()
-        e2e = {"value": P * world * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s",
-               "h2d_bytes_per_step": int(tme.h2d_bytes) or h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(e_ms.item()) / n_e,
-               "host_input_bytes_per_step": h2d, "frames_narrowed_on_host": int(tme.narrowed_images),
+        e2e = {"value": P_total * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s",
+               "h2d_bytes_per_step": int(bytes_t[0].item()), "d2h_bytes_per_step": int(bytes_t[1].item()),
+               "ms_per_step": float(e_ms.item()) / n_e,
+               "host_input_bytes_per_step": int(bytes_t[2].item()), "frames_narrowed_on_host": int(bytes_t[3].item()),
+               "frames_uploaded_per_step": int(bytes_t[4].item()),
                "host_threads": int(os.environ.get("IAM_HOST_THREADS", "0")) or None,
-               "mean_matches_per_pair": float(count.mean()), "bare_h2d_ms_same_bytes": h2d_ms,
-               "timeline_ms": {"host_enqueue": eng.timing().host_enqueue_ms, "upload_span": eng.timing().upload_span_ms,
-                               "compute_span": eng.timing().compute_span_ms, "total_span": eng.timing().total_span_ms,
-                               "waves": eng.timing().waves},
-               "bare_h2d_gb_per_s": h2d / h2d_ms / 1e6}
+               "mean_matches_per_pair": float(count.mean()), "bare_h2d_ms_same_bytes_rank0": h2d_ms,
+               "timeline_ms_rank0": {"host_enqueue": tme.host_enqueue_ms, "upload_span": tme.upload_span_ms,
+                                     "compute_span": tme.compute_span_ms, "total_span": tme.total_span_ms,
+                                     "waves": tme.waves},
+               "bare_h2d_gb_per_s_rank0": h2d / h2d_ms / 1e6,
+               "includes": "H2D of every touched frame's float32 descriptors + conversion + matching + D2H of this rank's "
+                           "tables" + (" + compact all-gather of all tables" if world > 1 else "")}
+
+    # ---- BASELINE configs[2]: a short ORB leg folded into the default line ---------
+    orb = None
+    if not args.no_orb and world == 1 and args.detector == "SIFT" and args.workload == "strip":
+        orb = orb_leg(args, dev, local, stream, tm.mma_kind)
 
     if world > 1:
         torch.distributed.barrier()
@@ -447,30 +534,10 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a %.0f ms step)" % (ms / args.steps) \
-        if peaks else "fallback (B200_PROFILING.md sustained 1.4 PFLOP/s)"
-    work = FLOP_PER_PAIR_L2 if args.detector == "SIFT" else OP_PER_PAIR_HAMMING
-    work *= (args.desc / 5000.0) ** 2
-    achieved = P * work / (knn_kernel_ms / 1e3) / 1e12 if knn_kernel_ms > 0 else None  # rank 0's shard, rank 0's kernel time
-    traffic = None
-    tj = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tj):
-        traffic = json.load(open(tj)).get("knn_umma_dram_bytes_per_launch")
-    mma_kind = {0: "kind::f16", 1: "kind::f8f6f4", 2: "kind::i8"}.get(tm.mma_kind, "none (SIMT)")
-    kind_rate = 2.0 if tm.mma_kind in (1, 2) else 1.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                "peak_burst": peaks.get("bf16_tflops"),
-                "frac_of_burst": (achieved / peaks["bf16_tflops"]) if achieved and peaks.get("bf16_tflops") else None,
-                "kernel": "knn_umma_kernel (tcgen05 %s)" % mma_kind,
-                # The contract's denominator is the measured dense bf16 peak.  kind::i8 / kind::f8f6f4 issue at twice the
-                # f16 rate (nominal 4.5 vs 2.25 P dense): the fraction of THAT pipe's peak is stated next to it.
-                "mma_kind": mma_kind, "kind_rate_vs_bf16": kind_rate,
-                "frac_of_kind_peak": (achieved / (peak * kind_rate)) if achieved else None,
-                "kernel_ms_per_launch": knn_kernel_ms, "reduce_ms_per_step": reduce_ms,
-                "algorithmic_work_per_pair": work, "allgather_ms_per_step": gather_ms,
-                "engine": {1: "umma", 2: "simt"}.get(tm.engine_used)}
+    roofline = make_roofline(args, tm.mma_kind, P, knn_kernel_ms, peaks, clocks)
+    roofline.update({"reduce_ms_per_step": reduce_ms, "allgather_ms_per_step": gather_ms,
+                     "engine": {1: "umma", 2: "simt"}.get(tm.engine_used),
+                     "gather": None if world == 1 else dict(gathered, mode=args.gather)})
     cpu = None
     if not args.no_cpu and world == 1:
         cpu = cpu_pairs_per_s(des_u8, pairs, args.detector, args.cpu_pairs, repeats=2, context=True)
@@ -478,9 +545,90 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if bates else "weak", "vs_baseline": None,
             "dtype": {0: "f16", 1: "e4m3", 2: "u8 (s32 accumulate)"}.get(tm.mma_kind, "u8"), "data": "synthetic",
-            "config": workload_config(args, P_total if bates else P, world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches, "clocks": clocks}
+            "config": workload_config(args, P_total, world, P, T), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "parity_spot": spot, "orb": orb, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
+
+
+def make_roofline(args, mma_kind_id, n_pairs, knn_kernel_ms, peaks, clocks, detector=None):
+    """Tensor roofline of the kNN kernel: algorithmic work (one N x M x D product per pair) over the kernel's
+    own time (CUDA events on the launching stream), against the measured peak of the MMA kind the kernel issues."""
+    detector = detector or args.detector
+    capped = bool(clocks and "sw_power_cap" in (clocks.get("reasons") or []))
+    burst, sustained = peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")
+    if peaks:
+        bf16_peak = (sustained if capped and sustained else burst) or 1590.0
+        src = "measured (MEASURED_PEAKS.json %s: %s)" % (
+            "bf16_tflops_sustained" if capped and sustained else "bf16_tflops",
+            "sw_power_cap was sampled during the timed region" if capped else
+            "no power cap sampled during the timed region, SM clock at %s MHz" % (clocks or {}).get("sm_mhz"))
+    else:
+        bf16_peak, src = 1590.0, "fallback (B200_PROFILING.md burst 1.59 PFLOP/s)"
+    work = FLOP_PER_PAIR_L2 if detector == "SIFT" else OP_PER_PAIR_HAMMING
+    work *= (args.desc / 5000.0) ** 2
+    achieved = n_pairs * work / (knn_kernel_ms / 1e3) / 1e12 if knn_kernel_ms > 0 else None
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj) and detector == "SIFT":
+        traffic = json.load(open(tj)).get("knn_umma_dram_bytes_per_launch")
+    mma_kind = {0: "kind::f16", 1: "kind::f8f6f4", 2: "kind::i8"}.get(mma_kind_id, "none (SIMT)")
+    # kind::i8 and kind::f8f6f4 issue at twice the f16 rate (K = 32 bytes per instruction in the same cycles; nominal
+    # 4.5 vs 2.25 P dense).  There is no measured int8 / fp8 GEMM peak in MEASURED_PEAKS.json: the kind's peak is taken
+    # as 2 x the measured bf16 peak, and the bf16 figures are kept next to it as context.
+    kind_rate = 2.0 if mma_kind_id in (1, 2) else 1.0
+    peak = bf16_peak * kind_rate
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s" if mma_kind_id == 0 else "TOP/s",
+            "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+            "peak_source": src + ("; x2 for %s" % mma_kind if kind_rate == 2.0 else ""),
+            "kernel": "knn_umma_kernel (tcgen05 %s)" % mma_kind, "mma_kind": mma_kind, "kind_rate_vs_bf16": kind_rate,
+            "context_bf16": {"peak_burst": burst, "peak_sustained": sustained,
+                             "frac_of_bf16_burst": (achieved / burst) if achieved and burst else None,
+                             "frac_of_bf16_sustained": (achieved / sustained) if achieved and sustained else None},
+            "kernel_ms_per_launch": knn_kernel_ms, "algorithmic_work_per_pair": work,
+            "issued_work_note": "the kernel issues one product per DIRECTION (2 per pair) with K = 160 (L2 bytes) / 288 "
+                                "(Hamming e4m3) instead of 128 / 256: tensor-pipe activity is ~2.6x / 2.3x the algorithmic share"}
+
+
+def orb_leg(args, dev, local, stream, _kind):
+    """BASELINE configs[2]: 500 frames x 5000 ORB descriptors (256 bit), 1990 pairs, device-resident, 5 timed steps;
+    one pair against the CPU oracle.  Reported inside the default line as "orb"."""
+    import torch
+    from imageanalysis_b200 import _capi
+    frames, n = 500, args.desc
+    des = make_frames_gpu(frames, n, "ORB", seed=SEED, device=dev)
+    pairs = pair_list(frames, "sequential")
+    eng = _capi.Engine(_capi.NORM_HAMMING, 32, local)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_profiling(True)
+    prm = _capi.Engine.make_params(max_distance=64.0)
+    for f in range(frames):
+        eng.upload(f, des[f])
+    eng.synchronize()
+    for _ in range(2):
+        eng.match_pairs_device(pairs, prm)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 5
+    e0.record(stream)
+    for _ in range(steps):
+        eng.match_pairs_device(pairs, prm)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    tm = eng.timing()
+    table, count = eng.fetch_tables(len(pairs), prm.cap)
+    spot = parity_spot(des, pairs, table, count, "ORB", [0, len(pairs) - 1])
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    rl = make_roofline(args, tm.mma_kind, len(pairs), tm.knn_ms, peaks, None, detector="ORB")
+    eng.close()
+    return {"config": "BASELINE configs[2]: 500 frames x %d ORB descriptors (256 bit), Hamming, 1990 pairs, device-resident" % n,
+            "value": len(pairs) / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms, "steps": steps,
+            "kernel_ms_per_launch": tm.knn_ms, "mma_kind": rl["mma_kind"], "achieved_tops": rl["achieved"],
+            "frac": rl["frac"], "frac_of_bf16_burst": rl["context_bf16"]["frac_of_bf16_burst"],
+            "parity_spot": spot["status"], "mean_matches_per_pair": float(count.mean())}
 
 
 if __name__ == "__main__":

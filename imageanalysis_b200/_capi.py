@@ -30,7 +30,7 @@ EXPORTS = (
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -138,6 +138,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_match_pairs_device.argtypes = [vp, vp, C.c_int, C.POINTER(MatchParams), C.POINTER(vp), C.POINTER(vp)]
     lib.iam_match_images.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, C.c_int, C.POINTER(MatchParams), vp, vp]
     lib.iam_fetch_tables.argtypes = [vp, vp, vp]
+    lib.iam_pack_tables_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_longlong)]
     lib.iam_ransac_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int,
                                      C.c_uint32, vp, vp, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
@@ -369,6 +370,14 @@ class Engine:
         count = np.zeros((n_pairs,), np.int32)
         self._check(self._lib.iam_fetch_tables(self._h, _ptr(table), _ptr(count)), "iam_fetch_tables")
         return table, count
+
+    def pack_tables_device(self) -> Tuple[int, int, int]:
+        """Compact (CSR) form of the last match call's tables, left on the device (iam_pack_tables_device):
+        returns (d_rows, d_offsets, total) -- raw pointers to int32 [total, 2] and int32 [n_pairs + 1]."""
+        dr, do, tot = C.c_void_p(), C.c_void_p(), C.c_longlong()
+        self._check(self._lib.iam_pack_tables_device(self._h, C.byref(dr), C.byref(do), C.byref(tot)),
+                    "iam_pack_tables_device")
+        return dr.value or 0, do.value or 0, int(tot.value)
 
     def debug_tile(self, q_id, t_id, q_tile=0, t_tile=0, lbo=128, sbo=2304, kstep_bytes=256, ksteps=9):
         out = np.zeros((128, 128), np.float32)

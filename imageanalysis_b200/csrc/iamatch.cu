@@ -129,7 +129,7 @@ struct iam_ctx {
   bool imgs_dirty = true;
   Buffer d_imgs, stage;
   Buffer units, jobs, knn_idx, knn_dist, cand_metric, cand_qt, job_table, job_count, out_table, out_count, packed_i,
-      packed_d;
+      packed_d, csr_rows, csr_off;
   int last_pairs = 0, last_cap = 0;
   Plan plan;                 // cached work list: rebuilt only when the pair list or an image's size changes
   uint64_t plan_key = 0;
@@ -532,7 +532,7 @@ int iam_destroy(iam_ctx* c) {
   Buffer* ba_bufs[] = {&c->ba_params, &c->ba_cam_idx, &c->ba_pt_idx, &c->ba_obs, &c->ba_res, &c->ba_jac};
   for (Buffer* b : ba_bufs) b->release();
   Buffer* bufs[] = {&c->d_imgs, &c->stage, &c->units, &c->jobs, &c->knn_idx, &c->knn_dist, &c->cand_metric,
-                    &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d};
+                    &c->cand_qt, &c->job_table, &c->job_count, &c->out_table, &c->out_count, &c->packed_i, &c->packed_d, &c->csr_rows, &c->csr_off};
   for (Buffer* b : bufs) b->release();
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -1392,6 +1392,28 @@ int iam_fetch_tables(iam_ctx* c, int32_t* out_table, int32_t* out_count) {
     CU(cudaMemcpyAsync(out_table, c->out_table.p, size_t(c->last_pairs) * c->last_cap * 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_pack_tables_device(iam_ctx* c, void** d_rows, void** d_offsets, long long* total) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!d_rows || !d_offsets || !total) return fail(IAM_E_ARG, "null output");
+  const int n = c->last_pairs;
+  CU(c->csr_off.ensure(size_t(n + 1) * sizeof(int)));
+  cudaError_t e = iam::launch_scan_counts(c->out_count.as<int>(), n, c->csr_off.as<int>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "scan launch: %s", cudaGetErrorString(e));
+  int tot = 0;
+  CU(cudaMemcpyAsync(&tot, c->csr_off.as<int>() + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // the payload's size decides the allocation (and the caller's collective)
+  CU(c->csr_rows.ensure(std::max<size_t>(1, size_t(tot)) * 2 * sizeof(int)));
+  e = iam::launch_pack_tables(c->out_table.as<int>(), c->out_count.as<int>(), c->csr_off.as<int>(), n, c->last_cap,
+                              c->csr_rows.as<int>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "pack launch: %s", cudaGetErrorString(e));
+  c->timing.total_launches += n > 0 ? 2 : 1;
+  *d_rows = c->csr_rows.p;
+  *d_offsets = c->csr_off.p;
+  *total = tot;
   return IAM_OK;
 }
 

@@ -366,6 +366,15 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_PACK_IMAD
 #define IAM_PACK_IMAD 1          // A/B aid: 0 = literal multipliers (ptxas emits LEA / IADD on the ALU pipe)
 #endif
+#ifndef IAM_SPARSE2
+#define IAM_SPARSE2 0            // A/B aid: 1 = slices where few lanes have a candidate take a divergent second half (only those
+#endif                           // lanes run; runner-up from the first half's group maxima by a switch on the winner's column).
+                                 // Fewer instructions (~36 against 59) but measured SLOWER: 17.2 / 17.5 / 17.9 / 18.6 ms with at
+                                 // most 2 / 4 / 8 / 32 lanes on that route against 15.85 ms (the compare tree of the switch and
+                                 // the re-convergence lengthen the warp's critical path; 72 registers spill)
+#ifndef IAM_SPARSE2_MAX
+#define IAM_SPARSE2_MAX 4        // at most this many lanes with a candidate take the sparse route; more: the knock-out
+#endif
 #ifndef IAM_PACKED_FMA_SUBS
 #define IAM_PACKED_FMA_SUBS 8    // columns whose knock-out subtraction is an IMAD + tree (FMA pipe); the others: fused add-max chains. 32: all IMAD
 #endif
@@ -402,6 +411,43 @@ __device__ __forceinline__ uint32_t umax_tree(const uint32_t* x) {
     if constexpr (N % 3 == 2) y[kM - 1] = max(x[N - 2], x[N - 1]);
     return umax_tree<kM>(y);
   }
+}
+
+// maximum of N signed values by three-input maxima
+template <int N>
+__device__ __forceinline__ int imax_tree(const int* x) {
+  if constexpr (N == 1) {
+    return x[0];
+  } else if constexpr (N == 2) {
+    return max(x[0], x[1]);
+  } else if constexpr (N == 3) {
+    return imax3(x[0], x[1], x[2]);
+  } else {
+    constexpr int kM = (N + 2) / 3;
+    int y[kM];
+#pragma unroll
+    for (int i = 0; i < N / 3; ++i) y[i] = imax3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+    if constexpr (N % 3 == 1) y[kM - 1] = x[N - 1];
+    if constexpr (N % 3 == 2) y[kM - 1] = max(x[N - 2], x[N - 1]);
+    return imax_tree<kM>(y);
+  }
+}
+// The first half leaves the maxima b[g] of the column groups {0..8}, {9..17}, {18..26}, {27..31}.  When column J holds the
+// slice's best key, the runner-up is the largest of the other groups' maxima and the other columns of J's own group:
+// 11 (or 7) values picked at compile time -- five (three) three-input maxima, against ~40 instructions of knock-out.
+template <int J>
+__device__ __forceinline__ int runner_up(const int (&k)[32], const int (&b)[4]) {
+  constexpr int kG = J < 27 ? J / 9 : 3;
+  constexpr int kLo = kG * 9, kHi = kG < 3 ? kLo + 9 : 32;
+  int x[3 + (kHi - kLo) - 1];
+  int n = 0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g != kG) x[n++] = b[g];
+#pragma unroll
+  for (int j = kLo; j < kHi; ++j)
+    if (j != J) x[n++] = k[j];
+  return imax_tree<3 + (kHi - kLo) - 1>(x);
 }
 template <typename F, int... Js>
 __device__ __forceinline__ void static_for32(F&& f, std::integer_sequence<int, Js...>) {
@@ -446,7 +492,35 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
   // admissible: acc > te  <=>  key > te * 32 + 31
   int te_key;
   asm("mad.lo.s32 %0, %1, %2, 31;" : "=r"(te_key) : "r"(te), "r"(mul32));
+#if IAM_SPARSE2
+  if constexpr (kMode == 0) {
+    // Late in a unit one or two of a warp's 32 rows have a candidate in a slice: those lanes alone run the second
+    // half.  The low five bits of the best key name its column, the switch picks the compile-time set of registers
+    // the runner-up can sit in.  Slices where many lanes qualify (the first tiles of a unit) take the knock-out below.
+    const uint32_t cand = __ballot_sync(0xffffffffu, m1 > te_key);
+    if (cand == 0) return;
+    if (__popc(cand) <= IAM_SPARSE2_MAX) {
+      if (m1 > te_key) {
+        const int bb[4] = {b0, b1, b2, b3};
+        int m2 = 0;
+        switch (m1 & 31) {  // = 31 - column
+#define IAM_RU(J) case 31 - J: m2 = runner_up<J>(k, bb); break;
+          IAM_RU(0) IAM_RU(1) IAM_RU(2) IAM_RU(3) IAM_RU(4) IAM_RU(5) IAM_RU(6) IAM_RU(7)
+          IAM_RU(8) IAM_RU(9) IAM_RU(10) IAM_RU(11) IAM_RU(12) IAM_RU(13) IAM_RU(14) IAM_RU(15)
+          IAM_RU(16) IAM_RU(17) IAM_RU(18) IAM_RU(19) IAM_RU(20) IAM_RU(21) IAM_RU(22) IAM_RU(23)
+          IAM_RU(24) IAM_RU(25) IAM_RU(26) IAM_RU(27) IAM_RU(28) IAM_RU(29) IAM_RU(30) IAM_RU(31)
+#undef IAM_RU
+        }
+        tk.insert(m1 >> 5, (m1 & 31) | tp32);
+        if (m2 > te_key) tk.insert(m2 >> 5, (m2 & 31) | tp32);
+      }
+      return;
+    }
+  }
+  const bool hit = kMode == 0 ? true : kMode == 2 ? any_lane(m1 > -1) : any_lane(m1 > te_key);
+#else
   const bool hit = kMode == 2 ? any_lane(m1 > -1) : any_lane(m1 > te_key);
+#endif
   if (hit && kMode != 1) {
 #endif
     const int neg_m1 = -m1;

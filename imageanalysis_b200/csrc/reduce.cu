@@ -257,7 +257,72 @@ crosscheck_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ job_t
   if (threadIdx.x == 255) out_count[p] = s_scan[255];
 }
 
+
+// Compact form of the per-pair tables for the multi-GPU gather ("counts first, then the payload"):
+// offsets[p] = exclusive prefix sum of the counts (one CTA walks the list with a running carry), rows = the valid
+// rows of every pair back to back, in pair order.
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const int* __restrict__ count, int n, int* __restrict__ offsets) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? count[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int incl = carry + x + (warp > 0 ? s_warp[warp - 1] : 0);
+    if (i < n) offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+pack_tables_kernel(const int2* __restrict__ table, const int* __restrict__ count, const int* __restrict__ offsets, int cap,
+                   int2* __restrict__ rows) {
+  const int p = blockIdx.x;
+  const int c = count[p];
+  const int2* src = table + static_cast<size_t>(p) * cap;
+  int2* dst = rows + offsets[p];
+  for (int e = threadIdx.x; e < c; e += blockDim.x) dst[e] = src[e];
+}
+
 }  // namespace
+
+cudaError_t launch_scan_counts(const int* count, int n, int* offsets, cudaStream_t stream) {
+  scan_counts_kernel<<<1, 1024, 0, stream>>>(count, n, offsets);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_tables(const int* table, const int* count, const int* offsets, int n_pairs, int cap, int* rows,
+                               cudaStream_t stream) {
+  if (n_pairs <= 0) return cudaSuccess;
+  pack_tables_kernel<<<n_pairs, 256, 0, stream>>>(reinterpret_cast<const int2*>(table), count, offsets, cap,
+                                                  reinterpret_cast<int2*>(rows));
+  return cudaGetLastError();
+}
 
 cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, const float* knn_dist, int k,
                           const ReduceParams& prm, double* cand_metric, int2* cand_qt, int cand_stride,

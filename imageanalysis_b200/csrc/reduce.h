@@ -36,4 +36,10 @@ cudaError_t launch_dedupe(const RedJob* jobs, int n_jobs, const ImgDev* imgs, in
 cudaError_t launch_crosscheck(const RedJob* jobs, int n_pairs, const int* job_table, const int* job_count, int cap,
                               int cross_check, int max_n_t, int* out_table, int* out_count, cudaStream_t stream);
 
+// Compact (CSR) form of the per-pair tables: offsets [n+1] = exclusive prefix sums of count [n]; rows = the valid
+// rows of every pair back to back in pair order (what the multi-GPU gather moves instead of the padded tables).
+cudaError_t launch_scan_counts(const int* count, int n, int* offsets, cudaStream_t stream);
+cudaError_t launch_pack_tables(const int* table, const int* count, const int* offsets, int n_pairs, int cap, int* rows,
+                               cudaStream_t stream);
+
 }  // namespace iam

@@ -215,6 +215,14 @@ int iam_match_pairs_device(iam_ctx* ctx, const int32_t* pairs, int n_pairs,
 /* Copy the device tables of the last iam_match_pairs_device() to the host. */
 int iam_fetch_tables(iam_ctx* ctx, int32_t* out_table, int32_t* out_count);
 
+/* Compact (CSR) form of the tables of the last iam_match_pairs_device() / iam_match_images() call, left in device
+ * memory: d_offsets [n_pairs + 1] int32 = exclusive prefix sums of the counts, d_rows [total][2] int32 = the valid
+ * [queryIdx, trainIdx] rows of every pair back to back, in pair order; *total = d_offsets[n_pairs] (the call
+ * synchronises to return it).  This is what the pair-sharded multi-GPU job all-gathers instead of the padded
+ * tables: the per-pair results the reference stores with `i1.match_list[i2.name] = ...` (matcher.py:979-980)
+ * are lists of very different lengths.  Pointers stay valid until the next call on this context. */
+int iam_pack_tables_device(iam_ctx* ctx, void** d_rows, void** d_offsets, long long* total);
+
 /* ---- RANSAC: replaces cv2.findEssentialMat(..., RANSAC, threshold) ---- */
 
 /* Batched robust model fit for filter_by_transform (matcher.py:90-142;

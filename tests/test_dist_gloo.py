@@ -68,6 +68,40 @@ def test_allgather_tables_world2_equal_shards(tmp_path):
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
 
 
+def _worker_packed(rank, world, port, n_total, cap, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from imageanalysis_b200 import dist
+    dist.init("gloo")
+    pairs = np.stack([np.arange(n_total), np.arange(n_total) + 1], 1).astype(np.int32)
+    local, b, e = dist.shard_pairs(pairs, rank, world)
+    rows, count = [], []
+    for p in range(b, e):          # pair p has (p * 7) % cap rows [p, k]: ragged, some empty
+        c = (p * 7) % cap
+        count.append(c)
+        rows += [[p, k] for k in range(c)]
+    rows = torch.tensor(rows, dtype=torch.int32).reshape(-1, 2)
+    count = torch.tensor(count, dtype=torch.int32)
+    r_all, c_all = dist.allgather_packed(rows, count, n_total, rank, world)
+    torch.save((r_all, c_all), os.path.join(out_dir, "p%d.pt" % rank))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_allgather_packed_world2(tmp_path):
+    """The compact gather (counts, then one padded payload): CSR of every pair's rows, in work-list order, on all ranks."""
+    for n_total in (11, 12, 3):
+        world, cap = 2, 5
+        mp.spawn(_worker_packed, args=(world, _free_port(), n_total, cap, str(tmp_path)), nprocs=world, join=True)
+        res = [torch.load(os.path.join(tmp_path, "p%d.pt" % r)) for r in range(world)]
+        want_c = [(p * 7) % cap for p in range(n_total)]
+        want_r = [[p, k] for p in range(n_total) for k in range((p * 7) % cap)]
+        for r_all, c_all in res:
+            assert c_all.tolist() == want_c
+            assert r_all.reshape(-1, 2).tolist() == want_r
+
+
 def test_allgather_single_rank_is_identity():
     sys.path.insert(0, ROOT)
     from imageanalysis_b200 import dist
