@@ -22,7 +22,7 @@ DTYPE_U8, DTYPE_F32 = 0, 1
 ENGINE_AUTO, ENGINE_UMMA, ENGINE_SIMT, ENGINE_UMMA_F16 = 0, 1, 2, 3
 KIND_F16, KIND_F8, KIND_I8 = 0, 1, 2
 REDUCE_LOWE, REDUCE_REF_METRIC = 0, 1
-MODEL_ESSENTIAL, MODEL_HOMOGRAPHY = 0, 1
+MODEL_ESSENTIAL, MODEL_HOMOGRAPHY, MODEL_FUNDAMENTAL = 0, 1, 2
 
 # every symbol include/iamatch.h declares; tests check the library exports them all
 EXPORTS = (

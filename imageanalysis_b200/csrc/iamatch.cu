@@ -1486,7 +1486,8 @@ int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2
   int rc = bind(c);
   if (rc) return rc;
   if (n_pairs < 0 || !off || !out_mask || !out_model || !out_inliers) return fail(IAM_E_ARG, "bad arguments");
-  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY) return fail(IAM_E_ARG, "unknown model %d", model);
+  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL)
+    return fail(IAM_E_ARG, "unknown model %d", model);
   if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
   std::string err;
   rc = iam::ransac_pairs(model, pts1, pts2, off, n_pairs, K, threshold_px, prob, max_iters, seed, out_mask, out_model,

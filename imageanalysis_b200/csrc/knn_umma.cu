@@ -57,8 +57,13 @@ namespace {
 #ifndef IAM_DUAL_ISSUE
 #define IAM_DUAL_ISSUE 1
 #endif
-constexpr int kParts = kBRows / 32;              // 32-column parts of a B tile, one epilogue warp each (per A tile and lane quadrant)
-constexpr int kWarpsPerATile = 4 * kParts;
+// Column parts of a B tile, one epilogue warp each (per A tile and lane quadrant).  IAM_PART_COLS = columns a thread
+// holds per slice in the packed-key path (byte layout, k = 2): 32 (three parts, 24 epilogue warps), 48 (two parts, 16
+// warps, 96 registers) or 96 (one part, 8 warps, no exchange of bounds between threads at all).  Wider slices spread
+// the per-slice overhead (barrier wait, tensor-memory load, exchange, vote) over more columns.
+#ifndef IAM_PART_COLS
+#define IAM_PART_COLS 32
+#endif
 
 // Per-kind, per-shape kernel configuration: operand layout (layout.h) + tensor-memory / shared-memory budget.
 // kT = query tiles (128 rows each) resident per CTA:
@@ -67,9 +72,14 @@ constexpr int kWarpsPerATile = 4 * kParts;
 //      front-loaded (every row starts with empty lists: the first eight of ~53 train tiles carry 60 % of all
 //      insertions), so one CTA alternates between an ALU-bound phase with an idle tensor pipe and an MMA-bound phase
 //      with idle ALUs; two co-resident CTAs drift out of phase and fill each other's gaps.
-template <Kind kKind, int kT>
+template <Kind kKind, int kT, int kPC = 32>
 struct Cfg : LayD<kKind> {
   using L = LayD<kKind>;
+  static constexpr int kPartCols = kPC;
+  static constexpr int kParts = kBRows / kPC;
+  static_assert(kParts * kPC == kBRows && (kPC == 32 || kPC == 48 || kPC == 96), "part columns");
+  static constexpr int kWarpsPerATile = 4 * kParts;
+  static constexpr int kKeyMul = kPC <= 32 ? 32 : kPC <= 64 ? 64 : 128;   // packed key = acc * kKeyMul + (kKeyMul - 1 - column)
   static constexpr int kEpiWarps = kT * kWarpsPerATile;          // 24 (6 per SM sub-partition) / 12
   static constexpr int kThreads = 128 + 32 * kEpiWarps;          // 896 / 512
   static constexpr int kCtasPerSm = kT == 1 ? 2 : 1;
@@ -587,6 +597,47 @@ __device__ __forceinline__ void consume32_packed(const int (&v)[32], int tp32, T
   }
 }
 
+// The packed-key scheme for slices of NC columns (IAM_PART_COLS = 48 / 96): key = acc * kMul + (kMul - 1 - column),
+// kMul = 64 / 128 (acc <= 128 * 255^2 + kI8Cap < 2^24, so the key stays below 2^31); the running lists carry the index
+// e = tpk | (kMul - 1 - j) with tpk = kMul * slice number.  Same two halves as consume32_packed: kMul-ary packing by
+// IMAD (FMA pipe), a three-input max tree, ONE vote, then the knock-out (first kNF columns as subtraction + tree, the
+// rest as four fused add-max chains) and two insertions.
+template <int NC, int kMode = 0>
+__device__ __forceinline__ void consume_packed_n(const int (&v)[NC], int tpk, TopK<2, Ord<Kind::I8>>& tk, int pb,
+                                                 uint32_t mul, uint32_t one) {
+  constexpr int kMul = NC <= 32 ? 32 : NC <= 64 ? 64 : 128;
+  constexpr int kShift = kMul == 32 ? 5 : kMul == 64 ? 6 : 7;
+  (void)one;
+  const int te = max(tk.d[1], pb);
+  int k[NC];
+  static_for32([&](auto j) { asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(k[j]) : "r"(v[j]), "r"(mul), "n"(kMul - 1 - decltype(j)::value)); },
+               std::make_integer_sequence<int, NC>{});
+  const int m1 = imax_tree<NC>(k);
+  int te_key;
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(te_key) : "r"(te), "r"(mul), "n"(kMul - 1));
+  const bool hit = kMode == 2 ? any_lane(m1 > -1) : any_lane(m1 > te_key);
+  if (hit && kMode != 1) {
+    constexpr int kNF = IAM_PACKED_FMA_SUBS >= 32 ? 8 : IAM_PACKED_FMA_SUBS;
+    const uint32_t nm = static_cast<uint32_t>(-m1);
+    uint32_t u[kNF];
+#pragma unroll
+    for (int j = 0; j < kNF; ++j) u[j] = static_cast<uint32_t>(k[j]) - static_cast<uint32_t>(m1);
+    uint32_t s0 = umax_tree<kNF / 2>(u), s1 = umax_tree<kNF / 2>(u + kNF / 2), s2 = 0, s3 = 0;
+    constexpr int kQ = (NC - kNF) / 4;
+#pragma unroll
+    for (int j = 0; j < kQ; ++j) {
+      s0 = max(s0, static_cast<uint32_t>(k[kNF + j]) + nm);
+      s1 = max(s1, static_cast<uint32_t>(k[kNF + kQ + j]) + nm);
+      s2 = max(s2, static_cast<uint32_t>(k[kNF + 2 * kQ + j]) + nm);
+    }
+#pragma unroll
+    for (int j = kNF + 3 * kQ; j < NC; ++j) s3 = max(s3, static_cast<uint32_t>(k[j]) + nm);
+    const int m2 = m1 + static_cast<int>(max(umax3(s0, s1, s2), s3));
+    tk.insert(m1 >> kShift, (m1 & (kMul - 1)) | tpk);
+    tk.insert(m2 >> kShift, (m2 & (kMul - 1)) | tpk);
+  }
+}
+
 // Packed-key path for Hamming (kind::f8f6f4, k = 2).  The operand layout makes every fp32 accumulator the exact
 // integer  key_j = 32 * distance + j  (convert_hamming_kernel; j = column inside the thread's 32-column slice),
 // unique, ordered like (distance, column): SMALLER = nearer, ties to the lower column.  m1 = min_j key_j by
@@ -632,12 +683,15 @@ __device__ __forceinline__ const uint8_t* a_src(const ImgDev& im) { return kKind
 template <Kind kKind>
 __device__ __forceinline__ const uint8_t* b_src(const ImgDev& im) { return kKind == Kind::I8 ? im.i8_form : im.b_form; }
 
-template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg, int kT>
-__global__ void __launch_bounds__((Cfg<kKind, kT>::kThreads), (Cfg<kKind, kT>::kCtasPerSm))
+template <Kind kKind, int KTOP, bool kATmem, bool kCluster, int kDbg, int kT, int kPC>
+__global__ void __launch_bounds__((Cfg<kKind, kT, kPC>::kThreads), (Cfg<kKind, kT, kPC>::kCtasPerSm))
 knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ units, int n_units,
                 int* __restrict__ out_idx, float* __restrict__ out_d2, uint32_t pack_mul, uint32_t pack_one) {
-  using C = Cfg<kKind, kT>;
+  using C = Cfg<kKind, kT, kPC>;
   constexpr int kEpiWarps = C::kEpiWarps;
+  constexpr int kParts = C::kParts;
+  constexpr int kWarpsPerATile = C::kWarpsPerATile;
+  constexpr int kKeyMul = C::kKeyMul;
   constexpr int kRows = C::kRows;
   constexpr int kItems = C::kItems;
   constexpr uint32_t kTmemCols = C::kTmemCols;
@@ -840,19 +894,20 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     const uint32_t share_row = smem_u32(share) + urow * 8;
     const uint32_t bar_full0 = pin_reg(smem_u32(&bars->t_full[0]));
     constexpr uint32_t kEmptyOff = kSlots * 8;                  // t_empty[] follows t_full[] in Barriers
-    const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * 32);
+    const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * kPC);
     const bool lane0 = lane == 0;
     TopK<KTOP, O> tk;
     constexpr bool kPacked = IAM_PACKED && kKind == Kind::I8 && KTOP == 2;
+    static_assert(kPC == 32 || kPacked, "wide slices exist for the packed-key path only");
     constexpr bool kPackedF = IAM_PACKED && IAM_PACKED_HAMMING && kKind == Kind::F8 && KTOP == 2;
     constexpr bool kKeyF = kKind == Kind::F8;  // accumulators are keys 32 * distance + column (convert_hamming_kernel)
     // Multipliers ptxas cannot fold (kernel parameters 32 and 1): with a literal 32 the packing multiply-adds are strength-reduced
     // to LEA, an ALU-pipe instruction; as register operands they stay IMADs on the otherwise idle FMA pipe.
-    const uint32_t mul32 = IAM_PACK_IMAD ? pack_mul : 32u, one = IAM_PACK_IMAD ? pack_one : 1u;
+    const uint32_t mul32 = IAM_PACK_IMAD ? pack_mul : static_cast<uint32_t>(kKeyMul), one = IAM_PACK_IMAD ? pack_one : 1u;
     (void)mul32;
     (void)one;
     uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kT + a, slot = sq % kSlots
-    constexpr bool kPair = kPacked && kDual && kSlots == 2 * kT && kParts > 1 && (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5);
+    constexpr bool kPair = kPacked && kDual && kSlots == 2 * kT && (kParts > 1 || kPC != 32) && (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5);
     const uint32_t bar_a = pin_reg(bar_full0 + a * 8);       // kPair: t_full of this tile's first slot (second: + kT * 8)
     const uint32_t tm_a = pin_reg(tm_warp + a * kBRows);     // kPair: its accumulator columns (second slot: + kT * kBRows)
     int phase = 0;
@@ -885,15 +940,22 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         // nothing worse than the best of the k-th bests can end up in the merged list.  Ties are admitted (loosen;
         // the final merge orders them by index).  Stale values are still valid bounds: plain volatile traffic.
         auto exchange = [&]() {
+          if constexpr (kParts == 1) return;  // the whole row is this thread's: nothing to exchange
 #if IAM_ROW_BOUND
           // The row's true second best so far: every part publishes (second best, best); the second largest of the
           // six values is  max(second largest of the three bests, largest of the three second bests).
-          static_assert(!IAM_ROW_BOUND || kParts == 3, "row-exact bound: three column parts");
-          const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride), e2 = lds_volatile_v2b32_a(rd + 2 * kPartStride);
-          const T h0 = O::from_bits(e0.y), h1 = O::from_bits(e1.y), h2 = O::from_bits(e2.y);
-          const T second_h = O::best3(min(h0, h1), min(h0, h2), min(h1, h2));
-          const T g = O::best(second_h, O::best3(O::from_bits(e0.x), O::from_bits(e1.x), O::from_bits(e2.x)));
-          pb = O::best(pb, O::loosen(g));
+          static_assert(!IAM_ROW_BOUND || kParts <= 3, "row-exact bound: up to three column parts");
+          if constexpr (kParts == 3) {
+            const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride), e2 = lds_volatile_v2b32_a(rd + 2 * kPartStride);
+            const T h0 = O::from_bits(e0.y), h1 = O::from_bits(e1.y), h2 = O::from_bits(e2.y);
+            const T second_h = O::best3(min(h0, h1), min(h0, h2), min(h1, h2));
+            const T g = O::best(second_h, O::best3(O::from_bits(e0.x), O::from_bits(e1.x), O::from_bits(e2.x)));
+            pb = O::best(pb, O::loosen(g));
+          } else if constexpr (kParts == 2) {  // four values: max(worse of the two bests, better of the two second bests)
+            const uint2 e0 = lds_volatile_v2b32_a(rd), e1 = lds_volatile_v2b32_a(rd + kPartStride);
+            const T g = O::best3(min(O::from_bits(e0.y), O::from_bits(e1.y)), O::from_bits(e0.x), O::from_bits(e1.x));
+            pb = O::best(pb, O::loosen(g));
+          }
 #else
           T g = O::from_bits(lds_volatile_b32_a(rd));
 #pragma unroll
@@ -902,45 +964,51 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 #endif
         };
         // `ex`: this is the pair's first tile -- the exchange of bounds runs while the tensor-memory load is in flight
-        auto tile = [&](auto sl, int tp32, bool ex) {
+        auto tile = [&](auto sl, int tpk, bool ex) {
           constexpr uint32_t kSl = decltype(sl)::value;
           const uint32_t bar = bar_a + kSl * (kT * 8);
           mbar_wait_bare_a(bar, par);
           tc_fence_after();
           if constexpr (kDbg != 1) {
-            int v[32];
+            int v[kPC];
 #if !IAM_EPI_NOSYNC
             __syncwarp();
 #endif
-            tmem_ld32(tm_a + kSl * (kT * kBRows), v);
+            if constexpr (kPC == 32) tmem_ld32(tm_a + kSl * (kT * kBRows), v);
+            else tmem_ld_n<kPC>(tm_a + kSl * (kT * kBRows), v);
             if (IAM_LAT_EX && ex) exchange();
-            tmem_ld_wait(v);
+            if constexpr (kPC == 32) tmem_ld_wait(v);
+            else tmem_ld_wait_n<kPC>(v);
             // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
 #if !IAM_EPI_NOSYNC
             __syncwarp();
 #endif
             tc_fence_before();
             if (lane0) mbar_arrive_a(bar + kEmptyOff);
-            consume32_packed<kDbg == 5 ? 2 : kDbg == 4 ? 1 : 0>(v, tp32, tk, pb, mul32, one);
+            if constexpr (kPC == 32) consume32_packed<kDbg == 5 ? 2 : kDbg == 4 ? 1 : 0>(v, tpk, tk, pb, mul32, one);
+            else consume_packed_n<kPC, kDbg == 5 ? 2 : kDbg == 4 ? 1 : 0>(v, tpk, tk, pb, mul32, one);
           } else {  // IAM_UMMA_DEBUG=1: MMA/TMA pipeline only, accumulators dropped
             __syncwarp();
             tc_fence_before();
             if (lane0) mbar_arrive_a(bar + kEmptyOff);
           }
         };
-        int tp32 = part * 32 - phase * (kBRows);  // 32 * (tile * kParts + part) of the pair's first tile
-        for (int tb = -phase; tb < n_tb; tb += 2, tp32 += 2 * kBRows) {
+        constexpr int kTileStep = kKeyMul * kParts;           // key-space distance between successive tiles (96 = kBRows for 32-column parts)
+        int tpk = part * kKeyMul - phase * kTileStep;          // kKeyMul * (tile * kParts + part) of the pair's first tile
+        for (int tb = -phase; tb < n_tb; tb += 2, tpk += 2 * kTileStep) {
           if (!IAM_LAT_EX || kDbg == 1) exchange();
-          if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tp32, true);
+          if (tb >= 0) tile(std::integral_constant<uint32_t, 0>{}, tpk, true);
           if (tb + 1 < n_tb) {
-            tile(std::integral_constant<uint32_t, 1>{}, tp32 + kBRows, tb < 0);
+            tile(std::integral_constant<uint32_t, 1>{}, tpk + kTileStep, tb < 0);
             par ^= 1;
           }
+          if constexpr (kParts > 1) {
 #if IAM_ROW_BOUND
-          sts_volatile_v2b32_a(wr, O::bits(tk.d[KTOP - 1]), O::bits(tk.d[0]));
+            sts_volatile_v2b32_a(wr, O::bits(tk.d[KTOP - 1]), O::bits(tk.d[0]));
 #else
-          sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
+            sts_volatile_b32_a(wr, O::bits(tk.d[KTOP - 1]));
 #endif
+          }
         }
         phase = (phase + n_tb) & 1;
       } else {
@@ -961,24 +1029,32 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           mbar_wait_bare_a(bar, par);
           tc_fence_after();
           if (kDbg != 1) {
-            T v[32];
+            T v[kPC];
             __syncwarp();
-            tmem_ld32(tm_warp + slot * kBRows, v);
-            tmem_ld_wait(v);
+            if constexpr (kPC == 32) {
+              tmem_ld32(tm_warp + slot * kBRows, v);
+              tmem_ld_wait(v);
+            } else {
+              tmem_ld_n<kPC>(tm_warp + slot * kBRows, v);
+              tmem_ld_wait_n<kPC>(v);
+            }
             // the values are in registers: hand the accumulator slot back to the MMA issuer before consuming them
             __syncwarp();
             tc_fence_before();
             if (lane0) mbar_arrive_a(bar + kEmptyOff);
             if (kDbg == 0) {
-              if constexpr (kPacked) consume32_packed<0>(v, tp * 32, tk, pb, mul32, one);
+              if constexpr (kPacked && kPC != 32) consume_packed_n<kPC, 0>(v, tp * kKeyMul, tk, pb, mul32, one);
+              else if constexpr (kPacked) consume32_packed<0>(v, tp * 32, tk, pb, mul32, one);
               else if constexpr (kPackedF) consume32_packed_f<0>(v, tp * 32, tk, pb);
               else consume32<KTOP, O, false, kKeyF>(v, tp, tk, pb);
             } else if (kDbg == 5) {  // profiling aid (IAM_UMMA_DEBUG=5): identical slow-path work in every warp and tile
-              if constexpr (kPacked) consume32_packed<2>(v, tp * 32, tk, pb, mul32, one);
+              if constexpr (kPacked && kPC != 32) consume_packed_n<kPC, 2>(v, tp * kKeyMul, tk, pb, mul32, one);
+              else if constexpr (kPacked) consume32_packed<2>(v, tp * 32, tk, pb, mul32, one);
               else if constexpr (kPackedF) consume32_packed_f<2>(v, tp * 32, tk, pb);
               else consume32<KTOP, O, true, kKeyF>(v, tp, tk, pb);
             } else if (kDbg == 4) {  // profiling aid (IAM_UMMA_DEBUG=4): tests + votes + branches, never taken
-              if constexpr (kPacked) consume32_packed<1>(v, tp * 32, tk, pb, mul32, one);
+              if constexpr (kPacked && kPC != 32) consume_packed_n<kPC, 1>(v, tp * kKeyMul, tk, pb, mul32, one);
+              else if constexpr (kPacked) consume32_packed<1>(v, tp * 32, tk, pb, mul32, one);
               else if constexpr (kPackedF) consume32_packed_f<1>(v, tp * 32, tk, pb);
               else consume32<KTOP, O, false, kKeyF>(v, tp, tk, O::never());
             } else if (kDbg == 3) {  // profiling aid (IAM_UMMA_DEBUG=3): accumulator read-out only, results NOT valid
@@ -1016,7 +1092,11 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         for (int s = 0; s < KTOP; ++s) {
           const int enc = tk.i[s];
           if (kKind == Kind::I8) {
-            const int rank = enc == 0x7fffffff ? 0x7fffffff : (kPacked ? (enc ^ 31) : dec_index(enc));
+            int rank;
+            if constexpr (kPacked && kPC != 32)  // e = kKeyMul * slice | (kKeyMul - 1 - column in slice), slices of kPC columns
+              rank = enc == 0x7fffffff ? 0x7fffffff : (enc / kKeyMul) * kPC + (kKeyMul - 1 - (enc & (kKeyMul - 1)));
+            else
+              rank = enc == 0x7fffffff ? 0x7fffffff : (kPacked ? (enc ^ 31) : dec_index(enc));
             if (rank < t.n) {  // d^2 = ||q||^2 + 2 CAP + (||t||^2 & 1) - 2 acc, exact (layout.h)
               fin.d[s] = static_cast<float>(rowc + (rank >= n_even ? 1 : 0) - 2 * static_cast<int>(tk.d[s]));
               fin.i[s] = t.perm[rank];
@@ -1036,7 +1116,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           merge[((part - 1) * kRows + urow) * KTOP + s] = make_float2(fin.d[s], __int_as_float(fin.i[s]));
       }
       // only the kParts warps that own these 32 rows meet here: the other row groups run on
-      asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");
+      if constexpr (kParts > 1) asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");
       if (part == 0) {
 #pragma unroll
         for (int pp = 0; pp < kParts - 1; ++pp) {
@@ -1056,7 +1136,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
           }
         }
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");  // merge area is free again
+      if constexpr (kParts > 1) asm volatile("bar.sync %0, %1;" ::"r"(group_bar), "n"(32 * kParts) : "memory");  // merge area is free again
     }
   }
 
@@ -1133,7 +1213,7 @@ umma_tile_debug_kernel(const uint8_t* __restrict__ a_tile, const uint8_t* __rest
   }
 }
 
-template <Kind kKind, int KTOP, int kT>
+template <Kind kKind, int KTOP, int kT, int kPC = 32>
 cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, int* out_idx, float* out_d2, int num_sms,
                          cudaStream_t stream) {
   static const bool a_tmem = [] {
@@ -1148,22 +1228,22 @@ cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, 
     const char* e = getenv("IAM_UMMA_DEBUG");  // profiling aid, results invalid when set: 1 = no epilogue, 2 = fast path only, 3 = accumulator read-out only, 4 = group tests never taken, 5 = fixed slow-path work
     return e ? atoi(e) : 0;
   }();
-  using C = Cfg<kKind, kT>;
+  using C = Cfg<kKind, kT, kPC>;
   using KernT = void (*)(const ImgDev*, const KnnUnit*, int, int*, float*, uint32_t, uint32_t);
   const int n_items = n_units * C::kItems;
   const bool use_cluster = cluster && (n_items % 2 == 0);
   KernT kern;
   if (flags != 0) {  // profiling variants exist for the production configuration only
     if (!use_cluster || !a_tmem || flags < 0 || flags > 5) return cudaErrorInvalidValue;
-    kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1, kT>
-           : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2, kT>
-           : flags == 3 ? knn_umma_kernel<kKind, KTOP, true, true, 3, kT>
-           : flags == 4 ? knn_umma_kernel<kKind, KTOP, true, true, 4, kT>
-                        : knn_umma_kernel<kKind, KTOP, true, true, 5, kT>;
+    kern = flags == 1   ? knn_umma_kernel<kKind, KTOP, true, true, 1, kT, kPC>
+           : flags == 2 ? knn_umma_kernel<kKind, KTOP, true, true, 2, kT, kPC>
+           : flags == 3 ? knn_umma_kernel<kKind, KTOP, true, true, 3, kT, kPC>
+           : flags == 4 ? knn_umma_kernel<kKind, KTOP, true, true, 4, kT, kPC>
+                        : knn_umma_kernel<kKind, KTOP, true, true, 5, kT, kPC>;
   } else if (use_cluster) {
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0, kT> : knn_umma_kernel<kKind, KTOP, false, true, 0, kT>;
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, true, 0, kT, kPC> : knn_umma_kernel<kKind, KTOP, false, true, 0, kT, kPC>;
   } else {
-    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0, kT> : knn_umma_kernel<kKind, KTOP, false, false, 0, kT>;
+    kern = a_tmem ? knn_umma_kernel<kKind, KTOP, true, false, 0, kT, kPC> : knn_umma_kernel<kKind, KTOP, false, false, 0, kT, kPC>;
   }
   constexpr size_t kSmemTotal = C::kSmemTotal;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemTotal);
@@ -1190,7 +1270,7 @@ cudaError_t launch_shape(const ImgDev* imgs, const KnnUnit* units, int n_units, 
     cfg.numAttrs = 1;
   }
   cfg.gridDim = dim3(grid);
-  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, 32u, 1u);  // the key-packing multipliers, as run-time values
+  return cudaLaunchKernelEx(&cfg, kern, imgs, units, n_units, out_idx, out_d2, static_cast<uint32_t>(C::kKeyMul), 1u);  // the key-packing multipliers, as run-time values
 }
 
 template <Kind kKind, int KTOP>
@@ -1204,6 +1284,8 @@ cudaError_t launch_t(const ImgDev* imgs, const KnnUnit* units, int n_units, int*
       return e ? atoi(e) : 2;
     }();
     if (tiles == 1) return launch_shape<kKind, KTOP, 1>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
+    if constexpr (KTOP == 2 && IAM_PACKED && IAM_PART_COLS != 32)
+      return launch_shape<kKind, KTOP, 2, IAM_PART_COLS>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
   }
   return launch_shape<kKind, KTOP, 2>(imgs, units, n_units, out_idx, out_d2, num_sms, stream);
 }

@@ -365,6 +365,40 @@ __device__ __forceinline__ void tmem_ld_wait(T (&v)[32]) {
                : "memory");
 }
 
+// TMEM -> registers: this warp's 32 lanes x 16 consecutive 32-bit columns.
+template <typename T>
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, T* v) {
+  static_assert(sizeof(T) == 4, "32-bit accumulator cells");
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// NC (a multiple of 16) consecutive columns as x32 loads plus at most one x16 load, all in flight together.
+template <int NC, typename T>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, T (&v)[NC]) {
+  static_assert(NC % 16 == 0, "whole x16 loads");
+#pragma unroll
+  for (int c = 0; c + 32 <= NC; c += 32) tmem_ld32(taddr + c, *reinterpret_cast<T(*)[32]>(&v[c]));
+  if constexpr (NC % 32 == 16) tmem_ld16(taddr + NC - 16, &v[NC - 16]);
+}
+
+// Wait for outstanding tcgen05.ld of NC registers: the wait itself, then every loaded register passes through an
+// empty volatile asm as an in/out operand -- volatile asms keep their order, so no use of v[] can be hoisted above
+// the wait (the same guarantee tmem_ld_wait gives with one 32-operand statement).
+template <int NC, typename T>
+__device__ __forceinline__ void tmem_ld_wait_n(T (&v)[NC]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+#pragma unroll
+  for (int j = 0; j < NC; ++j) asm volatile("" : "+r"(r[j]));
+}
+
 // 16-byte shared-memory accesses that the compiler may neither cache nor split
 __device__ __forceinline__ float4 lds_volatile_v4(const void* p) {
   float4 v;

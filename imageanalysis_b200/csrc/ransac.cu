@@ -424,14 +424,128 @@ IAM_HD int four_point(const float* x1, const float* y1, const float* x2, const f
   return 1;
 }
 
+// ---- 7-point fundamental matrix (normalised coordinates): up to 3 rank-2 F with x2^T F x1 = 0 ----
+// The published minimal method behind cv2.findFundamentalMat(..., RANSAC): the 7 x 9 epipolar system has a
+// two-dimensional null space {F1, F2}; det(l F1 + (1 - l) F2) = 0 is a cubic in l (Hartley & Zisserman 11.1.2).
+IAM_HD inline double det3(const double* m) {
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+IAM_HD int seven_point(const float* x1, const float* y1, const float* x2, const float* y2, const int* s, float* F_out) {
+  double M[7][9];
+  for (int r = 0; r < 7; ++r) {
+    const double x = x1[s[r]], y = y1[s[r]], u = x2[s[r]], v = y2[s[r]];
+    double* a = M[r];
+    a[0] = u * x; a[1] = u * y; a[2] = u; a[3] = v * x; a[4] = v * y; a[5] = v; a[6] = x; a[7] = y; a[8] = 1.0;
+  }
+  // Gauss-Jordan with full pivoting: 7 pivot columns, 2 free ones
+  int pcol[7];
+  bool used[9] = {false, false, false, false, false, false, false, false, false};
+  for (int r = 0; r < 7; ++r) {
+    int br = r, bc = -1;
+    double best = 0.0;
+    for (int i = r; i < 7; ++i)
+      for (int c = 0; c < 9; ++c)
+        if (!used[c] && fabs(M[i][c]) > best) {
+          best = fabs(M[i][c]);
+          br = i;
+          bc = c;
+        }
+    if (bc < 0 || best < 1e-12) return 0;
+    if (br != r)
+      for (int c = 0; c < 9; ++c) {
+        const double t = M[r][c];
+        M[r][c] = M[br][c];
+        M[br][c] = t;
+      }
+    used[bc] = true;
+    pcol[r] = bc;
+    const double inv = 1.0 / M[r][bc];
+    for (int c = 0; c < 9; ++c) M[r][c] *= inv;
+    for (int i = 0; i < 7; ++i)
+      if (i != r) {
+        const double f = M[i][bc];
+        if (f != 0.0)
+          for (int c = 0; c < 9; ++c) M[i][c] -= f * M[r][c];
+      }
+  }
+  double N[2][9];
+  int nf = 0;
+  for (int c = 0; c < 9 && nf < 2; ++c)
+    if (!used[c]) {
+      for (int e = 0; e < 9; ++e) N[nf][e] = 0.0;
+      N[nf][c] = 1.0;
+      for (int r = 0; r < 7; ++r) N[nf][pcol[r]] = -M[r][c];
+      ++nf;
+    }
+  if (nf != 2) return 0;
+  // det(N1 + l * D), D = N0 - N1:  c0 + c1 l + c2 l^2 + c3 l^3 from the determinant at l = 0, +1, -1 and det(D)
+  double D[9], P[9], Q[9];
+  for (int e = 0; e < 9; ++e) {
+    D[e] = N[0][e] - N[1][e];
+    P[e] = N[1][e] + D[e];
+    Q[e] = N[1][e] - D[e];
+  }
+  const double c0 = det3(N[1]), c3 = det3(D), dp = det3(P), dm = det3(Q);
+  const double c2 = 0.5 * (dp + dm) - c0, c1 = 0.5 * (dp - dm) - c3;
+  double roots[3];
+  int nr = 0;
+  const double scale = fabs(c0) + fabs(c1) + fabs(c2) + fabs(c3);
+  if (!(scale > 0.0)) return 0;
+  if (fabs(c3) < 1e-12 * scale) {  // quadratic (or lower)
+    if (fabs(c2) < 1e-12 * scale) {
+      if (fabs(c1) > 0.0) roots[nr++] = -c0 / c1;
+    } else {
+      const double disc = c1 * c1 - 4.0 * c2 * c0;
+      if (disc >= 0.0) {
+        const double q = -0.5 * (c1 + (c1 >= 0.0 ? sqrt(disc) : -sqrt(disc)));
+        roots[nr++] = q / c2;
+        if (q != 0.0) roots[nr++] = c0 / q;
+      }
+    }
+  } else {  // x^3 + a x^2 + b x + c = 0 (Numerical Recipes 5.6)
+    const double a = c2 / c3, b = c1 / c3, c = c0 / c3;
+    const double Qq = (a * a - 3.0 * b) / 9.0, R = (2.0 * a * a * a - 9.0 * a * b + 27.0 * c) / 54.0;
+    if (R * R < Qq * Qq * Qq) {
+      const double th = acos(fmax(-1.0, fmin(1.0, R / sqrt(Qq * Qq * Qq)))), sq = -2.0 * sqrt(Qq);
+      roots[nr++] = sq * cos(th / 3.0) - a / 3.0;
+      roots[nr++] = sq * cos((th + 6.283185307179586) / 3.0) - a / 3.0;
+      roots[nr++] = sq * cos((th - 6.283185307179586) / 3.0) - a / 3.0;
+    } else {
+      const double A = -(R >= 0.0 ? 1.0 : -1.0) * cbrt(fabs(R) + sqrt(R * R - Qq * Qq * Qq));
+      const double B = A != 0.0 ? Qq / A : 0.0;
+      roots[nr++] = (A + B) - a / 3.0;
+    }
+  }
+  int n_out = 0;
+  for (int i = 0; i < nr; ++i) {
+    double l = roots[i];
+    for (int nw = 0; nw < 2; ++nw) {  // Newton polish
+      const double f = ((c3 * l + c2) * l + c1) * l + c0, df = (3.0 * c3 * l + 2.0 * c2) * l + c1;
+      if (fabs(df) > 0.0) l -= f / df;
+    }
+    double F[9], nn = 0.0;
+    for (int e = 0; e < 9; ++e) {
+      F[e] = N[1][e] + l * D[e];
+      nn += F[e] * F[e];
+    }
+    if (!(nn > 0.0) || !isfinite(nn)) continue;
+    nn = 1.0 / sqrt(nn);
+    for (int e = 0; e < 9; ++e) F_out[n_out * 9 + e] = static_cast<float>(F[e] * nn);
+    ++n_out;
+  }
+  return n_out;
+}
+
 struct PairXform {  // per-pair point normalisation (host computed)
   float a1x, a1y, s1x, s1y;  // image 1: xn = (x - a1x) * s1x
   float a2x, a2y, s2x, s2y;
-  float thr2;                // squared threshold in normalised units
-  int pad[3];
+  float thr2;                // squared threshold in normalised units (errors measured in image 2)
+  float thr2b;               // fundamental: squared threshold for the error measured in image 1
+  int pad[2];
 };
 
-__device__ __forceinline__ float model_error(int model, const float* M, float x1, float y1, float x2, float y2) {
+__device__ __forceinline__ float model_error(int model, const float* M, float x1, float y1, float x2, float y2,
+                                             float thr_ratio = 1.0f) {
   if (model == 0) {  // Sampson distance of x2^T E x1
     const float ex = M[0] * x1 + M[1] * y1 + M[2];
     const float ey = M[3] * x1 + M[4] * y1 + M[5];
@@ -440,6 +554,19 @@ __device__ __forceinline__ float model_error(int model, const float* M, float x1
     const float ty = M[1] * x2 + M[4] * y2 + M[7];
     const float r = x2 * ex + y2 * ey + ez;
     return r * r / (ex * ex + ey * ey + tx * tx + ty * ty);
+  }
+  if (model == 2) {
+    // cv2.findFundamentalMat's RANSAC error: the larger of the two squared point-to-epipolar-line distances
+    // (line F x1 in image 2, line F^T x2 in image 1).  The two images carry their own normalisation scales, so the
+    // distance in image 1 is rescaled to image-2 units (thr_ratio = thr2 / thr2b) and one comparison serves both.
+    const float a = M[0] * x1 + M[1] * y1 + M[2];
+    const float b = M[3] * x1 + M[4] * y1 + M[5];
+    const float c = M[6] * x1 + M[7] * y1 + M[8];
+    const float ta = M[0] * x2 + M[3] * y2 + M[6];
+    const float tb = M[1] * x2 + M[4] * y2 + M[7];
+    const float r = x2 * a + y2 * b + c;
+    const float r2 = r * r;
+    return fmaxf(r2 / (a * a + b * b), thr_ratio * r2 / (ta * ta + tb * tb));
   }
   const float w = M[6] * x1 + M[7] * y1 + M[8];
   const float iw = 1.0f / w;
@@ -462,8 +589,9 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
   const int p = blockIdx.x;
   const int o = off[p];
   const int n = off[p + 1] - o;
-  const int msize = (model == 0) ? 5 : 4;
+  const int msize = (model == 0) ? 5 : (model == 2) ? 7 : 4;
   const PairXform X = xf[p];
+  const float thr_ratio = (model == 2 && X.thr2b > 0.f) ? X.thr2 / X.thr2b : 1.0f;
   float* sx1 = s_pts;
   float* sy1 = sx1 + n;
   float* sx2 = sy1 + n;
@@ -489,7 +617,7 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
         int nc = 0;
         const int it = base + lane;
         if (it < s_niters) {
-          int s[5];
+          int s[7];
           uint32_t h = hash32(seed ^ hash32(uint32_t(p) * 0x9e3779b9u + uint32_t(it)));
           for (int k = 0; k < msize; ++k) {
             for (int tries = 0; tries < 64; ++tries) {
@@ -504,8 +632,9 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
               if (tries == 63) s[k] = (s[k > 0 ? k - 1 : 0] + 1 + k) % n;
             }
           }
-          nc = (model == 0) ? five_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
-                            : four_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9]);
+          nc = (model == 0)   ? five_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
+               : (model == 2) ? seven_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
+                              : four_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9]);
         }
         s_ncand[lane] = nc;
       }
@@ -517,7 +646,7 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
         float M[9];
         for (int e = 0; e < 9; ++e) M[e] = s_cand[c * 9 + e];
         int cnt = 0;
-        for (int i = lane; i < n; i += 32) cnt += model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i]) <= X.thr2;
+        for (int i = lane; i < n; i += 32) cnt += model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i], thr_ratio) <= X.thr2;
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0) s_score[c] = cnt;
       }
@@ -555,7 +684,7 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
   for (int e = 0; e < 9; ++e) M[e] = s_best[e];
   const bool have = s_best_count > 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
-    out_mask[o + i] = (have && model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i]) <= X.thr2) ? 1 : 0;
+    out_mask[o + i] = (have && model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i], thr_ratio) <= X.thr2) ? 1 : 0;
   if (threadIdx.x < 9) out_model[p * 9 + threadIdx.x] = have ? M[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) out_inliers[p] = have ? s_best_count : 0;
 }
@@ -563,8 +692,9 @@ ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict
 }  // namespace
 
 int debug_minimal_solver(int model, const float* x1, const float* y1, const float* x2, const float* y2, float* out) {
-  const int s[5] = {0, 1, 2, 3, 4};
-  return model == 0 ? five_point(x1, y1, x2, y2, s, out) : four_point(x1, y1, x2, y2, s, out);
+  const int s[7] = {0, 1, 2, 3, 4, 5, 6};
+  return model == 0 ? five_point(x1, y1, x2, y2, s, out) : model == 2 ? seven_point(x1, y1, x2, y2, s, out)
+                                                                        : four_point(x1, y1, x2, y2, s, out);
 }
 
 int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t* off, int n_pairs, const double* K,
@@ -625,6 +755,8 @@ int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t*
       X.a2x = float(m2x); X.a2y = float(m2y); X.s2x = X.s2y = float(s2);
       const double t = threshold_px * double(X.s2x);
       X.thr2 = float(t * t);
+      const double tb = threshold_px * double(X.s1x);
+      X.thr2b = float(tb * tb);
     }
   }
 
@@ -672,6 +804,24 @@ int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t*
     double* o = out_model + size_t(p) * 9;
     if (model == 0) {
       for (int i = 0; i < 9; ++i) o[i] = m[i];
+    } else if (model == 2) {
+      // F_pixel = T2^T Fn T1, scaled to unit f33 like cv2.findFundamentalMat reports it
+      const PairXform& X = xf[p];
+      const double T1[9] = {X.s1x, 0, -X.s1x * X.a1x, 0, X.s1y, -X.s1y * X.a1y, 0, 0, 1};
+      const double T2[9] = {X.s2x, 0, -X.s2x * X.a2x, 0, X.s2y, -X.s2y * X.a2y, 0, 0, 1};
+      double t[9], r[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          t[i * 3 + j] = 0;
+          for (int k = 0; k < 3; ++k) t[i * 3 + j] += double(m[i * 3 + k]) * T1[k * 3 + j];
+        }
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          r[i * 3 + j] = 0;
+          for (int k = 0; k < 3; ++k) r[i * 3 + j] += T2[k * 3 + i] * t[k * 3 + j];
+        }
+      const double sc = std::fabs(r[8]) > 1e-300 ? 1.0 / r[8] : 1.0;
+      for (int i = 0; i < 9; ++i) o[i] = r[i] * sc;
     } else {
       const PairXform& X = xf[p];
       // Hp = T2^-1 Hn T1, T = [[s,0,-s*a],[0,s,-s*b],[0,0,1]]

@@ -202,12 +202,14 @@ def filter_by_transform(K, i1, i2, transform):
     p2 = np.float32([i2.uv_list[pair[1]] for pair in matches])
     if transform == "none":
         status = np.ones(len(matches))
-    elif transform in ("essential", "homography"):
+    elif transform in ("essential", "homography", "fundamental"):           # matcher.py:121-126
         eng = the_matcher.engine(128 if _norm == _capi.NORM_L2 else 32)
-        model = _capi.MODEL_ESSENTIAL if transform == "essential" else _capi.MODEL_HOMOGRAPHY
+        model = {"essential": _capi.MODEL_ESSENTIAL, "homography": _capi.MODEL_HOMOGRAPHY,
+                 "fundamental": _capi.MODEL_FUNDAMENTAL}[transform]
         status, M, ninl = eng.ransac_pairs(model, p1, p2, np.int32([0, len(matches)]), np.asarray(K, np.float64), tol)
     else:
-        raise _capi.IamError("transform '%s' has no GPU implementation (essential, homography, none)" % transform)
+        # the reference falls through to a NameError on `status` for any other string (matcher.py:129)
+        raise _capi.IamError("unknown transform '%s' (homography, fundamental, essential, none)" % transform)
     log("  %s vs %s: %d / %d  inliers/matched" % (i1.name, i2.name, np.sum(status), len(status)))
     kept = []
     for k, flag in enumerate(status):
@@ -329,90 +331,363 @@ def bidirectional_pair_matches(i1, i2, review=False):
     return filter_cross_check(idx_pairs1, idx_pairs2)
 
 
-def _homography_bins(i1, i2, bins, tol):
-    """Shared tail of ratio_pair_matches / bruteforce_pair_matches: fit a
-    homography per candidate bin on the GPU (all bins in ONE batched call)
-    and keep the bin with the most unique inliers (matcher.py:632-662, :797-830)."""
-    best, best_count = [], 20
-    live = [b for b in bins if len(b) >= min_pairs]
-    if not live:
-        return []
-    off = np.zeros(len(live) + 1, np.int32)
-    p1, p2 = [], []
-    for n, b in enumerate(live):
-        off[n + 1] = off[n] + len(b)
-        p1.extend(i1.kp_list[m.queryIdx].pt for m in b)
-        p2.extend(i2.kp_list[m.trainIdx].pt for m in b)
+def _knn3_arrays(i1, i2, k):
+    """raw_matches (matcher.py:203-216) as arrays: (idx [N,k], dist [N,k]) or None where raw_matches returns []."""
+    if i1.des_list is None or i2.des_list is None:
+        return None
+    if len(i1.des_list.shape) == 0 or i1.des_list.shape[0] <= 1:
+        return None
+    if len(i2.des_list.shape) == 0 or i2.des_list.shape[0] <= 1:
+        return None
+    idx, dist = the_matcher.knn_arrays(np.array(i1.des_list), np.array(i2.des_list), k)
+    qlog("  raw matches:", idx.shape[0])
+    return idx, dist
+
+
+def _kp_arrays(img):
+    pts = np.float32([k.pt for k in img.kp_list]).reshape(-1, 2)
+    size = np.float64([k.size for k in img.kp_list])
+    angle = np.float64([k.angle for k in img.kp_list])
+    return pts, size, angle
+
+
+def _batched_homographies(i1, i2, groups, tol):
+    """cv2.findHomography(src, dst, cv2.RANSAC, tol) (matcher.py:532, :637, :803) for every candidate group in ONE
+    batched GPU call.  groups: list of (q [n], t [n]) index arrays.  Returns per group (status [n] bool, H [3,3])."""
+    off = np.zeros(len(groups) + 1, np.int32)
+    for n, (q, t) in enumerate(groups):
+        off[n + 1] = off[n] + len(q)
+    if off[-1] == 0:
+        return [(np.zeros(0, bool), np.eye(3)) for _ in groups]
+    pts1 = np.float32([k.pt for k in i1.kp_list]).reshape(-1, 2)
+    pts2 = np.float32([k.pt for k in i2.kp_list]).reshape(-1, 2)
+    p1 = np.concatenate([pts1[q] for q, _ in groups])
+    p2 = np.concatenate([pts2[t] for _, t in groups])
     eng = the_matcher.engine(128 if _norm == _capi.NORM_L2 else 32)
-    mask, H, ninl = eng.ransac_pairs(_capi.MODEL_HOMOGRAPHY, np.float32(p1), np.float32(p2), off, None, float(tol))
-    for n, b in enumerate(live):
-        fit = [m for m, f in zip(b, mask[off[n]:off[n + 1]]) if f]
-        uniq = count_unique(i1, i2, fit)
-        if uniq > best_count:
-            best, best_count = fit, uniq
-    return best
+    mask, H, _ = eng.ransac_pairs(_capi.MODEL_HOMOGRAPHY, p1, p2, off, None, float(tol))
+    return [(mask[off[n]:off[n + 1]].astype(bool), H[n]) for n in range(len(groups))]
 
 
-def _finish_bins(i1, i2, matches_best):
-    if len(matches_best) >= min_pairs:
-        idx_pairs = filter_duplicates(i1, i2, [[m.queryIdx, m.trainIdx] for m in matches_best])
+def _count_unique_idx(i1, i2, q, t):
+    return len(filter_duplicates(i1, i2, [[int(a), int(b)] for a, b in zip(q, t)]))
+
+
+def _finish_pairs(i1, i2, q, t, label):
+    """Common tail of the strategies (matcher.py:579-593, :681-694, :836-850)."""
+    if len(q) >= min_pairs:
+        idx_pairs = filter_duplicates(i1, i2, [[int(a), int(b)] for a, b in zip(q, t)])
         if len(idx_pairs) >= min_pairs:
-            qlog("  found matches =", len(idx_pairs))
+            qlog("  %s matches =" % label, len(idx_pairs))
             return idx_pairs, [[p[1], p[0]] for p in idx_pairs]
     return [], []
 
 
-def ratio_pair_matches(i1, i2, review=False, est_rotation=False):
-    """matcher.py:595-694: bins of increasing Lowe-ratio cut-off, one
-    homography RANSAC per bin, best bin by unique inliers."""
-    matches = raw_matches(i1, i2, k=2)
+def _image_diag_tol(rounded):
     w, h = _image_size()
     diag = int(math.sqrt(h * h + w * w))
-    tol = max(5, int(round(diag * 0.005)))
+    tol = int(round(diag * 0.005)) if rounded else int(diag * 0.005)   # matcher.py:610 rounds, :482 / :761 truncate
+    return w, h, diag, max(tol, 5)
+
+
+def ratio_pair_matches(i1, i2, review=False, est_rotation=False):
+    """matcher.py:595-694: cumulative bins of increasing Lowe-ratio cut-off, one homography RANSAC per bin
+    (all bins in one batched GPU call), the first bin with the most unique inliers (> 20) wins."""
+    knn = _knn3_arrays(i1, i2, 2)
+    if knn is None:
+        return [], []
+    idx, dist = knn
+    w, h, diag, tol = _image_diag_tol(rounded=True)
+    d0, d1 = dist[:, 0].astype(np.float64), dist[:, 1].astype(np.float64)
+    ok = (idx[:, 1] >= 0) & (d1 != 0.0)          # the reference divides unguarded (:620) and would raise on d1 == 0
+    ratio = np.full(d0.shape, np.inf)
+    ratio[ok] = d0[ok] / d1[ok]
     cutoffs = [0.5, 0.55, 0.6, 0.65, 0.7, 0.75, 0.8, 0.85]
-    bins = [[] for _ in cutoffs]
-    for m in matches:
-        if len(m) < 2 or m[1].distance == 0:
-            continue
-        ratio = m[0].distance / m[1].distance
-        for i, c in enumerate(cutoffs):
-            if ratio <= c:
-                bins[i].append(m[0])
-    return _finish_bins(i1, i2, _homography_bins(i1, i2, bins, tol))
+    groups = []
+    for c in cutoffs:                            # :622-630
+        q = np.nonzero(ratio <= c)[0]
+        groups.append((q, idx[q, 0]))
+    live = [n for n, (q, _) in enumerate(groups) if len(q) >= min_pairs]
+    fits = _batched_homographies(i1, i2, [groups[n] for n in live], tol)
+    best_q, best_t, best_count = [], [], 20
+    for n, (status, _H) in zip(live, fits):      # :632-662
+        q, t = groups[n]
+        fq, ft = q[status], t[status]
+        uniq = _count_unique_idx(i1, i2, fq, ft)
+        if uniq > best_count:
+            best_q, best_t, best_count = fq, ft, uniq
+    return _finish_pairs(i1, i2, best_q, best_t, "found")
+
+
+def _best_of_neighbours(idx, dist, kp1, kp2, match_ratio, dist_limit, pred1=None):
+    """The per-query selection shared by smart_pair_matches (:484-514) and bruteforce_pair_matches (:709-753): walk
+    the k neighbours in order, stop at the first with distance >= dist_limit or d0/dj < match_ratio, skip those whose
+    key-point size ratio exceeds 1.25, keep the one with the smallest metric (first on ties).
+    pred1 = predicted positions of image-1 key points in image 2 (smart: metric = raw_dist * size_diff / ratio);
+    None = bruteforce (metric = size_diff / ratio, raw_dist = length of the displacement p2 - p1).
+    Returns (rows [m], best_j [m], raw_dist [m], vangle [m])."""
+    pts1, size1, _ = kp1
+    pts2, size2, _ = kp2
+    n, k = idx.shape
+    d = dist.astype(np.float64)
+    alive = np.ones(n, bool)
+    best_metric = np.full(n, np.inf)
+    best_j = np.full(n, -1, np.int64)
+    best_dist = np.zeros(n)
+    best_vangle = np.zeros(n)
+    src = pts1 if pred1 is None else pred1
+    for j in range(k):
+        have = idx[:, j] >= 0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = d[:, 0] / d[:, j]
+        stop = ~have | (d[:, j] >= dist_limit) | ~(ratio >= match_ratio)     # NaN (0/0) stops the walk too
+        alive &= ~stop
+        t = np.where(have, idx[:, j], 0)
+        v = (pts2[t] - src).astype(np.float32)                               # float32 arithmetic as np.float32(kp.pt) (:725-727)
+        raw = np.sqrt((v.astype(np.float32) ** 2).sum(1, dtype=np.float32)).astype(np.float64)
+        s1, s2 = size1, size2[t]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            size_diff = np.where(s1 > s2, s1 / s2, s2 / s1)
+            metric = (raw * size_diff / ratio) if pred1 is not None else (size_diff / ratio)
+        cand = alive & (size_diff <= 1.25)
+        take = cand & ((best_j < 0) | (metric < best_metric))
+        best_metric[take] = metric[take]
+        best_j[take] = j
+        best_dist[take] = raw[take]
+        va = np.arctan2(v[:, 1].astype(np.float64), v[:, 0].astype(np.float64))
+        va = np.where(va < 0, va + 2 * math.pi, va)
+        best_vangle[take] = va[take]
+    rows = np.nonzero(best_j >= 0)[0]
+    return rows, best_j[rows], best_dist[rows], best_vangle[rows]
 
 
 def bruteforce_pair_matches(i1, i2, review=False):
-    """matcher.py:696-850: k=3 neighbours, binned by displacement length and
-    direction, one homography RANSAC per populated bin."""
+    """matcher.py:696-850.  k = 3 neighbours; per query the neighbour with the smallest size_diff / ratio among those
+    with distance < 290, ratio >= match_ratio and size ratio <= 1.25 (:709-753); the survivors are spread into 41
+    displacement-length bins x 21 displacement-direction bins, each spilling into its two neighbours (:755-795); one
+    homography RANSAC per populated direction bin; the bin with the most RANSAC inliers (num_fit, from 0) wins, and the
+    walk over the length bins stops early once more than 50 fitted and the current length bin gave fewer than 10
+    (:797-830).  The kNN and ALL homography fits of the pair run on the GPU (one batched call); the early stop is
+    replayed on the host over the batched results, so the selection is the reference's."""
     match_ratio = matcher_node.getFloat('match_ratio')
+    w, h, diag, tol = _image_diag_tol(rounded=False)
+    knn = _knn3_arrays(i1, i2, 3)
+    if knn is None:
+        return [], []
+    idx, dist = knn
+    kp1, kp2 = _kp_arrays(i1), _kp_arrays(i2)
+    rows, bj, best_dist, best_vangle = _best_of_neighbours(idx, dist, kp1, kp2, match_ratio, 290.0)
+    mq = rows
+    mt = idx[rows, bj]
+    maxdist = int(diag * 0.55)
+    divs = 40
+    step = maxdist / divs
+    dist_bins = [[] for _ in range(divs + 1)]                 # :762-771 (entries = positions into mq / mt)
+    for e, bd in enumerate(best_dist):
+        b = int(round(bd / step))
+        if b < len(dist_bins):
+            dist_bins[b].append(e)
+            if b > 0:
+                dist_bins[b - 1].append(e)
+            if b < len(dist_bins) - 1:
+                dist_bins[b + 1].append(e)
+    adivs = 20
+    astep = 2 * math.pi / adivs
+    groups, where = [], []                                    # every direction bin with >= min_pairs entries
+    for bi, entries in enumerate(dist_bins):                  # :774-795
+        angle_bins = [[] for _ in range(adivs + 1)]
+        for e in entries:
+            b = int(round(best_vangle[e] / astep))
+            angle_bins[b].append(e)
+            if b == 0:
+                angle_bins[-1].append(e)
+                angle_bins[b + 1].append(e)
+            elif b == adivs:
+                angle_bins[b - 1].append(e)
+                angle_bins[0].append(e)
+            else:
+                angle_bins[b - 1].append(e)
+                angle_bins[b + 1].append(e)
+        for ab in angle_bins:
+            if len(ab) >= min_pairs:
+                ee = np.asarray(ab, np.int64)
+                groups.append((mq[ee], mt[ee]))
+                where.append(bi)
+    fits = _batched_homographies(i1, i2, groups, tol) if groups else []
+    best_fitted, fit_q, fit_t = 0, [], []
+    g = 0
+    for bi in range(len(dist_bins)):                          # :797-830, replayed in order over the batched fits
+        best_of_bin = 0
+        while g < len(groups) and where[g] == bi:
+            status, _H = fits[g]
+            num_fit = int(np.count_nonzero(status))
+            best_of_bin = max(best_of_bin, num_fit)
+            if num_fit > best_fitted:
+                fit_q, fit_t = groups[g][0][status], groups[g][1][status]
+                best_fitted = num_fit
+            g += 1
+        if best_fitted > 50 and best_of_bin < 10:
+            break
+    return _finish_pairs(i1, i2, fit_q, fit_t, "initial")
+
+
+def _fit_homography_lsq(src, dst):
+    """cv2.findHomography(src, dst, 0) (matcher.py:452): all-point least squares -- normalised DLT (Hartley)."""
+    src = np.asarray(src, np.float64).reshape(-1, 2)
+    dst = np.asarray(dst, np.float64).reshape(-1, 2)
+
+    def norm(p):
+        c = p.mean(0)
+        s = math.sqrt(2.0) / max(np.sqrt(((p - c) ** 2).sum(1)).mean(), 1e-12)
+        T = np.array([[s, 0, -s * c[0]], [0, s, -s * c[1]], [0, 0, 1.0]])
+        return (p - c) * s, T
+    a, Ta = norm(src)
+    b, Tb = norm(dst)
+    A = np.zeros((2 * len(a), 9))
+    A[0::2, 0:2], A[0::2, 2] = a, 1.0
+    A[0::2, 6:8], A[0::2, 8] = -b[:, :1] * a, -b[:, 0]
+    A[1::2, 3:5], A[1::2, 5] = a, 1.0
+    A[1::2, 6:8], A[1::2, 8] = -b[:, 1:] * a, -b[:, 1]
+    _, _, vt = np.linalg.svd(A)
+    H = np.linalg.inv(Tb) @ vt[-1].reshape(3, 3) @ Ta
+    return H / H[2, 2] if abs(H[2, 2]) > 1e-12 else H
+
+
+def _project_points(pts_ned, R, tvec, K, dist):
+    """cv2.projectPoints (matcher.py:435): pinhole + (k1, k2, p1, p2, k3) distortion."""
+    X = (np.asarray(pts_ned, np.float64) @ np.asarray(R, np.float64).T) + np.asarray(tvec, np.float64).reshape(1, 3)
+    x, y = X[:, 0] / X[:, 2], X[:, 1] / X[:, 2]
+    k1, k2, p1, p2, k3 = (list(np.asarray(dist, np.float64).ravel()) + [0.0] * 5)[:5]
+    r2 = x * x + y * y
+    rad = 1 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2
+    xd = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return np.stack([K[0, 0] * xd + K[0, 2], K[1, 1] * yd + K[1, 2]], 1)
+
+
+# smart_pair_matches: predicted homography image 1 -> image 2.  A caller may install its own predictor
+# (i1, i2, est_rotation) -> 3x3 here; None = the reference's pose-based prediction when the images carry poses
+# (get_body2ned / get_cam2body / get_camera_pose), else the identity.
+predict_homography = None
+
+
+def _quat_matrix(q):
+    """transformations.quaternion_matrix (used by image.py:537-539), rotation part."""
+    q = np.asarray(q, np.float64)
+    n = np.dot(q, q)
+    if n < np.finfo(float).eps * 4.0:
+        return np.identity(3)
+    q = q * math.sqrt(2.0 / n)
+    q = np.outer(q, q)
+    return np.array([[1.0 - q[2, 2] - q[3, 3], q[1, 2] - q[3, 0], q[1, 3] + q[2, 0]],
+                     [q[1, 2] + q[3, 0], 1.0 - q[1, 1] - q[3, 3], q[2, 3] - q[1, 0]],
+                     [q[1, 3] - q[2, 0], q[2, 3] + q[1, 0], 1.0 - q[1, 1] - q[2, 2]]])
+
+
+def _rot_x(angle_rad):
+    c, s = math.cos(angle_rad), math.sin(angle_rad)
+    return np.array([[1.0, 0, 0], [0, c, -s], [0, s, c]])      # rotation_matrix(angle, [1, 0, 0])[:3, :3]
+
+
+def _pose_prediction(i1, i2, est_rotation):
+    """matcher.py:359-454: project an 8 x 8-step grid of image-2 pixels onto the assumed ground plane, re-project the
+    3-D points into image 1 and fit the homography image 1 -> image 2 through the 81 correspondences."""
+    need = ("get_body2ned", "get_cam2body", "get_camera_pose")
+    if not all(hasattr(i1, a) and hasattr(i2, a) for a in need):
+        return None
+    cam = getNode('/config/camera', True)
+    K = np.array([cam.getFloatEnum('K', i) for i in range(9)], np.float64).reshape(3, 3)     # camera.get_K()
+    if abs(K[0, 0]) < 1e-9:
+        return None
+    dist = [cam.getFloatEnum('dist_coeffs', i) for i in range(5)] if cam.hasChild('dist_coeffs') else [0.0] * 5
     w, h = _image_size()
-    diag = int(math.sqrt(h * h + w * w))
-    tol = max(5, int(round(diag * 0.005)))
-    matches = raw_matches(i1, i2, k=3)
-    dist_steps, angle_steps = 8, 8
-    bins = [[[] for _ in range(angle_steps)] for _ in range(dist_steps)]
-    for m in matches:
-        for j in range(len(m)):
-            if j + 1 < len(m) and not (m[j].distance <= m[j + 1].distance * match_ratio) and j > 0:
-                continue
-            p1 = i1.kp_list[m[j].queryIdx].pt
-            p2 = i2.kp_list[m[j].trainIdx].pt
-            dx, dy = p2[0] - p1[0], p2[1] - p1[1]
-            di = min(dist_steps - 1, int(math.hypot(dx, dy) / max(diag, 1) * dist_steps))
-            ai = int(((math.atan2(dy, dx) + math.pi) / (2 * math.pi)) * angle_steps) % angle_steps
-            bins[di][ai].append(m[j])
-    flat = [b for row in bins for b in row]
-    return _finish_bins(i1, i2, _homography_bins(i1, i2, flat, tol))
+    IK = np.linalg.inv(K)
+    steps = 8
+    grid = np.array([[u, v] for v in np.linspace(0, h, steps + 1) for u in np.linspace(0, w, steps + 1)])   # gen_grid :349-356
+    if matcher_node.hasChild("ground_m"):
+        ground_m = matcher_node.getFloat("ground_m")
+    elif _smart is not None:
+        ground_m = _smart.get_surface_estimate(i1, i2)
+    else:
+        return None
+    y1 = _smart.get_yaw_error_estimate(i1) if _smart is not None else 0.0
+    y2 = _smart.get_yaw_error_estimate(i2) if _smart is not None else 0.0
+    if abs(y1) < 0.0001 and abs(y2) > 0.0001:      # :385-388
+        y1 = y2
+    if abs(y1) > 0.0001 and abs(y2) < 0.0001:
+        y2 = y1
+    body2ned2 = np.asarray(i2.get_body2ned(), np.float64)
+    if est_rotation:
+        body2ned2 = body2ned2 @ _rot_x(y2 * d2r)
+    cam2body2 = np.asarray(i2.get_cam2body(), np.float64)
+    uvh = np.concatenate([grid, np.ones((len(grid), 1))], 1)
+    rays = (body2ned2 @ cam2body2 @ IK @ uvh.T).T                                            # project.projectVectors :536-548
+    rays /= np.linalg.norm(rays, axis=1, keepdims=True)
+    ned2 = np.asarray(i2.get_camera_pose()[0], np.float64)
+    if -ned2[2] < ground_m:
+        ground_m = -ned2[2] - 2
+    pts = np.tile(ned2, (len(rays), 1))                                                     # intersectVectorsWithGroundPlane :553-565
+    down = rays[:, 2] > 0.0
+    factor = -(ned2[2] + ground_m) / rays[down, 2]
+    pts[down] = ned2 + rays[down] * factor[:, None]
+    body2ned1 = np.asarray(i1.get_body2ned(), np.float64)                                   # Image.get_proj, image.py:543-553
+    if est_rotation and abs(y1) > 0.001:
+        body2ned1 = body2ned1 @ _rot_x(y1 * d2r)
+    R = np.asarray(i1.get_cam2body(), np.float64).T @ body2ned1.T
+    ned1 = np.asarray(i1.get_camera_pose()[0], np.float64)
+    reproj = _project_points(pts, R, -R @ ned1, K, dist)
+    return _fit_homography_lsq(reproj, grid)
 
 
 def smart_pair_matches(i1, i2, review=False, est_rotation=False):
-    """matcher.py:358-593 needs the reference's pose/SRTM machinery
-    (lib.smart, lib.srtm, camera mounts) to predict feature locations; that
-    is outside the accelerated path.  The k=3 neighbour
-    search it starts from (:465) is `raw_matches(i1, i2, k=3)`."""
-    raise NotImplementedError(
-        "strategy 'smart' depends on lib.smart/lib.srtm pose prediction which this module does not "
-        "re-implement; use strategy 'traditional', 'bestratio' or 'bruteforce'")
+    """matcher.py:358-593.  Start from a homography predicted from the two camera poses and the ground estimate
+    (:359-454), then iterate (:472-577): move image-1 key points through the current homography, pick per query the
+    neighbour (k = 3) with the smallest  predicted-position error x size ratio / Lowe ratio, bin the survivors by that
+    error (cumulative cut-offs 32 ... 2048 px), fit one homography per bin with RANSAC and keep the bin with the most
+    unique inliers; repeat from its homography until no bin improves.  The kNN and every round's homography fits
+    (one batched call per round) run on the GPU; the prediction comes from `predict_homography` when installed, else
+    from the poses the images carry (same arithmetic as lib.project / Image.get_proj), else it is the identity."""
+    match_ratio = matcher_node.getFloat("match_ratio")
+    w, h, diag, tol = _image_diag_tol(rounded=False)
+    H = None
+    if predict_homography is not None:
+        H = predict_homography(i1, i2, est_rotation)
+    if H is None:
+        H = _pose_prediction(i1, i2, est_rotation)
+    if H is None:
+        log("  smart: no pose information on", i1.name, i2.name, "-- starting from the identity")
+        H = np.eye(3)
+    knn = _knn3_arrays(i1, i2, 3)
+    if knn is None:
+        return [], []
+    idx, dist = knn
+    kp1, kp2 = _kp_arrays(i1), _kp_arrays(i2)
+    src = kp1[0].astype(np.float64)
+    best_count, best_q, best_t = 20, [], []
+    cutoffs = [32, 64, 128, 256, 512, 1024, 2048]
+    while True:
+        ph = np.concatenate([src, np.ones((len(src), 1))], 1) @ np.asarray(H, np.float64).T     # cv2.perspectiveTransform :474
+        with np.errstate(divide="ignore", invalid="ignore"):
+            trans = (ph[:, :2] / ph[:, 2:3]).astype(np.float32)
+        rows, bj, best_dist, _ = _best_of_neighbours(idx, dist, kp1, kp2, match_ratio, 300.0, pred1=trans)
+        mq, mt = rows, idx[rows, bj]
+        groups = []
+        for c in cutoffs:                                   # :519-524
+            e = np.nonzero(best_dist < c)[0]
+            groups.append((mq[e], mt[e]))
+        live = [n for n, (q, _) in enumerate(groups) if len(q) >= min_pairs]
+        fits = _batched_homographies(i1, i2, [groups[n] for n in live], tol)
+        done = True
+        for n, (status, H_test) in zip(live, fits):         # :526-560
+            q, t = groups[n]
+            fq, ft = q[status], t[status]
+            uniq = _count_unique_idx(i1, i2, fq, ft)
+            if uniq > best_count:
+                done = False
+                H = np.array(H_test, np.float64)
+                best_q, best_t, best_count = fq, ft, uniq
+        if done:
+            break
+    return _finish_pairs(i1, i2, best_q, best_t, "found")
 
 
 # ---------------------------------------------------------------------------

@@ -59,8 +59,9 @@ extern "C" {
 #define IAM_REDUCE_REF_METRIC  1  /* metric=d0*(d0/d1) sorted, < max_distance*ratio, best `cap`  (matcher.py:253-269) */
 
 /* RANSAC models of filter_by_transform (matcher.py:121-128). */
-#define IAM_MODEL_ESSENTIAL   0
-#define IAM_MODEL_HOMOGRAPHY  1
+#define IAM_MODEL_ESSENTIAL    0   /* cv2.findEssentialMat  (matcher.py:126): 5-point, Sampson error          */
+#define IAM_MODEL_HOMOGRAPHY   1   /* cv2.findHomography    (matcher.py:122): 4-point, transfer error         */
+#define IAM_MODEL_FUNDAMENTAL  2   /* cv2.findFundamentalMat (matcher.py:124): 7-point, epipolar-line distance */
 
 #define IAM_OK           0
 #define IAM_E_ARG       -1
@@ -229,7 +230,7 @@ int iam_pack_tables_device(iam_ctx* ctx, void** d_rows, void** d_offsets, long l
  * the call being replaced is :126 / :122).  Pair p owns points
  * pts1[off[p] .. off[p+1]) / pts2[...] (float32 xy, pixel coordinates, HOST).
  * K is the row-major 3x3 camera matrix (double).  Outputs (HOST):
- * out_mask[off[P]] (1 = inlier), out_model[P][9] double (E or H, row-major),
+ * out_mask[off[P]] (1 = inlier), out_model[P][9] double (E, H or F, row-major),
  * out_inliers[P].  `seed` makes the sampler reproducible. */
 int iam_ransac_pairs(iam_ctx* ctx, int model, const float* pts1, const float* pts2,
                      const int32_t* off, int n_pairs, const double* K,

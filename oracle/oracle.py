@@ -272,7 +272,7 @@ def _gms_nb9(cell: int, gw: int, gh: int):
     return out
 
 
-def _gms_run(lcell, rcell, n_right, gw_r, gh_r, rot, factor):
+def _gms_run(lcell, rcell, n_right, gw_r, gh_r, rot, factor, archive_wrap=False):
     """One GmsMatcher.run(RotationType) (gms_matcher.py:187-209): the four half-cell shifted left grids,
     each with its own statistics, cell pairing and verification; a match is an inlier if any of the four accepts it.
     lcell: [4][n] left cell per grid type (-1 = outside); rcell: [n] right cell."""
@@ -305,13 +305,24 @@ def _gms_run(lcell, rcell, n_right, gw_r, gh_r, rot, factor):
                 numpair += 1
             pair[i] = j if score >= factor * np.sqrt(thresh / numpair) else -2
         for i in range(n):                                        # mark inliers :203-207
-            if lcell[g][i] >= 0 and pair[lcell[g][i]] == rcell[i]:
+            lc = lcell[g][i]
+            if lc < 0:
+                # A key point in the last half cell has no cell in a shifted grid (index -1).  OpenCV's C++
+                # (gms.cpp run(): "if (mvMatchPairs[i].first >= 0)") skips the match for that grid; the archive
+                # Python has no such test and reads mCellPairs[-1], i.e. wraps around to the LAST cell (:205).
+                # archive_wrap=True restates the Python literally (tests pin it against the module); the default is
+                # the C++ rule, which is what the call site (cv2.xfeatures2d.matchGMS, matcher.py:285) executes and
+                # what the CUDA kernel does.
+                if not archive_wrap:
+                    continue
+                lc = n_left - 1
+            if pair[lc] == rcell[i]:
                 mask[i] = True
     return mask
 
 
 def gms_mask(pts1, pts2, size1, size2, matches, with_rotation: bool = True, with_scale: bool = False,
-             threshold_factor: float = 5.0) -> np.ndarray:
+             threshold_factor: float = 5.0, archive_wrap: bool = False) -> np.ndarray:
     """Inlier mask over `matches` ([[queryIdx, trainIdx], ...]) as GmsMatcher.GetInlierMask returns it
     (gms_matcher.py:129-176): the rotation (and scale) hypothesis with the most inliers, first one on ties;
     the reference calls it with withRotation=True, withScale=False, thresholdFactor=5.0 (matcher.py:285).
@@ -334,7 +345,7 @@ def gms_mask(pts1, pts2, size1, size2, matches, with_rotation: bool = True, with
         gh = int(GMS_GRID * GMS_SCALES[sc])
         rcell = np.floor(p2[:, 0] * gw).astype(np.int64) + np.floor(p2[:, 1] * gh).astype(np.int64) * gw  # :248-251
         for rot in (range(8) if with_rotation else (0,)):
-            last = _gms_run(lcell, rcell, gw * gh, gw, gh, rot, threshold_factor)
+            last = _gms_run(lcell, rcell, gw * gh, gw, gh, rot, threshold_factor, archive_wrap)
             c = int(last.sum())
             if c > best:
                 best, best_mask = c, last
@@ -415,3 +426,47 @@ def ba_jacobian_fd(params, n_cam, n_pts, cam_idx, pt_idx, obs_uv, K4, dist, rel_
         step = h[cam_idx] if col < 7 else h[pt_idx]
         J[:, :, col] = (f1 - f0) / (2.0 * step[:, None])
     return J
+
+
+# --------------------------------------------------------------------------
+# per-query neighbour selection of the bin-fitting strategies, restated literally
+# (scripts/lib/matcher.py:484-514 smart_pair_matches, :709-753 bruteforce_pair_matches)
+# --------------------------------------------------------------------------
+def best_of_neighbours_literal(idx, dist, pts1, size1, pts2, size2, match_ratio, dist_limit, pred1=None):
+    """For every query row walk its k neighbours exactly as the reference's Python loops do.  pred1 = predicted
+    positions of the image-1 key points in image 2 (smart: metric = raw_dist * size_diff / ratio, :505); None =
+    bruteforce (metric = size_diff / ratio, :744; raw_dist = |p2 - p1| in float32, :725-728).
+    Returns [(row, best_j, raw_dist, vangle), ...] for rows with a surviving neighbour."""
+    import math
+    out = []
+    for i in range(idx.shape[0]):
+        best_index, best_metric, best_dist, best_vangle = -1, 9, 0.0, 0.0
+        for j in range(idx.shape[1]):
+            if idx[i, j] < 0:
+                break
+            if dist[i, j] >= dist_limit:                      # :491 / :718
+                break
+            if float(dist[i, j]) == 0.0 and float(dist[i, 0]) == 0.0:
+                break                                         # the reference would raise ZeroDivisionError here
+            with np.errstate(divide="ignore"):
+                ratio = float(dist[i, 0]) / float(dist[i, j]) if dist[i, j] != 0 else float("inf")
+            if ratio < match_ratio:                           # :494 / :721
+                break
+            t = int(idx[i, j])
+            p1 = np.float32(pts1[i]) if pred1 is None else np.float32(pred1[i])
+            p2 = np.float32(pts2[t])
+            v = p2 - p1
+            raw_dist = float(np.linalg.norm(v))
+            vangle = math.atan2(float(v[1]), float(v[0]))
+            if vangle < 0:
+                vangle += 2 * math.pi
+            s1, s2 = float(size1[i]), float(size2[t])
+            size_diff = s1 / s2 if s1 > s2 else s2 / s1       # :499-502 / :736-739
+            if size_diff > 1.25:
+                continue
+            metric = (raw_dist * size_diff / ratio) if pred1 is not None else (size_diff / ratio)
+            if best_index < 0 or metric < best_metric:
+                best_metric, best_index, best_dist, best_vangle = metric, j, raw_dist, vangle
+        if best_index >= 0:
+            out.append((i, best_index, best_dist, best_vangle))
+    return out

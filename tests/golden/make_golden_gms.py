@@ -6,10 +6,12 @@ reference's own restatement of that algorithm, scripts/lib/archive/gms_matcher.p
 imported UNMODIFIED from /root/reference and run with the threshold factor the
 reference's call site passes (thresholdFactor=5.0; the module constant is 6).
 
-Key points are kept inside the first 97 % of the image: for a point in the last
-half cell the archive module indexes mCellPairs[-1] (Python wrap-around to cell
-399) where the C++ original skips the match; the oracle and the CUDA kernel follow
-the C++ behaviour and tests/test_gms.py covers that edge separately.
+Key points of the main scenes are kept inside the first 97 % of the image: for a
+point in the last half cell the archive module indexes mCellPairs[-1] (Python
+wrap-around to cell 399) where the C++ original skips the match.  The CUDA kernel
+follows the C++ behaviour (it replaces the cv2 call); the oracle restates both
+(archive_wrap=True is the literal Python) and the "edge_strip" scene pins the
+archive behaviour on exactly that strip.
 
 usage: python tests/golden/make_golden_gms.py      (from the repo root; needs /root/reference)
 """
@@ -142,6 +144,28 @@ def main():
         print("flags", ws, wr, "->", n_in)
         out["flags_s%d_r%d_mask" % (ws, wr)] = mask
     out["flags_pts1"], out["flags_pts2"], out["flags_matches"], out["flags_size"] = pts1, pts2, matches, np.array(size, np.int32)
+    # Key points in the LAST HALF CELL of the image (no cell in the shifted grids): here the archive module wraps
+    # around to cell 399 (mCellPairs[-1], gms_matcher.py:205) where OpenCV's C++ skips the match.  The scene puts a
+    # cluster of consistent matches into cell 399 -> the same right cell, so that the wrap-around really admits
+    # edge-strip matches the C++ rule drops: the fixture pins the archive behaviour, tests/test_gms.py documents both.
+    rng = np.random.default_rng(9)
+    n = 900
+    p1 = rng.uniform(0.05, 0.9, (n, 2))
+    p2 = p1 + rng.normal(0, 0.002, (n, 2))
+    p1[:120] = rng.uniform(0.955, 0.972, (120, 2))              # cell 399 (x, y in [0.95, 1)) minus its last half
+    p2[:120] = p1[:120] - 0.3 + rng.normal(0, 0.001, (120, 2))  # all land in one right cell
+    p1[120:160, 0] = rng.uniform(0.976, 0.999, 40)              # x in the last half cell: index -1 in grids 2 and 4
+    p1[120:160, 1] = rng.uniform(0.3, 0.6, 40)
+    p2[120:160] = p2[:40]                                       # ... paired with the right cell that cell 399 maps to
+    w, h = 2000, 1000
+    pts1 = (p1 * [w, h]).astype(np.float32)
+    pts2 = (p2 * [w, h]).astype(np.float32)
+    matches = np.stack([np.arange(n), np.arange(n)], 1).astype(np.int32)
+    mask, n_in = run_ref(pts1, pts2, matches, (w, h), False, True)
+    print("edge_strip", n, "matches ->", n_in, "inliers;", int(mask[120:160].sum()), "of the 40 edge-strip matches kept by the wrap-around")
+    out["edge_strip_pts1"], out["edge_strip_pts2"], out["edge_strip_matches"] = pts1, pts2, matches
+    out["edge_strip_size"] = np.array((w, h), np.int32)
+    out["edge_strip_mask"] = mask
     out["names"] = np.array(sorted(cases))
     np.savez_compressed(os.path.join(HERE, "gms_reference.npz"), **out)
     gen_pipeline()

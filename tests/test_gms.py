@@ -24,23 +24,29 @@ def test_oracle_gms_equals_reference_module():
         assert (mask == g["flags_s%d_r%d_mask" % (ws, wr)]).all(), (ws, wr)
 
 
-def test_oracle_gms_edge_points_are_skipped_not_wrapped():
-    """Points in the last half cell have no cell in the shifted grids (index -1).  The C++ original skips such a
-    match for that grid; the archive Python would index mCellPairs[-1].  The oracle follows the C++ rule: moving an
-    accepted match into the last half cell can only remove it from the shifted grids, never alias it to cell 399."""
-    rng = np.random.default_rng(3)
-    n = 600
-    p1 = rng.uniform(0.05, 0.9, (n, 2))
-    p2 = p1 + rng.normal(0, 0.002, (n, 2))
-    p1[:40, 0] = rng.uniform(0.976, 0.999, 40)          # x in the last half cell
-    p2[:40] = p1[:40]
-    size = (2000, 1000)
-    pts1 = (p1 * size).astype(np.float32)
-    pts2 = (p2 * size).astype(np.float32)
-    m = np.stack([np.arange(n), np.arange(n)], 1)
-    mask = oracle.gms_mask(pts1, pts2, size, size, m)
-    assert mask[40:].mean() > 0.9
-    assert mask.dtype == bool and len(mask) == n
+def test_gms_last_half_cell_documents_both_rules():
+    """Key points in the last half cell have no cell in the shifted grids (index -1).  The reference's archive Python
+    (gms_matcher.py:205) reads mCellPairs[-1] there -- a wrap-around to cell 399; OpenCV's C++ matchGMS, which is what
+    the call site (matcher.py:285) executes, skips such a match for that grid.  The oracle restates both:
+    archive_wrap=True equals the unmodified archive module on the "edge_strip" fixture (a scene built so that the
+    wrap-around really admits edge-strip matches), the default (C++ rule, what the CUDA kernel does) keeps a subset --
+    it can only drop matches of that strip, never add one, and never touches a match elsewhere."""
+    g = load_golden("gms_reference.npz")
+    pts1, pts2, matches, size = _case(g, "edge_strip")
+    ref = g["edge_strip_mask"]
+    py = oracle.gms_mask(pts1, pts2, size, size, matches, archive_wrap=True)
+    cxx = oracle.gms_mask(pts1, pts2, size, size, matches, archive_wrap=False)
+    assert (py == ref).all()                              # the literal restatement is pinned by the module itself
+    diff = np.nonzero(py != cxx)[0]
+    assert len(diff) > 0                                  # the fixture does exercise the deviation
+    assert (py[diff] & ~cxx[diff]).all()                  # the C++ rule only ever drops
+    x = pts1[matches[diff, 0], 0] / size[0]
+    y = pts1[matches[diff, 0], 1] / size[1]
+    assert ((x >= 0.975) | (y >= 0.975)).all()            # ... and only matches whose key point lies in the last half cell
+    # away from the strip (every other fixture) the two rules coincide
+    for name in g["names"]:
+        p1, p2, m, sz = _case(g, str(name))
+        assert (oracle.gms_mask(p1, p2, sz, sz, m, archive_wrap=True) == g[str(name) + "_mask"]).all(), name
 
 
 def test_oracle_pipeline_with_gms_equals_reference_module():
@@ -75,6 +81,11 @@ def test_gpu_gms_equals_reference_module():
     for ws, wr in ((False, False), (True, False), (True, True)):
         mask = eng.gms_filter(pts1, pts2, matches, size, with_rotation=wr, with_scale=ws)
         assert (mask == g["flags_s%d_r%d_mask" % (ws, wr)]).all(), (ws, wr)
+    # the last-half-cell strip: the kernel follows OpenCV's C++ rule (skip), not the archive Python's wrap-around
+    pts1, pts2, matches, size = _case(g, "edge_strip")
+    mask = eng.gms_filter(pts1, pts2, matches, size)
+    assert (mask == oracle.gms_mask(pts1, pts2, size, size, matches, archive_wrap=False)).all()
+    assert (g["edge_strip_mask"] | ~mask).all() and (mask != g["edge_strip_mask"]).sum() > 0   # a strict subset of the archive result
     eng.close()
 
 

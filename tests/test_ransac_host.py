@@ -68,3 +68,25 @@ def test_degenerate_samples_return_no_model():
     z = np.zeros(5, np.float32)
     assert len(_capi.minimal_solver_host(0, z, z, z, z)) == 0
     assert len(_capi.minimal_solver_host(1, z, z, z, z)) == 0
+
+
+def test_seven_point_recovers_the_true_fundamental_matrix():
+    """The 7-point solver behind the 'fundamental' branch (matcher.py:124): every root is rank 2 and satisfies the
+    seven sample constraints; one of them is the true geometry (all 60 noise-free points fit)."""
+    hits = 0
+    for seed in range(12):
+        p1, p2, _ = synth.two_view_scene(60, 0.0, K, seed=seed, noise_px=0.0)
+        n1, n2 = _norm(p1), _norm(p2)          # any well-conditioned coordinates do: F is not tied to K
+        Fs = _capi.minimal_solver_host(_capi.MODEL_FUNDAMENTAL, n1[:7, 0], n1[:7, 1], n2[:7, 0], n2[:7, 1])
+        assert 1 <= len(Fs) <= 3
+        h1, h2 = np.c_[n1, np.ones(60)], np.c_[n2, np.ones(60)]
+        best = np.inf
+        for F in Fs.astype(np.float64):
+            r = np.abs(np.einsum("ni,ij,nj->n", h2, F, h1))
+            assert r[:7].max() < 1e-5
+            assert abs(np.linalg.det(F)) < 1e-7
+            best = min(best, np.median(r))
+        hits += best < 1e-5
+    assert hits >= 11
+    z = np.zeros(7, np.float32)
+    assert len(_capi.minimal_solver_host(_capi.MODEL_FUNDAMENTAL, z, z, z, z)) == 0
