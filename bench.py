@@ -53,9 +53,11 @@ def parse():
     ap.add_argument("--desc", type=int, default=5000)
     ap.add_argument("--detector", default="SIFT", choices=["SIFT", "ORB"])
     ap.add_argument("--pairs", default="sequential", choices=["sequential", "all"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "strip", "bates"],
+    ap.add_argument("--workload", default="auto", choices=["auto", "strip", "bates", "pipeline"],
                     help="auto: strip (BASELINE configs[1]) on one GPU, bates (configs[3], pair-sharded) on several; "
-                         "strip with --gpus N > 1 = N independent replicas (weak scaling)")
+                         "strip with --gpus N > 1 = N independent replicas (weak scaling); pipeline: BASELINE configs[4] -- "
+                         "the bates project end to end: match + essential-matrix RANSAC per pair + bundle-adjustment "
+                         "residual/Jacobian evaluation")
     ap.add_argument("--engine", default="auto", choices=["auto", "umma", "umma_f16", "simt"])
     ap.add_argument("--gather", default="packed", choices=["packed", "padded"])
     ap.add_argument("--no-e2e", action="store_true")
@@ -249,7 +251,7 @@ def resolve_workload(args, world):
     if args.workload == "auto":
         args.workload = "strip" if world == 1 else "bates"
     if not args.frames:
-        args.frames = 2812 if args.workload == "bates" else 500
+        args.frames = 2812 if args.workload in ("bates", "pipeline") else 500
     return args.workload
 
 
@@ -332,11 +334,258 @@ def parity_spot(des_u8, pairs, table, count, detector, which):
             "checker": "oracle.bidirectional (CPU restatement of matcher.py:218-318), whole tables compared"}
 
 
+
+# ----------------------------------------------------------------------------- BASELINE configs[4]: the whole project
+PIPE_K = np.array([[3666.666504, 0.0, 2736.0], [0.0, 3666.666504, 1824.0], [0.0, 0.0, 1.0]])   # cameras/DJI_FC6310S.json
+PIPE_W, PIPE_H = 5472, 3648
+
+
+def make_project_gpu(frames, n, seed, device, keep, ba_per_frame=175):
+    """The survey as a consistent 3-D scene: every descriptor row of a frame belongs to a ground point, a planted row
+    (40 % of a frame, copied with noise from the previous frame, as make_frames_gpu does) inherits the point of the row
+    it was copied from, every other row gets a new point inside the frame's footprint; key points = the projection of
+    the points through the frame's nadir camera (survey_grid_neds pose, a few degrees of yaw) + 0.5 px noise.  So the
+    matches the kNN finds between ANY two frames obey one two-view geometry each, which is what the essential-matrix
+    RANSAC stage needs.  Also returns the bundle-adjustment problem of the shape Optimizer.setup() builds
+    (optimizer.py:283-420) from `ba_per_frame` inherited points per consecutive frame pair (two observations each).
+    Returns (des {f: u8 [n,128]}, uv {f: f32 [n,2]}, ba dict)."""
+    import torch
+    from imageanalysis_b200 import synth
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    neds = torch.tensor(synth.survey_grid_neds()[:frames], dtype=f64, device=device)
+    K = torch.tensor(PIPE_K, dtype=f64, device=device)
+    IK = torch.linalg.inv(K)
+    cam2body = torch.tensor([[0.0, 0, 1], [1, 0, 0], [0, 1, 0]], dtype=f64, device=device)
+    yaw = (torch.rand(frames, generator=g, device=device, dtype=f64) - 0.5) * np.deg2rad(6.0)
+    pitch = torch.full((frames,), -np.pi / 2, dtype=f64, device=device)
+    cy, sy, cp, sp = torch.cos(yaw / 2), torch.sin(yaw / 2), torch.cos(pitch / 2), torch.sin(pitch / 2)
+    quat = torch.stack([cp * cy, -sp * sy, sp * cy, cp * sy], 1)       # body -> ned, ZYX euler (yaw, pitch, roll = 0)
+
+    def b2n(q):
+        w, x, y, z = q
+        return torch.stack([torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)]),
+                            torch.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)]),
+                            torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)])])
+    des_out, uv_out = {}, {}
+    prev = prev_X = prev_uv = None
+    ba_cam, ba_uv, ba_X = [], [], []
+    last = max(keep)
+    for f in range(last + 1):
+        v = torch._standard_gamma(torch.full((n, 128), 0.6, device=device), generator=g)
+        v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        v = v.clamp_max(0.2)
+        v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-12)
+        d = (v * 512.0).round().clamp(0, 255).to(torch.uint8)
+        R_b2n = b2n(quat[f])
+        # new ground points: a uniformly random pixel's ray, cut at rough ground (D = N(0, 1.5 m))
+        pix = torch.stack([torch.rand(n, generator=g, device=device, dtype=f64) * PIPE_W,
+                           torch.rand(n, generator=g, device=device, dtype=f64) * PIPE_H, torch.ones(n, dtype=f64, device=device)], 1)
+        ray = pix @ (R_b2n @ cam2body @ IK).T
+        ground = torch.randn(n, generator=g, device=device, dtype=f64) * 1.5
+        t = (ground - neds[f, 2]) / ray[:, 2]
+        X = neds[f] + ray * t[:, None]
+        src = dst = None
+        if prev is not None:
+            m = int(0.4 * n)
+            src = torch.randperm(n, device=device, generator=g)[:m]
+            dst = torch.randperm(n, device=device, generator=g)[:m]
+            noise = torch.randint(-3, 4, (m, 128), device=device, generator=g)
+            d[dst] = (prev[src].to(torch.int32) + noise).clamp(0, 255).to(torch.uint8)
+            X[dst] = prev_X[src]
+        Rc = cam2body.T @ R_b2n.T                                       # ned -> camera (Image.get_proj, image.py:543-553)
+        Xc = (X - neds[f]) @ Rc.T
+        uvh = Xc @ K.T
+        uv = uvh[:, :2] / uvh[:, 2:3] + torch.randn(n, 2, generator=g, device=device, dtype=f64) * 0.5
+        if src is not None and ba_per_frame > 0:                       # two observations of each of the first inherited points
+            k = ba_per_frame
+            ba_cam.append(torch.stack([torch.full((k,), f - 1, device=device), torch.full((k,), f, device=device)], 1))
+            ba_uv.append(torch.stack([prev_uv[src[:k]], uv[dst[:k]]], 1))
+            ba_X.append(X[dst[:k]])
+        prev, prev_X, prev_uv = d, X, uv
+        if f in keep:
+            des_out[f] = d.cpu().numpy()
+            uv_out[f] = uv.to(torch.float32).cpu().numpy()
+    ba = None
+    if ba_cam:
+        cam = torch.cat(ba_cam).cpu().numpy()            # [n_pts, 2]
+        uvs = torch.cat(ba_uv).cpu().numpy()             # [n_pts, 2, 2]
+        Xs = torch.cat(ba_X).cpu().numpy()
+        n_pts = len(Xs)
+        cam_idx = cam.reshape(-1).astype(np.int32)
+        pt_idx = np.repeat(np.arange(n_pts, dtype=np.int32), 2)
+        obs = uvs.reshape(-1, 2)
+        order = np.argsort(cam_idx, kind="stable")       # by camera, then list order (optimizer.py:396-404)
+        cams7 = np.concatenate([neds.cpu().numpy(), quat.cpu().numpy()], 1)[:last + 1]
+        rng = np.random.default_rng(seed)
+        params = np.concatenate([cams7.ravel(), (Xs + rng.normal(0, 0.3, Xs.shape)).ravel()])
+        ba = dict(n_cam=last + 1, n_pts=n_pts, cam_idx=cam_idx[order], pt_idx=pt_idx[order], uv=obs[order], params=params,
+                  K4=(PIPE_K[0, 0], PIPE_K[1, 1], PIPE_K[0, 2], PIPE_K[1, 2]), dist=np.zeros(5))
+    return des_out, uv_out, ba
+
+
+def run_pipeline(args):
+    """BASELINE configs[4]: 2812 frames end to end -- match (kNN both ways + reduction + cross-check) ->
+    filter_by_transform(..., 'essential') for every pair on the device tables (matcher.py:90-142) -> one evaluation of
+    the bundle-adjustment residual + analytic Jacobian (Optimizer.fun, optimizer.py:174-279).  One JSON line with the
+    per-stage device times and each stage's roofline; `e2e` = the same job with host descriptors / key points /
+    parameters in and host tables / masks / Jacobian out."""
+    import torch
+    from imageanalysis_b200 import _capi, dist
+    rank, world, local = dist.init()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    all_pairs = bates_pairs(args.frames)
+    pairs, _, _ = dist.shard_pairs(all_pairs, rank, world)
+    P, P_total = len(pairs), len(all_pairs)
+    touched = sorted({int(i) for p in pairs for i in p})
+    T = len(touched)
+    des_u8, uv, ba = make_project_gpu(args.frames, args.desc, SEED, dev, set(touched))
+    host = torch.empty((T, args.desc, 128), dtype=torch.float32).pin_memory()
+    host_np = host.numpy()
+    for k, f in enumerate(touched):
+        host_np[k] = des_u8[f]
+    eng = _capi.Engine(_capi.NORM_L2, 128, local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_profiling(True)
+    prm = _capi.Engine.make_params(max_distance=270.0)
+    tol = max(1.0, PIPE_W ** 0.25)                           # matcher.py:94-96
+    for k, f in enumerate(touched):
+        eng.upload(f, host_np[k], pinned=True)
+        eng.upload_keypoints(f, uv[f])
+    eng.ba_setup(ba["n_cam"], ba["n_pts"], ba["cam_idx"], ba["pt_idx"], ba["uv"])
+    eng.ba_upload_params(ba["params"])
+    eng.synchronize()
+    n_obs = len(ba["cam_idx"])
+
+    def step(evs=None):
+        if evs:
+            evs[0].record(stream)
+        eng.match_pairs_device(pairs, prm)
+        if evs:
+            evs[1].record(stream)
+        eng.ransac_tables(_capi.MODEL_ESSENTIAL, PIPE_K, tol, P, prm.cap, min_pairs=25, compact=True, want_model=False,
+                          want_mask=False, host_outputs=False)
+        if evs:
+            evs[2].record(stream)
+        eng.ba_eval_device(ba["K4"], ba["dist"], jac=True)
+        if evs:
+            evs[3].record(stream)
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    launches0 = eng.timing().total_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    stage_ev = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        step(evs)
+        stage_ev.append(evs)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t_ms = torch.tensor([ms], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    tm = eng.timing()
+    launches = tm.total_launches - launches0
+    st = [statistics.median(e[i].elapsed_time(e[i + 1]) for e in stage_ev) for i in range(3)]
+    # results of the last step: inlier statistics of the RANSAC stage, residual of the BA stage
+    table, count = eng.fetch_tables(P, prm.cap)
+    res = None
+    # ---- e2e: host buffers in, host results out ---------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ids = np.asarray(touched, dtype=np.int32)
+        frames_host = [host_np[k] for k in range(T)]
+        out_table = torch.empty((P, prm.cap, 2), dtype=torch.int32, pin_memory=True).numpy()
+        out_count = torch.zeros((P,), dtype=torch.int32, pin_memory=True).numpy()
+
+        def step_e2e():
+            for f in touched:
+                eng.upload_keypoints(f, uv[f])
+            eng.match_images(ids, frames_host, pairs, prm, out=(out_table, out_count))
+            _, _, inl = eng.ransac_tables(_capi.MODEL_ESSENTIAL, PIPE_K, tol, P, prm.cap, min_pairs=25, compact=True,
+                                          want_model=False)
+            t2, c2 = eng.fetch_tables(P, prm.cap)
+            r, J = eng.ba_eval(ba["params"], ba["K4"], ba["dist"], jac=True)
+            return inl, c2, r
+        step_e2e()
+        torch.cuda.synchronize()
+        n_e = max(1, args.steps // 3)
+        t0 = time.perf_counter()
+        for _ in range(n_e):
+            inl, c2, res = step_e2e()
+        torch.cuda.synchronize()
+        e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(e_ms, op=torch.distributed.ReduceOp.MAX)
+        tme = eng.timing()
+        h2d = int(tme.h2d_bytes) + T * args.desc * 8 + ba["params"].nbytes
+        d2h = 2 * P * (prm.cap * 2 + 1) * 4 + P * 4 + n_obs * (2 + 20) * 8
+        e2e = {"value": P_total * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s", "ms_per_step": float(e_ms.item()) / n_e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "includes": "H2D of float32 descriptors (narrowed on the host), key points and BA parameters; D2H of the match "
+                           "tables before and after the RANSAC filter, inlier counts, BA residual and Jacobian blocks"}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    rl = make_roofline(args, tm.mma_kind, P, tm.knn_ms, peaks, clocks)
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    ba_gbs = n_obs * 280 / (st[2] / 1e3) / 1e9
+    filled = count[count > 0]
+    line = {"metric": "image-pairs matched + RANSAC-filtered/sec, with one BA residual+Jacobian evaluation per pass (5000 SIFT desc/img)",
+            "value": P_total * args.steps / (ms / 1e3), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 (s32 accumulate) match / f32+f64 RANSAC / f64 BA", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: %d frames (38 x 74 survey grid) x %d SIFT descriptors, %d geotag pairs: "
+                                   "match + essential-matrix RANSAC per pair + BA residual/Jacobian over %d observations" % (
+                                       args.frames, args.desc, P_total, n_obs),
+                       "frames": args.frames, "pairs_total": P_total, "pairs_per_gpu": P, "ba_observations": n_obs,
+                       "ba_cameras": ba["n_cam"], "ba_points": ba["n_pts"], "ransac_threshold_px": tol,
+                       "l2_hygiene": "inputs larger than L2"},
+            "stages": {
+                "match": {"ms": st[0], "pairs_per_s": P / (st[0] / 1e3), "roofline": rl},
+                "ransac_essential": {"ms": st[1], "pairs_per_s": P / (st[1] / 1e3), "pairs_with_matches": int(len(filled)),
+                                     "mean_inliers_of_those": float(filled.mean()) if len(filled) else 0.0,
+                                     "bound": "FP64 5-point solves + FP32 Sampson scoring (SURVEY 8d); one warp per pair",
+                                     "reference": "cv2.findEssentialMat(p1, p2, K, cv2.RANSAC, threshold=tol) (matcher.py:126)"},
+                "ba_residual_jacobian": {"ms": st[2], "observations_per_s": n_obs / (st[2] / 1e3),
+                                         "roofline": {"bound": "hbm", "achieved": ba_gbs, "peak": hbm, "unit": "GB/s",
+                                                      "frac": ba_gbs / hbm, "algorithmic_bytes_per_observation": 280},
+                                         "rms_residual_px": float(np.sqrt(np.mean(res ** 2))) if res is not None else None}},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line))
+
 # ----------------------------------------------------------------------------- main
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "pipeline":
+        resolve_workload(args, int(os.environ.get("WORLD_SIZE", "1")))
+        run_pipeline(args)
         return
     import torch
     from imageanalysis_b200 import _capi, dist

@@ -30,7 +30,7 @@ EXPORTS = (
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -141,6 +141,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_pack_tables_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_longlong)]
     lib.iam_ransac_pairs.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, C.c_double, C.c_double, C.c_int,
                                      C.c_uint32, vp, vp, vp]
+    lib.iam_ransac_tables.argtypes = [vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     lib.iam_debug_minimal_solver.argtypes = [C.c_int, vp, vp, vp, vp, vp]
     lib.iam_debug_narrow.argtypes = [vp, vp, C.c_size_t]
@@ -438,3 +439,18 @@ class Engine:
                                                float(threshold), float(prob), int(max_iters), int(seed), _ptr(mask),
                                                _ptr(model_out), _ptr(inl)), "iam_ransac_pairs")
         return mask, model_out.reshape(P, 3, 3), inl
+
+
+    def ransac_tables(self, model: int, K: Optional[np.ndarray], threshold: float, n_pairs: int, cap: int, min_pairs: int = 25,
+                      compact: bool = True, prob: float = 0.999, max_iters: int = 1000, seed: int = 0, want_mask: bool = False,
+                      want_model: bool = True, host_outputs: bool = True):
+        """filter_by_transform for every pair of the last match call, on the device tables (iam_ransac_tables).
+        Returns (mask [P, cap] or None, models [P, 3, 3] or None, inliers [P])."""
+        Kc = None if K is None else np.ascontiguousarray(K, np.float64).reshape(3, 3)
+        mask = np.zeros((n_pairs, cap), np.uint8) if want_mask else None
+        models = np.zeros((n_pairs, 9), np.float64) if want_model else None
+        inl = np.zeros((n_pairs,), np.int32) if host_outputs else None   # all outputs None: the call only enqueues
+        self._check(self._lib.iam_ransac_tables(self._h, model, _ptr(Kc), float(threshold), float(prob), int(max_iters),
+                                                int(seed), int(min_pairs), int(compact), _ptr(mask), _ptr(models), _ptr(inl)),
+                    "iam_ransac_tables")
+        return mask, (models.reshape(n_pairs, 3, 3) if want_model else None), inl

@@ -100,6 +100,7 @@ struct Plan {
   std::vector<int> chunk_pair_begin;  // pair index where each chunk starts (+ sentinel)
   std::vector<int> chunk_unit_begin;
   std::vector<size_t> chunk_rows;
+  std::vector<int32_t> pairs;         // the list this plan was built for (a hash hit is confirmed against it)
   int max_n = 0;
   size_t max_chunk_rows = 0;
 };
@@ -149,6 +150,9 @@ struct iam_ctx {
   int last_kind = -1;
   // bundle-adjustment problem (iam_ba_*): structure resident, parameters re-uploaded per evaluation
   Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac;
+  // robust fits (iam_ransac_*): device block kept between calls, outputs of the table form
+  iam::RansacScratch ransac_scratch;
+  Buffer ransac_mask, ransac_model, ransac_inl;
   int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
   // iam_match_images, float32 L2 descriptors: worker threads narrow them to bytes (host_narrow.h) into a pinned arena
   std::unique_ptr<iam::NarrowPool> narrow_pool;
@@ -400,11 +404,14 @@ int upload_plan(iam_ctx* c, const Plan& pl);
 int prepare_plan(iam_ctx* c, const int32_t* pairs, int n_pairs, int k, bool both, int waves_override = 0) {
   const int waves = waves_override > 0 ? waves_override : pick_waves(c);
   const uint64_t key = plan_hash(c, pairs, n_pairs, k, both, waves);
-  if (c->plan_valid && c->plan_key == key) return IAM_OK;
+  if (c->plan_valid && c->plan_key == key && c->plan.pairs.size() == size_t(n_pairs) * 2 &&
+      (n_pairs == 0 || memcmp(c->plan.pairs.data(), pairs, size_t(n_pairs) * 2 * sizeof(int32_t)) == 0))
+    return IAM_OK;
   c->plan_valid = false;
   c->plan = Plan{};
   int rc = build_plan(c, pairs, n_pairs, k, both, waves, &c->plan);
   if (rc != IAM_OK) return rc;
+  c->plan.pairs.assign(pairs, pairs + size_t(n_pairs) * 2);
   if ((rc = upload_plan(c, c->plan)) != IAM_OK) return rc;
   c->plan_key = key;
   c->plan_valid = true;
@@ -986,6 +993,13 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
     return fail(IAM_E_ARG, "bad arguments");
   if (dtype != IAM_DTYPE_U8 && dtype != IAM_DTYPE_F32) return fail(IAM_E_ARG, "unknown dtype %d", dtype);
   if (c->norm == IAM_NORM_HAMMING && dtype != IAM_DTYPE_U8) return fail(IAM_E_ARG, "Hamming descriptors must be uint8");
+  if (n_pairs < 0 || (n_pairs && !pairs) || !prm) return fail(IAM_E_ARG, "bad arguments");
+  if (key_ptrs)  // the keys index bitsets sized by the descriptor count (dedupe_kernel): same rule as iam_upload_keypoint_keys
+    for (int i = 0; i < n_images; ++i)
+      if (key_ptrs[i])
+        for (int k = 0; k < counts[i]; ++k)
+          if (key_ptrs[i][k] < 0 || key_ptrs[i][k] >= counts[i])
+            return fail(IAM_E_ARG, "keypoint key %d of image %d out of range [0, %d)", key_ptrs[i][k], image_ids[i], counts[i]);
   UploadFeed feed;
   feed.ptrs = host_ptrs;
   feed.keys = key_ptrs;
@@ -1491,9 +1505,49 @@ int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2
   if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
   std::string err;
   rc = iam::ransac_pairs(model, pts1, pts2, off, n_pairs, K, threshold_px, prob, max_iters, seed, out_mask, out_model,
-                         out_inliers, c->stream, &err);
+                         out_inliers, &c->ransac_scratch, c->stream, &err);
   if (rc != 0) return fail(rc, "%s", err.c_str());
   c->timing.total_launches += 1;
+  return IAM_OK;
+}
+
+int iam_ransac_tables(iam_ctx* c, int model, const double* K, double threshold_px, double prob, int max_iters,
+                      uint32_t seed, int min_pairs, int compact, uint8_t* out_mask, double* out_model,
+                      int32_t* out_inliers) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL)
+    return fail(IAM_E_ARG, "unknown model %d", model);
+  if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
+  const int n = c->last_pairs, cap = c->last_cap;
+  if (n <= 0) return IAM_OK;
+  if (!c->plan_valid || (int)c->plan.jobs.size() != 2 * n) return fail(IAM_E_STATE, "no match tables resident: call iam_match_pairs_device / iam_match_images first");
+  for (size_t j = 0; j < c->plan.jobs.size(); j += 2) {
+    const Image& a = c->images[c->plan.jobs[j].q_slot];
+    const Image& b = c->images[c->plan.jobs[j].t_slot];
+    if ((a.n > 0 && (!a.kp || a.kp_n != a.n)) || (b.n > 0 && (!b.kp || b.kp_n != b.n)))
+      return fail(IAM_E_STATE, "iam_ransac_tables needs iam_upload_keypoints for images %d and %d", c->plan.jobs[j].q_slot, c->plan.jobs[j].t_slot);
+  }
+  if ((rc = sync_imgs(c)) != IAM_OK) return rc;
+  if (out_mask) CU(c->ransac_mask.ensure(size_t(n) * cap));
+  CU(c->ransac_model.ensure(size_t(n) * 9 * sizeof(float)));
+  CU(c->ransac_inl.ensure(size_t(n) * sizeof(int)));
+  std::string err;
+  rc = iam::ransac_tables(model, c->out_table.as<int>(), c->out_count.as<int>(), cap, n, c->jobs.as<iam::RedJob>(),
+                          c->d_imgs.as<iam::ImgDev>(), K, threshold_px, prob, max_iters, seed, min_pairs, compact != 0,
+                          out_mask ? c->ransac_mask.as<uint8_t>() : nullptr, c->ransac_model.as<float>(),
+                          c->ransac_inl.as<int>(), c->stream, &err);
+  if (rc != 0) return fail(rc, "%s", err.c_str());
+  c->timing.total_launches += 1;
+  if (out_mask) CU(cudaMemcpyAsync(out_mask, c->ransac_mask.p, size_t(n) * cap, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<float> hm;
+  if (out_model) {
+    hm.resize(size_t(n) * 9);
+    CU(cudaMemcpyAsync(hm.data(), c->ransac_model.p, hm.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (out_inliers) CU(cudaMemcpyAsync(out_inliers, c->ransac_inl.p, size_t(n) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (out_mask || out_model || out_inliers) CU(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < hm.size(); ++i) out_model[i] = hm[i];
   return IAM_OK;
 }
 

@@ -62,7 +62,7 @@ namespace {
 // warps, 96 registers) or 96 (one part, 8 warps, no exchange of bounds between threads at all).  Wider slices spread
 // the per-slice overhead (barrier wait, tensor-memory load, exchange, vote) over more columns.
 #ifndef IAM_PART_COLS
-#define IAM_PART_COLS 32
+#define IAM_PART_COLS 48         // measured (1990 pairs): 32 -> 15.86 ms, 48 -> 15.28 ms, 96 -> 16.5 ms
 #endif
 
 // Per-kind, per-shape kernel configuration: operand layout (layout.h) + tensor-memory / shared-memory budget.
@@ -98,8 +98,8 @@ struct Cfg : LayD<kKind> {
     uint64_t a_empty[kT];
     uint64_t b_full[kBStages];
     uint64_t b_empty[kBStages];
-    uint64_t t_full[kSlots];
-    uint64_t t_empty[kSlots];
+    uint64_t t_full[kSlots * kParts];    // per (slot, part) when the products are split by part (IAM_SPLIT_N), else [kSlots] used
+    uint64_t t_empty[kSlots * kParts];
     uint32_t tmem_base;
     uint32_t pad;
   };
@@ -385,6 +385,13 @@ __device__ __forceinline__ void consume32(const typename O::T (&v)[32], int tp, 
 #ifndef IAM_SPARSE2_MAX
 #define IAM_SPARSE2_MAX 4        // at most this many lanes with a candidate take the sparse route; more: the knock-out
 #endif
+#ifndef IAM_SPLIT_N
+#define IAM_SPLIT_N 0            // A/B aid: 1 = every column part of an accumulator slot is its own product (kKSteps MMAs of
+#endif                           // N = 32 / 48 instead of N = 96) with its own full / empty barriers, so that a slot waits for
+                                 // the 4 warps of ONE part instead of all 12 of the tile (profile: 15 % of the epilogue warps'
+                                 // time goes into waiting for accumulators while the tensor pipe is 45 % busy).  Measured
+                                 // SLOWER: 18.8 against 15.9 ms (32-column parts), 15.8 against 15.3 ms (48-column parts):
+                                 // three times the MMA instructions, and narrow MMAs do not run at the N = 96 rate
 #ifndef IAM_PACKED_FMA_SUBS
 #define IAM_PACKED_FMA_SUBS 8    // columns whose knock-out subtraction is an IMAD + tree (FMA pipe); the others: fused add-max chains. 32: all IMAD
 #endif
@@ -702,6 +709,11 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
   constexpr int kBStages = C::kBStages;
   constexpr int kSlots = C::kSlots;
   constexpr bool kDual = C::kDual && kATmem;
+  constexpr bool kPackedK = IAM_PACKED && kKind == Kind::I8 && KTOP == 2;
+  constexpr bool kPairK = kPackedK && kDual && kSlots == 2 * kT && (kParts > 1 || kPC != 32) &&
+                          (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5);
+  constexpr bool kSplit = IAM_SPLIT_N && kPairK && kParts > 1;   // one product (and one pair of barriers) per column part
+  constexpr int kBarsPerSlot = kSplit ? kParts : 1;
   constexpr int kKSteps = C::kKSteps;
   constexpr uint32_t kTileBytes = C::kTileBytes;
   constexpr uint32_t kBTileBytes = C::kBTileBytes;
@@ -738,9 +750,9 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
       mbar_init(&bars->b_full[i], 1);
       mbar_init(&bars->b_empty[i], kCtas * (kDual ? kT : 1));  // every consumer of every CTA that received the tile
     }
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < kSlots * kBarsPerSlot; ++i) {
       mbar_init(&bars->t_full[i], 1);
-      mbar_init(&bars->t_empty[i], kWarpsPerATile);  // the warps of whichever A tile last used the slot
+      mbar_init(&bars->t_empty[i], kWarpsPerATile / kBarsPerSlot);  // the warps of whichever A tile last used the slot (of one part when split)
     }
     fence_barrier_init();
   } else if (role == 2) {
@@ -802,7 +814,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     // descriptor arithmetic lives in the uniform datapath instead of vector registers + R2UR); one elected lane
     // issues the tcgen05 instructions.  With kDual each query tile has its own issuer (roles 1 and 2) with its own
     // half of the accumulator slots; otherwise one warp issues the products of both tiles in turn.
-    constexpr uint32_t idesc = make_idesc_kind<kKind>(128, kBRows);
+    constexpr uint32_t idesc = make_idesc_kind<kKind>(128, kSplit ? kPC : kBRows);
     constexpr int kMyTiles = kDual ? 1 : kT;                  // query tiles this warp issues for
     constexpr int kSlotStep = kDual ? kT : 1;                 // distance between successive slots of this warp
     const int a0 = kDual ? role - 1 : 0;
@@ -842,6 +854,26 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
 #pragma unroll
         for (int am = 0; am < kMyTiles; ++am) {
           const int a = a0 + am;
+          if constexpr (kSplit) {
+            // one product per column part: kKSteps MMAs of N = kPC on that part's train rows (whole core-matrix
+            // groups: kPC / 8 groups of kSBO bytes) into its own columns of the slot, gated by its own barriers
+#pragma unroll
+            for (int pt = 0; pt < kParts; ++pt) {
+              mbar_wait_a(bars_addr + offsetof(Barriers, t_empty) + (slot * kParts + pt) * 8, tpar, 31);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t taddr = tm + slot * kBRows + pt * kPC;
+                const uint32_t b_lo_p = b_lo + ((pt * (kPC / 8) * kSBO) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                  const uint64_t bdesc = pack_desc(b_lo_p + (C::b_koff(ks) >> 4), smem_desc_hi(kSBO));
+                  umma_ts<kKind>(taddr, tm_a + a * kTmemAColsPerTile + ks * 8, bdesc, idesc, ks > 0 ? 1u : 0u);
+                }
+                umma_commit_a(bars_addr + offsetof(Barriers, t_full) + (slot * kParts + pt) * 8);
+              }
+              __syncwarp();
+            }
+          } else {
           mbar_wait_a(bars_addr + offsetof(Barriers, t_empty) + slot * 8, tpar, 31);
           tc_fence_after();
           if (elect_one()) {
@@ -858,6 +890,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
             }
             if (!kATmem && tb == n_tb - 1) umma_commit(&bars->a_empty[a]);
             umma_commit_a(bars_addr + offsetof(Barriers, t_full) + slot * 8);
+          }
           }
           __syncwarp();
           slot += kSlotStep;
@@ -893,7 +926,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     constexpr uint32_t kParityStride = kParts * kPartStride;    // bytes between the two unit-parity buffers
     const uint32_t share_row = smem_u32(share) + urow * 8;
     const uint32_t bar_full0 = pin_reg(smem_u32(&bars->t_full[0]));
-    constexpr uint32_t kEmptyOff = kSlots * 8;                  // t_empty[] follows t_full[] in Barriers
+    constexpr uint32_t kEmptyOff = kSlots * kParts * 8;         // t_empty[] follows t_full[] in Barriers
     const uint32_t tm_warp = pin_reg(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + part * kPC);
     const bool lane0 = lane == 0;
     TopK<KTOP, O> tk;
@@ -907,8 +940,11 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
     (void)mul32;
     (void)one;
     uint32_t slot = a % kSlots, par = 0;  // position in the accumulator ring: sq = it*kT + a, slot = sq % kSlots
-    constexpr bool kPair = kPacked && kDual && kSlots == 2 * kT && (kParts > 1 || kPC != 32) && (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5);
-    const uint32_t bar_a = pin_reg(bar_full0 + a * 8);       // kPair: t_full of this tile's first slot (second: + kT * 8)
+    constexpr bool kPair = kPairK;
+    static_assert(kPairK == (kPacked && kDual && kSlots == 2 * kT && (kParts > 1 || kPC != 32) && (kDbg == 0 || kDbg == 1 || kDbg == 4 || kDbg == 5)), "pair-loop condition");
+    // kPair: t_full of this tile's first slot (of this warp's column part when the products are split); second slot: + kSlotBar
+    constexpr uint32_t kSlotBar = kT * kBarsPerSlot * 8;
+    const uint32_t bar_a = pin_reg(bar_full0 + (kSplit ? (a * kParts + part) : a) * 8);
     const uint32_t tm_a = pin_reg(tm_warp + a * kBRows);     // kPair: its accumulator columns (second slot: + kT * kBRows)
     int phase = 0;
     (void)bar_a;
@@ -966,7 +1002,7 @@ knn_umma_kernel(const ImgDev* __restrict__ imgs, const KnnUnit* __restrict__ uni
         // `ex`: this is the pair's first tile -- the exchange of bounds runs while the tensor-memory load is in flight
         auto tile = [&](auto sl, int tpk, bool ex) {
           constexpr uint32_t kSl = decltype(sl)::value;
-          const uint32_t bar = bar_a + kSl * (kT * 8);
+          const uint32_t bar = bar_a + kSl * kSlotBar;
           mbar_wait_bare_a(bar, par);
           tc_fence_after();
           if constexpr (kDbg != 1) {

@@ -17,15 +17,19 @@
 // results agree as inlier SETS (tests: IoU >= 0.95), not bit for bit.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
 #include "ransac.h"
 
+#include "layout.h"
+#include "reduce.h"
+
 namespace iam {
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 32;     // one warp per image pair
 constexpr int kRound = 32;       // minimal samples per round
 constexpr int kMaxCand = 10;     // models per sample
 
@@ -293,59 +297,107 @@ IAM_HD int five_point(const float* x1, const float* y1, const float* x2, const f
     zmul(B[0][2], 4, u1, 6, t3);
     for (int i = 0; i < 11; ++i) poly[i] += t3[i];
   }
-  // 6. roots of the degree-10 polynomial: Durand-Kerner on the monic form
+  // 6. REAL roots of the degree-10 polynomial by Sturm sequences (the method of Nister's paper): the k-th smallest
+  //    real root is bracketed by bisection on the root count N(x) = V(-R) - V(x) until it is alone in its bracket,
+  //    then plain bisection on the sign of the polynomial narrows it; Newton steps below polish it.  (The previous
+  //    Durand-Kerner iteration on all ten complex roots took 80 % of the kernel's time: a warp runs until its slowest
+  //    lane has converged.)
   double mx = 0.0;
   for (int i = 0; i < 11; ++i) mx = fmax(mx, fabs(poly[i]));
   if (!(mx > 0.0) || !isfinite(mx)) return 0;
   int deg = 10;
   while (deg > 0 && fabs(poly[deg]) < 1e-13 * mx) --deg;
   if (deg < 1) return 0;
-  double a[11];
-  for (int i = 0; i <= deg; ++i) a[i] = poly[i] / poly[deg];
+  double st[11][11];   // Sturm chain, st[k] has degree sd[k] (coefficients low -> high)
+  int sd[11];
+  int ns = 2;
+  for (int i = 0; i <= deg; ++i) st[0][i] = poly[i] / poly[deg];
+  sd[0] = deg;
+  for (int i = 0; i < deg; ++i) st[1][i] = st[0][i + 1] * (i + 1);
+  sd[1] = deg - 1;
   double rad = 0.0;
-  for (int i = 0; i < deg; ++i) rad = fmax(rad, fabs(a[i]));
+  for (int i = 0; i < deg; ++i) rad = fmax(rad, fabs(st[0][i]));
   rad = fmin(1.0 + rad, 1e6);
-  Cplx root[10];
-  {
-    Cplx w = {1.0, 0.0};
-    const Cplx step = {0.4, 0.9};
-    for (int i = 0; i < deg; ++i) {
-      root[i] = {w.re * rad * 0.5, w.im * rad * 0.5};
-      w = cmul(w, step);
-      const double n = sqrt(w.re * w.re + w.im * w.im);
-      w.re /= n;
-      w.im /= n;
-      w = cmul(w, Cplx{cos(0.37 * (i + 1)), sin(0.37 * (i + 1))});
+  while (sd[ns - 1] > 0 && ns < 11) {   // st[ns] = -rem(st[ns-2], st[ns-1]), scaled to unit size
+    double r[11];
+    const int da = sd[ns - 2], db = sd[ns - 1];
+    for (int i = 0; i <= da; ++i) r[i] = st[ns - 2][i];
+    const double lead = st[ns - 1][db];
+    for (int k = da; k >= db; --k) {
+      const double q = r[k] / lead;
+      for (int j = 0; j <= db; ++j) r[k - db + j] -= q * st[ns - 1][j];
     }
+    int dr = db - 1;
+    double big = 0.0;
+    for (int i = 0; i <= dr; ++i) big = fmax(big, fabs(r[i]));
+    while (dr > 0 && fabs(r[dr]) <= 1e-14 * big) --dr;
+    if (!(big > 0.0)) break;            // exact division: repeated roots, the chain ends here
+    const double sc = -1.0 / big;
+    for (int i = 0; i <= dr; ++i) st[ns][i] = r[i] * sc;
+    sd[ns] = dr;
+    ++ns;
   }
-  for (int it = 0; it < 120; ++it) {
-    double delta = 0.0;
-    for (int i = 0; i < deg; ++i) {
-      Cplx p = {1.0, 0.0};
-      for (int k = deg - 1; k >= 0; --k) {
-        p = cmul(p, root[i]);
-        p.re += a[k];
+  auto sign_changes = [&](double x) {
+    int v = 0, last = 0;
+    for (int k = 0; k < ns; ++k) {
+      double p = st[k][sd[k]];
+      for (int i = sd[k] - 1; i >= 0; --i) p = p * x + st[k][i];
+      const int sg = p > 0.0 ? 1 : (p < 0.0 ? -1 : 0);
+      if (sg != 0) {
+        if (last != 0 && sg != last) ++v;
+        last = sg;
       }
-      Cplx den = {1.0, 0.0};
-      for (int j = 0; j < deg; ++j)
-        if (j != i) den = cmul(den, csub(root[i], root[j]));
-      if (den.re * den.re + den.im * den.im < 1e-300) continue;
-      const Cplx d = cdiv(p, den);
-      root[i] = csub(root[i], d);
-      delta = fmax(delta, fabs(d.re) + fabs(d.im));
     }
-    if (delta < 1e-13) break;
+    return v;
+  };
+  auto pval = [&](double x) {
+    double p = st[0][deg];
+    for (int i = deg - 1; i >= 0; --i) p = p * x + st[0][i];
+    return p;
+  };
+  const int v_lo = sign_changes(-rad);
+  const int n_real = v_lo - sign_changes(rad);
+  double rroot[10];
+  int n_roots = 0;
+  for (int k = 1; k <= n_real && n_roots < 10; ++k) {
+    // smallest x with N(x) >= k
+    double lo = -rad, hi = rad;
+    int n_lo = 0, n_hi = n_real;        // N(lo) < k <= N(hi)
+    int it = 0;
+    for (; it < 64 && !(n_hi - n_lo == 1 && it >= 6); ++it) {
+      const double mid = 0.5 * (lo + hi);
+      const int nm = v_lo - sign_changes(mid);
+      if (nm >= k) {
+        hi = mid;
+        n_hi = nm;
+      } else {
+        lo = mid;
+        n_lo = nm;
+      }
+      if (hi - lo <= 1e-15 * (1.0 + fabs(lo))) break;
+    }
+    if (n_hi - n_lo == 1) {             // alone in (lo, hi]: bisection on the sign of the polynomial
+      const double plo = pval(lo);
+      for (int b = 0; b < 40; ++b) {
+        const double mid = 0.5 * (lo + hi);
+        const double pm = pval(mid);
+        if ((pm > 0.0) == (plo > 0.0) && pm != 0.0) lo = mid; else hi = mid;
+      }
+    } else {
+      k += n_hi - n_lo - 1;             // a cluster narrower than the resolution: one representative
+    }
+    rroot[n_roots++] = 0.5 * (lo + hi);
   }
+  const double* polyn = st[0];
   // 7. back-substitute every real root
   int n_out = 0;
-  for (int i = 0; i < deg && n_out < kMaxCand; ++i) {
-    if (fabs(root[i].im) > 1e-7 * (1.0 + fabs(root[i].re))) continue;
-    double z = root[i].re;
+  for (int i = 0; i < n_roots && n_out < kMaxCand; ++i) {
+    double z = rroot[i];
     for (int nw = 0; nw < 3; ++nw) {  // Newton polish on the real polynomial
-      double p = poly[deg], dp = 0.0;
+      double p = polyn[deg], dp = 0.0;
       for (int k = deg - 1; k >= 0; --k) {
         dp = dp * z + p;
-        p = p * z + poly[k];
+        p = p * z + polyn[k];
       }
       if (fabs(dp) > 0.0) z -= p / dp;
     }
@@ -536,16 +588,15 @@ IAM_HD int seven_point(const float* x1, const float* y1, const float* x2, const 
   return n_out;
 }
 
-struct PairXform {  // per-pair point normalisation (host computed)
+struct PairXform {  // per-pair point normalisation
   float a1x, a1y, s1x, s1y;  // image 1: xn = (x - a1x) * s1x
   float a2x, a2y, s2x, s2y;
   float thr2;                // squared threshold in normalised units (errors measured in image 2)
-  float thr2b;               // fundamental: squared threshold for the error measured in image 1
-  int pad[2];
+  float thr_ratio;           // fundamental: thr2 / (squared threshold of the error measured in image 1)
 };
 
 __device__ __forceinline__ float model_error(int model, const float* M, float x1, float y1, float x2, float y2,
-                                             float thr_ratio = 1.0f) {
+                                             float thr_ratio) {
   if (model == 0) {  // Sampson distance of x2^T E x1
     const float ex = M[0] * x1 + M[1] * y1 + M[2];
     const float ey = M[3] * x1 + M[4] * y1 + M[5];
@@ -558,7 +609,7 @@ __device__ __forceinline__ float model_error(int model, const float* M, float x1
   if (model == 2) {
     // cv2.findFundamentalMat's RANSAC error: the larger of the two squared point-to-epipolar-line distances
     // (line F x1 in image 2, line F^T x2 in image 1).  The two images carry their own normalisation scales, so the
-    // distance in image 1 is rescaled to image-2 units (thr_ratio = thr2 / thr2b) and one comparison serves both.
+    // distance in image 1 is rescaled to image-2 units (thr_ratio) and one comparison serves both.
     const float a = M[0] * x1 + M[1] * y1 + M[2];
     const float b = M[3] * x1 + M[4] * y1 + M[5];
     const float c = M[6] * x1 + M[7] * y1 + M[8];
@@ -575,118 +626,270 @@ __device__ __forceinline__ float model_error(int model, const float* M, float x1
   return dx * dx + dy * dy;
 }
 
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+struct RansacArgs {
+  int model;
+  int max_iters;
+  uint32_t seed;
+  float fx, fy, cx, cy;   // essential: K
+  float thr_px;
+  double prob;
+  // direct mode: packed point lists
+  const float* pts1;
+  const float* pts2;
+  const int* off;
+  // gather mode (pts1 == nullptr): the device match tables of the last match call + the images' key points
+  const int* table;       // [P][cap][2]
+  int* count;             // [P]
+  int cap;
+  int compact;            // gather mode: drop the outliers from the tables in place (filter_by_transform, matcher.py:134-141)
+  int min_pairs;          // gather mode: pairs with fewer rows are emptied without a fit (matcher.py:99-101)
+  const RedJob* jobs;     // forward job of pair p = jobs[2p]: q_slot / t_slot
+  const ImgDev* imgs;
+  // outputs
+  unsigned char* out_mask;  // direct: [off[P]]; gather: [P][cap] (may be null)
+  float* out_model;         // [P][9]: E for normalised image coordinates, H / F for pixels
+  int* out_inliers;         // [P]
+};
+
+// One WARP per image pair: its 32 lanes solve 32 minimal samples (the solvers are long fp64 routines: with one
+// lane per sample no lane idles, where a wider CTA would leave every warp but one waiting), then the same warp scores
+// every candidate model, lanes striding the points.  Several pairs share an SM (registers: ~250 per thread).
 __global__ void __launch_bounds__(kThreads)
-ransac_kernel(int model, const float* __restrict__ pts1, const float* __restrict__ pts2, const int* __restrict__ off,
-              const PairXform* __restrict__ xf, double prob, int max_iters, uint32_t seed,
-              unsigned char* __restrict__ out_mask, float* __restrict__ out_model, int* __restrict__ out_inliers) {
+ransac_kernel(const RansacArgs A) {
   extern __shared__ float s_pts[];
   __shared__ float s_cand[kRound * kMaxCand * 9];
   __shared__ int s_ncand[kRound];
   __shared__ int s_score[kRound * kMaxCand];
-  __shared__ float s_best[9];
-  __shared__ int s_best_count, s_niters, s_done;
 
   const int p = blockIdx.x;
-  const int o = off[p];
-  const int n = off[p + 1] - o;
+  const int lane = threadIdx.x;
+  const int model = A.model;
+  const bool gather = A.pts1 == nullptr;
+  const int o = gather ? 0 : A.off[p];
+  const int n = gather ? A.count[p] : A.off[p + 1] - o;
   const int msize = (model == 0) ? 5 : (model == 2) ? 7 : 4;
-  const PairXform X = xf[p];
-  const float thr_ratio = (model == 2 && X.thr2b > 0.f) ? X.thr2 / X.thr2b : 1.0f;
+  if (gather && n < A.min_pairs) {  // matcher.py:99-101: too few matches, the list is cleared
+    if (lane == 0) {
+      if (A.compact) A.count[p] = 0;
+      A.out_inliers[p] = 0;
+      for (int e = 0; e < 9; ++e) A.out_model[p * 9 + e] = 0.f;
+    }
+    if (A.out_mask)
+      for (int i = lane; i < n; i += 32) A.out_mask[p * A.cap + i] = 0;
+    return;
+  }
   float* sx1 = s_pts;
   float* sy1 = sx1 + n;
   float* sx2 = sy1 + n;
   float* sy2 = sx2 + n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    sx1[i] = (pts1[2 * (o + i)] - X.a1x) * X.s1x;
-    sy1[i] = (pts1[2 * (o + i) + 1] - X.a1y) * X.s1y;
-    sx2[i] = (pts2[2 * (o + i)] - X.a2x) * X.s2x;
-    sy2[i] = (pts2[2 * (o + i) + 1] - X.a2y) * X.s2y;
+  const int2* tab = gather ? reinterpret_cast<const int2*>(A.table) + static_cast<size_t>(p) * A.cap : nullptr;
+  if (gather) {
+    const RedJob jb = A.jobs[2 * p];
+    const float2* k1 = A.imgs[jb.q_slot].kp_xy;
+    const float2* k2 = A.imgs[jb.t_slot].kp_xy;
+    for (int i = lane; i < n; i += 32) {
+      const int2 qt = tab[i];
+      const float2 a = k1[qt.x], b = k2[qt.y];
+      sx1[i] = a.x; sy1[i] = a.y; sx2[i] = b.x; sy2[i] = b.y;
+    }
+  } else {
+    for (int i = lane; i < n; i += 32) {
+      sx1[i] = A.pts1[2 * (o + i)]; sy1[i] = A.pts1[2 * (o + i) + 1];
+      sx2[i] = A.pts2[2 * (o + i)]; sy2[i] = A.pts2[2 * (o + i) + 1];
+    }
   }
-  if (threadIdx.x == 0) {
-    s_best_count = 0;
-    s_niters = max_iters;
-    s_done = 0;
-    for (int e = 0; e < 9; ++e) s_best[e] = 0.f;
+  __syncwarp();
+  // normalisation
+  PairXform X;
+  if (model == 0) {
+    // K^-1 with fx, fy, cx, cy; threshold / mean focal (how OpenCV's findEssentialMat treats pixel thresholds)
+    X.a1x = X.a2x = A.cx;
+    X.a1y = X.a2y = A.cy;
+    X.s1x = X.s2x = 1.0f / A.fx;
+    X.s1y = X.s2y = 1.0f / A.fy;
+    const double t = double(A.thr_px) / ((double(A.fx) + double(A.fy)) / 2.0);
+    X.thr2 = float(t * t);
+    X.thr_ratio = 1.0f;
+  } else {
+    // Hartley normalisation; the transfer error lives in image 2, so its isotropic scale carries the threshold
+    double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
+    for (int i = lane; i < n; i += 32) {
+      m1x += sx1[i]; m1y += sy1[i]; m2x += sx2[i]; m2y += sy2[i];
+    }
+    const double inv = n > 0 ? 1.0 / n : 0.0;
+    m1x = warp_sum(m1x) * inv; m1y = warp_sum(m1y) * inv; m2x = warp_sum(m2x) * inv; m2y = warp_sum(m2y) * inv;
+    double d1 = 0, d2 = 0;
+    for (int i = lane; i < n; i += 32) {
+      d1 += hypot(double(sx1[i]) - m1x, double(sy1[i]) - m1y);
+      d2 += hypot(double(sx2[i]) - m2x, double(sy2[i]) - m2y);
+    }
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    const double s1 = d1 > 0 ? sqrt(2.0) * n / d1 : 1.0;
+    const double s2 = d2 > 0 ? sqrt(2.0) * n / d2 : 1.0;
+    X.a1x = float(m1x); X.a1y = float(m1y); X.s1x = X.s1y = float(s1);
+    X.a2x = float(m2x); X.a2y = float(m2y); X.s2x = X.s2y = float(s2);
+    const double t = double(A.thr_px) * double(X.s2x), tb = double(A.thr_px) * double(X.s1x);
+    X.thr2 = float(t * t);
+    X.thr_ratio = tb > 0 ? float((t * t) / (tb * tb)) : 1.0f;
   }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) {
+    sx1[i] = (sx1[i] - X.a1x) * X.s1x;
+    sy1[i] = (sy1[i] - X.a1y) * X.s1y;
+    sx2[i] = (sx2[i] - X.a2x) * X.s2x;
+    sy2[i] = (sy2[i] - X.a2y) * X.s2y;
+  }
+  __syncwarp();
 
+  float best[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // warp-uniform
+  int best_count = 0, niters = A.max_iters;
   if (n >= msize) {
-    for (int base = 0; base < max_iters; base += kRound) {
-      if (warp == 0) {
-        int nc = 0;
-        const int it = base + lane;
-        if (it < s_niters) {
-          int s[7];
-          uint32_t h = hash32(seed ^ hash32(uint32_t(p) * 0x9e3779b9u + uint32_t(it)));
-          for (int k = 0; k < msize; ++k) {
-            for (int tries = 0; tries < 64; ++tries) {
-              h = hash32(h + 0x6d2b79f5u);
-              const int cand = int(h % uint32_t(n));
-              bool dup = false;
-              for (int q = 0; q < k; ++q) dup = dup || (s[q] == cand);
-              if (!dup) {
-                s[k] = cand;
-                break;
-              }
-              if (tries == 63) s[k] = (s[k > 0 ? k - 1 : 0] + 1 + k) % n;
+    for (int base = 0; base < A.max_iters && base < niters; base += kRound) {
+      int nc = 0;
+      const int it = base + lane;
+      if (it < niters) {
+        int s[7];
+        uint32_t h = hash32(A.seed ^ hash32(uint32_t(p) * 0x9e3779b9u + uint32_t(it)));
+        for (int k = 0; k < msize; ++k) {
+          for (int tries = 0; tries < 64; ++tries) {
+            h = hash32(h + 0x6d2b79f5u);
+            const int cand = int(h % uint32_t(n));
+            bool dup = false;
+            for (int q = 0; q < k; ++q) dup = dup || (s[q] == cand);
+            if (!dup) {
+              s[k] = cand;
+              break;
             }
+            if (tries == 63) s[k] = (s[k > 0 ? k - 1 : 0] + 1 + k) % n;
           }
-          nc = (model == 0)   ? five_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
-               : (model == 2) ? seven_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
-                              : four_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9]);
         }
-        s_ncand[lane] = nc;
+        nc = (model == 0)   ? five_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
+             : (model == 2) ? seven_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
+                            : four_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9]);
       }
-      __syncthreads();
-      // score all candidates: one warp per candidate, lanes stride the points
-      for (int c = warp; c < kRound * kMaxCand; c += kThreads / 32) {
+      s_ncand[lane] = nc;
+      __syncwarp();
+      // score every candidate of the round: lanes stride the points, warp-shuffle reduction of the counts
+      for (int c = 0; c < kRound * kMaxCand; ++c) {
         const int smp = c / kMaxCand, r = c % kMaxCand;
-        if (r >= s_ncand[smp]) continue;
+        if (r >= s_ncand[smp]) {
+          c += kMaxCand - 1 - r;   // the rest of this sample's slots are empty too
+          continue;
+        }
         float M[9];
         for (int e = 0; e < 9; ++e) M[e] = s_cand[c * 9 + e];
         int cnt = 0;
-        for (int i = lane; i < n; i += 32) cnt += model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i], thr_ratio) <= X.thr2;
+        for (int i = lane; i < n; i += 32) cnt += model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i], X.thr_ratio) <= X.thr2;
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0) s_score[c] = cnt;
       }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int smp = 0; smp < kRound && base + smp < s_niters; ++smp) {
-          for (int r = 0; r < s_ncand[smp]; ++r) {
-            const int cnt = s_score[smp * kMaxCand + r];
-            if (cnt > max(s_best_count, msize - 1)) {
-              s_best_count = cnt;
-              for (int e = 0; e < 9; ++e) s_best[e] = s_cand[(smp * kMaxCand + r) * 9 + e];
-              // adaptive iteration count (the standard RANSAC bound)
-              const double ep = fmin(fmax(1.0 - double(cnt) / double(n), 0.0), 1.0);
-              const double num = log(fmax(1.0 - prob, 1e-300));
-              const double den = 1.0 - pow(1.0 - ep, double(msize));
-              int ni = max_iters;
-              if (den < 1e-300)
-                ni = 0;
-              else {
-                const double lden = log(den);
-                if (!(lden >= 0.0) && -num < double(max_iters) * (-lden)) ni = int(rint(num / lden));
-              }
-              s_niters = min(s_niters, ni);
+      __syncwarp();
+      // every lane walks the scores identically: the best model and the iteration bound stay warp-uniform
+      for (int smp = 0; smp < kRound && base + smp < niters; ++smp) {
+        for (int r = 0; r < s_ncand[smp]; ++r) {
+          const int cnt = s_score[smp * kMaxCand + r];
+          if (cnt > max(best_count, msize - 1)) {
+            best_count = cnt;
+            for (int e = 0; e < 9; ++e) best[e] = s_cand[(smp * kMaxCand + r) * 9 + e];
+            // adaptive iteration count (the standard RANSAC bound, OpenCV's RANSACUpdateNumIters)
+            const double ep = fmin(fmax(1.0 - double(cnt) / double(n), 0.0), 1.0);
+            const double num = log(fmax(1.0 - A.prob, 1e-300));
+            const double den = 1.0 - pow(1.0 - ep, double(msize));
+            int ni = A.max_iters;
+            if (den < 1e-300)
+              ni = 0;
+            else {
+              const double lden = log(den);
+              if (!(lden >= 0.0) && -num < double(A.max_iters) * (-lden)) ni = int(rint(num / lden));
             }
+            niters = min(niters, ni);
           }
         }
-        s_done = (base + kRound >= s_niters);
       }
-      __syncthreads();
-      if (s_done) break;
+      __syncwarp();
     }
   }
   // final mask with the best model
-  float M[9];
-  for (int e = 0; e < 9; ++e) M[e] = s_best[e];
-  const bool have = s_best_count > 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    out_mask[o + i] = (have && model_error(model, M, sx1[i], sy1[i], sx2[i], sy2[i], thr_ratio) <= X.thr2) ? 1 : 0;
-  if (threadIdx.x < 9) out_model[p * 9 + threadIdx.x] = have ? M[threadIdx.x] : 0.f;
-  if (threadIdx.x == 0) out_inliers[p] = have ? s_best_count : 0;
+  const bool have = best_count > 0;
+  const int mask_base = gather ? p * A.cap : o;
+  int kept = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const bool in = i < n && have && model_error(model, best, sx1[i], sy1[i], sx2[i], sy2[i], X.thr_ratio) <= X.thr2;
+    if (A.out_mask && i < n) A.out_mask[mask_base + i] = in ? 1 : 0;
+    if (gather && A.compact) {  // order-preserving compaction of the table rows (matcher.py:134-141)
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      int2 row = make_int2(0, 0);
+      if (in) row = tab[i];
+      __syncwarp();
+      if (in) const_cast<int2*>(tab)[kept + __popc(bal & ((1u << lane) - 1u))] = row;
+      kept += __popc(bal);
+      __syncwarp();
+    }
+  }
+  if (gather && A.compact && lane == 0) A.count[p] = kept;
+  if (lane == 0) {
+    // back to caller units: E is reported for normalised image coordinates like cv2.findEssentialMat does
+    // (x2n^T E x1n = 0); H and F are mapped back to pixels and scaled to a unit last element.
+    double o9[9];
+    if (!have) {
+      for (int e = 0; e < 9; ++e) o9[e] = 0.0;
+    } else if (model == 0) {
+      for (int e = 0; e < 9; ++e) o9[e] = best[e];
+    } else {
+      const double T1[9] = {X.s1x, 0, -double(X.s1x) * X.a1x, 0, X.s1y, -double(X.s1y) * X.a1y, 0, 0, 1};
+      double L[9];  // homography: T2^-1; fundamental: T2^T
+      if (model == 1) {
+        const double l[9] = {1.0 / X.s2x, 0, X.a2x, 0, 1.0 / X.s2y, X.a2y, 0, 0, 1};
+        for (int e = 0; e < 9; ++e) L[e] = l[e];
+      } else {
+        const double l[9] = {X.s2x, 0, 0, 0, X.s2y, 0, -double(X.s2x) * X.a2x, -double(X.s2y) * X.a2y, 1};
+        for (int e = 0; e < 9; ++e) L[e] = l[e];
+      }
+      double t[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          t[i * 3 + j] = 0;
+          for (int k = 0; k < 3; ++k) t[i * 3 + j] += double(best[i * 3 + k]) * T1[k * 3 + j];
+        }
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          o9[i * 3 + j] = 0;
+          for (int k = 0; k < 3; ++k) o9[i * 3 + j] += L[i * 3 + k] * t[k * 3 + j];
+        }
+      const double sc = fabs(o9[8]) > 1e-300 ? 1.0 / o9[8] : 1.0;
+      for (int e = 0; e < 9; ++e) o9[e] *= sc;
+    }
+    for (int e = 0; e < 9; ++e) A.out_model[p * 9 + e] = static_cast<float>(o9[e]);
+    A.out_inliers[p] = have ? best_count : 0;
+  }
+}
+
+cudaError_t launch(const RansacArgs& a, int n_pairs, int max_n, cudaStream_t stream) {
+  const size_t smem = size_t(std::max(max_n, 1)) * 4 * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  ransac_kernel<<<n_pairs, kThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+void fill_common(RansacArgs& a, int model, const double* K, double threshold_px, double prob, int max_iters, uint32_t seed) {
+  a.model = model;
+  a.max_iters = max_iters <= 0 ? 1000 : max_iters;
+  a.prob = (prob > 0.0 && prob < 1.0) ? prob : 0.999;
+  a.seed = seed;
+  a.thr_px = float(threshold_px);
+  a.fx = K ? float(K[0]) : 1.f;
+  a.fy = K ? float(K[4]) : 1.f;
+  a.cx = K ? float(K[2]) : 0.f;
+  a.cy = K ? float(K[5]) : 0.f;
 }
 
 }  // namespace
@@ -697,9 +900,13 @@ int debug_minimal_solver(int model, const float* x1, const float* y1, const floa
                                                                         : four_point(x1, y1, x2, y2, s, out);
 }
 
+RansacScratch::~RansacScratch() {
+  if (buf) cudaFree(buf);
+}
+
 int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t* off, int n_pairs, const double* K,
                  double threshold_px, double prob, int max_iters, uint32_t seed, uint8_t* out_mask, double* out_model,
-                 int32_t* out_inliers, cudaStream_t stream, std::string* err) {
+                 int32_t* out_inliers, RansacScratch* scratch, cudaStream_t stream, std::string* err) {
   auto bad = [&](int code, const char* what, cudaError_t e) {
     if (err) *err = std::string(what) + ": " + cudaGetErrorString(e);
     return code;
@@ -718,129 +925,70 @@ int ransac_pairs(int model, const float* pts1, const float* pts2, const int32_t*
     if (err) *err = "more than 12000 correspondences in one pair";
     return -5;
   }
-  if (max_iters <= 0) max_iters = 1000;
-  if (!(prob > 0.0 && prob < 1.0)) prob = 0.999;
-
-  // per-pair normalisation
-  std::vector<PairXform> xf(n_pairs);
-  for (int p = 0; p < n_pairs; ++p) {
-    PairXform& X = xf[p];
-    const int o = off[p], n = off[p + 1] - o;
-    if (model == 0) {
-      // K^-1 with fx, fy, cx, cy; threshold / mean focal (how OpenCV's findEssentialMat treats pixel thresholds)
-      const double fx = K[0], fy = K[4], cx = K[2], cy = K[5];
-      X.a1x = X.a2x = float(cx);
-      X.a1y = X.a2y = float(cy);
-      X.s1x = X.s2x = float(1.0 / fx);
-      X.s1y = X.s2y = float(1.0 / fy);
-      const double t = threshold_px / ((fx + fy) / 2.0);
-      X.thr2 = float(t * t);
-    } else {
-      // Hartley normalisation; the transfer error lives in image 2, so its isotropic scale carries the threshold
-      double m1x = 0, m1y = 0, m2x = 0, m2y = 0;
-      for (int i = 0; i < n; ++i) {
-        m1x += pts1[2 * (o + i)]; m1y += pts1[2 * (o + i) + 1];
-        m2x += pts2[2 * (o + i)]; m2y += pts2[2 * (o + i) + 1];
-      }
-      const double inv = n > 0 ? 1.0 / n : 0.0;
-      m1x *= inv; m1y *= inv; m2x *= inv; m2y *= inv;
-      double d1 = 0, d2 = 0;
-      for (int i = 0; i < n; ++i) {
-        d1 += std::hypot(pts1[2 * (o + i)] - m1x, pts1[2 * (o + i) + 1] - m1y);
-        d2 += std::hypot(pts2[2 * (o + i)] - m2x, pts2[2 * (o + i) + 1] - m2y);
-      }
-      const double s1 = d1 > 0 ? std::sqrt(2.0) * n / d1 : 1.0;
-      const double s2 = d2 > 0 ? std::sqrt(2.0) * n / d2 : 1.0;
-      X.a1x = float(m1x); X.a1y = float(m1y); X.s1x = X.s1y = float(s1);
-      X.a2x = float(m2x); X.a2y = float(m2y); X.s2x = X.s2y = float(s2);
-      const double t = threshold_px * double(X.s2x);
-      X.thr2 = float(t * t);
-      const double tb = threshold_px * double(X.s1x);
-      X.thr2b = float(tb * tb);
-    }
-  }
-
-  float *d_p1 = nullptr, *d_p2 = nullptr, *d_model = nullptr;
-  int *d_off = nullptr, *d_inl = nullptr;
-  unsigned char* d_mask = nullptr;
-  PairXform* d_xf = nullptr;
+  // one device block, kept between calls: [pts1][pts2][off][model][inliers][mask]
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t pb = up(size_t(std::max(total, 1)) * 2 * sizeof(float));
+  const size_t o_p2 = pb, o_off = 2 * pb, o_model = o_off + up(size_t(n_pairs + 1) * sizeof(int));
+  const size_t o_inl = o_model + up(size_t(n_pairs) * 9 * sizeof(float)), o_mask = o_inl + up(size_t(n_pairs) * sizeof(int));
+  const size_t bytes = o_mask + up(size_t(std::max(total, 1)));
   cudaError_t e;
-  const size_t pb = size_t(std::max(total, 1)) * 2 * sizeof(float);
-#define RA(call)                                  \
-  if ((e = (call)) != cudaSuccess) {              \
-    cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_model); cudaFree(d_off); cudaFree(d_inl); cudaFree(d_mask); cudaFree(d_xf); \
-    return bad(-2, #call, e);                     \
+  RansacScratch local;
+  RansacScratch* sc = scratch ? scratch : &local;
+  if (sc->cap < bytes) {
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return bad(-2, "sync", e);
+    if (sc->buf) cudaFree(sc->buf);
+    sc->buf = nullptr;
+    sc->cap = 0;
+    if ((e = cudaMalloc(&sc->buf, bytes + bytes / 4)) != cudaSuccess) return bad(-3, "cudaMalloc", e);
+    sc->cap = bytes + bytes / 4;
   }
-  RA(cudaMalloc(&d_p1, pb));
-  RA(cudaMalloc(&d_p2, pb));
-  RA(cudaMalloc(&d_model, size_t(n_pairs) * 9 * sizeof(float)));
-  RA(cudaMalloc(&d_off, size_t(n_pairs + 1) * sizeof(int)));
-  RA(cudaMalloc(&d_inl, size_t(n_pairs) * sizeof(int)));
-  RA(cudaMalloc(&d_mask, size_t(std::max(total, 1))));
-  RA(cudaMalloc(&d_xf, size_t(n_pairs) * sizeof(PairXform)));
+  uint8_t* d = static_cast<uint8_t*>(sc->buf);
+#define RA(call) \
+  if ((e = (call)) != cudaSuccess) return bad(-2, #call, e);
   if (total > 0) {
-    RA(cudaMemcpyAsync(d_p1, pts1, size_t(total) * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
-    RA(cudaMemcpyAsync(d_p2, pts2, size_t(total) * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    RA(cudaMemcpyAsync(d, pts1, size_t(total) * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    RA(cudaMemcpyAsync(d + o_p2, pts2, size_t(total) * 2 * sizeof(float), cudaMemcpyHostToDevice, stream));
   }
-  RA(cudaMemcpyAsync(d_off, off, size_t(n_pairs + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-  RA(cudaMemcpyAsync(d_xf, xf.data(), size_t(n_pairs) * sizeof(PairXform), cudaMemcpyHostToDevice, stream));
-  const size_t smem = size_t(std::max(max_n, 1)) * 4 * sizeof(float);
-  if (smem > 48 * 1024) RA(cudaFuncSetAttribute(ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ransac_kernel<<<n_pairs, kThreads, smem, stream>>>(model, d_p1, d_p2, d_off, d_xf, prob, max_iters, seed, d_mask,
-                                                     d_model, d_inl);
-  RA(cudaGetLastError());
+  RA(cudaMemcpyAsync(d + o_off, off, size_t(n_pairs + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  RansacArgs a{};
+  fill_common(a, model, K, threshold_px, prob, max_iters, seed);
+  a.pts1 = reinterpret_cast<const float*>(d);
+  a.pts2 = reinterpret_cast<const float*>(d + o_p2);
+  a.off = reinterpret_cast<const int*>(d + o_off);
+  a.out_mask = d + o_mask;
+  a.out_model = reinterpret_cast<float*>(d + o_model);
+  a.out_inliers = reinterpret_cast<int*>(d + o_inl);
+  RA(launch(a, n_pairs, max_n, stream));
   std::vector<float> h_model(size_t(n_pairs) * 9);
-  if (total > 0) RA(cudaMemcpyAsync(out_mask, d_mask, size_t(total), cudaMemcpyDeviceToHost, stream));
-  RA(cudaMemcpyAsync(h_model.data(), d_model, h_model.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
-  RA(cudaMemcpyAsync(out_inliers, d_inl, size_t(n_pairs) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  if (total > 0) RA(cudaMemcpyAsync(out_mask, d + o_mask, size_t(total), cudaMemcpyDeviceToHost, stream));
+  RA(cudaMemcpyAsync(h_model.data(), d + o_model, h_model.size() * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  RA(cudaMemcpyAsync(out_inliers, d + o_inl, size_t(n_pairs) * sizeof(int), cudaMemcpyDeviceToHost, stream));
   RA(cudaStreamSynchronize(stream));
 #undef RA
-  cudaFree(d_p1); cudaFree(d_p2); cudaFree(d_model); cudaFree(d_off); cudaFree(d_inl); cudaFree(d_mask); cudaFree(d_xf);
+  for (size_t i = 0; i < h_model.size(); ++i) out_model[i] = h_model[i];
+  return 0;
+}
 
-  // back to caller units: E is reported for normalised image coordinates like
-  // cv2.findEssentialMat does (x2n^T E x1n = 0); H is mapped back to pixels.
-  for (int p = 0; p < n_pairs; ++p) {
-    const float* m = &h_model[size_t(p) * 9];
-    double* o = out_model + size_t(p) * 9;
-    if (model == 0) {
-      for (int i = 0; i < 9; ++i) o[i] = m[i];
-    } else if (model == 2) {
-      // F_pixel = T2^T Fn T1, scaled to unit f33 like cv2.findFundamentalMat reports it
-      const PairXform& X = xf[p];
-      const double T1[9] = {X.s1x, 0, -X.s1x * X.a1x, 0, X.s1y, -X.s1y * X.a1y, 0, 0, 1};
-      const double T2[9] = {X.s2x, 0, -X.s2x * X.a2x, 0, X.s2y, -X.s2y * X.a2y, 0, 0, 1};
-      double t[9], r[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          t[i * 3 + j] = 0;
-          for (int k = 0; k < 3; ++k) t[i * 3 + j] += double(m[i * 3 + k]) * T1[k * 3 + j];
-        }
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          r[i * 3 + j] = 0;
-          for (int k = 0; k < 3; ++k) r[i * 3 + j] += T2[k * 3 + i] * t[k * 3 + j];
-        }
-      const double sc = std::fabs(r[8]) > 1e-300 ? 1.0 / r[8] : 1.0;
-      for (int i = 0; i < 9; ++i) o[i] = r[i] * sc;
-    } else {
-      const PairXform& X = xf[p];
-      // Hp = T2^-1 Hn T1, T = [[s,0,-s*a],[0,s,-s*b],[0,0,1]]
-      const double T1[9] = {X.s1x, 0, -X.s1x * X.a1x, 0, X.s1y, -X.s1y * X.a1y, 0, 0, 1};
-      const double T2i[9] = {1.0 / X.s2x, 0, X.a2x, 0, 1.0 / X.s2y, X.a2y, 0, 0, 1};
-      double t[9], r[9];
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          t[i * 3 + j] = 0;
-          for (int k = 0; k < 3; ++k) t[i * 3 + j] += double(m[i * 3 + k]) * T1[k * 3 + j];
-        }
-      for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-          r[i * 3 + j] = 0;
-          for (int k = 0; k < 3; ++k) r[i * 3 + j] += T2i[i * 3 + k] * t[k * 3 + j];
-        }
-      const double s = std::fabs(r[8]) > 1e-300 ? 1.0 / r[8] : 1.0;
-      for (int i = 0; i < 9; ++i) o[i] = r[i] * s;
-    }
+int ransac_tables(int model, int* d_table, int* d_count, int cap, int n_pairs, const RedJob* d_jobs, const ImgDev* d_imgs,
+                  const double* K, double threshold_px, double prob, int max_iters, uint32_t seed, int min_pairs,
+                  bool compact, uint8_t* d_mask, float* d_model, int* d_inliers, cudaStream_t stream, std::string* err) {
+  if (n_pairs == 0) return 0;
+  RansacArgs a{};
+  fill_common(a, model, K, threshold_px, prob, max_iters, seed);
+  a.table = d_table;
+  a.count = d_count;
+  a.cap = cap;
+  a.compact = compact ? 1 : 0;
+  a.min_pairs = min_pairs;
+  a.jobs = d_jobs;
+  a.imgs = d_imgs;
+  a.out_mask = d_mask;
+  a.out_model = d_model;
+  a.out_inliers = d_inliers;
+  const cudaError_t e = launch(a, n_pairs, cap, stream);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("ransac launch: ") + cudaGetErrorString(e);
+    return -2;
   }
   return 0;
 }

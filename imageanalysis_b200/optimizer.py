@@ -47,13 +47,15 @@ class Optimizer():
     # -- problem structure -> device (once per problem) -----------------------
     def _engine(self):
         if self._eng is None:
-            self._eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+            from . import matcher as _matcher          # one process per GPU: the device configure() uses
+            self._eng = _capi.Engine(_capi.NORM_L2, 128, int(getattr(_matcher, "device", 0)))
         return self._eng
 
+    def rebind(self):
+        """Forget the resident problem structure (the next fun()/jac() uploads it again)."""
+        self._key = None
+
     def _bind(self, n_cameras, n_points, by_camera_point_indices, by_camera_points_2d):
-        key = (id(by_camera_point_indices), id(by_camera_points_2d), n_cameras, n_points)
-        if key == self._key:
-            return
         cam_idx, pt_idx, uv = [], [], []
         for i in range(n_cameras):                 # cameras without observations are skipped (:203-204)
             idx = np.asarray(by_camera_point_indices[i], np.int64).ravel()
@@ -65,6 +67,15 @@ class Optimizer():
         cam_idx = np.concatenate(cam_idx) if cam_idx else np.zeros(0, np.int32)
         pt_idx = np.concatenate(pt_idx) if pt_idx else np.zeros(0, np.int32)
         uv = np.concatenate(uv) if uv else np.zeros((0, 2))
+        # The resident structure is keyed on its CONTENT (ids of the caller's lists can be reused by CPython once a
+        # previous problem is freed, and the lists can be edited in place): a hash of the flattened arrays.
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for a in (cam_idx, pt_idx, np.ascontiguousarray(uv)):
+            h.update(a.tobytes())
+        key = (h.digest(), n_cameras, n_points)
+        if key == self._key:
+            return
         self._engine().ba_setup(n_cameras, n_points, cam_idx, pt_idx, uv)
         self.camera_indices, self.point_indices = cam_idx, pt_idx
         self._key = key
@@ -75,7 +86,10 @@ class Optimizer():
             c = np.asarray(params, np.float64)[n_cameras * self.ncp + n_points * 3:]
             return (c[0], c[0], c[1], c[2]), c[3:8]
         K = np.asarray(self.K, np.float64)
-        return (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), np.asarray(self.distCoeffs, np.float64).ravel()[:5]
+        d = np.zeros(5)                                   # (k1, k2, p1, p2, k3); shorter lists are zero-padded as cv2 does
+        dc = np.asarray(self.distCoeffs if self.distCoeffs is not None else [], np.float64).ravel()[:5]
+        d[:len(dc)] = dc
+        return (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), d
 
     # -- optimizer.py:174-279 --------------------------------------------------
     def fun(self, params, n_cameras, n_points, by_camera_point_indices, by_camera_points_2d):

@@ -237,6 +237,18 @@ int iam_ransac_pairs(iam_ctx* ctx, int model, const float* pts1, const float* pt
                      double threshold_px, double prob, int max_iters, uint32_t seed,
                      uint8_t* out_mask, double* out_model, int32_t* out_inliers);
 
+/* The same fit on the DEVICE tables of the last iam_match_pairs_device() / iam_match_images() call: the batched form
+ * of find_matches' per-pair filter_by_transform(K, i1, i2, transform) (matcher.py:90-142).  The correspondences of
+ * pair p are its table rows looked up in the resident key-point coordinates (iam_upload_keypoints; give it the images'
+ * uv_list, matcher.py:112-113).  Pairs with fewer than min_pairs rows are emptied without a fit (matcher.py:99-101).
+ * compact != 0 removes the outliers from the tables in place, order kept (matcher.py:134-141): iam_fetch_tables /
+ * iam_pack_tables_device then return the filtered tables.  Outputs are HOST buffers and any may be NULL (with all NULL
+ * the call only enqueues): out_mask [P][cap] (1 = inlier, rows beyond a pair's count untouched), out_model [P][9]
+ * double, out_inliers [P]. */
+int iam_ransac_tables(iam_ctx* ctx, int model, const double* K, double threshold_px, double prob, int max_iters,
+                      uint32_t seed, int min_pairs, int compact, uint8_t* out_mask, double* out_model,
+                      int32_t* out_inliers);
+
 /* ---- bundle adjustment: replaces Optimizer.fun (optimizer.py:174-279) -- */
 
 /* The reprojection residual of every observation in one launch, and its

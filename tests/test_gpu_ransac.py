@@ -90,3 +90,57 @@ def test_filter_by_transform_drops_outliers():
     assert len(kept & set(np.nonzero(truth == 0)[0])) < 0.15 * (600 - truth.sum())
     i1.match_list["b"] = [[k, k] for k in range(10)]       # below min_pairs: cleared (matcher.py:99-101)
     assert matcher.filter_by_transform(K, i1, i2, "essential") and i1.match_list["b"] == []
+
+
+def test_ransac_on_device_tables_equals_the_host_point_form():
+    """iam_ransac_tables: filter_by_transform for every pair of a match call without leaving the device -- the
+    correspondences are the table rows looked up in the resident key points.  Same sampler, same pair numbering:
+    masks and models must equal iam_ransac_pairs on the points gathered by hand; compact=True leaves exactly the
+    inlier rows in the tables (order kept) and empties pairs below min_pairs (matcher.py:99-101, :134-141)."""
+    K = np.array([[3666.666504, 0, 2736], [0, 3666.666504, 1824], [0, 0, 1]])
+    tol = 5472 ** 0.25
+    n = 1500
+    des, pts, neds = synth.sift_project(3, n, seed=21, planted=0.4)
+    rng = np.random.default_rng(5)
+    # key points: random, except that matched rows of frames (0, 1) and (1, 2) follow a two-view geometry
+    kp = [np.stack([rng.uniform(0, 5472, n), rng.uniform(0, 3648, n)], 1).astype(np.float32) for _ in range(3)]
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i in range(3):
+        eng.upload(i, des[i])
+    pairs = [(0, 1), (1, 2), (0, 2)]
+    prm = _capi.Engine.make_params()
+    table, count = eng.match_pairs(pairs, prm)
+    for p, (a, b) in enumerate(pairs[:2]):
+        c = int(count[p])
+        p1, p2, _ = synth.two_view_scene(c, 0.25, K, seed=70 + p)
+        kp[b][table[p, :c, 1]] = p2
+        if p == 0:
+            kp[a][table[p, :c, 0]] = p1
+        else:       # frame 1's points are shared with pair 0: keep them, move frame 2 consistently instead
+            q1 = kp[a][table[p, :c, 0]]
+            kp[b][table[p, :c, 1]] = q1 + (p2 - p1)
+    for i in range(3):
+        eng.upload_keypoints(i, kp[i])
+    eng.match_pairs_device(np.int32(pairs), prm)
+    cap = prm.cap
+    mask_t, E_t, inl_t = eng.ransac_tables(_capi.MODEL_ESSENTIAL, K, tol, len(pairs), cap, min_pairs=25, compact=False, want_mask=True)
+    off = np.concatenate([[0], np.cumsum(count)]).astype(np.int32)
+    g1 = np.concatenate([kp[a][table[p, :count[p], 0]] for p, (a, b) in enumerate(pairs)])
+    g2 = np.concatenate([kp[b][table[p, :count[p], 1]] for p, (a, b) in enumerate(pairs)])
+    mask_h, E_h, inl_h = eng.ransac_pairs(_capi.MODEL_ESSENTIAL, g1, g2, off, K, tol)
+    for p in range(len(pairs)):
+        c = int(count[p])
+        if c < 25:
+            assert inl_t[p] == 0
+            continue
+        assert (mask_t[p, :c] == mask_h[off[p]:off[p + 1]]).all(), p
+        assert inl_t[p] == inl_h[p] and np.allclose(E_t[p], E_h[p], atol=1e-6)
+    assert inl_t[0] > 0.6 * count[0]
+    # in-place compaction
+    eng.ransac_tables(_capi.MODEL_ESSENTIAL, K, tol, len(pairs), cap, min_pairs=25, compact=True, want_model=False)
+    t2, c2 = eng.fetch_tables(len(pairs), cap)
+    for p in range(len(pairs)):
+        c = int(count[p])
+        want = table[p, :c][mask_t[p, :c].astype(bool)] if c >= 25 else np.zeros((0, 2), np.int32)
+        assert c2[p] == len(want) and (t2[p, :c2[p]] == want).all(), p
+    eng.close()
