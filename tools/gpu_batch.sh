@@ -1,4 +1,4 @@
-bash tools/gpu_ab.sh 2>&1 | grep -v "^\.\.\."
-echo "== ncu full ransac"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ransac_kernel -s 1 -c 1 -f -o gpurun_out/ransac python tools/bench_stages.py --frames 20 --steps 1 --warmup 1 > gpurun_out/ncu_ransac_full.log 2>&1
-ls -la gpurun_out/ransac.ncu-rep
+echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+echo "== stage benchmarks (ransac)"; timeout 900 python tools/bench_stages.py --frames 60 --steps 3 --warmup 1 2>&1 | grep ransac | cut -c1-700
+echo "== pipeline (configs[4]) 1 GPU"; timeout 1200 python bench.py --workload pipeline --steps 3 --warmup 1 2>&1 | tee gpurun_out/bench_pipeline_n1.log | tail -1 | cut -c1-5000
+echo "== default bench"; timeout 900 python bench.py 2>&1 | tee gpurun_out/bench_default.log | tail -1 | cut -c1-1500
