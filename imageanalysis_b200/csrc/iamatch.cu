@@ -24,6 +24,7 @@
 #include "host_narrow.h"
 #include "knn.h"
 #include "layout.h"
+#include "orb.h"
 #include "ransac.h"
 #include "reduce.h"
 
@@ -1551,6 +1552,31 @@ int iam_ransac_tables(iam_ctx* c, int model, const double* K, double threshold_p
   return IAM_OK;
 }
 
+
+// ---- ORB detect + describe (image.py:243-245, :324) -------------------------------------------------------------
+
+int iam_orb_detect(iam_ctx* c, const uint8_t* gray, int width, int height, int nfeatures, int max_out, float* out_kp,
+                   uint8_t* out_des, int* out_n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!gray || !out_kp || !out_des || !out_n || max_out < 0) return fail(IAM_E_ARG, "bad arguments");
+  if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(IAM_E_ARG, "image size %d x %d out of range", width, height);
+  std::string err;
+  rc = iam::orb_detect(gray, width, height, nfeatures, iam::orb_pattern(), max_out, out_kp, out_des, out_n, c->stream, &err);
+  if (rc < 0) return fail(rc == -5 ? IAM_E_UNSUPPORTED : rc == -1 ? IAM_E_ARG : IAM_E_CUDA, "%s", err.c_str());
+  c->timing.total_launches += rc;
+  return IAM_OK;
+}
+
+int iam_debug_orb_fast(iam_ctx* c, const uint8_t* gray, int width, int height, uint8_t* out_score) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!gray || !out_score || width <= 0 || height <= 0) return fail(IAM_E_ARG, "bad arguments");
+  std::string err;
+  rc = iam::orb_debug_fast_scores(gray, width, height, out_score, c->stream, &err);
+  if (rc) return fail(IAM_E_CUDA, "%s", err.c_str());
+  return IAM_OK;
+}
 
 // ---- bundle-adjustment residual / Jacobian (optimizer.py:174-279) ----------------------------------------------
 

@@ -791,12 +791,16 @@ def _batched_traditional(image_list, todo):
                                    reduce_mode=_capi.REDUCE_REF_METRIC, cap=2000, min_pairs=int(min_pairs),
                                    cross_check=True, dedupe=True, gms=gms_enabled, gms_rotation=True, gms_scale=False,
                                    gms_threshold=5.0, size=(w, h))
-    # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching
-    table, count = eng.match_images(used, arrays, np.int32(todo), prm, keys=keys)
-    out = []
-    for p in range(len(todo)):
-        fwd = table[p, :count[p]].tolist()
-        out.append((fwd, [[t, q] for q, t in fwd]))
+    # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching.  The call uploads an image right
+    # before the first pair that needs it: handing it the pairs sorted by their LATER image lets matching start after
+    # the first few images instead of after everything the first image's neighbours reach (results are independent
+    # of the order, matcher.py:928-980; they are mapped back to the work-list order below).
+    order = sorted(range(len(todo)), key=lambda p: (max(todo[p]), min(todo[p])))
+    table, count = eng.match_images(used, arrays, np.int32([todo[p] for p in order]), prm, keys=keys)
+    out = [None] * len(todo)
+    for k, p in enumerate(order):
+        fwd = table[k, :count[k]].tolist()
+        out[p] = (fwd, [[t, q] for q, t in fwd])
     return out
 
 

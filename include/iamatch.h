@@ -249,6 +249,23 @@ int iam_ransac_tables(iam_ctx* ctx, int model, const double* K, double threshold
                       uint32_t seed, int min_pairs, int compact, uint8_t* out_mask, double* out_model,
                       int32_t* out_inliers);
 
+/* ---- feature detection: replaces cv2.ORB_create(n).detectAndCompute ---- */
+
+/* ORB detect + describe with OpenCV's defaults (8 levels, scale 1.2, edge threshold 31, patch 31, FAST threshold
+ * 20, Harris score, WTA_K 2): what `detector = cv2.ORB_create(max_features)` / `detector.detectAndCompute(scaled,
+ * None)` return in Image.detect_features (image.py:243-245, :324).  gray: HOST uint8 [height][width], row-major (a
+ * colour image must be converted first, as cv2 does internally).  Outputs (HOST): out_kp [max_out][6] float =
+ * pt.x, pt.y, size, angle (degrees), response, octave; out_des [max_out][32] uint8; *out_n = number of key points
+ * (listed level by level, raster order inside a level; cv2's order inside a level is unspecified).  max_out should
+ * leave room for ties (retainBest keeps every key point that ties with the last one): nfeatures + 256 is ample;
+ * IAM_E_UNSUPPORTED if it does not fit. */
+int iam_orb_detect(iam_ctx* ctx, const uint8_t* gray, int width, int height, int nfeatures, int max_out,
+                   float* out_kp, uint8_t* out_des, int* out_n);
+
+/* Debug aid: the FAST-9/16 corner score of every pixel of a grey image (threshold 20, no non-maximum suppression),
+ * HOST in, HOST out [height][width]; what cv2.FastFeatureDetector reports as `response` at its key points. */
+int iam_debug_orb_fast(iam_ctx* ctx, const uint8_t* gray, int width, int height, uint8_t* out_score);
+
 /* ---- bundle adjustment: replaces Optimizer.fun (optimizer.py:174-279) -- */
 
 /* The reprojection residual of every observation in one launch, and its
