@@ -153,6 +153,7 @@ struct iam_ctx {
   Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac;
   // robust fits (iam_ransac_*): device block kept between calls, outputs of the table form
   iam::RansacScratch ransac_scratch;
+  iam::OrbScratch orb_scratch;
   Buffer ransac_mask, ransac_model, ransac_inl;
   int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
   // iam_match_images, float32 L2 descriptors: worker threads narrow them to bytes (host_narrow.h) into a pinned arena
@@ -1562,7 +1563,7 @@ int iam_orb_detect(iam_ctx* c, const uint8_t* gray, int width, int height, int n
   if (!gray || !out_kp || !out_des || !out_n || max_out < 0) return fail(IAM_E_ARG, "bad arguments");
   if (width <= 0 || height <= 0 || width > 65535 || height > 65535) return fail(IAM_E_ARG, "image size %d x %d out of range", width, height);
   std::string err;
-  rc = iam::orb_detect(gray, width, height, nfeatures, iam::orb_pattern(), max_out, out_kp, out_des, out_n, c->stream, &err);
+  rc = iam::orb_detect(gray, width, height, nfeatures, iam::orb_pattern(), max_out, out_kp, out_des, out_n, &c->orb_scratch, c->stream, &err);
   if (rc < 0) return fail(rc == -5 ? IAM_E_UNSUPPORTED : rc == -1 ? IAM_E_ARG : IAM_E_CUDA, "%s", err.c_str());
   c->timing.total_launches += rc;
   return IAM_OK;

@@ -203,12 +203,11 @@ __global__ void harris_kernel(const uint8_t* __restrict__ pyr, Params P, const i
   const int l = blockIdx.y;
   const Level L = P.lv[l];
   const int n = min(cand_count[l], L.cand_cap);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
   Cand c = cand[L.cand_off + i];
   if (c.resp < (float)fast_thr[l]) {
     cand[L.cand_off + i].resp = -INFINITY;   // dropped by the first retainBest
-    return;
+    continue;
   }
   const uint8_t* img = pyr + L.img_off;
   const int st = L.pitch;
@@ -229,6 +228,16 @@ __global__ void harris_kernel(const uint8_t* __restrict__ pyr, Params P, const i
   const float ab = __fadd_rn(fa, fb);
   const float r = __fsub_rn(__fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc)), __fmul_rn(__fmul_rn(0.04f, ab), ab));
   cand[L.cand_off + i].resp = __fmul_rn(r, s4);
+  }
+}
+
+__global__ void kp_base_kernel(Params P, const int* __restrict__ out_count, int* __restrict__ kp_base) {
+  int total = 0;
+  for (int l = 0; l < kLevels; ++l) {
+    kp_base[l] = total;
+    total += min(out_count[l], P.lv[l].cand_cap);
+  }
+  kp_base[kLevels] = total;
 }
 
 __device__ __forceinline__ uint32_t order_key(float f) {   // larger float -> larger key
@@ -329,13 +338,13 @@ struct KpOut {
 // one warp per key point: orientation, then the 32 descriptor bytes (lane = byte)
 __global__ void __launch_bounds__(256)
 describe_kernel(const uint8_t* __restrict__ pyr, Params P, const int* __restrict__ out_count, const int* __restrict__ kp_base,
-                const Cand* __restrict__ kps, KpOut* __restrict__ out_kp, uint8_t* __restrict__ out_des) {
+                const Cand* __restrict__ kps, KpOut* __restrict__ out_kp, uint8_t* __restrict__ out_des, int max_out) {
   const int l = blockIdx.y;
   const Level L = P.lv[l];
   const int n = min(out_count[l], L.cand_cap);
-  const int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (i >= n) return;
+  for (int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x / 32)) {
+  if (kp_base[l] + i >= max_out) return;
   const Cand c = kps[L.cand_off + i];
   const int st = L.pitch;
   const uint8_t* center = pyr + L.img_off + (size_t)(c.y + kBorder) * st + c.x + kBorder;
@@ -386,6 +395,7 @@ describe_kernel(const uint8_t* __restrict__ pyr, Params P, const int* __restrict
     k.octave = l;
     out_kp[o] = k;
   }
+  }
 }
 
 // ---- the blur ORB applies before the descriptors: separable float 7-tap Gaussian ------------------------------
@@ -422,7 +432,7 @@ const int8_t kPattern[1024] = {
 const int8_t* orb_pattern() { return kPattern; }
 
 int orb_detect(const uint8_t* gray, int w, int h, int nfeatures, const int8_t* pattern256x4, int max_out, float* out_kp6,
-               uint8_t* out_des, int* out_n, cudaStream_t stream, std::string* err) {
+               uint8_t* out_des, int* out_n, OrbScratch* scratch, cudaStream_t stream, std::string* err) {
   auto fail = [&](int code, const std::string& what) {
     if (err) *err = what;
     return code;
@@ -464,31 +474,36 @@ int orb_detect(const uint8_t* gray, int w, int h, int nfeatures, const int8_t* p
     cand_total += L.cand_cap;
   }
   const size_t pyr_bytes = off;
-  size_t tmp_floats = (size_t)P.lv[0].pitch * (P.lv[0].h + 2 * kBorder);
-  uint8_t* d_pyr = nullptr;
-  uint8_t* d_src = nullptr;
-  float* d_tmp = nullptr;
-  Cand *d_cand = nullptr, *d_keep = nullptr;
-  int* d_ints = nullptr;   // [cand_count 8][hist 8*256][fast_thr 8][out_count 8][kp_base 8]
-  KpOut* d_kp = nullptr;
-  uint8_t* d_des = nullptr;
+  const size_t tmp_floats = (size_t)P.lv[0].pitch * (P.lv[0].h + 2 * kBorder);
+  // one device block kept between calls (grow only): [pyramid][source][float rows][candidates][survivors][ints][kp][des]
+  auto up2 = [](size_t x) { return (x + 255) / 256 * 256; };
+  const int n_ints = 8 + 8 * 256 + 8 + 8 + 16;
+  const size_t o_src = up2(pyr_bytes), o_tmp = o_src + up2((size_t)w * h), o_cand = o_tmp + up2(tmp_floats * sizeof(float));
+  const size_t o_keep = o_cand + up2((size_t)cand_total * sizeof(Cand)), o_ints = o_keep + up2((size_t)cand_total * sizeof(Cand));
+  const size_t o_kp = o_ints + up2(n_ints * sizeof(int)), o_des = o_kp + up2((size_t)std::max(max_out, 1) * sizeof(KpOut));
+  const size_t total_bytes = o_des + up2((size_t)std::max(max_out, 1) * 32);
   cudaError_t e = cudaSuccess;
-  auto cleanup = [&]() {
-    cudaFree(d_pyr); cudaFree(d_src); cudaFree(d_tmp); cudaFree(d_cand); cudaFree(d_keep); cudaFree(d_ints); cudaFree(d_kp);
-    cudaFree(d_des);
-  };
 #define OC(call)                                                          \
-  if ((e = (call)) != cudaSuccess) {                                      \
-    cleanup();                                                            \
-    return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e));   \
+  if ((e = (call)) != cudaSuccess) return fail(-2, std::string(#call) + ": " + cudaGetErrorString(e));
+  OrbScratch local;
+  OrbScratch* sc = scratch ? scratch : &local;
+  if (sc->cap < total_bytes) {
+    OC(cudaStreamSynchronize(stream));
+    if (sc->buf) cudaFree(sc->buf);
+    sc->buf = nullptr;
+    sc->cap = 0;
+    OC(cudaMalloc(&sc->buf, total_bytes));
+    sc->cap = total_bytes;
   }
-  const int n_ints = 8 + 8 * 256 + 8 + 8 + 8;
-  OC(cudaMalloc(&d_pyr, pyr_bytes));
-  OC(cudaMalloc(&d_src, (size_t)w * h));
-  OC(cudaMalloc(&d_tmp, tmp_floats * sizeof(float)));
-  OC(cudaMalloc(&d_cand, (size_t)cand_total * sizeof(Cand)));
-  OC(cudaMalloc(&d_keep, (size_t)cand_total * sizeof(Cand)));
-  OC(cudaMalloc(&d_ints, n_ints * sizeof(int)));
+  uint8_t* base_p = static_cast<uint8_t*>(sc->buf);
+  uint8_t* d_pyr = base_p;
+  uint8_t* d_src = base_p + o_src;
+  float* d_tmp = reinterpret_cast<float*>(base_p + o_tmp);
+  Cand* d_cand = reinterpret_cast<Cand*>(base_p + o_cand);
+  Cand* d_keep = reinterpret_cast<Cand*>(base_p + o_keep);
+  int* d_ints = reinterpret_cast<int*>(base_p + o_ints);   // [cand_count 8][hist 8*256][fast_thr 8][out_count 8][kp_base 9 ..]
+  KpOut* d_kp = reinterpret_cast<KpOut*>(base_p + o_kp);
+  uint8_t* d_des = base_p + o_des;
   OC(cudaMemsetAsync(d_ints, 0, n_ints * sizeof(int), stream));
   int* d_count = d_ints;
   int* d_hist = d_ints + 8;
@@ -519,10 +534,11 @@ int orb_detect(const uint8_t* gray, int w, int h, int nfeatures, const int8_t* p
   OC(cudaMemcpyAsync(d_src, gray, (size_t)w * h, cudaMemcpyHostToDevice, stream));
   const dim3 blk(32, 8);
   auto grid = [&](int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); };
-  int launches = 0;
+  int launches = 0, max_cap = 1;
   for (int l = 0; l < kLevels; ++l) {
     const Level& L = P.lv[l];
     if (L.w < 1 || L.h < 1) continue;
+    max_cap = std::max(max_cap, L.cand_cap);
     uint8_t* img = d_pyr + L.img_off;
     if (l == 0)
       upload_kernel<<<grid(L.w, L.h), blk, 0, stream>>>(d_src, w, h, img, L.pitch);
@@ -536,45 +552,32 @@ int orb_detect(const uint8_t* gray, int w, int h, int nfeatures, const int8_t* p
                                                                         d_pyr + L.blur_off);
     launches += 6;
   }
+  // No host round trip between the stages: grids are sized by the capacities, kernels read the counts on the device
   fast_threshold_kernel<<<1, 32, 0, stream>>>(d_hist, d_count, P, d_thr);
+  const int harris_blocks = std::min((max_cap + 255) / 256, 4096);   // more FAST survivors than 1 M per level cannot pass the first cut
+  harris_kernel<<<dim3(harris_blocks, kLevels), 256, 0, stream>>>(d_pyr, P, d_count, d_thr, d_cand);
+  harris_select_kernel<<<kLevels, 1024, 0, stream>>>(P, d_count, d_cand, d_out_count, d_keep);
+  kp_base_kernel<<<1, 1, 0, stream>>>(P, d_out_count, d_kp_base);
+  const int desc_blocks = (std::min(max_cap, std::max(max_out, 1)) + 7) / 8;
+  describe_kernel<<<dim3(desc_blocks, kLevels), 256, 0, stream>>>(d_pyr, P, d_out_count, d_kp_base, d_keep, d_kp, d_des, max_out);
+  launches += 5;
+  int h_ints[8 + 8 + 9];
   int h_count[8];
   OC(cudaMemcpyAsync(h_count, d_count, sizeof h_count, cudaMemcpyDeviceToHost, stream));
+  OC(cudaMemcpyAsync(h_ints, d_out_count, (8 + 9) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  std::vector<KpOut> hk(std::max(max_out, 1));
+  std::vector<uint8_t> hd((size_t)std::max(max_out, 1) * 32);
+  if (max_out > 0) {
+    OC(cudaMemcpyAsync(hk.data(), d_kp, (size_t)max_out * sizeof(KpOut), cudaMemcpyDeviceToHost, stream));
+    OC(cudaMemcpyAsync(hd.data(), d_des, (size_t)max_out * 32, cudaMemcpyDeviceToHost, stream));
+  }
   OC(cudaStreamSynchronize(stream));
-  int max_cand = 1;
-  for (int l = 0; l < kLevels; ++l) {
-    if (h_count[l] > P.lv[l].cand_cap) {
-      cleanup();
-      return fail(-5, "more FAST corners than the candidate buffer holds");
-    }
-    max_cand = std::max(max_cand, h_count[l]);
-  }
-  harris_kernel<<<dim3((max_cand + 255) / 256, kLevels), 256, 0, stream>>>(d_pyr, P, d_count, d_thr, d_cand);
-  harris_select_kernel<<<kLevels, 1024, 0, stream>>>(P, d_count, d_cand, d_out_count, d_keep);
-  launches += 3;
-  int h_out[8];
-  OC(cudaMemcpyAsync(h_out, d_out_count, sizeof h_out, cudaMemcpyDeviceToHost, stream));
-  OC(cudaStreamSynchronize(stream));
-  int base[8], total = 0, max_out_l = 1;
-  for (int l = 0; l < kLevels; ++l) {
-    base[l] = total;
-    total += h_out[l];
-    max_out_l = std::max(max_out_l, h_out[l]);
-  }
-  if (total > max_out) {
-    cleanup();
-    return fail(-5, "more key points than the output buffers hold");
-  }
+#undef OC
+  for (int l = 0; l < kLevels; ++l)
+    if (h_count[l] > P.lv[l].cand_cap) return fail(-5, "more FAST corners than the candidate buffer holds");
+  const int total = h_ints[8 + 8];   // kp_base[8]
+  if (total > max_out) return fail(-5, "more key points than the output buffers hold");
   if (total > 0) {
-    OC(cudaMemcpyAsync(d_kp_base, base, sizeof base, cudaMemcpyHostToDevice, stream));
-    OC(cudaMalloc(&d_kp, (size_t)total * sizeof(KpOut)));
-    OC(cudaMalloc(&d_des, (size_t)total * 32));
-    describe_kernel<<<dim3((max_out_l + 7) / 8, kLevels), 256, 0, stream>>>(d_pyr, P, d_out_count, d_kp_base, d_keep, d_kp, d_des);
-    ++launches;
-    std::vector<KpOut> hk(total);
-    std::vector<uint8_t> hd((size_t)total * 32);
-    OC(cudaMemcpyAsync(hk.data(), d_kp, (size_t)total * sizeof(KpOut), cudaMemcpyDeviceToHost, stream));
-    OC(cudaMemcpyAsync(hd.data(), d_des, (size_t)total * 32, cudaMemcpyDeviceToHost, stream));
-    OC(cudaStreamSynchronize(stream));
     // deterministic order: level, then raster order of the level coordinates (the append order on the device is not)
     std::vector<int> order(total);
     for (int i = 0; i < total; ++i) order[i] = i;
@@ -590,10 +593,12 @@ int orb_detect(const uint8_t* gray, int w, int h, int nfeatures, const int8_t* p
       std::copy(hd.begin() + (size_t)order[i] * 32, hd.begin() + (size_t)order[i] * 32 + 32, out_des + (size_t)i * 32);
     }
   }
-#undef OC
-  cleanup();
   *out_n = total;
   return launches;
+}
+
+OrbScratch::~OrbScratch() {
+  if (buf) cudaFree(buf);
 }
 
 // Debug aid: the FAST-9/16 score map of the grey image itself (pyramid level 0), no suppression.
