@@ -254,14 +254,15 @@ class Engine:
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
         self._check(self._lib.iam_upload_keypoints(self._h, image_id, _ptr(xy), xy.shape[0]), "iam_upload_keypoints")
 
-    def gms_filter(self, xy1, xy2, matches, size, with_rotation=True, with_scale=False, threshold_factor=5.0):
+    def gms_filter(self, xy1, xy2, matches, size, with_rotation=True, with_scale=False, threshold_factor=5.0,
+                   archive_wrap=False):
         """Inlier mask of cv2.xfeatures2d.matchGMS over `matches` ([[queryIdx, trainIdx], ...]); matcher.py:285."""
         xy1 = np.ascontiguousarray(xy1, np.float32).reshape(-1, 2)
         xy2 = np.ascontiguousarray(xy2, np.float32).reshape(-1, 2)
         m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
         mask = np.zeros((m.shape[0],), np.uint8)
         self._check(self._lib.iam_gms_filter(self._h, _ptr(xy1), xy1.shape[0], _ptr(xy2), xy2.shape[0], _ptr(m), m.shape[0],
-                                             int(size[0]), int(size[1]), int(with_rotation), int(with_scale),
+                                             int(size[0]), int(size[1]), int(with_rotation), int(bool(with_scale)) | (2 if archive_wrap else 0),
                                              float(threshold_factor), _ptr(mask)), "iam_gms_filter")
         return mask.astype(bool)
 
@@ -301,7 +302,7 @@ class Engine:
         p.min_pairs = int(min_pairs)
         p.cross_check = int(bool(cross_check))
         p.dedupe = int(bool(dedupe))
-        p.gms = int(bool(gms))                       # matcher.py:285 defaults: withRotation=True, withScale=False, 5.0
+        p.gms = int(gms) if isinstance(gms, int) and not isinstance(gms, bool) else int(bool(gms))   # 2: archive-Python last-half-cell rule
         p.gms_rotation = int(bool(gms_rotation))
         p.gms_scale = int(bool(gms_scale))
         p.gms_threshold = float(gms_threshold)

@@ -199,8 +199,11 @@ gms_kernel(const RedJob* __restrict__ jobs, const ImgDev* __restrict__ imgs, Gms
       }
       __syncthreads();
       for (int m = tid; m < n; m += blockDim.x) {  // mark inliers (:203-207), one bit per rotation
-        const int l = lc[m];
-        if (l < 0) continue;
+        int l = lc[m];
+        if (l < 0) {
+          if (!prm.archive_wrap) continue;   // OpenCV's C++ skips the match for this grid
+          l = kLeftCells - 1;                // the archive Python reads mCellPairs[-1]: the last cell
+        }
         const int r = s.rcell[m];
         uint32_t bits = s.bits[m];
         for (int rot = 0; rot < n_rot; ++rot)

@@ -15,7 +15,8 @@ struct GmsParams {
   int with_rotation;        // matcher.py:285: True
   int with_scale;           // matcher.py:285: False
   int gate_min_pairs;       // > 0: fewer survivors than this empty the table (used when no filter_duplicates gate follows)
-  int pad;
+  int archive_wrap;         // != 0: a key point in the last half cell is looked up in cell 399 when inliers are marked (the
+                            // wrap-around of the reference's archive Python, gms_matcher.py:205); 0: skipped (OpenCV's C++)
 };
 
 // In place on the per-job tables (order preserved).  Needs ImgDev::kp_xy of both images of every non-empty job.

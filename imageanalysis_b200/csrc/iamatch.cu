@@ -464,7 +464,7 @@ __global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jo
 
 extern "C" {
 
-int iam_abi_version(void) { return 4; }
+int iam_abi_version(void) { return 5; }
 const char* iam_last_error(void) { return g_err.c_str(); }
 
 int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
@@ -862,7 +862,8 @@ int iam_gms_filter(iam_ctx* c, const float* xy1, int n1, const float* xy2, int n
   gp.width = width_px;
   gp.height = height_px;
   gp.with_rotation = with_rotation;
-  gp.with_scale = with_scale;
+  gp.with_scale = with_scale & 1;
+  gp.archive_wrap = (with_scale & 2) != 0;
   gp.gate_min_pairs = 0;
   cudaError_t e = iam::launch_gms(reinterpret_cast<const iam::RedJob*>(d + o_job), 1, reinterpret_cast<const iam::ImgDev*>(d + o_img), gp,
                                   n_matches, reinterpret_cast<int*>(d + o_tab), reinterpret_cast<int*>(d + o_cnt), c->stream);
@@ -1346,11 +1347,11 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     if (prof) CU(cudaEventRecord(pev[0], c->stream));
     if ((rc = launch_knn(c, engine, kind, k, u0, u1 - u0)) != IAM_OK) return rc;
     if (prof) CU(cudaEventRecord(pev[1], c->stream));
-    cudaError_t e = iam::launch_finish_dist(c->norm, c->knn_dist.as<float>(), c->knn_idx.as<int>(), pl.chunk_rows[ch] * k, c->stream);
-    if (e != cudaSuccess) return fail(IAM_E_CUDA, "finish launch: %s", cudaGetErrorString(e));
+    // the finishing pass over the lists (sqrt, padding rows: launch_finish_dist in iam_knn_pairs) is folded into the reduction
     const iam::RedJob* jobs = c->jobs.as<iam::RedJob>() + size_t(p0) * 2;
-    e = iam::launch_reduce(jobs, (p1 - p0) * 2, c->knn_idx.as<int>(), c->knn_dist.as<float>(), k, rp, c->cand_metric.as<double>(),
-                           c->cand_qt.as<int2>(), cand_stride, c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
+    cudaError_t e = iam::launch_reduce(jobs, (p1 - p0) * 2, c->knn_idx.as<int>(), c->knn_dist.as<float>(), k, rp, c->cand_metric.as<double>(),
+                           c->cand_qt.as<int2>(), cand_stride, c->job_table.as<int>(), c->job_count.as<int>(),
+                           c->norm == IAM_NORM_L2 ? 1 : 2, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "reduce launch: %s", cudaGetErrorString(e));
     if (prm->gms) {  // matcher.py:285, between the metric reduction and filter_duplicates
       iam::GmsParams gp{};
@@ -1359,6 +1360,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
       gp.height = prm->height_px;
       gp.with_rotation = prm->gms_rotation;
       gp.with_scale = prm->gms_scale;
+      gp.archive_wrap = prm->gms == 2;
       gp.gate_min_pairs = prm->dedupe ? 0 : prm->min_pairs;  // the gate of matcher.py:296-298 follows filter_duplicates
       e = iam::launch_gms(jobs, (p1 - p0) * 2, c->d_imgs.as<iam::ImgDev>(), gp, prm->cap, c->job_table.as<int>(), c->job_count.as<int>(), c->stream);
       if (e != cudaSuccess) return fail(IAM_E_CUDA, "GMS launch: %s", cudaGetErrorString(e));
@@ -1373,7 +1375,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     e = iam::launch_crosscheck(jobs, p1 - p0, c->job_table.as<int>(), c->job_count.as<int>(), prm->cap, prm->cross_check, pl.max_n,
                                c->out_table.as<int>() + size_t(p0) * cap * 2, c->out_count.as<int>() + p0, c->stream);
     if (e != cudaSuccess) return fail(IAM_E_CUDA, "cross-check launch: %s", cudaGetErrorString(e));
-    c->timing.total_launches += 3;
+    c->timing.total_launches += 2;
     if (prof) CU(cudaEventRecord(pev[2], c->stream));
     if (feed) {
       const size_t w = feed->waves_done.size();

@@ -659,7 +659,10 @@ struct RansacArgs {
 // One WARP per image pair: its 32 lanes solve 32 minimal samples (the solvers are long fp64 routines: with one
 // lane per sample no lane idles, where a wider CTA would leave every warp but one waiting), then the same warp scores
 // every candidate model, lanes striding the points.  Several pairs share an SM (registers: ~250 per thread).
-__global__ void __launch_bounds__(kThreads)
+#ifndef IAM_RANSAC_MIN_BLOCKS
+#define IAM_RANSAC_MIN_BLOCKS 1   // A/B aid: e.g. 16 caps the kernel at 128 registers (more pairs per SM, more spills)
+#endif
+__global__ void __launch_bounds__(kThreads, IAM_RANSAC_MIN_BLOCKS)
 ransac_kernel(const RansacArgs A) {
   extern __shared__ float s_pts[];
   __shared__ float s_cand[kRound * kMaxCand * 9];

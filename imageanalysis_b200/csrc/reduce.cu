@@ -21,7 +21,7 @@ constexpr int kRankTile = 1024;
 __global__ void __launch_bounds__(kRedThreads)
 metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ knn_idx, const float* __restrict__ knn_dist,
               int k, ReduceParams prm, double* __restrict__ cand_metric, int2* __restrict__ cand_qt, int cand_stride,
-              int* __restrict__ job_table, int* __restrict__ job_count, int sort_cap) {
+              int* __restrict__ job_table, int* __restrict__ job_count, int sort_cap, int raw_d2) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_count;
   __shared__ double s_m[kRankTile];
@@ -40,8 +40,19 @@ metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ kn
     const size_t o = (static_cast<size_t>(jb.out_base) + r) * k;
     const int i0 = knn_idx[o], i1 = knn_idx[o + 1];
     if (i0 < 0 || i1 < 0) continue;
-    const double d0 = static_cast<double>(knn_dist[o]);
-    const double d1 = static_cast<double>(knn_dist[o + 1]);
+    float f0 = knn_dist[o], f1 = knn_dist[o + 1];
+    if (raw_d2 != 0) {
+      // the lists still hold what the kNN kernel wrote (squared L2 distance / Hamming distance): the finishing pass
+      // (padding rows sit at >= 2^24 / >= 257; L2: correctly rounded float sqrt, as cv2 reports it) is folded in here
+      const float pad_thr = raw_d2 == 1 ? 16777216.0f : 257.0f;
+      if (f0 >= pad_thr || f1 >= pad_thr) continue;
+      if (raw_d2 == 1) {
+        f0 = sqrtf(f0);
+        f1 = sqrtf(f1);
+      }
+    }
+    const double d0 = static_cast<double>(f0);
+    const double d1 = static_cast<double>(f1);
     bool keep;
     double metric;
     if (prm.mode == 0) {  // plain Lowe gate, matcher.py:227
@@ -85,6 +96,8 @@ metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ kn
       }
     }
     __syncthreads();
+    // a warp's 32 consecutive elements exchange among themselves while the stride is below 32: runs of such steps
+    // need only warp-level synchronisation (34 of the 66 steps at 2048 elements)
     for (int k2 = 2; k2 <= npow2; k2 <<= 1) {
       for (int j = k2 >> 1; j > 0; j >>= 1) {
         for (int e = threadIdx.x; e < npow2; e += blockDim.x) {
@@ -102,7 +115,10 @@ metric_reduce_kernel(const RedJob* __restrict__ jobs, const int* __restrict__ kn
             }
           }
         }
-        __syncthreads();
+        // block-wide barrier when this step or the next one exchanges across warps; otherwise the warp's own
+        const int next_j = j > 1 ? (j >> 1) : k2;   // first stride of the next merge size: (2 k2) / 2
+        if (j >= 32 || next_j >= 32 || (k2 == npow2 && j == 1)) __syncthreads();
+        else __syncwarp();
       }
     }
     const int n_out = min(c, prm.cap);  // matcher.py:265-269
@@ -326,7 +342,7 @@ cudaError_t launch_pack_tables(const int* table, const int* count, const int* of
 
 cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, const float* knn_dist, int k,
                           const ReduceParams& prm, double* cand_metric, int2* cand_qt, int cand_stride,
-                          int* job_table, int* job_count, cudaStream_t stream) {
+                          int* job_table, int* job_count, int raw_d2, cudaStream_t stream) {
   if (n_jobs <= 0) return cudaSuccess;
   // shared-memory sort capacity: next power of two of the largest possible candidate count, at most 8192
   int sort_cap = 1;
@@ -337,7 +353,7 @@ cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, co
     if (e != cudaSuccess) return e;
   }
   metric_reduce_kernel<<<n_jobs, kRedThreads, smem, stream>>>(jobs, knn_idx, knn_dist, k, prm, cand_metric, cand_qt,
-                                                           cand_stride, job_table, job_count, sort_cap);
+                                                           cand_stride, job_table, job_count, sort_cap, raw_d2);
   return cudaGetLastError();
 }
 

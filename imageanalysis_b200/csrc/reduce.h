@@ -23,9 +23,11 @@ struct ReduceParams {
   int pad;
 };
 
+// raw_d2: 0 = knn_dist holds finished distances; 1 = squared L2 distances, 2 = Hamming distances straight from the
+// kNN kernel (the finishing pass -- sqrt, padding rows -- is folded into the reduction: no extra sweep over the lists)
 cudaError_t launch_reduce(const RedJob* jobs, int n_jobs, const int* knn_idx, const float* knn_dist, int k,
                           const ReduceParams& prm, double* cand_metric, int2* cand_qt, int cand_stride,
-                          int* job_table, int* job_count, cudaStream_t stream);
+                          int* job_table, int* job_count, int raw_d2, cudaStream_t stream);
 
 // filter_duplicates (matcher.py:157-182) + the min_pairs gate that follows it (:296-298),
 // in place on the per-job tables.  `imgs` supplies the per-image keypoint key arrays.

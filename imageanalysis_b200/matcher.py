@@ -61,6 +61,10 @@ detect_scale = 0.40
 # The reference always runs the GMS grid filter inside basic_pair_matches (matcher.py:285).  False skips the stage
 # (what an identity matchGMS would give); it exists for comparisons against pre-GMS fixtures, not for production.
 gms_enabled = True
+# Key points in the last half cell of the image: False = OpenCV's C++ matchGMS skips them in the half-cell-shifted
+# grids (what cv2.xfeatures2d.matchGMS at matcher.py:285 executes); True = the wrap-around of the reference's archive
+# Python restatement (scripts/lib/archive/gms_matcher.py:205), for bit-for-bit agreement with that module.
+gms_archive_rule = False
 the_matcher = None
 max_distance = None
 min_pairs = 25
@@ -289,7 +293,8 @@ def _gms(i1, i2, idx_pairs, dist_of):
         return idx_pairs
     eng = the_matcher.engine(128 if _norm == _capi.NORM_L2 else 32)
     mask = eng.gms_filter(np.float32([k.pt for k in i1.kp_list]), np.float32([k.pt for k in i2.kp_list]),
-                          np.int32(idx_pairs), (w, h), with_rotation=True, with_scale=False, threshold_factor=5.0)
+                          np.int32(idx_pairs), (w, h), with_rotation=True, with_scale=False, threshold_factor=5.0,
+                          archive_wrap=gms_archive_rule)
     return [p for p, keep in zip(idx_pairs, mask) if keep]
 
 
@@ -789,7 +794,8 @@ def _batched_traditional(image_list, todo):
             eng.upload_keypoints(i, np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2))
     prm = _capi.Engine.make_params(match_ratio=matcher_node.getFloat('match_ratio'), max_distance=float(max_distance),
                                    reduce_mode=_capi.REDUCE_REF_METRIC, cap=2000, min_pairs=int(min_pairs),
-                                   cross_check=True, dedupe=True, gms=gms_enabled, gms_rotation=True, gms_scale=False,
+                                   cross_check=True, dedupe=True, gms=(2 if gms_archive_rule else 1) if gms_enabled else 0,
+                                   gms_rotation=True, gms_scale=False,
                                    gms_threshold=5.0, size=(w, h))
     # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching.  The call uploads an image right
     # before the first pair that needs it: handing it the pairs sorted by their LATER image lets matching start after

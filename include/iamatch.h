@@ -143,7 +143,8 @@ int iam_upload_keypoints(iam_ctx* ctx, int image_id, const float* xy, int n);
 /* Stand-alone GMS grid filter on one HOST match list: what
  * cv2.xfeatures2d.matchGMS((w,h), (w,h), kp1, kp2, matches, withRotation, withScale, thresholdFactor)
  * returns at matcher.py:285, as a mask over `matches` ([n][2] = queryIdx, trainIdx; at most 4096).
- * Duplicate (queryIdx, trainIdx) rows are not supported. */
+ * Duplicate (queryIdx, trainIdx) rows are not supported.  with_scale: bit 0 = withScale; bit 1 selects the
+ * last-half-cell rule of the archive Python restatement (see iam_match_params.gms = 2). */
 int iam_gms_filter(iam_ctx* ctx, const float* xy1, int n1, const float* xy2, int n2,
                    const int32_t* matches, int n_matches, int width_px, int height_px,
                    int with_rotation, int with_scale, double threshold_factor, uint8_t* out_mask);
@@ -159,9 +160,12 @@ typedef struct iam_match_params {
   int    cross_check;   /* !=0: filter_cross_check (matcher.py:187-200)            */
   int    dedupe;        /* !=0: filter_duplicates (matcher.py:157-182, :294) + its min_pairs gate (:296-298);
                            uses the keys given to iam_upload_keypoint_keys (identity keys if none)  */
-  int    gms;           /* !=0: GMS grid filter between the metric reduction and filter_duplicates, as
+  int    gms;           /* 1 or 2: GMS grid filter between the metric reduction and filter_duplicates, as
                            cv2.xfeatures2d.matchGMS(size, size, kp1, kp2, matches, withRotation, withScale,
-                           thresholdFactor) at matcher.py:285; needs iam_upload_keypoints for both images */
+                           thresholdFactor) at matcher.py:285; needs iam_upload_keypoints for both images.
+                           1 = OpenCV's C++ rule for key points in the last half cell of the image (the match is
+                           skipped for the half-cell-shifted grids); 2 = the rule of the reference's archive Python
+                           restatement (scripts/lib/archive/gms_matcher.py:205: wrap-around to the last cell) */
   int    gms_rotation;  /* withRotation (matcher.py:285: True)                     */
   int    gms_scale;     /* withScale    (matcher.py:285: False)                    */
   double gms_threshold; /* thresholdFactor (matcher.py:285: 5.0)                   */

@@ -33,15 +33,31 @@ def _features():
     return _cache["f"]
 
 
+def _strip(pt):
+    """Key point in the last half cell of the 20 x 20 GMS grid (no cell in the half-cell-shifted grids)?"""
+    return pt[0] >= 0.975 * gen.W or pt[1] >= 0.975 * gen.H
+
+
 def test_config0_oracle_equals_reference_driver_on_sample_pairs():
+    """The reference driver ran with its archive Python GMS, which wraps a key point of the last half cell around to
+    cell 399 (gms_matcher.py:205): with archive_wrap=True the oracle reproduces the recorded match lists exactly --
+    including pair (5, 8), where that wrap-around admits one match that OpenCV's C++ rule (the oracle's default, the
+    kernel's behaviour) drops."""
     g, feats = _features()
     assert int(g["n"]) == 16 and len(feats) == 16 and min(len(p) for p, _ in feats) > 2500
-    for i, j in ((0, 1), (7, 10), (11, 15)):
+    for i, j in ((0, 1), (5, 8), (11, 15)):
         (p1, d1), (p2, d2) = feats[i], feats[j]
-        f, r = oracle.bidirectional(d1.astype(np.uint8), d2.astype(np.uint8), oracle.NORM_L2, 0.75, 270.0, threads=4,
-                                    pts_q=p1, pts_t=p2, size=(gen.W, gen.H), dedupe=True)
-        assert f == g["match_frame%02d_frame%02d" % (i, j)].tolist(), (i, j)
+        kw = dict(threads=4, pts_q=p1, pts_t=p2, size=(gen.W, gen.H), dedupe=True)
+        f, r = oracle.bidirectional(d1.astype(np.uint8), d2.astype(np.uint8), oracle.NORM_L2, 0.75, 270.0,
+                                    gms_kw=dict(archive_wrap=True), **kw)
+        want = g["match_frame%02d_frame%02d" % (i, j)].tolist()
+        assert f == want, (i, j)
         assert r == g["match_frame%02d_frame%02d" % (j, i)].tolist(), (j, i)
+        if (i, j) == (5, 8):
+            fc, _ = oracle.bidirectional(d1.astype(np.uint8), d2.astype(np.uint8), oracle.NORM_L2, 0.75, 270.0, **kw)
+            gone = [m for m in want if m not in fc]
+            assert fc == [m for m in want if m not in gone] and len(gone) == 1
+            assert _strip(p1[gone[0][0]]) or _strip(p2[gone[0][1]])
 
 
 @pytest.mark.gpu
@@ -67,12 +83,34 @@ def test_config0_find_matches_equals_reference_driver(tmp_path):
     proj = types.SimpleNamespace(image_list=imgs, analysis_dir=str(tmp_path))
     K = np.array([[1388.0, 0, 960.0], [0, 1388.0, 540.0], [0, 0, 1]])
     matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
-    checked = matches = 0
+    checked = matches = dropped = 0
+    pts = {im.name: f[0] for im, f in zip(imgs, feats)}
+    for im in imgs:
+        want = {k[len("match_%s_" % im.name):]: g[k].tolist() for k in g.files if k.startswith("match_%s_" % im.name)}
+        assert set(im.match_list) == set(want), im.name
+        for other, ref in want.items():
+            got = im.match_list[other]
+            if got != ref:
+                # the one documented deviation: the reference ran its ARCHIVE GMS, which admits key points of the
+                # last half cell through a wrap-around; the kernel follows OpenCV's C++ rule and drops them there
+                gone = [m for m in ref if m not in got]
+                assert got == [m for m in ref if m not in gone], (im.name, other)
+                assert all(_strip(pts[im.name][q]) or _strip(pts[other][t]) for q, t in gone), (im.name, other, gone)
+                dropped += len(gone)
+            matches += len(got)
+        if all(im.match_list[o] == want[o] for o in want):
+            assert pickle.dumps(im.match_list) == pickle.dumps(want)      # the .match file of this image
+        checked += len(want)
+    assert dropped <= 8          # (5, 8) and its mirror on this project: 1 match each
+    # with the archive rule selected the device pipeline reproduces the reference driver bit for bit
+    matcher.gms_archive_rule = True
+    for im in imgs:
+        im.match_list = {}
+    matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
+    matcher.gms_archive_rule = False
     for im in imgs:
         want = {k[len("match_%s_" % im.name):]: g[k].tolist() for k in g.files if k.startswith("match_%s_" % im.name)}
         assert im.match_list == want, im.name
         assert pickle.dumps(im.match_list) == pickle.dumps(want)          # the .match file of this image
-        checked += len(want)
-        matches += sum(len(v) for v in want.values())
     assert checked == 108 and matches > 50000
     matcher.gms_enabled = False

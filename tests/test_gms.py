@@ -86,6 +86,8 @@ def test_gpu_gms_equals_reference_module():
     mask = eng.gms_filter(pts1, pts2, matches, size)
     assert (mask == oracle.gms_mask(pts1, pts2, size, size, matches, archive_wrap=False)).all()
     assert (g["edge_strip_mask"] | ~mask).all() and (mask != g["edge_strip_mask"]).sum() > 0   # a strict subset of the archive result
+    # ... and reproduces the archive module bit for bit when its rule is selected
+    assert (eng.gms_filter(pts1, pts2, matches, size, archive_wrap=True) == g["edge_strip_mask"]).all()
     eng.close()
 
 
