@@ -30,7 +30,7 @@ EXPORTS = (
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_orb_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -143,6 +143,7 @@ def load_library(path: Optional[str] = None):
                                      C.c_uint32, vp, vp, vp]
     lib.iam_ransac_tables.argtypes = [vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_orb_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    lib.iam_sift_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
     lib.iam_debug_orb_fast.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
     lib.iam_debug_minimal_solver.argtypes = [C.c_int, vp, vp, vp, vp, vp]
@@ -472,6 +473,21 @@ class Engine:
         self._check(self._lib.iam_orb_detect(self._h, _ptr(g), g.shape[1], g.shape[0], int(nfeatures), cap, _ptr(kp), _ptr(des),
                                              C.byref(n)), "iam_orb_detect")
         return kp[:n.value].copy(), des[:n.value].copy()
+
+    def sift_detect(self, gray: np.ndarray, max_out: int = 0):
+        """cv2.SIFT_create().detectAndCompute(gray, None) on the GPU (iam_sift_detect).
+        Returns (kp [n, 5] float32 = x, y, size, angle, response; octave [n] int32; des [n, 128] uint8)."""
+        g = np.ascontiguousarray(gray, np.uint8)
+        if g.ndim != 2:
+            raise IamError("sift_detect wants a 2-D uint8 image")
+        cap = int(max_out) if max_out > 0 else max(65536, g.size // 8)
+        kp = np.empty((cap, 5), np.float32)
+        octv = np.empty((cap,), np.int32)
+        des = np.empty((cap, 128), np.uint8)
+        n = C.c_int(0)
+        self._check(self._lib.iam_sift_detect(self._h, _ptr(g), g.shape[1], g.shape[0], cap, _ptr(kp), _ptr(octv), _ptr(des),
+                                              C.byref(n)), "iam_sift_detect")
+        return kp[:n.value].copy(), octv[:n.value].copy(), des[:n.value].copy()
 
     def debug_orb_fast(self, gray: np.ndarray) -> np.ndarray:
         g = np.ascontiguousarray(gray, np.uint8)

@@ -25,6 +25,7 @@
 #include "knn.h"
 #include "layout.h"
 #include "orb.h"
+#include "sift.h"
 #include "ransac.h"
 #include "reduce.h"
 
@@ -154,6 +155,7 @@ struct iam_ctx {
   // robust fits (iam_ransac_*): device block kept between calls, outputs of the table form
   iam::RansacScratch ransac_scratch;
   iam::OrbScratch orb_scratch;
+  iam::SiftScratch sift_scratch;
   Buffer ransac_mask, ransac_model, ransac_inl;
   int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
   // iam_match_images, float32 L2 descriptors: worker threads narrow them to bytes (host_narrow.h) into a pinned arena
@@ -1567,6 +1569,21 @@ int iam_orb_detect(iam_ctx* c, const uint8_t* gray, int width, int height, int n
   std::string err;
   rc = iam::orb_detect(gray, width, height, nfeatures, iam::orb_pattern(), max_out, out_kp, out_des, out_n, &c->orb_scratch, c->stream, &err);
   if (rc < 0) return fail(rc == -5 ? IAM_E_UNSUPPORTED : rc == -1 ? IAM_E_ARG : IAM_E_CUDA, "%s", err.c_str());
+  c->timing.total_launches += rc;
+  return IAM_OK;
+}
+
+// ---- SIFT detect + describe (image.py:236-237, :324) ------------------------------------------------------------
+
+int iam_sift_detect(iam_ctx* c, const uint8_t* gray, int width, int height, int max_out, float* out_kp, int32_t* out_octave,
+                    uint8_t* out_des, int* out_n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (!gray || !out_kp || !out_octave || !out_des || !out_n || max_out < 0) return fail(IAM_E_ARG, "bad arguments");
+  if (width < 2 || height < 2 || width > 16384 || height > 16384) return fail(IAM_E_ARG, "image size %d x %d out of range", width, height);
+  std::string err;
+  rc = iam::sift_detect(gray, width, height, max_out, out_kp, out_octave, out_des, out_n, &c->sift_scratch, c->stream, &err);
+  if (rc < 0) return fail(rc == -5 ? IAM_E_UNSUPPORTED : rc == -1 ? IAM_E_ARG : rc == -3 ? IAM_E_NOMEM : IAM_E_CUDA, "%s", err.c_str());
   c->timing.total_launches += rc;
   return IAM_OK;
 }

@@ -1,8 +1,8 @@
 // orb.cu — ORB detect + describe on the GPU, standing in for
 //   detector = cv2.ORB_create(max_features); detector.detectAndCompute(scaled, None)
 // (reference scripts/lib/image.py:243-245, :324).  OpenCV's defaults: 8 pyramid levels, scale 1.2, edge threshold 31,
-// patch 31, FAST threshold 20, Harris score, WTA_K 2.  Stage by stage the arithmetic is OpenCV's (restated in
-// oracle/orb.py, which is pinned against live cv2):
+// patch 31, FAST threshold 20, Harris score, WTA_K 2.  Stage by stage the arithmetic is OpenCV's (the CPU checker of
+// the test suite restates it and is pinned against live cv2):
 //   pyramid      each level from the previous one, bilinear with 8.8 fixed-point weights (INTER_LINEAR_EXACT), plus a
 //                32-pixel reflect-101 border so that every later stage reads without bounds tests
 //   FAST-9/16    score = largest threshold at which the pixel is still a corner; 3x3 non-maximum suppression

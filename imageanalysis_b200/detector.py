@@ -1,8 +1,13 @@
 """Drop-in for the feature detector the reference builds in Image.make_detector
 (scripts/lib/image.py:230-251) and calls in Image.detect_features (:324):
 
-    detector = cv2.ORB_create(max_features)
+    detector = cv2.SIFT_create()                  # the default, :236-237
+    detector = cv2.ORB_create(max_features)       # :243-245
     self.kp_list, self.des_list = detector.detectAndCompute(scaled, None)
+
+`SIFT_create()` returns an object with the same call that builds the Gaussian / difference-of-Gaussian pyramid, finds
+and refines the scale-space extrema, assigns orientations and computes the 128-byte descriptors on the GPU
+(csrc/sift.cu through iam_sift_detect).
 
 `ORB_create(n)` here returns an object with the same `detectAndCompute(image, mask)` call that runs FAST-9, the
 Harris ranking, the intensity-centroid orientation and the steered BRIEF descriptors of all 8 pyramid levels on the
@@ -39,6 +44,12 @@ def to_gray(image: np.ndarray) -> np.ndarray:
     raise _capi.IamError("image must be [H, W] or [H, W, 3|4] uint8")
 
 
+def sift_detect_and_compute(image: np.ndarray) -> dict:
+    """Arrays: pt [n, 2] f32, size, angle, response [n] f32, octave [n] i32 (cv2's packed field), des [n, 128] u8."""
+    kp, octv, des = _eng().sift_detect(to_gray(image))
+    return dict(pt=kp[:, 0:2].copy(), size=kp[:, 2].copy(), angle=kp[:, 3].copy(), response=kp[:, 4].copy(), octave=octv, des=des)
+
+
 def orb_detect_and_compute(image: np.ndarray, nfeatures: int = 500) -> dict:
     """Arrays: pt [n, 2] f32, size, angle, response [n] f32, octave [n] i32, des [n, 32] u8."""
     kp, des = _eng().orb_detect(to_gray(image), nfeatures)
@@ -58,6 +69,16 @@ class _KeyPoint:
         self.class_id = -1
 
 
+def _keypoints(r):
+    try:
+        import cv2
+        mk = lambda x, y, s, a, rs, o: cv2.KeyPoint(x=float(x), y=float(y), size=float(s), angle=float(a),  # noqa: E731
+                                                    response=float(rs), octave=int(o), class_id=-1)
+    except ImportError:
+        mk = _KeyPoint
+    return [mk(p[0], p[1], s, a, rs, o) for p, s, a, rs, o in zip(r["pt"], r["size"], r["angle"], r["response"], r["octave"])]
+
+
 class ORB:
     def __init__(self, nfeatures: int = 500):
         self.nfeatures = int(nfeatures)
@@ -66,14 +87,30 @@ class ORB:
         if mask is not None:
             raise _capi.IamError("masks are not supported (the reference passes None, image.py:324)")
         r = orb_detect_and_compute(image, self.nfeatures)
-        try:
-            import cv2
-            mk = lambda x, y, s, a, rs, o: cv2.KeyPoint(x=float(x), y=float(y), size=float(s), angle=float(a),  # noqa: E731
-                                                        response=float(rs), octave=int(o), class_id=-1)
-        except ImportError:
-            mk = _KeyPoint
-        kps = [mk(p[0], p[1], s, a, rs, o) for p, s, a, rs, o in zip(r["pt"], r["size"], r["angle"], r["response"], r["octave"])]
+        kps = _keypoints(r)
         return kps, (r["des"] if len(kps) else None)
+
+
+class SIFT:
+    """cv2.SIFT_create() with OpenCV's defaults; `uint8_descriptors=True` hands the descriptors out as the uint8 the
+    kernel produces (cv2 returns the same integers as float32; the matcher narrows them back, matcher.py:123)."""
+
+    def __init__(self, uint8_descriptors: bool = False):
+        self.uint8_descriptors = bool(uint8_descriptors)
+
+    def detectAndCompute(self, image, mask=None):
+        if mask is not None:
+            raise _capi.IamError("masks are not supported (the reference passes None, image.py:324)")
+        r = sift_detect_and_compute(image)
+        kps = _keypoints(r)
+        if not kps:
+            return kps, None
+        return kps, (r["des"] if self.uint8_descriptors else r["des"].astype(np.float32))
+
+
+def SIFT_create(uint8_descriptors: bool = False) -> SIFT:
+    """cv2.SIFT_create() (image.py:236-237): the reference passes no arguments."""
+    return SIFT(uint8_descriptors)
 
 
 def ORB_create(nfeatures: int = 500) -> ORB:

@@ -266,6 +266,18 @@ int iam_ransac_tables(iam_ctx* ctx, int model, const double* K, double threshold
 int iam_orb_detect(iam_ctx* ctx, const uint8_t* gray, int width, int height, int nfeatures, int max_out,
                    float* out_kp, uint8_t* out_des, int* out_n);
 
+/* SIFT detect + describe with OpenCV's defaults (3 layers per octave, sigma 1.6, contrast threshold 0.04, edge
+ * threshold 10, doubled base image): what `detector = cv2.SIFT_create()` / `detector.detectAndCompute(scaled, None)`
+ * return in Image.detect_features (image.py:236-237, :324) — the pipeline's default detector.  gray: HOST uint8
+ * [height][width].  Outputs (HOST): out_kp [max_out][5] float = pt.x, pt.y, size, angle (degrees), response;
+ * out_octave [max_out] = cv2's packed octave field; out_des [max_out][128] uint8 (cv2 hands the same integers out as
+ * float32; the matcher consumes uint8 directly); *out_n = number of key points, in cv2's order.  Float arithmetic:
+ * key points agree with cv2 to >= 99 % (position 1e-2 px), descriptors to +-1 per byte on those (tests/test_sift.py);
+ * the remainder are extrema on a decision boundary of the pyramid's float rounding.  IAM_E_UNSUPPORTED if more than
+ * max_out key points are found. */
+int iam_sift_detect(iam_ctx* ctx, const uint8_t* gray, int width, int height, int max_out, float* out_kp,
+                    int32_t* out_octave, uint8_t* out_des, int* out_n);
+
 /* Debug aid: the FAST-9/16 corner score of every pixel of a grey image (threshold 20, no non-maximum suppression),
  * HOST in, HOST out [height][width]; what cv2.FastFeatureDetector reports as `response` at its key points. */
 int iam_debug_orb_fast(iam_ctx* ctx, const uint8_t* gray, int width, int height, uint8_t* out_score);
