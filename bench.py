@@ -18,6 +18,8 @@ kNN (both directions) -> metric reduction -> cross-check -> per-pair match table
   roofline : algorithmic 2*N*M*128 FLOP per pair / the kNN kernel's own time, against the measured peak of the
           MMA kind the kernel issues
   parity_spot : after the timed region, three pairs of the run are compared with the CPU oracle
+  orb / sift_detect : short extra legs of the default N = 1 line -- BASELINE configs[2] (ORB, Hamming) and the SIFT
+          detect + describe stage in front of the matcher (one survey-sized frame, cv2 timed and compared beside it)
   cpu_baseline / --impl reference : the reference's CPU path (cv2.BFMatcher both directions + the Python
           reduction of matcher.py:253-269 + cross-check) on the box's host cores, on a bounded sample of the
           SAME frames and pair list
@@ -787,6 +789,11 @@ def main():
     if not args.no_orb and world == 1 and args.detector == "SIFT" and args.workload == "strip":
         orb = orb_leg(args, dev, local, stream, tm.mma_kind)
 
+    # ---- the detect stage in front of the matcher (image.py:236-237, :324): a short SIFT leg ----
+    sift = None
+    if not args.no_orb and world == 1 and args.detector == "SIFT" and args.workload == "strip":
+        sift = sift_leg(local)
+
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -809,7 +816,7 @@ def main():
             "higher_is_better": True, "scaling": "strong" if bates else "weak", "vs_baseline": None,
             "dtype": {0: "f16", 1: "e4m3", 2: "u8 (s32 accumulate)"}.get(tm.mma_kind, "u8"), "data": "synthetic",
             "config": workload_config(args, P_total, world, P, T), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "parity_spot": spot, "orb": orb, "gpu_launches": launches, "clocks": clocks}
+            "parity_spot": spot, "orb": orb, "sift_detect": sift, "gpu_launches": launches, "clocks": clocks}
     print(json.dumps(line))
 
 
@@ -892,6 +899,59 @@ def orb_leg(args, dev, local, stream, _kind):
             "kernel_ms_per_launch": tm.knn_ms, "mma_kind": rl["mma_kind"], "achieved_tops": rl["achieved"],
             "frac": rl["frac"], "frac_of_bf16_burst": rl["context_bf16"]["frac_of_bf16_burst"],
             "parity_spot": spot["status"], "mean_matches_per_pair": float(count.mean())}
+
+
+def survey_frame(h=1459, w=2189, seed=3):
+    """A synthetic grey frame at the reference's detection size (0.4 x a 5472 x 3648 photo): band-limited noise."""
+    rng = np.random.default_rng(seed)
+    f = rng.integers(0, 256, (h, w)).astype(np.float32)
+    k = np.exp(-0.5 * (np.arange(-6, 7) / 2.0) ** 2).astype(np.float32)
+    k /= k.sum()
+    for axis in (0, 1):
+        f = np.apply_along_axis(lambda r: np.convolve(r, k, "same"), axis, f)
+    return ((f - f.min()) / (f.max() - f.min()) * 255).astype(np.uint8)
+
+
+def sift_leg(local):
+    """The detector in front of the matcher: cv2.SIFT_create().detectAndCompute of one survey-sized frame through
+    detector.SIFT's C-ABI call (iam_sift_detect; host image in, host key points + descriptors out), with cv2 timed beside
+    it on the host cores and the key points / descriptors compared when cv2 is importable.  Reported as "sift_detect"."""
+    from imageanalysis_b200 import _capi
+    img = survey_frame()
+    eng = _capi.Engine(_capi.NORM_L2, 128, local)
+    for _ in range(3):
+        kp, octv, des = eng.sift_detect(img)
+    l0 = eng.timing().total_launches
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        kp, octv, des = eng.sift_detect(img)
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    launches = (eng.timing().total_launches - l0) // reps
+    eng.close()
+    out = {"config": "one 2189 x 1459 grey frame (the reference's 0.4 scale of a 5472 x 3648 photo), OpenCV's default SIFT "
+                     "parameters, host image in -> host key points + uint8 descriptors out",
+           "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "keypoints": int(len(kp)), "gpu_launches_per_frame": int(launches),
+           "timing": "host clock around the blocking C-ABI call, mean of %d" % reps}
+    try:
+        import cv2
+    except ImportError:
+        return out
+    det = cv2.SIFT_create()
+    t0 = time.perf_counter()
+    k2, d2 = det.detectAndCompute(img, None)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    from oracle import sift as osift     # the checker, outside every timed region
+    kr = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response] for k in k2], np.float32).reshape(-1, 5)
+    m = osift.match_keypoints(kr, kp)
+    ok = m >= 0
+    dd = np.abs(d2[ok].astype(np.int32) - des[m[ok]].astype(np.int32)).max(axis=1) if ok.any() else np.zeros(0, np.int32)
+    out["cpu_baseline"] = {"value": 1e3 / cpu_ms, "unit": "frames/s", "cores": cv2.getNumThreads(), "kind": "reference",
+                           "sample": "cv2.SIFT_create().detectAndCompute on the same frame, one call (%.0f ms)" % cpu_ms}
+    out["parity_vs_cv2"] = {"keypoints_cv2": int(len(kr)), "reproduced_within_0.02px_0.5deg": int(ok.sum()),
+                            "descriptors_identical": int((dd == 0).sum()), "descriptors_within_1": int((dd <= 1).sum()),
+                            "tolerance": "float pipeline: see tests/test_sift.py"}
+    return out
 
 
 if __name__ == "__main__":

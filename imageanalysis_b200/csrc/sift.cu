@@ -17,7 +17,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -33,6 +37,12 @@ constexpr int kMaxSteps = 5;      // SIFT_MAX_INTERP_STEPS
 constexpr int kOriBins = 36;
 constexpr int kMaxOctaves = 16;
 constexpr int kMaxKernel = 64;
+#ifndef IAM_SIFT_GENERIC_BLUR
+#define IAM_SIFT_GENERIC_BLUR 0
+#endif
+#ifndef IAM_SIFT_SEQ_DESC
+#define IAM_SIFT_SEQ_DESC 0
+#endif
 
 struct Octave {
   int w, h;
@@ -98,7 +108,9 @@ __global__ void blur_rows_kernel(const float* __restrict__ src, int w, int h, Bl
   }
   dst[(size_t)y * w + x] = s;
 }
-__global__ void blur_cols_kernel(const float* __restrict__ src, int w, int h, BlurKernel K, float* __restrict__ dst) {
+// column pass; with `prev` also writes the difference-of-Gaussian layer dog = dst - prev
+__global__ void blur_cols_kernel(const float* __restrict__ src, int w, int h, BlurKernel K, float* __restrict__ dst,
+                                 const float* __restrict__ prev, float* __restrict__ dog) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= w || y >= h) return;
   const int r = K.ksize >> 1;
@@ -108,15 +120,94 @@ __global__ void blur_cols_kernel(const float* __restrict__ src, int w, int h, Bl
   } else {
     for (int i = 0; i < K.ksize; ++i) s = __fadd_rn(s, __fmul_rn(K.k[i], src[(size_t)reflect101(y - r + i, h) * w + x]));
   }
-  dst[(size_t)y * w + x] = s;
+  const size_t at = (size_t)y * w + x;
+  dst[at] = s;
+  if (dog) dog[at] = __fsub_rn(s, prev[at]);
 }
+// The same two passes for the radii SIFT's six sigmas produce (5, 6, 8, 10, 13), unrolled: a row block stages 512 + halo
+// pixels in shared memory and every thread sums 4 neighbouring outputs from one register window (aligned 128-bit
+// reads); a column thread keeps 8 running sums so that every loaded pixel feeds 8 outputs.  Tap order per output is
+// unchanged (i = 0 .. 2R), so the results are bit-identical to the generic kernels above.
+constexpr int kRowTile = 512, kRowHalo = 16, kColRows = 8;
+template <int R>
+__global__ void __launch_bounds__(kRowTile / 4) blur_rows_t(const float* __restrict__ src, int w, int h, BlurKernel K,
+                                                          float* __restrict__ dst) {
+  static_assert(R <= kRowHalo, "halo too small");
+  __shared__ __align__(16) float tile[kRowTile + 2 * kRowHalo];
+  const int y = blockIdx.y, x0 = blockIdx.x * kRowTile, t = threadIdx.x;
+  const float* row = src + (size_t)y * w;
+  for (int s = t; s < kRowTile + 2 * kRowHalo; s += kRowTile / 4) {
+    const int x = x0 - kRowHalo + s;
+    tile[s] = (x >= 0 && x < w) ? row[x] : row[reflect101(min(x, 2 * w + kRowHalo), w)];
+  }
+  __syncthreads();
+  constexpr int kLead = (kRowHalo - R) & ~3, kMis = (kRowHalo - R) & 3, kVec = (kMis + 2 * R + 4 + 3) / 4;
+  float v[4 * kVec];
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const float4 q = *reinterpret_cast<const float4*>(&tile[4 * t + kLead + 4 * j]);
+    v[4 * j] = q.x;
+    v[4 * j + 1] = q.y;
+    v[4 * j + 2] = q.z;
+    v[4 * j + 3] = q.w;
+  }
+  float out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i <= 2 * R; ++i) a = __fadd_rn(a, __fmul_rn(K.k[i], v[kMis + q + i]));
+    out[q] = a;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tile[4 * t + q] = out[q];
+  __syncthreads();
+  float* orow = dst + (size_t)y * w;
+  for (int s = t; s < kRowTile; s += kRowTile / 4)
+    if (x0 + s < w) orow[x0 + s] = tile[s];
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) blur_cols_t(const float* __restrict__ src, int w, int h, BlurKernel K,
+                                                   float* __restrict__ dst, const float* __restrict__ prev,
+                                                   float* __restrict__ dog) {
+  const int x = blockIdx.x * 128 + threadIdx.x, y0 = blockIdx.y * kColRows;
+  if (x >= w) return;
+  float acc[kColRows];
+#pragma unroll
+  for (int j = 0; j < kColRows; ++j) acc[j] = 0.f;
+  const bool inside = y0 - R >= 0 && y0 + kColRows - 1 + R < h;
+#pragma unroll
+  for (int i = 0; i < 2 * R + kColRows; ++i) {
+    const int yy = y0 - R + i;
+    const float val = src[(size_t)(inside ? yy : reflect101(min(yy, 2 * h + R), h)) * w + x];
+#pragma unroll
+    for (int j = 0; j < kColRows; ++j) {
+      const int tap = i - j;
+      if (tap >= 0 && tap <= 2 * R) acc[j] = __fadd_rn(acc[j], __fmul_rn(K.k[tap], val));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kColRows; ++j) {
+    const int y = y0 + j;
+    if (y < h) {
+      const size_t at = (size_t)y * w + x;
+      dst[at] = acc[j];
+      if (dog) dog[at] = __fsub_rn(acc[j], prev[at]);
+    }
+  }
+}
+
+template <int R>
+void launch_blur_t(const float* src, float* tmp, float* dst, int W, int H, const BlurKernel& K, float* dog, cudaStream_t stream) {
+  blur_rows_t<R><<<dim3((W + kRowTile - 1) / kRowTile, H), kRowTile / 4, 0, stream>>>(src, W, H, K, tmp);
+  blur_cols_t<R><<<dim3((W + 127) / 128, (H + kColRows - 1) / kColRows), 128, 0, stream>>>(tmp, W, H, K, dst, src, dog);
+}
+
 __global__ void half_kernel(const float* __restrict__ src, int sw, float* __restrict__ dst, int w, int h) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x < w && y < h) dst[(size_t)y * w + x] = src[(size_t)(2 * y) * sw + 2 * x];
-}
-__global__ void sub_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float* __restrict__ d) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) d[i] = __fsub_rn(a[i], b[i]);
 }
 
 struct Cand {   // a refined scale-space extremum
@@ -318,8 +409,9 @@ __global__ void orientation_kernel(const float* __restrict__ base, Pyramid P, co
   }
 }
 
-// calcSIFTDescriptor: one thread per key point, OpenCV's loop order
-__global__ void descriptor_kernel(const float* __restrict__ base, Pyramid P, const KeyOut* __restrict__ keys, int n_keys,
+// calcSIFTDescriptor, one thread per key point in OpenCV's loop order: the A/B reference of descriptor_kernel
+// (-DIAM_SIFT_SEQ_DESC=1 selects it; bit-identical to the CPU restatement, about 4 x slower)
+__global__ void descriptor_seq_kernel(const float* __restrict__ base, Pyramid P, const KeyOut* __restrict__ keys, int n_keys,
                                   uint8_t* __restrict__ des) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_keys) return;
@@ -417,6 +509,139 @@ __global__ void descriptor_kernel(const float* __restrict__ base, Pyramid P, con
     }
 }
 
+// calcSIFTDescriptor, one WARP per key point.  The lanes share the (2 radius + 1)^2 window; the 8 tri-linear
+// contributions of every sample are added to the warp's histogram in shared memory as 64-bit fixed point (2^-40):
+// integer addition does not depend on the order the lanes arrive in, so the result is deterministic and equals the
+// exactly-rounded sum of the float contributions (OpenCV's sequential float sum carries ~1e-6 of rounding noise, which is
+// why descriptors agree to +-1 rather than bit for bit).  Lane 0 finishes with OpenCV's normalise / clip / quantise.
+constexpr int kDescWarps = 4;
+constexpr int kHistLen = 6 * 6 * 10;
+__global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const float* __restrict__ base, Pyramid P,
+                                                                     const KeyOut* __restrict__ keys, int n_keys,
+                                                                     uint8_t* __restrict__ des) {
+  __shared__ unsigned long long hist_s[kDescWarps][kHistLen];
+  __shared__ float fin_s[kDescWarps][kHistLen];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * kDescWarps + warp;
+  if (i >= n_keys) return;          // warp-uniform; no block-wide barrier below
+  unsigned long long* hq = hist_s[warp];
+  for (int k = lane; k < kHistLen; k += 32) hq[k] = 0ull;
+  __syncwarp();
+  const KeyOut kp = keys[i];
+  const Octave O = P.oct[kp.o];
+  const float* img = base + O.gauss[kp.layer];
+  const int w = O.w, h = O.h;
+  constexpr int d = 4, n = 8;
+  const int oct_pub = kp.o - 1;
+  const float sc = oct_pub >= 0 ? __fdiv_rn(1.f, (float)(1 << oct_pub)) : (float)(1 << -oct_pub);
+  const float ptx = __fmul_rn(__fmul_rn(kp.x, 0.5f), sc), pty = __fmul_rn(__fmul_rn(kp.y, 0.5f), sc);
+  const float scl = __fmul_rn(__fmul_rn(__fmul_rn(kp.size, 0.5f), sc), 0.5f);
+  float ori = __fsub_rn(360.f, kp.angle);
+  if (fabsf(__fsub_rn(ori, 360.f)) < 1.1920929e-07f) ori = 0.f;
+  const int px = __float2int_rn(ptx), py = __float2int_rn(pty);
+  const float rad = __fmul_rn(ori, 0.017453292519943295f);
+  float cos_t = (float)cos((double)rad), sin_t = (float)sin((double)rad);
+  const float bins_per_rad = 8.f / 360.f;
+  const float exp_scale = -1.f / (d * d * 0.5f);
+  const float hist_width = __fmul_rn(3.f, scl);
+  int radius = __float2int_rn(__fmul_rn(__fmul_rn(__fmul_rn(hist_width, 1.4142135623730951f), (float)(d + 1)), 0.5f));
+  radius = min(radius, (int)sqrt((double)w * w + (double)h * h));
+  cos_t = __fdiv_rn(cos_t, hist_width);
+  sin_t = __fdiv_rn(sin_t, hist_width);
+  const int side = 2 * radius + 1;
+  // rows of the window that lie inside the image (r > 0 && r < h - 1), then lanes stride over columns
+  const int di_lo = max(-radius, 1 - py), di_hi = min(radius, h - 2 - py);
+  const int dj_lo = max(-radius, 1 - px), dj_hi = min(radius, w - 2 - px);
+  const int ncol = dj_hi - dj_lo + 1;
+  (void)side;
+  if (ncol > 0) {
+    for (int di = di_lo; di <= di_hi; ++di) {
+      const float* row = img + (size_t)(py + di) * w;
+      for (int dj = dj_lo + lane; dj <= dj_hi; dj += 32) {
+        const float c_rot = __fsub_rn(__fmul_rn((float)dj, cos_t), __fmul_rn((float)di, sin_t));
+        const float r_rot = __fadd_rn(__fmul_rn((float)dj, sin_t), __fmul_rn((float)di, cos_t));
+        float rbin = __fsub_rn(__fadd_rn(r_rot, (float)(d / 2)), 0.5f);
+        float cbin = __fsub_rn(__fadd_rn(c_rot, (float)(d / 2)), 0.5f);
+        if (!(rbin > -1.f && rbin < (float)d && cbin > -1.f && cbin < (float)d)) continue;
+        const int c = px + dj;
+        const float dx = __fsub_rn(row[c + 1], row[c - 1]);
+        const float dy = __fsub_rn(row[c - w], row[c + w]);
+        const float wgt = expf(__fmul_rn(__fadd_rn(__fmul_rn(c_rot, c_rot), __fmul_rn(r_rot, r_rot)), exp_scale));
+        const float o_deg = fast_atan2_deg(dy, dx);
+        const float mag0 = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        float obin = __fmul_rn(__fsub_rn(o_deg, ori), bins_per_rad);
+        const float mag = __fmul_rn(mag0, wgt);
+        const int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin);
+        int o0 = (int)floorf(obin);
+        rbin = __fsub_rn(rbin, (float)r0);
+        cbin = __fsub_rn(cbin, (float)c0);
+        obin = __fsub_rn(obin, (float)o0);
+        if (o0 < 0) o0 += n;
+        if (o0 >= n) o0 -= n;
+        const float v_r1 = __fmul_rn(mag, rbin), v_r0 = __fsub_rn(mag, v_r1);
+        const float v_rc11 = __fmul_rn(v_r1, cbin), v_rc10 = __fsub_rn(v_r1, v_rc11);
+        const float v_rc01 = __fmul_rn(v_r0, cbin), v_rc00 = __fsub_rn(v_r0, v_rc01);
+        const float v111 = __fmul_rn(v_rc11, obin), v110 = __fsub_rn(v_rc11, v111);
+        const float v101 = __fmul_rn(v_rc10, obin), v100 = __fsub_rn(v_rc10, v101);
+        const float v011 = __fmul_rn(v_rc01, obin), v010 = __fsub_rn(v_rc01, v011);
+        const float v001 = __fmul_rn(v_rc00, obin), v000 = __fsub_rn(v_rc00, v001);
+        const int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
+        auto add = [&](int at, float v) {
+          atomicAdd(&hq[at], (unsigned long long)__float2ll_rn(__fmul_rn(v, 1099511627776.f)));   // * 2^40: exact
+        };
+        add(idx, v000);
+        add(idx + 1, v001);
+        add(idx + (n + 2), v010);
+        add(idx + (n + 3), v011);
+        add(idx + (d + 2) * (n + 2), v100);
+        add(idx + (d + 2) * (n + 2) + 1, v101);
+        add(idx + (d + 3) * (n + 2), v110);
+        add(idx + (d + 3) * (n + 2) + 1, v111);
+      }
+    }
+  }
+  __syncwarp();
+  float* hist = fin_s[warp];
+  for (int k = lane; k < kHistLen; k += 32) hist[k] = __fmul_rn(__ll2float_rn((long long)hq[k]), 9.094947017729282e-13f);   // 2^-40
+  __syncwarp();
+  if (lane == 0) {
+    float nrm2 = 0.f;
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) {
+        const int idx = ((a + 1) * (d + 2) + (b + 1)) * (n + 2);
+        hist[idx] = __fadd_rn(hist[idx], hist[idx + n]);
+        hist[idx + 1] = __fadd_rn(hist[idx + 1], hist[idx + n + 1]);
+        for (int k = 0; k < n; ++k) nrm2 = __fadd_rn(nrm2, __fmul_rn(hist[idx + k], hist[idx + k]));
+      }
+    const float thr = __fmul_rn(__fsqrt_rn(nrm2), 0.2f);
+    nrm2 = 0.f;
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) {
+        const int idx = ((a + 1) * (d + 2) + (b + 1)) * (n + 2);
+        for (int k = 0; k < n; ++k) {
+          const float val = fminf(hist[idx + k], thr);
+          hist[idx + k] = val;
+          nrm2 = __fadd_rn(nrm2, __fmul_rn(val, val));
+        }
+      }
+    hist[0] = __fdiv_rn(512.f, fmaxf(__fsqrt_rn(nrm2), 1.1920929e-07f));   // slot 0 is a border bin: free
+  }
+  __syncwarp();
+  const float s = hist[0];
+  uint8_t* out = des + (size_t)i * 128;
+  for (int e = lane; e < 128; e += 32) {
+    const int cell = e >> 3, k = e & 7;
+    const int idx = (((cell >> 2) + 1) * (d + 2) + ((cell & 3) + 1)) * (n + 2) + k;
+    out[e] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn(hist[idx], s))));
+  }
+}
+
+// descriptor rows (128 bytes = one warp of words) into their final order
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ order, int n, uint32_t* __restrict__ dst) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row < n) dst[(size_t)row * 32 + lane] = src[(size_t)order[row] * 32 + lane];
+}
+
 BlurKernel make_kernel(double sigma) {
   BlurKernel K{};
   int ks = (int)std::nearbyint(sigma * 4 * 2 + 1) | 1;
@@ -436,6 +661,7 @@ BlurKernel make_kernel(double sigma) {
 
 SiftScratch::~SiftScratch() {
   if (buf) cudaFree(buf);
+  if (pinned) cudaFreeHost(pinned);
 }
 
 int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, int32_t* out_octave, uint8_t* out_des,
@@ -446,6 +672,14 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   };
   *out_n = 0;
   if (w < 2 || h < 2 || max_out < 0) return fail(-1, "bad image size");
+  static const bool trace = std::getenv("IAM_SIFT_TRACE") != nullptr;   // stage times on stderr (debug aid)
+  auto t_prev = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (!trace) return;
+    const auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[sift] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   const int bw = 2 * w, bh = 2 * h;
   Pyramid P{};
   P.n_oct = (int)std::nearbyint(std::log((double)std::min(bw, bh)) / std::log(2.0) - 2.0) + 1;
@@ -475,7 +709,8 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t o_tmp = up(off * sizeof(float)), o_src = o_tmp + up(base_px * sizeof(float));
   const size_t o_cand = o_src + up((size_t)w * h), o_keys = o_cand + up((size_t)cand_cap * sizeof(Cand));
-  const size_t o_des = o_keys + up((size_t)key_cap * sizeof(KeyOut)), o_cnt = o_des + up((size_t)key_cap * 128);
+  const size_t o_des = o_keys + up((size_t)key_cap * sizeof(KeyOut)), o_des2 = o_des + up((size_t)key_cap * 128);
+  const size_t o_cnt = o_des2 + up((size_t)key_cap * 128);
   const size_t total = o_cnt + 256;
   cudaError_t e;
 #define SC(call) \
@@ -497,24 +732,35 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   Cand* d_cand = reinterpret_cast<Cand*>(blk + o_cand);
   KeyOut* d_keys = reinterpret_cast<KeyOut*>(blk + o_keys);
   uint8_t* d_des = blk + o_des;
+  uint8_t* d_des2 = blk + o_des2;
   int* d_cnt = reinterpret_cast<int*>(blk + o_cnt);
   SC(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), stream));
   SC(cudaMemcpyAsync(d_src, gray, (size_t)w * h, cudaMemcpyHostToDevice, stream));
   const dim3 blk2(32, 8);
   auto grid = [&](int W, int H) { return dim3((W + 31) / 32, (H + 7) / 8); };
   int launches = 0;
-  auto blur = [&](const float* src, float* dst, int W, int H, double sigma) {
+  auto blur = [&](const float* src, float* dst, int W, int H, double sigma, float* dog) {
     const BlurKernel K = make_kernel(sigma);
-    blur_rows_kernel<<<grid(W, H), blk2, 0, stream>>>(src, W, H, K, tmp);
-    blur_cols_kernel<<<grid(W, H), blk2, 0, stream>>>(tmp, W, H, K, dst);
     launches += 2;
+    if (W >= 64 && H >= 64 && !IAM_SIFT_GENERIC_BLUR) {
+      switch (K.ksize >> 1) {
+        case 5: return launch_blur_t<5>(src, tmp, dst, W, H, K, dog, stream);
+        case 6: return launch_blur_t<6>(src, tmp, dst, W, H, K, dog, stream);
+        case 8: return launch_blur_t<8>(src, tmp, dst, W, H, K, dog, stream);
+        case 10: return launch_blur_t<10>(src, tmp, dst, W, H, K, dog, stream);
+        case 13: return launch_blur_t<13>(src, tmp, dst, W, H, K, dog, stream);
+        default: break;
+      }
+    }
+    blur_rows_kernel<<<grid(W, H), blk2, 0, stream>>>(src, W, H, K, tmp);
+    blur_cols_kernel<<<grid(W, H), blk2, 0, stream>>>(tmp, W, H, K, dst, src, dog);
   };
   // base image: doubled, blurred from the assumed 2 * 0.5 to sigma 1.6
   const double sigma0 = 1.6;
-  float* dbl = base + P.oct[0].dog[0];   // scratch: overwritten by the DoG later
+  float* dbl = base + P.oct[0].dog[kNL + 1];   // scratch: overwritten by the last DoG layer later
   up2_kernel<<<grid(bw, bh), blk2, 0, stream>>>(d_src, w, h, dbl);
   ++launches;
-  blur(dbl, base + P.oct[0].gauss[0], bw, bh, std::sqrt(std::max(sigma0 * sigma0 - 0.5 * 0.5 * 4, 0.01)));
+  blur(dbl, base + P.oct[0].gauss[0], bw, bh, std::sqrt(std::max(sigma0 * sigma0 - 0.5 * 0.5 * 4, 0.01)), nullptr);
   double sig[kNL + 3];
   sig[0] = sigma0;
   const double k = std::pow(2.0, 1.0 / kNL);
@@ -531,13 +777,8 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
         half_kernel<<<grid(O.w, O.h), blk2, 0, stream>>>(base + P.oct[o - 1].gauss[kNL], P.oct[o - 1].w, dst, O.w, O.h);
         ++launches;
       } else {
-        blur(base + O.gauss[i - 1], dst, O.w, O.h, sig[i]);
+        blur(base + O.gauss[i - 1], dst, O.w, O.h, sig[i], base + O.dog[i - 1]);   // DoG layer i-1 = layer i - layer i-1
       }
-    }
-    const size_t npx = (size_t)O.w * O.h;
-    for (int i = 0; i < kNL + 2; ++i) {
-      sub_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, stream>>>(base + O.gauss[i + 1], base + O.gauss[i], npx, base + O.dog[i]);
-      ++launches;
     }
   }
   for (int o = 0; o < P.n_oct; ++o) {
@@ -550,38 +791,65 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   }
   orientation_kernel<<<(cand_cap + 127) / 128, 128, 0, stream>>>(base, P, d_cand, d_cnt, cand_cap, d_keys, d_cnt + 1, key_cap);
   ++launches;
+  mark("enqueue pyramid..orientation");
   int h_cnt[2];
   SC(cudaMemcpyAsync(h_cnt, d_cnt, sizeof h_cnt, cudaMemcpyDeviceToHost, stream));
   SC(cudaStreamSynchronize(stream));
+  mark("wait for the key point count");
   if (h_cnt[0] > cand_cap) return fail(-5, "more scale-space extrema than the candidate buffer holds");
   if (h_cnt[1] > key_cap) return fail(-5, "more key points than the output buffers hold");
   const int nk = h_cnt[1];
   if (nk > 0) {
-    descriptor_kernel<<<(nk + 63) / 64, 64, 0, stream>>>(base, P, d_keys, nk, d_des);
-    ++launches;
-    std::vector<KeyOut> hk(nk);
-    std::vector<uint8_t> hd((size_t)nk * 128);
-    SC(cudaMemcpyAsync(hk.data(), d_keys, (size_t)nk * sizeof(KeyOut), cudaMemcpyDeviceToHost, stream));
-    SC(cudaMemcpyAsync(hd.data(), d_des, (size_t)nk * 128, cudaMemcpyDeviceToHost, stream));
+    // page-locked staging owned by the scratch block: key points down, final order up
+    const size_t pin_need = (size_t)nk * (sizeof(KeyOut) + sizeof(int));
+    if (sc->pinned_cap < pin_need) {
+      if (sc->pinned) cudaFreeHost(sc->pinned);
+      sc->pinned = nullptr;
+      sc->pinned_cap = 0;
+      const size_t want = pin_need + pin_need / 2;
+      if ((e = cudaHostAlloc(&sc->pinned, want, cudaHostAllocDefault)) != cudaSuccess)
+        return fail(-3, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+      sc->pinned_cap = want;
+    }
+    KeyOut* hk = static_cast<KeyOut*>(sc->pinned);
+    int* h_order = reinterpret_cast<int*>(hk + nk);
+    SC(cudaMemcpyAsync(hk, d_keys, (size_t)nk * sizeof(KeyOut), cudaMemcpyDeviceToHost, stream));
     SC(cudaStreamSynchronize(stream));
+    mark("download key points");
+    // descriptors are computed in device order while the host sorts
+#if IAM_SIFT_SEQ_DESC
+    descriptor_seq_kernel<<<(nk + 63) / 64, 64, 0, stream>>>(base, P, d_keys, nk, d_des);
+#else
+    descriptor_kernel<<<(nk + kDescWarps - 1) / kDescWarps, kDescWarps * 32, 0, stream>>>(base, P, d_keys, nk, d_des);
+#endif
+    ++launches;
     // KeyPointsFilter::removeDuplicatedSorted: order by (x, y, size desc, angle, response desc, octave desc), drop
-    // key points that repeat (x, y, size, angle); then first octave -1: halve coordinates and size
-    std::vector<int> order(nk);
-    for (int i = 0; i < nk; ++i) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](int a, int b) {
-      const KeyOut &p = hk[a], &q = hk[b];
-      if (p.x != q.x) return p.x < q.x;
-      if (p.y != q.y) return p.y < q.y;
+    // key points that repeat (x, y, size, angle); then first octave -1: halve coordinates and size.
+    // x and y are positive floats, so their bit patterns order like the values: one 64-bit key decides all but ties.
+    struct SortKey {
+      uint64_t xy;
+      int idx;
+    };
+    std::vector<SortKey> sk(nk);
+    for (int i = 0; i < nk; ++i) {
+      uint32_t bx, by;
+      std::memcpy(&bx, &hk[i].x, 4);
+      std::memcpy(&by, &hk[i].y, 4);
+      sk[i] = {(uint64_t)bx << 32 | by, i};
+    }
+    std::sort(sk.begin(), sk.end(), [&](const SortKey& a, const SortKey& b) {
+      if (a.xy != b.xy) return a.xy < b.xy;
+      const KeyOut &p = hk[a.idx], &q = hk[b.idx];
       if (p.size != q.size) return p.size > q.size;
       if (p.angle != q.angle) return p.angle < q.angle;
       if (p.response != q.response) return p.response > q.response;
       if (p.octave_field != q.octave_field) return p.octave_field > q.octave_field;
-      return a < b;
+      return a.idx < b.idx;
     });
     int n_out = 0;
     const KeyOut* last = nullptr;
     for (int i = 0; i < nk; ++i) {
-      const KeyOut& kpt = hk[order[i]];
+      const KeyOut& kpt = hk[sk[i].idx];
       if (last && last->x == kpt.x && last->y == kpt.y && last->size == kpt.size && last->angle == kpt.angle) continue;
       last = &kpt;
       float* o5 = out_kp5 + (size_t)n_out * 5;
@@ -591,10 +859,19 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
       o5[3] = kpt.angle;
       o5[4] = kpt.response;
       out_octave[n_out] = (kpt.octave_field & ~255) | ((kpt.octave_field - 1) & 255);
-      std::copy(hd.begin() + (size_t)order[i] * 128, hd.begin() + (size_t)order[i] * 128 + 128, out_des + (size_t)n_out * 128);
-      ++n_out;
+      h_order[n_out++] = sk[i].idx;
     }
+    mark("host sort + key point output");
+    // descriptors leave the device already in the final order, straight into the caller's array
+    int* d_order = reinterpret_cast<int*>(d_cand);   // the candidate list is spent
+    SC(cudaMemcpyAsync(d_order, h_order, (size_t)n_out * sizeof(int), cudaMemcpyHostToDevice, stream));
+    gather_rows_kernel<<<(n_out + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_des), d_order, n_out,
+                                                           reinterpret_cast<uint32_t*>(d_des2));
+    ++launches;
+    SC(cudaMemcpyAsync(out_des, d_des2, (size_t)n_out * 128, cudaMemcpyDeviceToHost, stream));
+    SC(cudaStreamSynchronize(stream));
     *out_n = n_out;
+    mark("descriptors in order to host");
   }
 #undef SC
   return launches;

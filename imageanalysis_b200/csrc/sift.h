@@ -12,6 +12,8 @@ namespace iam {
 struct SiftScratch {
   void* buf = nullptr;
   size_t cap = 0;
+  void* pinned = nullptr;   // page-locked staging for the key point list
+  size_t pinned_cap = 0;
   SiftScratch() = default;
   SiftScratch(const SiftScratch&) = delete;
   SiftScratch& operator=(const SiftScratch&) = delete;

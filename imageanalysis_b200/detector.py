@@ -116,3 +116,14 @@ def SIFT_create(uint8_descriptors: bool = False) -> SIFT:
 def ORB_create(nfeatures: int = 500) -> ORB:
     """cv2.ORB_create(nfeatures) (image.py:244-245) with OpenCV's default parameters."""
     return ORB(nfeatures)
+
+
+def make_detector(name: str = "SIFT", max_features: int = 20000):
+    """The dispatch of Image.make_detector (image.py:230-251) on /config/detector/detector: 'SIFT' (built without
+    arguments there) and 'ORB' (orb_max_features) run on the GPU; 'SURF' and 'Star' are cv2.xfeatures2d detectors that
+    this framework does not replace."""
+    if name == "SIFT":
+        return SIFT_create()
+    if name == "ORB":
+        return ORB_create(max_features)
+    raise _capi.IamError("detector %r is not replaced by this framework (SIFT and ORB are)" % (name,))

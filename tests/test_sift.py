@@ -67,6 +67,15 @@ def test_golden_is_well_formed():
         assert layer.min() >= 1 and layer.max() <= 3
 
 
+def test_make_detector_dispatch():
+    from imageanalysis_b200 import _capi, detector
+    assert isinstance(detector.make_detector("SIFT"), detector.SIFT)
+    orb = detector.make_detector("ORB", 1234)
+    assert isinstance(orb, detector.ORB) and orb.nfeatures == 1234
+    with pytest.raises(_capi.IamError):
+        detector.make_detector("SURF")
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["small", "medium", "large"])

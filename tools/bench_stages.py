@@ -204,6 +204,12 @@ def main():
             print(json.dumps(line))
     except ImportError:
         pass
+    # ------------------------------------------------------------------ SIFT detect + describe (image.py:236-237, :324)
+    sys.path.insert(0, ROOT)
+    import bench as B
+    line = dict(stage="SIFT detect + describe (csrc/sift.cu), grey host image in -> host key points + descriptors out", **B.sift_leg(0))
+    out.append(line)
+    print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "stages.jsonl"), "w") as f:
         for l in out:
