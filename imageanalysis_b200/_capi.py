@@ -22,7 +22,7 @@ DTYPE_U8, DTYPE_F32 = 0, 1
 ENGINE_AUTO, ENGINE_UMMA, ENGINE_SIMT, ENGINE_UMMA_F16 = 0, 1, 2, 3
 KIND_F16, KIND_F8, KIND_I8 = 0, 1, 2
 REDUCE_LOWE, REDUCE_REF_METRIC = 0, 1
-MODEL_ESSENTIAL, MODEL_HOMOGRAPHY, MODEL_FUNDAMENTAL = 0, 1, 2
+MODEL_ESSENTIAL, MODEL_HOMOGRAPHY, MODEL_FUNDAMENTAL, MODEL_AFFINE_PARTIAL = 0, 1, 2, 3
 
 # every symbol include/iamatch.h declares; tests check the library exports them all
 EXPORTS = (
@@ -30,7 +30,7 @@ EXPORTS = (
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_triangulate_pairs", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -143,6 +143,7 @@ def load_library(path: Optional[str] = None):
                                      C.c_uint32, vp, vp, vp]
     lib.iam_ransac_tables.argtypes = [vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_orb_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    lib.iam_triangulate_pairs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.iam_sift_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
     lib.iam_debug_orb_fast.argtypes = [vp, vp, C.c_int, C.c_int, vp]
     lib.iam_debug_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, vp]
@@ -459,6 +460,24 @@ class Engine:
                     "iam_ransac_tables")
         return mask, (models.reshape(n_pairs, 3, 3) if want_model else None), inl
 
+
+    def triangulate_pairs(self, proj1, proj2, offsets, x1, x2, want_points: bool = True):
+        """cv2.triangulatePoints for many image pairs in one launch (iam_triangulate_pairs; smart.py:26-63, :116-131).
+        proj1/proj2 [P, 12] float64, offsets [P + 1], x1/x2 [total, 2] normalised image coordinates.
+        Returns (points [total, 3] float64 or None, stats [P, 2] = mean, std of Z)."""
+        p1 = np.ascontiguousarray(proj1, np.float64).reshape(-1, 12)
+        p2 = np.ascontiguousarray(proj2, np.float64).reshape(-1, 12)
+        off = np.ascontiguousarray(offsets, np.int32)
+        a = np.ascontiguousarray(x1, np.float64).reshape(-1, 2)
+        b = np.ascontiguousarray(x2, np.float64).reshape(-1, 2)
+        P = off.shape[0] - 1
+        if p1.shape[0] != P or p2.shape[0] != P or a.shape != b.shape or (P > 0 and a.shape[0] != off[-1]):
+            raise IamError("triangulate_pairs: inconsistent shapes")
+        pts = np.zeros((a.shape[0], 3), np.float64) if want_points else None
+        stats = np.zeros((P, 2), np.float64)
+        self._check(self._lib.iam_triangulate_pairs(self._h, P, _ptr(p1), _ptr(p2), _ptr(off), _ptr(a), _ptr(b), _ptr(pts),
+                                                    _ptr(stats)), "iam_triangulate_pairs")
+        return pts, stats
 
     def orb_detect(self, gray: np.ndarray, nfeatures: int):
         """cv2.ORB_create(nfeatures).detectAndCompute(gray, None) on the GPU (iam_orb_detect).

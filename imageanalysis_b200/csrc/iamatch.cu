@@ -26,6 +26,7 @@
 #include "layout.h"
 #include "orb.h"
 #include "sift.h"
+#include "triangulate.h"
 #include "ransac.h"
 #include "reduce.h"
 
@@ -157,6 +158,7 @@ struct iam_ctx {
   iam::OrbScratch orb_scratch;
   iam::SiftScratch sift_scratch;
   Buffer ransac_mask, ransac_model, ransac_inl;
+  Buffer tri_in, tri_out;
   int ba_n_cam = 0, ba_n_pts = 0, ba_n_obs = -1;
   // iam_match_images, float32 L2 descriptors: worker threads narrow them to bytes (host_narrow.h) into a pinned arena
   std::unique_ptr<iam::NarrowPool> narrow_pool;
@@ -466,7 +468,7 @@ __global__ void pack_knn_kernel(const iam::RedJob* jobs, int job_begin, int n_jo
 
 extern "C" {
 
-int iam_abi_version(void) { return 5; }
+int iam_abi_version(void) { return 6; }
 const char* iam_last_error(void) { return g_err.c_str(); }
 
 int iam_create(int device, int norm, int desc_bytes, iam_ctx** out) {
@@ -1506,7 +1508,7 @@ int iam_ransac_pairs(iam_ctx* c, int model, const float* pts1, const float* pts2
   int rc = bind(c);
   if (rc) return rc;
   if (n_pairs < 0 || !off || !out_mask || !out_model || !out_inliers) return fail(IAM_E_ARG, "bad arguments");
-  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL)
+  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL && model != IAM_MODEL_AFFINE_PARTIAL)
     return fail(IAM_E_ARG, "unknown model %d", model);
   if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
   std::string err;
@@ -1522,7 +1524,7 @@ int iam_ransac_tables(iam_ctx* c, int model, const double* K, double threshold_p
                       int32_t* out_inliers) {
   int rc = bind(c);
   if (rc) return rc;
-  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL)
+  if (model != IAM_MODEL_ESSENTIAL && model != IAM_MODEL_HOMOGRAPHY && model != IAM_MODEL_FUNDAMENTAL && model != IAM_MODEL_AFFINE_PARTIAL)
     return fail(IAM_E_ARG, "unknown model %d", model);
   if (model == IAM_MODEL_ESSENTIAL && !K) return fail(IAM_E_ARG, "K is required for the essential-matrix model");
   const int n = c->last_pairs, cap = c->last_cap;
@@ -1557,6 +1559,47 @@ int iam_ransac_tables(iam_ctx* c, int model, const double* K, double threshold_p
   return IAM_OK;
 }
 
+
+// ---- two-view triangulation (smart.py:26-63, :116-131) ---------------------------------------------------------
+
+int iam_triangulate_pairs(iam_ctx* c, int n_pairs, const double* proj1, const double* proj2, const int32_t* off,
+                          const double* x1, const double* x2, double* out_points, double* out_stats) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_pairs < 0 || (n_pairs > 0 && (!proj1 || !proj2 || !off || !out_stats))) return fail(IAM_E_ARG, "bad arguments");
+  if (n_pairs == 0) return IAM_OK;
+  if (off[0] != 0) return fail(IAM_E_ARG, "off[0] must be 0");
+  for (int p = 0; p < n_pairs; ++p)
+    if (off[p + 1] < off[p]) return fail(IAM_E_ARG, "offsets must not decrease (pair %d)", p);
+  const size_t total = size_t(off[n_pairs]);
+  if (total > 0 && (!x1 || !x2)) return fail(IAM_E_ARG, "bad arguments");
+  // one staging block: proj1 | proj2 | x1 | x2 | off
+  const size_t b_proj = size_t(n_pairs) * 12 * sizeof(double), b_x = total * 2 * sizeof(double);
+  const size_t b_off = (size_t(n_pairs) + 1) * sizeof(int32_t);
+  CU(c->tri_in.ensure(2 * b_proj + 2 * b_x + b_off + 64));
+  CU(c->tri_out.ensure((total * 3 + size_t(n_pairs) * 2) * sizeof(double) + 64));
+  uint8_t* in = c->tri_in.as<uint8_t>();
+  double* d_p1 = reinterpret_cast<double*>(in);
+  double* d_p2 = reinterpret_cast<double*>(in + b_proj);
+  double* d_x1 = reinterpret_cast<double*>(in + 2 * b_proj);
+  double* d_x2 = reinterpret_cast<double*>(in + 2 * b_proj + b_x);
+  int32_t* d_off = reinterpret_cast<int32_t*>(in + 2 * b_proj + 2 * b_x);
+  double* d_pts = c->tri_out.as<double>();
+  double* d_stats = d_pts + total * 3;
+  CU(cudaMemcpyAsync(d_p1, proj1, b_proj, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(d_p2, proj2, b_proj, cudaMemcpyHostToDevice, c->stream));
+  if (total) {
+    CU(cudaMemcpyAsync(d_x1, x1, b_x, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_x2, x2, b_x, cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaMemcpyAsync(d_off, off, b_off, cudaMemcpyHostToDevice, c->stream));
+  CU(iam::triangulate_pairs(n_pairs, d_p1, d_p2, d_off, d_x1, d_x2, d_pts, d_stats, c->stream));
+  c->timing.total_launches += 1;
+  if (out_points && total) CU(cudaMemcpyAsync(out_points, d_pts, total * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_stats, d_stats, size_t(n_pairs) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
 
 // ---- ORB detect + describe (image.py:243-245, :324) -------------------------------------------------------------
 

@@ -436,6 +436,21 @@ IAM_HD int five_point(const float* x1, const float* y1, const float* x2, const f
   return n_out;
 }
 
+// ---- 2-point similarity (cv2.estimateAffinePartial2D's model: rotation, uniform scale, translation) ----
+// [a -b tx; b a ty; 0 0 1] through two correspondences: (a + ib) = (q1 - q0) / (p1 - p0) as complex numbers.
+IAM_HD int two_point(const float* x1, const float* y1, const float* x2, const float* y2, const int* s, float* M_out) {
+  const double px = double(x1[s[1]]) - x1[s[0]], py = double(y1[s[1]]) - y1[s[0]];
+  const double qx = double(x2[s[1]]) - x2[s[0]], qy = double(y2[s[1]]) - y2[s[0]];
+  const double den = px * px + py * py;
+  if (!(den > 1e-24)) return 0;
+  const double a = (qx * px + qy * py) / den, b = (qy * px - qx * py) / den;
+  const double tx = x2[s[0]] - (a * x1[s[0]] - b * y1[s[0]]), ty = y2[s[0]] - (b * x1[s[0]] + a * y1[s[0]]);
+  M_out[0] = float(a); M_out[1] = float(-b); M_out[2] = float(tx);
+  M_out[3] = float(b); M_out[4] = float(a); M_out[5] = float(ty);
+  M_out[6] = 0.f; M_out[7] = 0.f; M_out[8] = 1.f;
+  return 1;
+}
+
 // ---- 4-point homography (normalised coordinates), h33 fixed by unit norm ----
 IAM_HD int four_point(const float* x1, const float* y1, const float* x2, const float* y2, const int* s,
                           float* H_out) {
@@ -675,7 +690,7 @@ ransac_kernel(const RansacArgs A) {
   const bool gather = A.pts1 == nullptr;
   const int o = gather ? 0 : A.off[p];
   const int n = gather ? A.count[p] : A.off[p + 1] - o;
-  const int msize = (model == 0) ? 5 : (model == 2) ? 7 : 4;
+  const int msize = (model == 0) ? 5 : (model == 2) ? 7 : (model == 3) ? 2 : 4;
   if (gather && n < A.min_pairs) {  // matcher.py:99-101: too few matches, the list is cleared
     if (lane == 0) {
       if (A.compact) A.count[p] = 0;
@@ -773,6 +788,7 @@ ransac_kernel(const RansacArgs A) {
         }
         nc = (model == 0)   ? five_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
              : (model == 2) ? seven_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
+             : (model == 3) ? two_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9])
                             : four_point(sx1, sy1, sx2, sy2, s, &s_cand[lane * kMaxCand * 9]);
       }
       s_ncand[lane] = nc;
@@ -836,6 +852,34 @@ ransac_kernel(const RansacArgs A) {
     }
   }
   if (gather && A.compact && lane == 0) A.count[p] = kept;
+  if (model == 3 && have) {
+    // cv2.estimateAffinePartial2D polishes the RANSAC model on its inliers (Levenberg-Marquardt, refineIters = 10); the
+    // model is linear in (a, b, tx, ty), so the optimum it converges to is the closed-form least-squares fit.  The
+    // mask stays the RANSAC model's, as in OpenCV.
+    double sp_x = 0, sp_y = 0, sq_x = 0, sq_y = 0, cnt = 0;
+    for (int i = lane; i < n; i += 32)
+      if (model_error(model, best, sx1[i], sy1[i], sx2[i], sy2[i], X.thr_ratio) <= X.thr2) {
+        sp_x += sx1[i]; sp_y += sy1[i]; sq_x += sx2[i]; sq_y += sy2[i]; cnt += 1;
+      }
+    sp_x = warp_sum(sp_x); sp_y = warp_sum(sp_y); sq_x = warp_sum(sq_x); sq_y = warp_sum(sq_y); cnt = warp_sum(cnt);
+    if (cnt >= 2) {
+      const double mpx = sp_x / cnt, mpy = sp_y / cnt, mqx = sq_x / cnt, mqy = sq_y / cnt;
+      double num_a = 0, num_b = 0, den = 0;
+      for (int i = lane; i < n; i += 32)
+        if (model_error(model, best, sx1[i], sy1[i], sx2[i], sy2[i], X.thr_ratio) <= X.thr2) {
+          const double px = sx1[i] - mpx, py = sy1[i] - mpy, qx = sx2[i] - mqx, qy = sy2[i] - mqy;
+          num_a += px * qx + py * qy;
+          num_b += px * qy - py * qx;
+          den += px * px + py * py;
+        }
+      num_a = warp_sum(num_a); num_b = warp_sum(num_b); den = warp_sum(den);
+      if (den > 1e-24) {
+        const double a = num_a / den, b = num_b / den;
+        best[0] = float(a); best[1] = float(-b); best[2] = float(mqx - (a * mpx - b * mpy));
+        best[3] = float(b); best[4] = float(a); best[5] = float(mqy - (b * mpx + a * mpy));
+      }
+    }
+  }
   if (lane == 0) {
     // back to caller units: E is reported for normalised image coordinates like cv2.findEssentialMat does
     // (x2n^T E x1n = 0); H and F are mapped back to pixels and scaled to a unit last element.
@@ -847,7 +891,7 @@ ransac_kernel(const RansacArgs A) {
     } else {
       const double T1[9] = {X.s1x, 0, -double(X.s1x) * X.a1x, 0, X.s1y, -double(X.s1y) * X.a1y, 0, 0, 1};
       double L[9];  // homography: T2^-1; fundamental: T2^T
-      if (model == 1) {
+      if (model == 1 || model == 3) {
         const double l[9] = {1.0 / X.s2x, 0, X.a2x, 0, 1.0 / X.s2y, X.a2y, 0, 0, 1};
         for (int e = 0; e < 9; ++e) L[e] = l[e];
       } else {
@@ -900,7 +944,7 @@ void fill_common(RansacArgs& a, int model, const double* K, double threshold_px,
 int debug_minimal_solver(int model, const float* x1, const float* y1, const float* x2, const float* y2, float* out) {
   const int s[7] = {0, 1, 2, 3, 4, 5, 6};
   return model == 0 ? five_point(x1, y1, x2, y2, s, out) : model == 2 ? seven_point(x1, y1, x2, y2, s, out)
-                                                                        : four_point(x1, y1, x2, y2, s, out);
+         : model == 3 ? two_point(x1, y1, x2, y2, s, out) : four_point(x1, y1, x2, y2, s, out);
 }
 
 RansacScratch::~RansacScratch() {

@@ -41,10 +41,7 @@ except ImportError:  # pragma: no cover - exercised in this repo's tests
 from . import _capi
 from . import pairs as _pairs
 
-try:  # sibling reference modules when this file is dropped into scripts/lib/
-    from . import smart as _smart  # type: ignore
-except ImportError:
-    _smart = None
+from . import smart as _smart          # the pair-wise side estimators (lib.smart's API, GPU numerics)
 try:
     from .logger import log, qlog  # type: ignore
 except ImportError:
@@ -755,8 +752,8 @@ def find_matches(proj, K, strategy="smart", transform="homography", sort=False, 
         if apply_transform_filter and len(match_fwd):
             filter_by_transform(K, i1, i2, transform)
             i2.match_list[i1.name] = [[p[1], p[0]] for p in i1.match_list[i2.name]]
-        if _smart is not None:                                        # matcher.py:987-1005
-            avg, std = _smart.update_surface_estimate(i1, i2)
+        if _smart is not None and all(hasattr(im, a) for im in (i1, i2) for a in ("get_proj", "get_aircraft_pose", "set_aircraft_yaw_error_estimate")):
+            avg, std = _smart.update_surface_estimate(i1, i2)         # matcher.py:987-1005
             i1.set_aircraft_yaw_error_estimate(_smart.update_yaw_error_estimate(i1, i2))
             i2.set_aircraft_yaw_error_estimate(_smart.update_yaw_error_estimate(i2, i1))
             if std and std >= 50 and len(i1.match_list[i2.name]) < 100:

@@ -62,6 +62,8 @@ extern "C" {
 #define IAM_MODEL_ESSENTIAL    0   /* cv2.findEssentialMat  (matcher.py:126): 5-point, Sampson error          */
 #define IAM_MODEL_HOMOGRAPHY   1   /* cv2.findHomography    (matcher.py:122): 4-point, transfer error         */
 #define IAM_MODEL_FUNDAMENTAL  2   /* cv2.findFundamentalMat (matcher.py:124): 7-point, epipolar-line distance */
+#define IAM_MODEL_AFFINE_PARTIAL 3 /* cv2.estimateAffinePartial2D (smart.py:88-89): 2-point similarity, transfer error,
+                                      least-squares polish on the inliers; rows 0-1 of the 3 x 3 output are the 2 x 3 matrix */
 
 #define IAM_OK           0
 #define IAM_E_ARG       -1
@@ -252,6 +254,21 @@ int iam_ransac_pairs(iam_ctx* ctx, int model, const float* pts1, const float* pt
 int iam_ransac_tables(iam_ctx* ctx, int model, const double* K, double threshold_px, double prob, int max_iters,
                       uint32_t seed, int min_pairs, int compact, uint8_t* out_mask, double* out_model,
                       int32_t* out_inliers);
+
+/* ---- pair-wise side estimators of the 'smart' strategy (scripts/lib/smart.py) ---- */
+
+/* Two-view triangulation of the matches of n_pairs image pairs in one launch: what smart.triangulate_features
+ * (smart.py:26-63) computes per pair with cv2.triangulatePoints(PROJ1, PROJ2, pts1, pts2) followed by `points /=
+ * points[3]`, and the statistics estimate_surface_elevation (smart.py:116-131) takes of it (np.average / np.std of the
+ * down coordinate).  proj1, proj2: HOST double [n_pairs][12], the row-major 3 x 4 matrices [R | t] of Image.get_proj;
+ * off: HOST int32 [n_pairs + 1] prefix offsets into the point lists; x1, x2: HOST double [off[n_pairs]][2] normalised
+ * image coordinates K^-1 (u, v, 1) (rows 0-1 of smart.py:58-59's pts1 / pts2, transposed).  Outputs (HOST): out_points
+ * [off[n_pairs]][3] = X, Y, Z after the division by the homogeneous coordinate (may be NULL); out_stats [n_pairs][2] =
+ * mean and population standard deviation of Z (NaN for a pair without points).  float64 throughout; agreement with
+ * cv2: 1e-9 relative on well-conditioned geometry (tests/test_smart.py).  The partial-affine fit of find_affine
+ * (smart.py:66-90, cv2.estimateAffinePartial2D) is iam_ransac_pairs with IAM_MODEL_AFFINE_PARTIAL. */
+int iam_triangulate_pairs(iam_ctx* ctx, int n_pairs, const double* proj1, const double* proj2, const int32_t* off,
+                          const double* x1, const double* x2, double* out_points, double* out_stats);
 
 /* ---- feature detection: replaces cv2.ORB_create(n).detectAndCompute ---- */
 

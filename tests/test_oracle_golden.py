@@ -158,7 +158,7 @@ def test_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.iam_abi_version.restype = ctypes.c_int
-    assert lib.iam_abi_version() == 5
+    assert lib.iam_abi_version() == 6
 
 
 def test_product_fails_loudly_without_gpu_or_library(monkeypatch):
