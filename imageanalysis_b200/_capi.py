@@ -30,7 +30,7 @@ EXPORTS = (
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
     "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_triangulate_pairs", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_ba_calib_jacobian", "iam_triangulate_pairs", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -143,6 +143,7 @@ def load_library(path: Optional[str] = None):
                                      C.c_uint32, vp, vp, vp]
     lib.iam_ransac_tables.argtypes = [vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_orb_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
+    lib.iam_ba_calib_jacobian.argtypes = [vp, vp, vp, vp]
     lib.iam_triangulate_pairs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.iam_sift_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
     lib.iam_debug_orb_fast.argtypes = [vp, vp, C.c_int, C.c_int, vp]
@@ -416,6 +417,15 @@ class Engine:
         J = np.empty((n_obs, 2, 10), np.float64) if jac else None
         self._check(self._lib.iam_ba_eval(self._h, _ptr(p), _ptr(k4), _ptr(d5), _ptr(res), _ptr(J)), "iam_ba_eval")
         return (res, J) if jac else res
+
+    def ba_calib_jacobian(self, K4, dist5):
+        """[n_obs, 2, 8] = d residual / d (f, cu, cv, k1, k2, p1, p2, k3) at the parameters last uploaded."""
+        n_obs = self._ba_shape[2]
+        k4 = np.ascontiguousarray(K4, np.float64)
+        d5 = np.ascontiguousarray(dist5, np.float64)
+        J = np.empty((n_obs, 2, 8), np.float64)
+        self._check(self._lib.iam_ba_calib_jacobian(self._h, _ptr(k4), _ptr(d5), _ptr(J)), "iam_ba_calib_jacobian")
+        return J
 
     def ba_upload_params(self, params):
         p = np.ascontiguousarray(params, np.float64)

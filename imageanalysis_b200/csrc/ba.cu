@@ -129,7 +129,70 @@ ba_kernel(const double* __restrict__ cams, const double* __restrict__ points, co
   }
 }
 
+// Global-calibration mode (optimizer.py:146-147, :160-166, :181-189): the eight dense columns every residual row also
+// has -- d/d(f, cu, cv, k1, k2, p1, p2, k3) with fx = fy = f.  One thread per observation; the 2 x 8 block is staged
+// through shared memory like the main Jacobian so that a warp writes 4096 contiguous bytes.
+constexpr int kCalCols = 8, kCalPad = 2 * kCalCols + 1;
+__global__ void __launch_bounds__(kBaThreads)
+ba_calib_kernel(const double* __restrict__ cams, const double* __restrict__ points, const int* __restrict__ cam_idx,
+                const int* __restrict__ pt_idx, int n_obs, BaCalib c, double* __restrict__ jac) {
+  __shared__ double s_jac[kBaThreads * kCalPad];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = blockIdx.x * kBaThreads; base < n_obs; base += gridDim.x * kBaThreads) {
+    const int i = base + threadIdx.x;
+    double* mine = s_jac + static_cast<size_t>(threadIdx.x) * kCalPad;
+    if (i < n_obs) {
+      const double* cam = cams + static_cast<size_t>(cam_idx[i]) * 7;
+      const double* X = points + static_cast<size_t>(pt_idx[i]) * 3;
+      const double w = cam[3], x = cam[4], y = cam[5], z = cam[6];
+      const double inv_n = 1.0 / (w * w + x * x + y * y + z * z);
+      const double M[3][3] = {{w * w + x * x - y * y - z * z, 2.0 * (x * y - z * w), 2.0 * (x * z + y * w)},
+                              {2.0 * (x * y + z * w), w * w - x * x + y * y - z * z, 2.0 * (y * z - x * w)},
+                              {2.0 * (x * z - y * w), 2.0 * (y * z + x * w), w * w - x * x - y * y + z * z}};
+      const double d[3] = {X[0] - cam[0], X[1] - cam[1], X[2] - cam[2]};
+      double Xb[3];
+      for (int k = 0; k < 3; ++k) Xb[k] = (M[0][k] * d[0] + M[1][k] * d[1] + M[2][k] * d[2]) * inv_n;
+      const double iz = 1.0 / Xb[0];
+      const double xn = Xb[1] * iz, yn = Xb[2] * iz;
+      const double r2 = xn * xn + yn * yn;
+      const double rad = 1.0 + r2 * (c.k1 + r2 * (c.k2 + r2 * c.k3));
+      const double xd = xn * rad + 2.0 * c.p1 * xn * yn + c.p2 * (r2 + 2.0 * xn * xn);
+      const double yd = yn * rad + c.p1 * (r2 + 2.0 * yn * yn) + 2.0 * c.p2 * xn * yn;
+      // residual = observed - (f * distorted + centre): every derivative carries a minus sign
+      const double du[kCalCols] = {-xd, -1.0, 0.0, -c.fx * xn * r2, -c.fx * xn * r2 * r2, -c.fx * 2.0 * xn * yn,
+                                   -c.fx * (r2 + 2.0 * xn * xn), -c.fx * xn * r2 * r2 * r2};
+      const double dv[kCalCols] = {-yd, 0.0, -1.0, -c.fy * yn * r2, -c.fy * yn * r2 * r2, -c.fy * (r2 + 2.0 * yn * yn),
+                                   -c.fy * 2.0 * xn * yn, -c.fy * yn * r2 * r2 * r2};
+#pragma unroll
+      for (int k = 0; k < kCalCols; ++k) {
+        mine[k] = du[k];
+        mine[kCalCols + k] = dv[k];
+      }
+    }
+    __syncwarp();
+    const int wbase = base + warp * 32;
+    const int wcount = min(32, n_obs - wbase);
+    const double* ws = s_jac + static_cast<size_t>(warp) * 32 * kCalPad;
+    for (int e = lane; e < wcount * 2 * kCalCols; e += 32) {
+      const int o = e / (2 * kCalCols), k = e - o * (2 * kCalCols);
+      jac[static_cast<size_t>(wbase) * 2 * kCalCols + e] = ws[o * kCalPad + k];
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_ba_calib(const double* cams, const double* points, const int* cam_idx, const int* pt_idx, int n_obs,
+                            const BaCalib& calib, double* jac_calib, cudaStream_t stream) {
+  if (n_obs <= 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int want = (n_obs + kBaThreads - 1) / kBaThreads;
+  ba_calib_kernel<<<want < sms * 4 ? want : sms * 4, kBaThreads, 0, stream>>>(cams, points, cam_idx, pt_idx, n_obs, calib, jac_calib);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_ba(const double* cams, const double* points, const int* cam_idx, const int* pt_idx,
                       const double* obs_uv, int n_obs, const BaCalib& calib, double* residual, double* jac,

@@ -22,4 +22,8 @@ cudaError_t launch_ba(const double* cams, const double* points, const int* cam_i
                       const double* obs_uv, int n_obs, const BaCalib& calib, double* residual, double* jac,
                       cudaStream_t stream);
 
+// Global-calibration mode: jac_calib[16*i..] = the 2 x 8 block d residual_i / d (f, cu, cv, k1, k2, p1, p2, k3), fx = fy = f.
+cudaError_t launch_ba_calib(const double* cams, const double* points, const int* cam_idx, const int* pt_idx, int n_obs,
+                            const BaCalib& calib, double* jac_calib, cudaStream_t stream);
+
 }  // namespace iam

@@ -152,7 +152,7 @@ struct iam_ctx {
   int* d_ctx_flag = nullptr;          // device word, cleared by a conversion that met such descriptors
   int last_kind = -1;
   // bundle-adjustment problem (iam_ba_*): structure resident, parameters re-uploaded per evaluation
-  Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac;
+  Buffer ba_params, ba_cam_idx, ba_pt_idx, ba_obs, ba_res, ba_jac, ba_jac_cal;
   // robust fits (iam_ransac_*): device block kept between calls, outputs of the table form
   iam::RansacScratch ransac_scratch;
   iam::OrbScratch orb_scratch;
@@ -1710,6 +1710,25 @@ int iam_ba_eval(iam_ctx* c, const double* params, const double* K4, const double
     if (out_jac)
       CU(cudaMemcpyAsync(out_jac, c->ba_jac.p, size_t(c->ba_n_obs) * 2 * iam::kBaJacCols * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
+  CU(cudaStreamSynchronize(c->stream));
+  return IAM_OK;
+}
+
+int iam_ba_calib_jacobian(iam_ctx* c, const double* K4, const double* dist5, double* out_jac_calib) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (c->ba_n_obs < 0) return fail(IAM_E_STATE, "iam_ba_setup has not been called");
+  if (!K4 || !dist5 || !out_jac_calib) return fail(IAM_E_ARG, "K4, dist5 and the output are required");
+  iam::BaCalib cal{K4[0], K4[1], K4[2], K4[3], dist5[0], dist5[1], dist5[2], dist5[3], dist5[4]};
+  const size_t bytes = std::max<size_t>(1, c->ba_n_obs) * 16 * sizeof(double);
+  CU(c->ba_jac_cal.ensure(bytes));
+  const double* cams = c->ba_params.as<double>();
+  cudaError_t e = iam::launch_ba_calib(cams, cams + size_t(c->ba_n_cam) * 7, c->ba_cam_idx.as<int>(), c->ba_pt_idx.as<int>(),
+                                       c->ba_n_obs, cal, c->ba_jac_cal.as<double>(), c->stream);
+  if (e != cudaSuccess) return fail(IAM_E_CUDA, "calibration Jacobian launch: %s", cudaGetErrorString(e));
+  c->timing.total_launches += 1;
+  if (c->ba_n_obs > 0)
+    CU(cudaMemcpyAsync(out_jac_calib, c->ba_jac_cal.p, size_t(c->ba_n_obs) * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return IAM_OK;
 }

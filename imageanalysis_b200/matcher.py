@@ -62,6 +62,11 @@ gms_enabled = True
 # grids (what cv2.xfeatures2d.matchGMS at matcher.py:285 executes); True = the wrap-around of the reference's archive
 # Python restatement (scripts/lib/archive/gms_matcher.py:205), for bit-for-bit agreement with that module.
 gms_archive_rule = False
+# find_matches('traditional'): how many images' descriptors are brought to the host per device call, and whether images
+# whose features this module loaded itself are dropped from the host once matched (the reference's cache flush,
+# matcher.py:1012-1026; key points come back through Image.load_features when a later step asks for them).
+host_block_images = 256
+flush_host_descriptors = True
 the_matcher = None
 max_distance = None
 min_pairs = 25
@@ -771,39 +776,68 @@ def find_matches(proj, K, strategy="smart", transform="homography", sort=False, 
 def _batched_traditional(image_list, todo):
     """bidirectional_pair_matches for every pair of `todo` in one device
     pipeline: kNN both ways -> metric reduction -> [GMS] -> filter_duplicates
-    -> min_pairs gates -> cross-check (reduce.cu)."""
+    -> min_pairs gates -> cross-check (reduce.cu).
+
+    The pair list is walked in blocks that bring at most `host_block_images` NEW images to the host at a time: their
+    descriptors are loaded (Image.detect_features / the .desc cache), handed to one iam_match_images call together with
+    the block's pairs (images of earlier blocks stay resident on the device), and -- when this function loaded them --
+    dropped from the host again right after the upload (later pairs read the device copy), which is what the reference's descriptor-cache flush
+    (matcher.py:1012-1026) is for: the float32 descriptors of a 2812-frame project are 7.2 GB, the device copies 1.8 GB."""
     if not todo:
         return []
-    used = sorted({i for p in todo for i in p})
-    for i in used:
-        _ensure_features(image_list[i])
-    arrays = [GpuKnnMatcher._as_device_dtype(image_list[i].des_list, _norm) for i in used]
-    if len({a.dtype for a in arrays}) > 1:   # mixed caches: widen everything to float32
-        arrays = [np.ascontiguousarray(a, np.float32) for a in arrays]
-    keys = [keypoint_keys(image_list[i].kp_list) for i in used]
-    eng = the_matcher.engine(int(arrays[0].shape[1]))
+    eng = None
     w, h = _image_size()
     if not w or not h:
         log("Zero image sizes will crash matchGMS():", w, h)
         quit()
-    if gms_enabled:   # keypoint coordinates for the GMS stage (matcher.py:285); the descriptors follow inside the call
-        for i in used:
-            eng.upload_keypoints(i, np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2))
     prm = _capi.Engine.make_params(match_ratio=matcher_node.getFloat('match_ratio'), max_distance=float(max_distance),
                                    reduce_mode=_capi.REDUCE_REF_METRIC, cap=2000, min_pairs=int(min_pairs),
                                    cross_check=True, dedupe=True, gms=(2 if gms_archive_rule else 1) if gms_enabled else 0,
                                    gms_rotation=True, gms_scale=False,
                                    gms_threshold=5.0, size=(w, h))
-    # one C call: uploads are enqueued wave by wave so PCIe overlaps the matching.  The call uploads an image right
-    # before the first pair that needs it: handing it the pairs sorted by their LATER image lets matching start after
-    # the first few images instead of after everything the first image's neighbours reach (results are independent
-    # of the order, matcher.py:928-980; they are mapped back to the work-list order below).
+    # The call uploads an image right before the first pair that needs it: handing it the pairs sorted by their LATER
+    # image lets matching start after the first few images instead of after everything the first image's neighbours
+    # reach (results are independent of the order, matcher.py:928-980; they are mapped back to the work-list order).
     order = sorted(range(len(todo)), key=lambda p: (max(todo[p]), min(todo[p])))
-    table, count = eng.match_images(used, arrays, np.int32([todo[p] for p in order]), prm, keys=keys)
     out = [None] * len(todo)
-    for k, p in enumerate(order):
-        fwd = table[k, :count[k]].tolist()
-        out[p] = (fwd, [[t, q] for q, t in fwd])
+    uploaded, ours = set(), set()
+    pos = 0
+    while pos < len(order):
+        new, end = [], pos
+        while end < len(order):
+            need = [i for i in sorted(set(todo[order[end]])) if i not in uploaded and i not in new]
+            if new and len(new) + len(need) > max(2, int(host_block_images)):
+                break
+            new += need
+            end += 1
+        for i in new:
+            img = image_list[i]
+            if img.des_list is None or img.kp_list is None or not len(img.kp_list):
+                ours.add(i)
+            _ensure_features(img)
+        arrays = [GpuKnnMatcher._as_device_dtype(image_list[i].des_list, _norm) for i in new]
+        if len({a.dtype for a in arrays}) > 1:   # mixed caches: widen everything to float32
+            arrays = [np.ascontiguousarray(a, np.float32) for a in arrays]
+        keys = [keypoint_keys(image_list[i].kp_list) for i in new]
+        if eng is None:
+            eng = the_matcher.engine(int(arrays[0].shape[1]))
+        if gms_enabled:   # keypoint coordinates for the GMS stage (matcher.py:285); the descriptors follow inside the call
+            for i in new:
+                eng.upload_keypoints(i, np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2))
+        table, count = eng.match_images(new, arrays, np.int32([todo[p] for p in order[pos:end]]).reshape(-1, 2), prm, keys=keys)
+        for k, p in enumerate(order[pos:end]):
+            fwd = table[k, :count[k]].tolist()
+            out[p] = (fwd, [[t, q] for q, t in fwd])
+        uploaded.update(new)
+        del arrays, keys, table, count
+        if flush_host_descriptors and not apply_transform_filter:
+            for i in [i for i in new if i in ours]:   # later pairs read the device copy: the host copy is not needed again
+                img = image_list[i]
+                img.kp_list = None
+                img.des_list = None
+                img.uv_list = None
+                ours.discard(i)
+        pos = end
     return out
 
 

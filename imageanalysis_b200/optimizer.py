@@ -103,21 +103,26 @@ class Optimizer():
         return error
 
     def jac(self, params, n_cameras, n_points, by_camera_point_indices, by_camera_points_2d):
-        """d fun / d params as scipy.sparse.csr_matrix of shape (2*n_obs, n_cameras*7 + n_points*3): the pattern
-        bundle_adjustment_sparsity() declares, filled analytically.  Only for optimize_calib == 'none'."""
+        """d fun / d params as scipy.sparse.csr_matrix of shape (2*n_obs, n_cameras*7 + n_points*3 [+ 8]): the pattern
+        bundle_adjustment_sparsity() declares, filled analytically -- in global-calibration mode including the eight
+        dense columns d/d(f, cu, cv, k1, k2, p1, p2, k3) at the end (:160-166)."""
         from scipy.sparse import csr_matrix
-        if self.optimize_calib != 'none':
-            raise NotImplementedError("analytic Jacobian with global calibration parameters is not offered")
         self._bind(n_cameras, n_points, by_camera_point_indices, by_camera_points_2d)
         K4, dist = self._calib(params, n_cameras, n_points)
         _, J = self._engine().ba_eval(params, K4, dist, jac=True)
         n_obs = self._shape[2]
-        cols = np.empty((n_obs, 10), np.int64)
+        glob = self.optimize_calib == 'global'
+        per = 18 if glob else 10
+        n_cols = n_cameras * 7 + n_points * 3 + (8 if glob else 0)
+        cols = np.empty((n_obs, per), np.int64)
         cols[:, :7] = self.camera_indices[:, None] * 7 + np.arange(7)
-        cols[:, 7:] = n_cameras * 7 + self.point_indices[:, None] * 3 + np.arange(3)
-        indices = np.repeat(cols, 2, axis=0).ravel()            # rows 2i and 2i+1 share their ten columns
-        indptr = np.arange(0, 20 * n_obs + 1, 10)
-        return csr_matrix((J.ravel(), indices, indptr), shape=(2 * n_obs, n_cameras * 7 + n_points * 3))
+        cols[:, 7:10] = n_cameras * 7 + self.point_indices[:, None] * 3 + np.arange(3)
+        if glob:
+            cols[:, 10:] = n_cameras * 7 + n_points * 3 + np.arange(8)
+            J = np.concatenate([J, self._engine().ba_calib_jacobian(K4, dist)], axis=2)
+        indices = np.repeat(cols, 2, axis=0).ravel()            # rows 2i and 2i+1 share their columns
+        indptr = np.arange(0, 2 * per * n_obs + 1, per)
+        return csr_matrix((J.ravel(), indices, indptr), shape=(2 * n_obs, n_cols))
 
     # -- optimizer.py:142-169 (same pattern, built without the Python loops) ---
     def bundle_adjustment_sparsity(self, n_cameras, n_points, camera_indices, point_indices):

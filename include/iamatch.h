@@ -324,6 +324,11 @@ int iam_ba_eval(iam_ctx* ctx, const double* params, const double* K4, const doub
 int iam_ba_upload_params(iam_ctx* ctx, const double* params);
 int iam_ba_eval_device(iam_ctx* ctx, const double* K4, const double* dist5, int want_jac,
                        void** d_residual, void** d_jac);
+/* Global-calibration mode (optimizer.py:146-147, :160-166, :181-189: K and distCoeffs are the last eight entries of the
+ * parameter vector, fx = fy): the eight dense Jacobian columns of every residual row, at the parameters last uploaded
+ * (iam_ba_eval / iam_ba_upload_params).  out_jac_calib (HOST) [n_obs][2][8] = d residual / d (f, cu, cv, k1, k2, p1,
+ * p2, k3), the column order of bundle_adjustment_sparsity's calibration block. */
+int iam_ba_calib_jacobian(iam_ctx* ctx, const double* K4, const double* dist5, double* out_jac_calib);
 /* Debug aid: the per-observation function of the kernel (same source) evaluated on the HOST.  Needs no GPU. */
 int iam_debug_ba_host(const double* cam7, const double* pt3, const double* uv, const double* K4,
                       const double* dist5, double* out_res2, double* out_jac20);

@@ -111,3 +111,48 @@ def test_gpu_optimizer_dropin_in_least_squares():
     r_fd = least_squares(opt.fun, prob["params"], jac_sparsity=A, **kw)
     assert r_an.cost < 0.2 * 0.5 * float(f0 @ f0)
     assert abs(r_an.cost - r_fd.cost) <= 1e-6 * r_fd.cost
+
+
+@pytest.mark.gpu
+def test_gpu_global_calibration_jacobian():
+    """optimize_calib == 'global' (optimizer.py:146-147, :160-166, :181-189): fun() with the calibration riding at the end
+    of the vector equals the reference golden, jac() has the declared sparsity pattern, and its eight dense columns
+    d/d(f, cu, cv, k1, k2, p1, p2, k3) equal central differences of the CPU oracle (1e-5 relative)."""
+    from imageanalysis_b200 import optimizer
+    g = load_golden("ba_reference.npz")
+    c = _case(g, "small")
+    p = np.array(g["small_global_params"], np.float64)
+    n_cam, n_pts = c["n_cam"], c["n_pts"]
+    n_obs = len(c["cam_idx"])
+    idx_lists = [c["pt_idx"][c["cam_idx"] == k] for k in range(n_cam)]
+    uv_lists = [c["obs_uv"][c["cam_idx"] == k] for k in range(n_cam)]
+    assert (np.diff(c["cam_idx"]) >= 0).all()          # observations are laid out camera by camera (:396-404)
+    opt = optimizer.Optimizer()
+    opt.optimize_calib = 'global'
+    f = opt.fun(p, n_cam, n_pts, idx_lists, uv_lists)
+    assert np.abs(f - g["small_global_residual"]).max() < 1e-9
+    J = opt.jac(p, n_cam, n_pts, idx_lists, uv_lists)
+    A = opt.bundle_adjustment_sparsity(n_cam, n_pts, c["cam_idx"], c["pt_idx"])
+    assert J.shape == A.shape == (2 * n_obs, n_cam * 7 + n_pts * 3 + 8)
+    assert (J.indices == A.indices).all() and (J.indptr == A.indptr).all()
+    Jd = J.toarray()
+    base = n_cam * 7 + n_pts * 3
+
+    def residual(q):
+        cal = q[base:]
+        return oracle.ba_residuals(q, n_cam, n_pts, c["cam_idx"], c["pt_idx"], c["obs_uv"], (cal[0], cal[0], cal[1], cal[2]), cal[3:])
+
+    for k in range(8):
+        h = 1e-6 * max(1.0, abs(p[base + k]))
+        hi, lo = p.copy(), p.copy()
+        hi[base + k] += h
+        lo[base + k] -= h
+        fd = (residual(hi) - residual(lo)) / (2 * h)
+        assert (np.abs(Jd[:, base + k] - fd) / (1.0 + np.abs(fd))).max() < 1e-5, k
+    # the camera / point columns are those of the fixed-calibration Jacobian at the same K
+    opt2 = optimizer.Optimizer()
+    cal = p[base:]
+    opt2.K = np.array([[cal[0], 0, cal[1]], [0, cal[0], cal[2]], [0, 0, 1.0]])
+    opt2.distCoeffs = cal[3:]
+    J2 = opt2.jac(p[:base], n_cam, n_pts, idx_lists, uv_lists).toarray()
+    assert np.array_equal(Jd[:, :base], J2)

@@ -461,6 +461,65 @@ def test_find_matches_equals_reference_driver():
     assert before == {im.name: im.match_list for im in imgs}
 
 
+def test_find_matches_loads_images_block_wise_and_flushes_them():
+    """The 'traditional' strategy brings at most `host_block_images` new images to the host per device call, keeps the
+    earlier ones resident on the device, and drops the features it loaded itself once no later pair needs them
+    (the reference's descriptor-cache flush, matcher.py:1012-1026).  Results are those of the one-call path."""
+    g = load_golden("reference_find_matches.npz")
+    matcher = _configure_matcher()
+    n = int(g["n"])
+
+    class LazyImage(FakeImage):
+        live, peak, loads = 0, 0, 0
+
+        def __init__(self, i):
+            super().__init__("frame%02d" % i, None, [], g["ned%d" % i])
+            self.i = i
+            self.kp_list = None
+
+        def detect_features(self, scale):          # the .feat / .desc cache hit of Image.detect_features (image.py:287-296)
+            pts = g["pts%d" % self.i]
+            self.des_list = g["des%d" % self.i].astype(np.float32)
+            self.kp_list = [types.SimpleNamespace(pt=(float(p[0]), float(p[1]))) for p in pts]
+            self.uv_list = [list(map(float, p)) for p in pts]
+            LazyImage.loads += 1
+
+    def live_now(imgs):
+        return sum(im.des_list is not None for im in imgs)
+
+    imgs = [LazyImage(i) for i in range(n)]
+    preloaded = imgs[3]
+    preloaded.detect_features(1.0)                  # the caller's own copy must survive
+    LazyImage.loads = 0
+    proj = types.SimpleNamespace(image_list=imgs, analysis_dir="/tmp")
+    K = np.array([[3666.666504, 0, 2736], [0, 3666.666504, 1824], [0, 0, 1]])
+    old = matcher.host_block_images
+    matcher.host_block_images = 2
+    peak = [0]
+    real = matcher._capi.Engine.match_images
+
+    def spy(self, ids, arrays, pairs, prm, keys=None, out=None):
+        assert len(ids) <= 2 or peak[0] == 0       # the first block holds the first pair's two images
+        peak[0] = max(peak[0], live_now(imgs))
+        return real(self, ids, arrays, pairs, prm, keys=keys, out=out)
+
+    matcher._capi.Engine.match_images = spy
+    try:
+        matcher.find_matches(proj, K, strategy="traditional")
+    finally:
+        matcher._capi.Engine.match_images = real
+        matcher.host_block_images = old
+    assert LazyImage.loads == n - 1                 # every image loaded exactly once
+    assert peak[0] <= 3                             # a block's two images + the caller's preloaded one, never all 7
+    assert preloaded.des_list is not None and live_now(imgs) == 1
+    checked = 0
+    for im in imgs:
+        for other, lst in im.match_list.items():
+            assert lst == g["match_%s_%s" % (im.name, other)].tolist(), (im.name, other)
+            checked += 1
+    assert checked == 2 * 18
+
+
 def test_find_matches_with_gms_equals_reference_driver():
     """find_matches() with the GMS stage live against the reference's own find_matches run with
     cv2.xfeatures2d.matchGMS served by its archive GmsMatcher (tests/golden/make_golden_gms.py)."""
@@ -518,6 +577,51 @@ def test_non_integer_descriptors_tolerance_path():
     oi, od = oracle.knn(q, t.astype(np.float32), 2, oracle.NORM_L2)
     assert (idx[0, :, 0] == oi[:, 0]).mean() > 0.99
     assert np.allclose(dist[0, :, 0], od[:, 0], rtol=2e-3, atol=2e-3)
+
+
+def test_non_integer_descriptors_ratio_and_tables():
+    """The tolerance path end to end (north_star: "within a stated tolerance on distance AND ratio"): non-integer float
+    descriptors of SIFT magnitude through fp16 operands.  Stated tolerance: distance 2e-3 relative, Lowe ratio d0/d1
+    4e-3 absolute on rows whose two neighbours agree (>= 99 % of rows), and the match tables of both reductions agree
+    with float64 arithmetic as SETS with IoU >= 0.97 -- every pair that differs sits within 1 % of a threshold."""
+    rng = np.random.default_rng(18)
+    n = 1500
+    base = synth.sift_like(n, seed=77).astype(np.float32)
+    q = base + rng.uniform(-0.5, 0.5, base.shape).astype(np.float32)              # non-integer: no exact byte path
+    perm = rng.permutation(n)
+    t = (base[perm] + rng.normal(0, 2.5, base.shape)).astype(np.float32)
+    t[n // 2:] = synth.sift_like(n - n // 2, seed=78).astype(np.float32) + 0.25     # half of the rows have no partner
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    eng.upload(0, q)
+    eng.upload(1, t)
+    assert eng.descriptors_exact(0) == 0 and eng.descriptors_exact(1) == 0
+    idx, dist, ridx, rdist = eng.knn_pairs([(0, 1)], 2, n, reverse=True)
+    oi, od = oracle.knn(q, t, 2, oracle.NORM_L2)
+    same = (idx[0] == oi).all(axis=1)
+    assert same.mean() >= 0.99
+    assert np.allclose(dist[0][same], od[same], rtol=2e-3, atol=0)
+    r_gpu, r_ref = dist[0][same, 0] / dist[0][same, 1], od[same, 0].astype(np.float64) / od[same, 1]
+    assert np.abs(r_gpu - r_ref).max() <= 4e-3
+    for mode, name in ((_capi.REDUCE_REF_METRIC, "ref_metric"), (_capi.REDUCE_LOWE, "lowe")):
+        prm = _capi.Engine.make_params(reduce_mode=mode, cross_check=True, min_pairs=25, cap=2000)
+        table, count = eng.match_pairs([(0, 1)], prm)
+        got = {tuple(r) for r in table[0, :count[0]].tolist()}
+        f, _ = oracle.bidirectional(q, t, oracle.NORM_L2, 0.75, 270.0, cap=2000, min_pairs=25, threads=4, mode=name, cross_check=True)
+        want = {tuple(r) for r in f}
+        assert len(want) > 300
+        iou = len(got & want) / len(got | want)
+        assert iou >= 0.97, (name, iou)
+        for qi, ti in got ^ want:         # every disagreement is a row on a threshold
+            d0, d1 = float(od[qi, 0]), float(od[qi, 1])
+            ratio = d0 / d1
+            metric = d0 * ratio
+            near = abs(ratio - 0.75) < 0.0075 if name == "lowe" else abs(metric - 270.0 * 0.75) < 2.1
+            # ... or its reverse-direction partner is (cross-check removes both)
+            if not near:
+                ro, rd = oracle.knn(t[ti:ti + 1], q, 2, oracle.NORM_L2)
+                e0, e1 = float(rd[0, 0]), float(rd[0, 1])
+                near = abs(e0 / e1 - 0.75) < 0.0075 if name == "lowe" else abs(e0 * e0 / e1 - 270.0 * 0.75) < 2.1
+            assert near, (name, qi, ti, ratio, metric)
 
 
 def test_error_paths():
