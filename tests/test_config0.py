@@ -114,3 +114,73 @@ def test_config0_find_matches_equals_reference_driver(tmp_path):
         assert pickle.dumps(im.match_list) == pickle.dumps(want)          # the .match file of this image
     assert checked == 108 and matches > 50000
     matcher.gms_enabled = False
+
+
+@pytest.mark.gpu
+def test_config0_detect_and_match_entirely_on_the_gpu(tmp_path):
+    """configs[0] with NOTHING left on the CPU but the resize: Image.detect_features' detector call served by the GPU SIFT
+    (detector.SIFT_create), the features cached in the reference's .feat / .desc formats, and find_matches on the GPU.
+    SIFT is a float pipeline (tests/test_sift.py), so a fraction of a per cent of the key points differ from cv2's and
+    the index lists cannot be compared literally: GPU key points are mapped onto cv2's (same position / size /
+    orientation) and the match SETS of every pair are compared with the reference driver's -- stated bar: at least
+    98 % of the reference's matches reproduced per pair on average, at least 95 % for every pair, and at most 3 %
+    extra."""
+    from test_gpu_parity import FakeImage
+    from imageanalysis_b200 import detector, featcache, matcher
+    from imageanalysis_b200.propshim import getNode
+    from oracle import sift as S
+    g, feats = _features()
+    det = detector.SIFT_create()
+    gpu_feats, to_ref = [], []
+    for n, (frame, (pts_ref, des_ref)) in enumerate(zip(gen.frames(), feats)):
+        scaled = cv2.resize(frame, (0, 0), fx=gen.SCALE, fy=gen.SCALE)                      # image.py:306
+        feat, desc = str(tmp_path / ("f%02d.feat" % n)), str(tmp_path / ("f%02d.desc" % n))
+        kps, des = featcache.detect_and_cache(scaled, gen.SCALE, feat, desc, det=det)        # :324, :343-349
+        kps, des = featcache.load_features(feat), featcache.load_descriptors(desc)           # what a later run loads
+        assert des.dtype == np.float32 and des.shape == (len(kps), 128)
+        pts = np.float32([k.pt for k in kps])
+        ref_kp = cv2.SIFT_create().detect(scaled, None)
+        a = np.float32([[k.pt[0] * gen.SCALE, k.pt[1] * gen.SCALE, k.size, k.angle, 0] for k in kps])
+        b = np.float32([[k.pt[0], k.pt[1], k.size, k.angle, 0] for k in ref_kp])
+        assert len(b) == len(pts_ref)
+        m = S.match_keypoints(a, b)
+        assert (m >= 0).mean() >= 0.99, n
+        gpu_feats.append((pts, des))
+        to_ref.append(m)
+    matcher.gms_enabled = True
+    matcher.gms_archive_rule = True
+    d = getNode("/config/detector", True)
+    d.setString("detector", "SIFT")
+    d.setFloat("scale", gen.SCALE)
+    mn = getNode("/config/matcher", True)
+    mn.setFloat("match_ratio", 0.75)
+    mn.setFloat("min_pairs", 25)
+    cam = getNode("/config/camera", True)
+    cam.setInt("width_px", gen.W)
+    cam.setInt("height_px", gen.H)
+    matcher.configure()
+    imgs = [FakeImage("frame%02d" % i, des, pts, (0.0, 12.0 * i, -60.0)) for i, (pts, des) in enumerate(gpu_feats)]
+    proj = types.SimpleNamespace(image_list=imgs, analysis_dir=str(tmp_path))
+    K = np.array([[1388.0, 0, 960.0], [0, 1388.0, 540.0], [0, 0, 1]])
+    try:
+        matcher.find_matches(proj, K, strategy="traditional", transform="homography", sort=False, review=False)
+    finally:
+        matcher.gms_archive_rule = False
+        matcher.gms_enabled = False
+    recall, extra = [], []
+    index = {im.name: i for i, im in enumerate(imgs)}
+    for im in imgs:
+        want = {k[len("match_%s_" % im.name):]: g[k].tolist() for k in g.files if k.startswith("match_%s_" % im.name)}
+        assert set(im.match_list) == set(want), im.name
+        for other, ref in want.items():
+            ma, mb = to_ref[index[im.name]], to_ref[index[other]]
+            got = {(int(ma[q]), int(mb[t])) for q, t in im.match_list[other] if ma[q] >= 0 and mb[t] >= 0}
+            ref = {tuple(r) for r in ref}
+            if len(ref) == 0:
+                assert len(im.match_list[other]) < 40, (im.name, other)
+                continue
+            recall.append(len(got & ref) / len(ref))
+            extra.append((len(im.match_list[other]) - len(got & ref)) / max(1, len(ref)))
+    assert len(recall) >= 100
+    assert np.mean(recall) >= 0.98 and min(recall) >= 0.95, (np.mean(recall), min(recall))
+    assert np.mean(extra) <= 0.03, np.mean(extra)
