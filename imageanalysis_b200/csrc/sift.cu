@@ -40,6 +40,9 @@ constexpr int kMaxKernel = 64;
 #ifndef IAM_SIFT_GENERIC_BLUR
 #define IAM_SIFT_GENERIC_BLUR 0
 #endif
+#ifndef IAM_SIFT_SEQ_ORI
+#define IAM_SIFT_SEQ_ORI 0
+#endif
 #ifndef IAM_SIFT_SEQ_DESC
 #define IAM_SIFT_SEQ_DESC 0
 #endif
@@ -300,9 +303,10 @@ __device__ bool adjust_extremum(const float* base, const Octave& O, int o, int l
   return true;
 }
 
-__global__ void extrema_kernel(const float* __restrict__ base, Pyramid P, int o, int layer, Cand* __restrict__ cand,
+__global__ void extrema_kernel(const float* __restrict__ base, Pyramid P, int o, Cand* __restrict__ cand,
                                int* __restrict__ n_cand, int cap) {
   const Octave O = P.oct[o];
+  const int layer = blockIdx.z + 1;   // the three inner DoG layers of the octave in one launch
   const int c = blockIdx.x * blockDim.x + threadIdx.x + kImgBorder, r = blockIdx.y * blockDim.y + threadIdx.y + kImgBorder;
   if (c >= O.w - kImgBorder || r >= O.h - kImgBorder) return;
   const int w = O.w;
@@ -348,8 +352,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
   return a;
 }
 
-// calcOrientationHist + the peak loop of findScaleSpaceExtrema: one thread per refined extremum
-__global__ void orientation_kernel(const float* __restrict__ base, Pyramid P, const Cand* __restrict__ cand,
+// calcOrientationHist + the peak loop of findScaleSpaceExtrema, one thread per refined extremum in OpenCV's loop order:
+// the A/B reference of orientation_kernel (-DIAM_SIFT_SEQ_ORI=1 selects it)
+__global__ void orientation_seq_kernel(const float* __restrict__ base, Pyramid P, const Cand* __restrict__ cand,
                                    const int* __restrict__ n_cand, int cand_cap, KeyOut* __restrict__ keys,
                                    int* __restrict__ n_keys, int key_cap) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -406,6 +411,79 @@ __global__ void orientation_kernel(const float* __restrict__ base, Pyramid P, co
         keys[pos] = k;
       }
     }
+  }
+}
+
+// calcOrientationHist + the peak loop of findScaleSpaceExtrema, one WARP per refined extremum (persistent warps stride
+// the candidate list, whose length only the device knows).  The lanes share the (2 radius + 1)^2 window; weighted
+// magnitudes are added to the 36-bin histogram as 64-bit fixed point (2^-40), so the sums are exact and do not depend
+// on the order the lanes arrive in; lane 0 smooths the histogram and emits one key point per peak.
+constexpr int kOriWarps = 4;
+__global__ void __launch_bounds__(kOriWarps * 32) orientation_kernel(const float* __restrict__ base, Pyramid P,
+                                                                    const Cand* __restrict__ cand, const int* __restrict__ n_cand,
+                                                                    int cand_cap, KeyOut* __restrict__ keys,
+                                                                    int* __restrict__ n_keys, int key_cap) {
+  __shared__ unsigned long long hist_s[kOriWarps][kOriBins];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = min(*n_cand, cand_cap);
+  unsigned long long* hq = hist_s[warp];
+  for (int i = blockIdx.x * kOriWarps + warp; i < total; i += gridDim.x * kOriWarps) {
+    for (int k = lane; k < kOriBins; k += 32) hq[k] = 0ull;
+    __syncwarp();
+    const Cand cd = cand[i];
+    const Octave O = P.oct[cd.o];
+    const float* img = base + O.gauss[cd.layer];
+    const int w = O.w, h = O.h, n = kOriBins;
+    const float scl_octv = __fdiv_rn(__fmul_rn(cd.size, 0.5f), (float)(1 << cd.o));
+    const int radius = __float2int_rn(__fmul_rn(4.5f, scl_octv));
+    const float sigma = __fmul_rn(1.5f, scl_octv);
+    const float expf_scale = __fdiv_rn(-1.f, __fmul_rn(__fmul_rn(2.f, sigma), sigma));
+    const int side = 2 * radius + 1;
+    for (int s = lane; s < side * side; s += 32) {
+      const int di = s / side - radius, dj = s % side - radius;
+      const int y = cd.r + di, x = cd.c + dj;
+      if (y <= 0 || y >= h - 1 || x <= 0 || x >= w - 1) continue;
+      const float dx = __fsub_rn(at(img, w, y, x + 1), at(img, w, y, x - 1));
+      const float dy = __fsub_rn(at(img, w, y - 1, x), at(img, w, y + 1, x));
+      const float wgt = expf(__fmul_rn((float)(di * di + dj * dj), expf_scale));
+      const float ori = fast_atan2_deg(dy, dx);
+      const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      int bin = __float2int_rn(__fmul_rn(0.1f, ori));   // (n / 360.f) * Ori
+      if (bin >= n) bin -= n;
+      if (bin < 0) bin += n;
+      atomicAdd(&hq[bin], (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(wgt, mag), 1099511627776.f)));
+    }
+    __syncwarp();
+    if (lane == 0) {
+      float temphist[kOriBins], hist[kOriBins];
+      for (int k = 0; k < n; ++k) temphist[k] = __fmul_rn(__ll2float_rn((long long)hq[k]), 9.094947017729282e-13f);
+      float omax = 0.f;
+      for (int k = 0; k < n; ++k) {
+        const float m2 = temphist[(k + n - 2) % n], m1 = temphist[(k + n - 1) % n], p1 = temphist[(k + 1) % n], p2 = temphist[(k + 2) % n];
+        hist[k] = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(m2, p2), 1.f / 16.f), __fmul_rn(__fadd_rn(m1, p1), 4.f / 16.f)),
+                            __fmul_rn(temphist[k], 6.f / 16.f));
+        omax = k == 0 ? hist[0] : fmaxf(omax, hist[k]);
+      }
+      const float mag_thr = __fmul_rn(omax, 0.8f);
+      for (int j = 0; j < n; ++j) {
+        const int l = j > 0 ? j - 1 : n - 1, r2 = j < n - 1 ? j + 1 : 0;
+        if (hist[j] > hist[l] && hist[j] > hist[r2] && hist[j] >= mag_thr) {
+          float bin = __fadd_rn((float)j, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(hist[l], hist[r2])),
+                                                    __fadd_rn(__fsub_rn(hist[l], __fmul_rn(2.f, hist[j])), hist[r2])));
+          bin = bin < 0.f ? __fadd_rn((float)n, bin) : (bin >= (float)n ? __fsub_rn(bin, (float)n) : bin);
+          float ang = __fsub_rn(360.f, __fmul_rn(10.f, bin));
+          if (fabsf(__fsub_rn(ang, 360.f)) < 1.1920929e-07f) ang = 0.f;
+          const int pos = atomicAdd(n_keys, 1);
+          if (pos < key_cap) {
+            KeyOut k;
+            k.x = cd.x; k.y = cd.y; k.size = cd.size; k.angle = ang; k.response = cd.response;
+            k.octave_field = cd.octave_field; k.o = cd.o; k.layer = cd.layer;
+            keys[pos] = k;
+          }
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -784,12 +862,16 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   for (int o = 0; o < P.n_oct; ++o) {
     const Octave& O = P.oct[o];
     if (O.w <= 2 * kImgBorder || O.h <= 2 * kImgBorder) continue;
-    for (int i = 1; i <= kNL; ++i) {
-      extrema_kernel<<<grid(O.w - 2 * kImgBorder, O.h - 2 * kImgBorder), blk2, 0, stream>>>(base, P, o, i, d_cand, d_cnt, cand_cap);
-      ++launches;
-    }
+    dim3 g3 = grid(O.w - 2 * kImgBorder, O.h - 2 * kImgBorder);
+    g3.z = kNL;
+    extrema_kernel<<<g3, blk2, 0, stream>>>(base, P, o, d_cand, d_cnt, cand_cap);
+    ++launches;
   }
-  orientation_kernel<<<(cand_cap + 127) / 128, 128, 0, stream>>>(base, P, d_cand, d_cnt, cand_cap, d_keys, d_cnt + 1, key_cap);
+#if IAM_SIFT_SEQ_ORI
+  orientation_seq_kernel<<<(cand_cap + 127) / 128, 128, 0, stream>>>(base, P, d_cand, d_cnt, cand_cap, d_keys, d_cnt + 1, key_cap);
+#else
+  orientation_kernel<<<148 * 8, kOriWarps * 32, 0, stream>>>(base, P, d_cand, d_cnt, cand_cap, d_keys, d_cnt + 1, key_cap);
+#endif
   ++launches;
   mark("enqueue pyramid..orientation");
   int h_cnt[2];

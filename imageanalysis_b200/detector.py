@@ -17,11 +17,14 @@ unchanged) and the uint8 [N, 32] descriptor array.  There is no CPU fallback.
 """
 from __future__ import annotations
 
+import queue
+
 import numpy as np
 
 from . import _capi
 
 _engine = None
+_pool = []
 device = 0
 
 
@@ -48,6 +51,32 @@ def sift_detect_and_compute(image: np.ndarray) -> dict:
     """Arrays: pt [n, 2] f32, size, angle, response [n] f32, octave [n] i32 (cv2's packed field), des [n, 128] u8."""
     kp, octv, des = _eng().sift_detect(to_gray(image))
     return dict(pt=kp[:, 0:2].copy(), size=kp[:, 2].copy(), angle=kp[:, 3].copy(), response=kp[:, 4].copy(), octave=octv, des=des)
+
+
+def sift_detect_many(images, workers: int = 2):
+    """sift_detect_and_compute for a list of images with `workers` contexts in flight (one host thread, stream and
+    pyramid block each): while one frame's key points are sorted on the host and its descriptors cross PCIe, the next
+    frame's pyramid is built.  Results are in the order of `images` and identical to the one-by-one calls."""
+    from concurrent.futures import ThreadPoolExecutor
+    images = list(images)
+    if workers <= 1 or len(images) <= 1:
+        return [sift_detect_and_compute(im) for im in images]
+    while len(_pool) < workers:                       # contexts (and their pyramid blocks) are kept between calls
+        _pool.append(_capi.Engine(_capi.NORM_HAMMING, 32, device))
+    free = queue.Queue()
+    for e in _pool[:workers]:
+        free.put(e)
+
+    def one(im):
+        eng = free.get()
+        try:
+            kp, octv, des = eng.sift_detect(to_gray(im))
+        finally:
+            free.put(eng)
+        return dict(pt=kp[:, 0:2].copy(), size=kp[:, 2].copy(), angle=kp[:, 3].copy(), response=kp[:, 4].copy(), octave=octv, des=des)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(one, images))
 
 
 def orb_detect_and_compute(image: np.ndarray, nfeatures: int = 500) -> dict:

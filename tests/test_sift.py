@@ -101,6 +101,18 @@ def test_gpu_sift_equals_oracle():
 
 
 @pytest.mark.gpu
+def test_gpu_sift_many_frames_in_flight_equal_one_by_one():
+    from imageanalysis_b200 import detector
+    g = load_golden("sift_reference.npz")
+    frames = [g["medium_image"], g["large_image"], g["small_image"], g["large_image"][::-1].copy(), g["medium_image"].T.copy()]
+    one = [detector.sift_detect_and_compute(f) for f in frames]
+    many = detector.sift_detect_many(frames, workers=3)
+    assert len(many) == len(one)
+    for a, b in zip(one, many):
+        assert all(np.array_equal(a[k], b[k]) for k in ("pt", "size", "angle", "response", "octave", "des"))
+
+
+@pytest.mark.gpu
 def test_gpu_sift_cv2_style_api_and_matching():
     """SIFT_create().detectAndCompute(img, None) -> (key points, float32 [N, 128]) and the descriptors feed the matcher:
     a shifted copy of the image matches back with the shift."""
