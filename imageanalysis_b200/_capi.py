@@ -514,7 +514,8 @@ class Engine:
         if bufs is None or bufs[0].shape[0] < cap:       # output arrays are kept between calls (no fresh page faults)
             bufs = self._sift_out = (np.empty((cap, 5), np.float32), np.empty((cap,), np.int32), np.empty((cap, 128), np.uint8))
         kp, octv, des = bufs
-        cap = kp.shape[0]
+        if max_out <= 0:
+            cap = kp.shape[0]
         n = C.c_int(0)
         self._check(self._lib.iam_sift_detect(self._h, _ptr(g), g.shape[1], g.shape[0], cap, _ptr(kp), _ptr(octv), _ptr(des),
                                               C.byref(n)), "iam_sift_detect")

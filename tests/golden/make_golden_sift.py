@@ -20,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import sift as S  # noqa: E402
 
-SIZES = {"small": (96, 128, 2.0), "medium": (240, 320, 2.0), "large": (384, 512, 2.0)}
+SIZES = {"small": (96, 128, 2.0), "medium": (240, 320, 2.0), "large": (384, 512, 2.0), "odd": (93, 127, 1.6), "tiny": (30, 40, 1.2)}
 
 
 def texture(h, w, sigma, seed):
@@ -29,7 +29,7 @@ def texture(h, w, sigma, seed):
     # a few large-scale blobs so that the upper octaves hold extrema as well
     yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
     for _ in range(6):
-        cy, cx, s, a = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(6, min(h, w) / 6), rng.uniform(-25, 25)
+        cy, cx, s, a = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(min(6, min(h, w) / 8), max(6.5, min(h, w) / 6)), rng.uniform(-25, 25)
         f += a * np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * s * s))
     return cv2.normalize(f, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8)
 
@@ -45,7 +45,7 @@ def main():
         assert np.array_equal(des, np.rint(des)) and des.min() >= 0 and des.max() <= 255
         out[name + "_image"], out[name + "_kp"], out[name + "_octave"], out[name + "_des"] = img, arr, octv, des.astype(np.uint8)
         print("%s %dx%d: %d key points, octaves %s" % (name, w, h, len(kp), sorted(set(((o & 255) ^ 128) - 128 for o in octv))))
-        if name != "large":
+        if name not in ("large",):
             k2, o2, d2 = S.detect_arrays(img)
             m = S.match_keypoints(arr, k2)
             ok = m >= 0

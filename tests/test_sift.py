@@ -24,7 +24,7 @@ def _check(kp, octv, des, kp_ref, octv_ref, des_ref, what, min_frac=0.99):
     assert abs(len(kp) - len(kp_ref)) <= max(2, len(kp_ref) // 100), (what, len(kp), len(kp_ref))
     m = S.match_keypoints(kp_ref, kp)
     ok = m >= 0
-    assert ok.mean() >= min_frac, (what, int(ok.sum()), len(kp_ref))
+    assert ok.sum() >= len(kp_ref) - max(1, int(np.ceil((1 - min_frac) * len(kp_ref)))), (what, int(ok.sum()), len(kp_ref))
     assert len(set(m[ok].tolist())) == int(ok.sum()), (what, "one key point matched twice")
     assert np.array_equal(octv_ref[ok] & 0xFFFF, octv[m[ok]] & 0xFFFF), what
     assert np.abs((octv_ref[ok] >> 16) - (octv[m[ok]] >> 16)).max() <= 1, what
@@ -49,18 +49,19 @@ def test_oracle_primitives():
     assert np.abs(a - np.array([0, 90, 180, 270, 45])).max() < 0.02
 
 
-def test_oracle_sift_equals_cv2_small():
+@pytest.mark.parametrize("name", ["small", "tiny"])
+def test_oracle_sift_equals_cv2_small(name):
     g = load_golden("sift_reference.npz")
-    kp, octv, des = S.detect_arrays(g["small_image"])
-    frac, same = _check(kp, octv, des, g["small_kp"], g["small_octave"], g["small_des"], "small")
-    assert frac == 1.0        # recorded by make_golden_sift.py: all 254 reproduced
+    kp, octv, des = S.detect_arrays(g[name + "_image"])
+    frac, same = _check(kp, octv, des, g[name + "_kp"], g[name + "_octave"], g[name + "_des"], name)
+    assert frac == 1.0        # recorded by make_golden_sift.py: all 254 / 39 reproduced
 
 
 def test_golden_is_well_formed():
     g = load_golden("sift_reference.npz")
-    for name in ("small", "medium", "large"):
+    for name in ("small", "medium", "large", "odd", "tiny"):
         kp, octv, des = g[name + "_kp"], g[name + "_octave"], g[name + "_des"]
-        assert len(kp) == len(octv) == len(des) > 100 and des.dtype == np.uint8
+        assert len(kp) == len(octv) == len(des) > 30 and des.dtype == np.uint8
         key = list(zip(kp[:, 0].tolist(), kp[:, 1].tolist(), (-kp[:, 2]).tolist(), kp[:, 3].tolist()))
         assert key == sorted(key)                  # cv2's order: x, y, size descending, angle
         layer = (octv >> 8) & 255
@@ -78,7 +79,7 @@ def test_make_detector_dispatch():
 
 # ------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["small", "medium", "large"])
+@pytest.mark.parametrize("name", ["small", "medium", "large", "odd", "tiny"])
 def test_gpu_sift_equals_cv2(name):
     from imageanalysis_b200 import detector
     g = load_golden("sift_reference.npz")
@@ -98,6 +99,24 @@ def test_gpu_sift_equals_oracle():
     kp = np.column_stack([r["pt"], r["size"], r["angle"], r["response"]]).astype(np.float32)
     ko, oo, do = S.detect_arrays(img)
     _check(kp, r["octave"], r["des"], ko, oo, do, "vs restatement", min_frac=0.995)
+
+
+@pytest.mark.gpu
+def test_gpu_sift_degenerate_inputs():
+    from imageanalysis_b200 import _capi, detector
+    eng = detector._eng()
+    for shape in ((2, 2), (5, 300), (300, 5), (11, 11), (16, 16)):          # too small for any extremum: empty result, no error
+        kp, octv, des = eng.sift_detect(np.random.default_rng(1).integers(0, 256, shape).astype(np.uint8))
+        assert kp.shape == (0, 5) and octv.shape == (0,) and des.shape == (0, 128)
+    with pytest.raises(_capi.IamError):
+        eng.sift_detect(np.zeros((1, 50), np.uint8))
+    with pytest.raises(_capi.IamError):
+        eng.sift_detect(np.zeros((4, 4, 3), np.uint8))
+    g = load_golden("sift_reference.npz")
+    with pytest.raises(_capi.IamError, match="key points"):                  # the caller's buffers are too small: loud, not truncated
+        eng.sift_detect(g["medium_image"], max_out=100)
+    kp, _, _ = eng.sift_detect(g["medium_image"])                            # the context is usable afterwards
+    assert abs(len(kp) - len(g["medium_kp"])) <= 15
 
 
 @pytest.mark.gpu
