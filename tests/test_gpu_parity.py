@@ -352,11 +352,15 @@ def test_match_images_one_call_equals_two_phase():
     assert (c2 == c3).all()
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "1:0.5", "1:0"])
 def test_match_images_host_narrowing(monkeypatch, mode):
     """float32 descriptors are narrowed to bytes on the host for transport (IAM_HOST_NARROW: 0 off, 1 adaptive,
     2 always): identical tables in every mode; a non-integer component is never narrowed away -- the call falls back
     to fp16 operands as it does without narrowing."""
+    frac = None
+    if ":" in mode:          # the planned split: this fraction of the images goes to the workers, the rest crosses as float32
+        mode, frac = mode.split(":")
+        monkeypatch.setenv("IAM_NARROW_FRACTION", frac)
     monkeypatch.setenv("IAM_HOST_NARROW", mode)
     des, _, _ = synth.sift_project(24, 700, seed=5)
     pairs = [(i, j) for i in range(24) for j in range(i + 1, min(24, i + 5))]
@@ -375,8 +379,11 @@ def test_match_images_host_narrowing(monkeypatch, mode):
             assert (t0[p, :c0[p]] == t1[p, :c1[p]]).all()
         if mode == "2" and (os.cpu_count() or 1) >= 2 and not os.environ.get("IAM_HOST_THREADS"):
             assert eng.timing().narrowed_images == 24 and eng.timing().h2d_bytes == 24 * 700 * 128
-        if mode == "0":
+        if mode == "0" or frac == "0":
             assert eng.timing().narrowed_images == 0 and eng.timing().h2d_bytes == 24 * 700 * 128 * 4
+        if frac == "0.5":
+            n = eng.timing().narrowed_images
+            assert n <= 12 and eng.timing().h2d_bytes == (n + 4 * (24 - n)) * 700 * 128
     eng.close()
     fl = [d.astype(np.float32) for d in des]
     fl[7][33, 5] += 0.5                       # not an integer: bytes cannot carry it
