@@ -1183,31 +1183,16 @@ int start_narrowing(iam_ctx* c, const Plan& pl, const int32_t* pairs, UploadFeed
     c->narrow_jobs.reset(new iam::NarrowJob[order.size()]);
     c->narrow_jobs_cap = (int)order.size();
   }
-  // Whether the workers take the images at all.  Narrowing trades host work (reads 4 bytes, writes 1 per element) for
-  // PCIe bytes; which one is scarce depends on the job.  A strip with 4 pairs per frame moves 2.6 MB of float32 per
-  // 32 us of matching: PCIe-bound without narrowing, and measured best with EVERY image narrowed (B200, 16 host
-  // threads, 1990 pairs: 99.9 k pairs/s; 85 % / 70 % / 50 % narrowed: 95.0 / 89.1 / 77.5 k -- float32 rows also cost
-  // a staging copy and a 2.5 x longer conversion kernel next to the matching kernel).  The 2812-frame survey (15 pairs
-  // per frame) is compute-bound either way (116.8 k pairs/s end to end with and without narrowing): when the float32
-  // rows cross PCIe in less than 0.85 of the estimated matching time the workers stay idle and the host cores stay
-  // free for the other ranks' processes.  IAM_NARROW_FRACTION=x overrides (the images sent as float32 are spread evenly
-  // over the order of first use); IAM_HOST_NARROW=2 (tests) narrows everything.
+  // Which images the workers take: all of them, unless IAM_NARROW_FRACTION=x (A/B aid) sends a share 1 - x as float32,
+  // spread evenly over the order of first use.  Measured on B200 (16 host threads): the 500-frame strip (4 pairs per
+  // frame, PCIe-bound without narrowing) does 99.9 k pairs/s end to end with every image narrowed and 95.0 / 89.1 /
+  // 77.5 k with 85 / 70 / 50 % -- float32 rows also cost a staging copy and a 2.5 x longer conversion kernel next to
+  // the matching kernel; the 2812-frame survey (15 pairs per frame, compute-bound) does 116.8 k either way.  When the
+  // workers cannot keep up (few host threads per rank) the enqueueing thread claims images for float32 upload as the
+  // bus runs dry (match_core), which splits the list between bus and workers where they meet.
   double frac = 1.0;
-  if (!feed->narrow_always) {
-    double cells = 0.0;
-    for (size_t ch = 0; ch + 1 < pl.chunk_pair_begin.size(); ++ch)
-      for (int p = pl.chunk_pair_begin[ch]; p < pl.chunk_pair_begin[ch + 1]; ++p) {
-        const int a = pairs[2 * p], b = pairs[2 * p + 1];
-        if (a >= 0 && b >= 0 && a < (int)c->images.size() && b < (int)c->images.size())
-          cells += double(std::max(c->images[a].n, 0)) * double(std::max(c->images[b].n, 0));
-      }
-    const double t_match = cells * (8.0e-6 / 25.0e6);          // s: 8 us per 5000 x 5000 pair (measured, kind::i8)
-    const double bw = 50.0e9;                                   // pinned H2D, one rank on its own link
-    const double f32_bytes = double(bytes) * 4.0;
-    frac = f32_bytes / bw <= 0.85 * t_match ? 0.0 : 1.0;
-    if (const char* env = getenv("IAM_NARROW_FRACTION")) frac = atof(env);
-    frac = std::min(1.0, std::max(0.0, frac));
-  }
+  if (const char* env = getenv("IAM_NARROW_FRACTION")) frac = std::min(1.0, std::max(0.0, atof(env)));
+  if (feed->narrow_always) frac = 1.0;
   size_t off = 0;
   double owed = 0.0;   // float32 uploads owed so far (error diffusion over the order of first use)
   for (size_t k = 0; k < order.size(); ++k) {
