@@ -588,22 +588,23 @@ __global__ void descriptor_seq_kernel(const float* __restrict__ base, Pyramid P,
 }
 
 // calcSIFTDescriptor, one WARP per key point.  The lanes share the (2 radius + 1)^2 window; the 8 tri-linear
-// contributions of every sample are added to the warp's histogram in shared memory as 64-bit fixed point (2^-40):
-// integer addition does not depend on the order the lanes arrive in, so the result is deterministic and equals the
-// exactly-rounded sum of the float contributions (OpenCV's sequential float sum carries ~1e-6 of rounding noise, which is
-// why descriptors agree to +-1 rather than bit for bit).  Lane 0 finishes with OpenCV's normalise / clip / quantise.
+// contributions of every sample are added to the warp's histogram in shared memory as fixed point (sixteenths in one
+// 32-bit counter, the exact remainder in units of 2^-24 in a second one: native 32-bit shared atomics, no CAS loop):
+// integer addition does not depend on the order the lanes arrive in, so the result is deterministic, and it is closer
+// to the true sum than OpenCV's sequential float sum (which carries ~1e-6 of rounding noise -- why descriptors agree
+// with cv2 to +-1 rather than bit for bit).  Lane 0 finishes with OpenCV's normalise / clip / quantise.
 constexpr int kDescWarps = 4;
 constexpr int kHistLen = 6 * 6 * 10;
 __global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const float* __restrict__ base, Pyramid P,
                                                                      const KeyOut* __restrict__ keys, int n_keys,
                                                                      uint8_t* __restrict__ des) {
-  __shared__ unsigned long long hist_s[kDescWarps][kHistLen];
+  __shared__ uint32_t hist_s[kDescWarps][2 * kHistLen];   // per bin: sixteenths, and the remainder in units of 2^-24
   __shared__ float fin_s[kDescWarps][kHistLen];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kDescWarps + warp;
   if (i >= n_keys) return;          // warp-uniform; no block-wide barrier below
-  unsigned long long* hq = hist_s[warp];
-  for (int k = lane; k < kHistLen; k += 32) hq[k] = 0ull;
+  uint32_t* hq = hist_s[warp];
+  for (int k = lane; k < 2 * kHistLen; k += 32) hq[k] = 0u;
   __syncwarp();
   const KeyOut kp = keys[i];
   const Octave O = P.oct[kp.o];
@@ -664,8 +665,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const float
         const float v011 = __fmul_rn(v_rc01, obin), v010 = __fsub_rn(v_rc01, v011);
         const float v001 = __fmul_rn(v_rc00, obin), v000 = __fsub_rn(v_rc00, v001);
         const int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
-        auto add = [&](int at, float v) {
-          atomicAdd(&hq[at], (unsigned long long)__float2ll_rn(__fmul_rn(v, 1099511627776.f)));   // * 2^40: exact
+        auto add = [&](int at, float v) {   // v = hi / 16 + rem exactly; both parts are native 32-bit shared atomics
+          const uint32_t hi = __float2uint_rd(__fmul_rn(v, 16.f));
+          const float rem = __fsub_rn(v, __fmul_rn((float)hi, 0.0625f));
+          atomicAdd(&hq[2 * at], hi);
+          atomicAdd(&hq[2 * at + 1], __float2uint_rn(__fmul_rn(rem, 16777216.f)));
         };
         add(idx, v000);
         add(idx + 1, v001);
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) descriptor_kernel(const float
   }
   __syncwarp();
   float* hist = fin_s[warp];
-  for (int k = lane; k < kHistLen; k += 32) hist[k] = __fmul_rn(__ll2float_rn((long long)hq[k]), 9.094947017729282e-13f);   // 2^-40
+  for (int k = lane; k < kHistLen; k += 32) hist[k] = (float)((double)hq[2 * k] * 0.0625 + (double)hq[2 * k + 1] * 5.9604644775390625e-08);
   __syncwarp();
   if (lane == 0) {
     float nrm2 = 0.f;
@@ -919,15 +923,40 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
       std::memcpy(&by, &hk[i].y, 4);
       sk[i] = {(uint64_t)bx << 32 | by, i};
     }
-    std::sort(sk.begin(), sk.end(), [&](const SortKey& a, const SortKey& b) {
-      if (a.xy != b.xy) return a.xy < b.xy;
-      const KeyOut &p = hk[a.idx], &q = hk[b.idx];
-      if (p.size != q.size) return p.size > q.size;
-      if (p.angle != q.angle) return p.angle < q.angle;
-      if (p.response != q.response) return p.response > q.response;
-      if (p.octave_field != q.octave_field) return p.octave_field > q.octave_field;
-      return a.idx < b.idx;
-    });
+    {
+      // LSD radix sort on the 64-bit key (four 16-bit digits, stable), then the few runs of equal (x, y) -- the extra
+      // orientations of one extremum -- by the remaining fields
+      std::vector<SortKey> tmp_sk(nk);
+      std::vector<uint32_t> hist(65536);
+      SortKey *src = sk.data(), *dst = tmp_sk.data();
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 16 * pass;
+        std::fill(hist.begin(), hist.end(), 0u);
+        for (int i = 0; i < nk; ++i) ++hist[(src[i].xy >> shift) & 0xFFFF];
+        uint32_t run = 0;
+        for (auto& hcount : hist) {
+          const uint32_t cnt = hcount;
+          hcount = run;
+          run += cnt;
+        }
+        for (int i = 0; i < nk; ++i) dst[hist[(src[i].xy >> shift) & 0xFFFF]++] = src[i];
+        std::swap(src, dst);
+      }                                     // four passes: the sorted list is back in sk
+      auto tie_less = [&](const SortKey& a, const SortKey& b) {
+        const KeyOut &p = hk[a.idx], &q = hk[b.idx];
+        if (p.size != q.size) return p.size > q.size;
+        if (p.angle != q.angle) return p.angle < q.angle;
+        if (p.response != q.response) return p.response > q.response;
+        if (p.octave_field != q.octave_field) return p.octave_field > q.octave_field;
+        return a.idx < b.idx;
+      };
+      for (int i = 0; i < nk;) {
+        int j = i + 1;
+        while (j < nk && sk[j].xy == sk[i].xy) ++j;
+        if (j - i > 1) std::sort(sk.begin() + i, sk.begin() + j, tie_less);
+        i = j;
+      }
+    }
     int n_out = 0;
     const KeyOut* last = nullptr;
     for (int i = 0; i < nk; ++i) {
