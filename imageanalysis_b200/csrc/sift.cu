@@ -792,7 +792,8 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
   const size_t o_tmp = up(off * sizeof(float)), o_src = o_tmp + up(base_px * sizeof(float));
   const size_t o_cand = o_src + up((size_t)w * h), o_keys = o_cand + up((size_t)cand_cap * sizeof(Cand));
   const size_t o_des = o_keys + up((size_t)key_cap * sizeof(KeyOut)), o_des2 = o_des + up((size_t)key_cap * 128);
-  const size_t o_cnt = o_des2 + up((size_t)key_cap * 128);
+  const size_t o_order = o_des2 + up((size_t)key_cap * 128);
+  const size_t o_cnt = o_order + up((size_t)key_cap * sizeof(int));
   const size_t total = o_cnt + 256;
   cudaError_t e;
 #define SC(call) \
@@ -974,7 +975,7 @@ int sift_detect(const uint8_t* gray, int w, int h, int max_out, float* out_kp5, 
     }
     mark("host sort + key point output");
     // descriptors leave the device already in the final order, straight into the caller's array
-    int* d_order = reinterpret_cast<int*>(d_cand);   // the candidate list is spent
+    int* d_order = reinterpret_cast<int*>(blk + o_order);
     SC(cudaMemcpyAsync(d_order, h_order, (size_t)n_out * sizeof(int), cudaMemcpyHostToDevice, stream));
     gather_rows_kernel<<<(n_out + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const uint32_t*>(d_des), d_order, n_out,
                                                            reinterpret_cast<uint32_t*>(d_des2));
