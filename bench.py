@@ -516,15 +516,29 @@ def run_pipeline(args):
         frames_host = [host_np[k] for k in range(T)]
         out_table = torch.empty((P, prm.cap, 2), dtype=torch.int32, pin_memory=True).numpy()
         out_count = torch.zeros((P,), dtype=torch.int32, pin_memory=True).numpy()
+        rows_cap = int(count.astype(np.int64).sum()) + 1024       # the filter only removes rows
+        out_rows = torch.empty((rows_cap, 2), dtype=torch.int32, pin_memory=True).numpy()
+        out_off = torch.empty((P + 1,), dtype=torch.int32, pin_memory=True).numpy()
+        out_res = torch.empty((2 * n_obs,), dtype=torch.float64, pin_memory=True).numpy()
+        out_jac = torch.empty((n_obs, 2, 10), dtype=torch.float64, pin_memory=True).numpy()
+
+        stage_ms = {}
 
         def step_e2e():
-            for f in touched:
-                eng.upload_keypoints(f, uv[f])
+            t = [time.perf_counter()]
+            eng.upload_keypoints_batch(touched, [uv[f] for f in touched])
+            t.append(time.perf_counter())
             eng.match_images(ids, frames_host, pairs, prm, out=(out_table, out_count))
+            t.append(time.perf_counter())
             _, _, inl = eng.ransac_tables(_capi.MODEL_ESSENTIAL, PIPE_K, tol, P, prm.cap, min_pairs=25, compact=True,
                                           want_model=False)
-            t2, c2 = eng.fetch_tables(P, prm.cap)
-            r, J = eng.ba_eval(ba["params"], ba["K4"], ba["dist"], jac=True)
+            t.append(time.perf_counter())
+            t2, c2 = eng.fetch_packed_tables(P, out_rows, out_off)    # the filtered match lists, compact (CSR)
+            t.append(time.perf_counter())
+            r, J = eng.ba_eval(ba["params"], ba["K4"], ba["dist"], jac=True, out=(out_res, out_jac))
+            t.append(time.perf_counter())
+            for name, a, b in zip(("upload_keypoints", "match_images", "ransac_tables", "fetch_packed_tables", "ba_eval"), t, t[1:]):
+                stage_ms[name] = (b - a) * 1e3          # host clock of the last step (every call blocks until its result is on the host)
             return inl, c2, r
         step_e2e()
         torch.cuda.synchronize()
@@ -538,11 +552,12 @@ def run_pipeline(args):
             torch.distributed.all_reduce(e_ms, op=torch.distributed.ReduceOp.MAX)
         tme = eng.timing()
         h2d = int(tme.h2d_bytes) + T * args.desc * 8 + ba["params"].nbytes
-        d2h = 2 * P * (prm.cap * 2 + 1) * 4 + P * 4 + n_obs * (2 + 20) * 8
+        d2h = P * (prm.cap * 2 + 1) * 4 + int(c2[-1]) * 8 + (P + 1) * 4 + P * 4 + n_obs * (2 + 20) * 8
         e2e = {"value": P_total * n_e / (float(e_ms.item()) / 1e3), "unit": "pairs/s", "ms_per_step": float(e_ms.item()) / n_e,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_ms_per_call_last_step": dict(stage_ms),
                "includes": "H2D of float32 descriptors (narrowed on the host), key points and BA parameters; D2H of the match "
-                           "tables before and after the RANSAC filter, inlier counts, BA residual and Jacobian blocks"}
+                           "tables (padded, as iam_match_images returns them), of the RANSAC-filtered match lists in compact form, "
+                           "inlier counts, BA residual and Jacobian blocks"}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -28,9 +28,9 @@ MODEL_ESSENTIAL, MODEL_HOMOGRAPHY, MODEL_FUNDAMENTAL, MODEL_AFFINE_PARTIAL = 0, 
 EXPORTS = (
     "iam_create", "iam_destroy", "iam_last_error", "iam_abi_version", "iam_set_stream",
     "iam_set_engine", "iam_synchronize", "iam_upload_descriptors",
-    "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
+    "iam_upload_descriptors_device", "iam_upload_keypoint_keys", "iam_upload_keypoints", "iam_upload_keypoints_batch", "iam_gms_filter", "iam_release_descriptors", "iam_num_descriptors",
     "iam_descriptors_exact", "iam_knn_pairs", "iam_match_pairs", "iam_match_pairs_device", "iam_match_images",
-    "iam_fetch_tables", "iam_pack_tables_device", "iam_ransac_pairs", "iam_ransac_tables", "iam_ba_calib_jacobian", "iam_triangulate_pairs", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
+    "iam_fetch_tables", "iam_pack_tables_device", "iam_fetch_packed_tables", "iam_ransac_pairs", "iam_ransac_tables", "iam_ba_calib_jacobian", "iam_triangulate_pairs", "iam_orb_detect", "iam_sift_detect", "iam_debug_orb_fast", "iam_set_profiling", "iam_get_timing", "iam_debug_tile",
     "iam_debug_minimal_solver", "iam_ba_setup", "iam_ba_eval", "iam_ba_upload_params", "iam_ba_eval_device",
     "iam_debug_ba_host", "iam_debug_narrow",
 )
@@ -129,6 +129,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_upload_descriptors_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
     lib.iam_upload_keypoint_keys.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.iam_upload_keypoints.argtypes = [vp, C.c_int, vp, C.c_int]
+    lib.iam_upload_keypoints_batch.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.iam_gms_filter.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, vp]
     lib.iam_release_descriptors.argtypes = [vp, C.c_int]
     lib.iam_num_descriptors.argtypes = [vp, C.c_int]
@@ -144,6 +145,7 @@ def load_library(path: Optional[str] = None):
     lib.iam_ransac_tables.argtypes = [vp, C.c_int, vp, C.c_double, C.c_double, C.c_int, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     lib.iam_orb_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_int)]
     lib.iam_ba_calib_jacobian.argtypes = [vp, vp, vp, vp]
+    lib.iam_fetch_packed_tables.argtypes = [vp, vp, C.c_longlong, vp, C.POINTER(C.c_longlong)]
     lib.iam_triangulate_pairs.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.iam_sift_detect.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.POINTER(C.c_int)]
     lib.iam_debug_orb_fast.argtypes = [vp, vp, C.c_int, C.c_int, vp]
@@ -256,6 +258,17 @@ class Engine:
         """xy: [N, 2] float32 pixel coordinates (cv2.KeyPoint.pt) for the GMS filter."""
         xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
         self._check(self._lib.iam_upload_keypoints(self._h, image_id, _ptr(xy), xy.shape[0]), "iam_upload_keypoints")
+
+    def upload_keypoints_batch(self, image_ids, xys):
+        """upload_keypoints for many images with one synchronisation (iam_upload_keypoints_batch)."""
+        ids = np.ascontiguousarray(image_ids, np.int32)
+        arrs = [np.ascontiguousarray(a, np.float32).reshape(-1, 2) for a in xys]
+        if len(arrs) != len(ids):
+            raise IamError("image_ids and xys differ in length")
+        n = len(arrs)
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data for a in arrs])
+        counts = np.ascontiguousarray([a.shape[0] for a in arrs], np.int32)
+        self._check(self._lib.iam_upload_keypoints_batch(self._h, n, _ptr(ids), ptrs, _ptr(counts)), "iam_upload_keypoints_batch")
 
     def gms_filter(self, xy1, xy2, matches, size, with_rotation=True, with_scale=False, threshold_factor=5.0,
                    archive_wrap=False):
@@ -378,6 +391,21 @@ class Engine:
         self._check(self._lib.iam_fetch_tables(self._h, _ptr(table), _ptr(count)), "iam_fetch_tables")
         return table, count
 
+    def fetch_packed_tables(self, n_pairs: int, rows_out: Optional[np.ndarray] = None, offsets_out: Optional[np.ndarray] = None):
+        """The last match call's tables in compact (CSR) form on the host (iam_fetch_packed_tables): (rows [total, 2],
+        offsets [n_pairs + 1]); pair p owns rows[offsets[p]:offsets[p + 1]].  rows_out / offsets_out: optional
+        caller-owned int32 arrays (page-locked ones make the download asynchronous inside the call)."""
+        off = offsets_out if offsets_out is not None else np.empty((n_pairs + 1,), np.int32)
+        tot = C.c_longlong(0)
+        if rows_out is None:
+            dr, do, total = self.pack_tables_device()
+            rows_out = np.empty((max(total, 1), 2), np.int32)
+        if rows_out.dtype != np.int32 or off.dtype != np.int32 or not rows_out.flags.c_contiguous or off.shape[0] < n_pairs + 1:
+            raise IamError("fetch_packed_tables wants C-contiguous int32 arrays (rows [cap, 2], offsets [n_pairs + 1])")
+        self._check(self._lib.iam_fetch_packed_tables(self._h, _ptr(rows_out), rows_out.shape[0], _ptr(off), C.byref(tot)),
+                    "iam_fetch_packed_tables")
+        return rows_out[:tot.value], off[:n_pairs + 1]
+
     def pack_tables_device(self) -> Tuple[int, int, int]:
         """Compact (CSR) form of the last match call's tables, left on the device (iam_pack_tables_device):
         returns (d_rows, d_offsets, total) -- raw pointers to int32 [total, 2] and int32 [n_pairs + 1]."""
@@ -405,16 +433,25 @@ class Engine:
                     "iam_ba_setup")
         self._ba_shape = (int(n_cam), int(n_pts), len(ci))
 
-    def ba_eval(self, params, K4, dist5, jac: bool = False):
-        """residual [2*n_obs] (and the Jacobian blocks [n_obs, 2, 10]) at `params` (cameras then points)."""
+    def ba_eval(self, params, K4, dist5, jac: bool = False, out=None):
+        """residual [2*n_obs] (and the Jacobian blocks [n_obs, 2, 10]) at `params` (cameras then points).
+        out: optional caller-owned (residual, jacobian) float64 arrays, e.g. page-locked ones."""
         n_cam, n_pts, n_obs = self._ba_shape
         p = np.ascontiguousarray(params, np.float64)
         if p.size < n_cam * 7 + n_pts * 3:
             raise IamError("parameter vector shorter than n_cam*7 + n_pts*3")
         k4 = np.ascontiguousarray(K4, np.float64)
         d5 = np.ascontiguousarray(dist5, np.float64)
-        res = np.empty(2 * n_obs, np.float64)
-        J = np.empty((n_obs, 2, 10), np.float64) if jac else None
+        if out is not None:
+            res, J = out
+            if (res.dtype != np.float64 or res.size != 2 * n_obs or not res.flags.c_contiguous or
+                    (jac and (J is None or J.dtype != np.float64 or J.size != n_obs * 20 or not J.flags.c_contiguous))):
+                raise IamError("out must be (float64 [2 n_obs], float64 [n_obs, 2, 10]) C-contiguous arrays")
+            if not jac:
+                J = None
+        else:
+            res = np.empty(2 * n_obs, np.float64)
+            J = np.empty((n_obs, 2, 10), np.float64) if jac else None
         self._check(self._lib.iam_ba_eval(self._h, _ptr(p), _ptr(k4), _ptr(d5), _ptr(res), _ptr(J)), "iam_ba_eval")
         return (res, J) if jac else res
 

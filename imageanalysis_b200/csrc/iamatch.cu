@@ -800,9 +800,7 @@ int iam_upload_keypoint_keys(iam_ctx* c, int id, const int32_t* keys, int n) {
   return IAM_OK;
 }
 
-int iam_upload_keypoints(iam_ctx* c, int id, const float* xy, int n) {
-  int rc = bind(c);
-  if (rc) return rc;
+static int upload_keypoints_one(iam_ctx* c, int id, const float* xy, int n, bool wait) {
   if (id < 0 || id > (1 << 24)) return fail(IAM_E_ARG, "bad image id %d", id);
   if (n < 0 || (n > 0 && !xy)) return fail(IAM_E_ARG, "bad keypoint buffer");
   if ((int)c->images.size() <= id) c->images.resize(id + 1);
@@ -821,10 +819,29 @@ int iam_upload_keypoints(iam_ctx* c, int id, const float* xy, int n) {
   im.kp_n = n;
   if (n > 0) {
     CU(cudaMemcpyAsync(im.kp, xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, c->up_stream));
-    CU(cudaStreamSynchronize(c->up_stream));
+    if (wait) CU(cudaStreamSynchronize(c->up_stream));
   }
   im.dev.kp_xy = (im.kp && im.kp_n == im.n) ? im.kp : nullptr;
   c->imgs_dirty = true;
+  return IAM_OK;
+}
+
+int iam_upload_keypoints(iam_ctx* c, int id, const float* xy, int n) {
+  int rc = bind(c);
+  if (rc) return rc;
+  return upload_keypoints_one(c, id, xy, n, true);
+}
+
+int iam_upload_keypoints_batch(iam_ctx* c, int n_images, const int32_t* ids, const float* const* xy, const int32_t* counts) {
+  int rc = bind(c);
+  if (rc) return rc;
+  if (n_images < 0 || (n_images > 0 && (!ids || !xy || !counts))) return fail(IAM_E_ARG, "bad arguments");
+  for (int i = 0; i < n_images; ++i)
+    if ((rc = upload_keypoints_one(c, ids[i], xy[i], counts[i], false)) != IAM_OK) {
+      cudaStreamSynchronize(c->up_stream);
+      return rc;
+    }
+  CU(cudaStreamSynchronize(c->up_stream));   // one wait for the whole batch: the caller's arrays are free again
   return IAM_OK;
 }
 
@@ -1450,6 +1467,18 @@ int iam_pack_tables_device(iam_ctx* c, void** d_rows, void** d_offsets, long lon
   *d_rows = c->csr_rows.p;
   *d_offsets = c->csr_off.p;
   *total = tot;
+  return IAM_OK;
+}
+
+int iam_fetch_packed_tables(iam_ctx* c, int32_t* out_rows, long long cap_rows, int32_t* out_offsets, long long* total) {
+  if (!out_offsets || !total || cap_rows < 0 || (cap_rows > 0 && !out_rows)) return fail(IAM_E_ARG, "bad arguments");
+  void *d_rows = nullptr, *d_off = nullptr;
+  int rc = iam_pack_tables_device(c, &d_rows, &d_off, total);
+  if (rc) return rc;
+  if (*total > cap_rows) return fail(IAM_E_UNSUPPORTED, "%lld match rows, the caller's array holds %lld", *total, cap_rows);
+  if (*total > 0) CU(cudaMemcpyAsync(out_rows, d_rows, size_t(*total) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out_offsets, d_off, size_t(c->last_pairs + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return IAM_OK;
 }
 

@@ -822,8 +822,7 @@ def _batched_traditional(image_list, todo):
         if eng is None:
             eng = the_matcher.engine(int(arrays[0].shape[1]))
         if gms_enabled:   # keypoint coordinates for the GMS stage (matcher.py:285); the descriptors follow inside the call
-            for i in new:
-                eng.upload_keypoints(i, np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2))
+            eng.upload_keypoints_batch(new, [np.float32([k.pt for k in image_list[i].kp_list]).reshape(-1, 2) for i in new])
         table, count = eng.match_images(new, arrays, np.int32([todo[p] for p in order[pos:end]]).reshape(-1, 2), prm, keys=keys)
         for k, p in enumerate(order[pos:end]):
             fwd = table[k, :count[k]].tolist()

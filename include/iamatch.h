@@ -141,6 +141,8 @@ int iam_knn_pairs(iam_ctx* ctx, const int32_t* pairs, int n_pairs, int k,
 /* Keypoint pixel coordinates (cv2.KeyPoint.pt, float32 xy interleaved, HOST) of an image whose
  * descriptors are resident; consumed by the GMS filter.  They stay until replaced or released. */
 int iam_upload_keypoints(iam_ctx* ctx, int image_id, const float* xy, int n);
+/* The same for many images with one synchronisation at the end: xy[i] = HOST float [counts[i]][2] of image ids[i]. */
+int iam_upload_keypoints_batch(iam_ctx* ctx, int n_images, const int32_t* ids, const float* const* xy, const int32_t* counts);
 
 /* Stand-alone GMS grid filter on one HOST match list: what
  * cv2.xfeatures2d.matchGMS((w,h), (w,h), kp1, kp2, matches, withRotation, withScale, thresholdFactor)
@@ -229,6 +231,11 @@ int iam_fetch_tables(iam_ctx* ctx, int32_t* out_table, int32_t* out_count);
  * tables: the per-pair results the reference stores with `i1.match_list[i2.name] = ...` (matcher.py:979-980)
  * are lists of very different lengths.  Pointers stay valid until the next call on this context. */
 int iam_pack_tables_device(iam_ctx* ctx, void** d_rows, void** d_offsets, long long* total);
+/* The same compact form on the HOST: out_rows [cap_rows][2] receives the *total valid rows back to back, out_offsets
+ * [n_pairs + 1] the prefix offsets (pair p owns rows offsets[p] .. offsets[p + 1]) -- the ragged `match_list` of
+ * matcher.py:979-980 without the padding of iam_fetch_tables (a few per cent to ~40 % of the padded bytes).
+ * IAM_E_UNSUPPORTED when cap_rows is too small (*total then holds the size needed). */
+int iam_fetch_packed_tables(iam_ctx* ctx, int32_t* out_rows, long long cap_rows, int32_t* out_offsets, long long* total);
 
 /* ---- RANSAC: replaces cv2.findEssentialMat(..., RANSAC, threshold) ---- */
 

@@ -278,6 +278,30 @@ def test_match_tables_equal_oracle(mode, cross):
     assert count[0] > 100 and count[3] < count[0] // 4   # neighbours match strongly, frames 4 apart barely
 
 
+def test_compact_tables_equal_padded_tables():
+    """iam_fetch_packed_tables / iam_pack_tables_device: the CSR form holds exactly the valid rows of the padded tables,
+    pair by pair; a too-small caller array is refused loudly with the size needed."""
+    des, _, _ = synth.sift_project(6, 900, seed=9)
+    pairs = [(0, 1), (1, 2), (0, 5), (2, 3), (3, 4), (4, 5), (0, 3)]
+    eng = _capi.Engine(_capi.NORM_L2, 128, 0)
+    for i, d in enumerate(des):
+        eng.upload(i, d)
+    prm = _capi.Engine.make_params(cross_check=True, min_pairs=25, cap=700)
+    eng.match_pairs_device(np.int32(pairs), prm)
+    table, count = eng.fetch_tables(len(pairs), prm.cap)
+    rows, off = eng.fetch_packed_tables(len(pairs))
+    assert off[0] == 0 and (np.diff(off) == count).all() and rows.shape == (int(count.sum()), 2) and count.max() > 100
+    for p in range(len(pairs)):
+        assert (rows[off[p]:off[p + 1]] == table[p, :count[p]]).all()
+    small = np.empty((10, 2), np.int32)
+    with pytest.raises(_capi.IamError, match="match rows"):
+        eng.fetch_packed_tables(len(pairs), rows_out=small)
+    big = np.empty((int(count.sum()) + 7, 2), np.int32)
+    rows2, off2 = eng.fetch_packed_tables(len(pairs), rows_out=big, offsets_out=np.empty(len(pairs) + 1, np.int32))
+    assert (rows2 == rows).all() and (off2 == off).all()
+    eng.close()
+
+
 def test_reduce_paths_small_sort_and_large_rank():
     """More than 8192 candidates per direction leaves the shared-memory sort for the
     rank-by-counting path; both must order exactly like Python's stable sorted()."""

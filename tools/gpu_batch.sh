@@ -1,6 +1,8 @@
-mkdir -p gpurun_out
-SK="up2_kernel|blur_rows|blur_cols|half_kernel|extrema_kernel|orientation_kernel|descriptor_kernel|gather_rows_kernel"
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"$SK" -c 400 --csv --log-file gpurun_out/launches_sift.csv python tools/sift_profile.py 2189 1459 2 > gpurun_out/ncu_sift.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"descriptor_kernel|orientation_kernel" -c 2 -f -o gpurun_out/sift_keypoint python tools/sift_profile.py 2189 1459 1 > gpurun_out/ncu_sift_full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"blur_cols_t|blur_rows_t|extrema_kernel" -s 8 -c 3 -f -o gpurun_out/sift_pyramid python tools/sift_profile.py 2189 1459 1 >> gpurun_out/ncu_sift_full.log 2>&1
-ls -la gpurun_out | tail -8
+#!/bin/bash
+# scratch: emulate the host-core budget of 8 ranks on 16 cores with 2 ranks on 4 cores, sweep the narrowing workers
+for t in 1 2 3; do
+  echo "== 4 cores, IAM_HOST_THREADS=$t"
+  IAM_HOST_THREADS=$t taskset -c 0-3 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2951$t \
+    bench.py --gpus 2 --steps 3 --warmup 3 --no-spot 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); e=d['e2e']; print(round(d['value']), round(e['value']), round(e['ms_per_step'],1), e['frames_narrowed_on_host'], e['h2d_bytes_per_step'], e['timeline_ms_rank0'])"
+done
