@@ -1103,7 +1103,11 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   c->narrowed_images = 0;
   feed.narrow_backward = c->narrow_pool && c->narrow_pool->backward();
   c->feed_mode = true;
-  c->reserve_sms = waves > 1 ? 8 : 0;
+  // SMs kept free of the matching kernel for the conversion kernels of later waves.  A strip (4 pairs per uploaded
+  // image) is upload-bound and wants 8 (4 / 6 / 12 reserved: 24.2 / 22.9 / 21.9 ms against 20.6); the survey job (15
+  // pairs per image) is compute-bound and runs 2.5 % faster end to end with 4 (361.3 -> 352.5 ms per 42 694 pairs;
+  // with 2 the conversions fall behind: the upload span grows from 104 to 298 ms).
+  c->reserve_sms = waves > 1 ? (n_images > 0 && n_pairs >= 8 * (long long)n_images ? 4 : 8) : 0;
   if (const char* env = getenv("IAM_RESERVE_SMS")) c->reserve_sms = waves > 1 ? std::max(0, atoi(env)) : 0;  // A/B aid
   rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr);
   c->feed_mode = false;
