@@ -775,6 +775,35 @@ def main():
                                device=dev, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(bytes_t)
+        # context: the same call fed with uint8 descriptors -- what this framework's own detector hands out
+        # (detector.SIFT_create(uint8_descriptors=True)); the headline e2e above keeps the reference's float32 arrays
+        u8_leg = None
+        if args.detector == "SIFT":
+            host_u8 = torch.empty((T, args.desc, 128), dtype=torch.uint8).pin_memory()
+            host_u8.numpy()[:] = host_np                    # integer-valued: exact
+            frames_u8 = [host_u8.numpy()[k] for k in range(T)]
+            sample = range(0, P, max(1, P // 64))
+            ref_count = np.array(count)                     # the float32 run's results (the output arrays are reused)
+            ref_rows = {p: np.array(table[p, :count[p]]) for p in sample}
+            frames_f32, frames_host = frames_host, frames_u8
+            step_e2e()
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_e):
+                table_u8, count_u8 = step_e2e()
+            torch.cuda.synchronize()
+            u_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(u_ms, op=torch.distributed.ReduceOp.MAX)
+            frames_host = frames_f32
+            same = bool(np.array_equal(count_u8, ref_count) and all(
+                np.array_equal(table_u8[p, :ref_count[p]], ref_rows[p]) for p in sample))
+            u8_leg = {"value": P_total * n_e / (float(u_ms.item()) / 1e3), "unit": "pairs/s", "ms_per_step": float(u_ms.item()) / n_e,
+                      "h2d_bytes_per_step_this_rank": int(eng.timing().h2d_bytes), "tables_equal_float32_run": same,
+                      "note": "context only: uint8 host descriptors as detector.SIFT_create(uint8_descriptors=True) returns them"}
+            del host_u8, frames_u8
         # context for the e2e number: what a bare pinned-host -> device copy of the same bytes costs on this box
         dst = torch.empty_like(host, device=dev)
         dst.copy_(host, non_blocking=True)
@@ -794,7 +823,7 @@ def main():
                "timeline_ms_rank0": {"host_enqueue": tme.host_enqueue_ms, "upload_span": tme.upload_span_ms,
                                      "compute_span": tme.compute_span_ms, "total_span": tme.total_span_ms,
                                      "waves": tme.waves},
-               "bare_h2d_gb_per_s_rank0": h2d / h2d_ms / 1e6,
+               "bare_h2d_gb_per_s_rank0": h2d / h2d_ms / 1e6, "uint8_input": u8_leg,
                "pair_order": "this rank's block sorted by the later frame of each pair (upload-friendly; tables returned in that order)",
                "includes": "H2D of every touched frame's float32 descriptors + conversion + matching + D2H of this rank's "
                            "tables" + (" + compact all-gather of all tables" if world > 1 else "")}
