@@ -802,6 +802,8 @@ def main():
                 np.array_equal(table_u8[p, :ref_count[p]], ref_rows[p]) for p in sample))
             u8_leg = {"value": P_total * n_e / (float(u_ms.item()) / 1e3), "unit": "pairs/s", "ms_per_step": float(u_ms.item()) / n_e,
                       "h2d_bytes_per_step_this_rank": int(eng.timing().h2d_bytes), "tables_equal_float32_run": same,
+                      "timeline_ms_rank0": {"host_enqueue": eng.timing().host_enqueue_ms, "upload_span": eng.timing().upload_span_ms,
+                                            "compute_span": eng.timing().compute_span_ms},
                       "note": "context only: uint8 host descriptors as detector.SIFT_create(uint8_descriptors=True) returns them"}
             del host_u8, frames_u8
         # context for the e2e number: what a bare pinned-host -> device copy of the same bytes costs on this box
