@@ -45,15 +45,16 @@ __device__ __forceinline__ void split_norm(float n, __half (&x)[4]) {
 }
 
 // One warp per row, 8 warps (one 8-row core-matrix group) per block.
+// `bx`: block index inside the image (the batched kernel below serves many images per launch).  src may alias raw
+// (a uint8 source copied straight to its final place): every thread reads its four bytes before it writes them.
 template <typename SrcT>
-__global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict__ src, int dim, int n, int n_pad,
-                                                         uint8_t* __restrict__ raw, uint8_t* __restrict__ a_form,
-                                                         uint8_t* __restrict__ b_form, int* __restrict__ meta,
-                                                         int* __restrict__ nrm_out, uint8_t* __restrict__ even_mask,
-                                                         int* __restrict__ ctx_flag) {
+__device__ __forceinline__ void convert_l2_body(const SrcT* src, int dim, int n, int n_pad, uint8_t* raw,
+                                                uint8_t* __restrict__ a_form, uint8_t* __restrict__ b_form,
+                                                int* __restrict__ meta, int* __restrict__ nrm_out,
+                                                uint8_t* __restrict__ even_mask, int* __restrict__ ctx_flag, int bx) {
   __shared__ int s_even[8];
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);  // n_pad is a multiple of 8: whole blocks only
+  const int r = bx * 8 + (threadIdx.x >> 5);  // n_pad is a multiple of 8: whole blocks only
   const bool valid = r < n;
 
   float v[4] = {0.f, 0.f, 0.f, 0.f};
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict_
       int m = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) m |= s_even[w] << w;
-      even_mask[blockIdx.x] = static_cast<uint8_t>(m);
+      even_mask[bx] = static_cast<uint8_t>(m);
     }
   }
 
@@ -153,13 +154,30 @@ __global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict_
 }
 
 
+template <typename SrcT>
+__global__ void __launch_bounds__(256) convert_l2_kernel(const SrcT* __restrict__ src, int dim, int n, int n_pad,
+                                                         uint8_t* __restrict__ raw, uint8_t* __restrict__ a_form,
+                                                         uint8_t* __restrict__ b_form, int* __restrict__ meta,
+                                                         int* __restrict__ nrm_out, uint8_t* __restrict__ even_mask,
+                                                         int* __restrict__ ctx_flag) {
+  convert_l2_body<SrcT>(src, dim, n, n_pad, raw, a_form, b_form, meta, nrm_out, even_mask, ctx_flag, blockIdx.x);
+}
+
+// One launch for a whole wave of uint8 images (iam_match_images): blockIdx.y = image, byte layout only.
+__global__ void __launch_bounds__(256) convert_l2_u8_batch_kernel(const ConvJob* __restrict__ jobs, int dim, int* __restrict__ ctx_flag) {
+  const ConvJob j = jobs[blockIdx.y];
+  if (static_cast<int>(blockIdx.x) * 8 >= j.n_pad) return;   // whole block: the body's barrier is safe
+  convert_l2_body<uint8_t>(j.src, dim, j.n, j.n_pad, j.raw, nullptr, nullptr, j.meta, j.nrm, reinterpret_cast<uint8_t*>(j.even_mask),
+                           ctx_flag, blockIdx.x);
+}
+
 // Byte layout (layout.h): 32 rows per block (one word of the even-norm mask), one warp per 4 rows.
 // rank(r) = #even rows before r                      (||r||^2 even)
 //         = #even rows in all + #odd rows before r   (odd)          -> stable partition, padding rows stay in place.
-__global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restrict__ raw, int dim, int n, int n_pad,
-                                                         const int* __restrict__ nrm, const uint32_t* __restrict__ even_mask,
-                                                         uint8_t* __restrict__ form, int* __restrict__ perm,
-                                                         int* __restrict__ rowc, int* __restrict__ meta) {
+__device__ __forceinline__ void convert_i8_body(const uint8_t* __restrict__ raw, int dim, int n, int n_pad,
+                                                const int* __restrict__ nrm, const uint32_t* __restrict__ even_mask,
+                                                uint8_t* __restrict__ form, int* __restrict__ perm,
+                                                int* __restrict__ rowc, int* __restrict__ meta, int bx) {
   __shared__ int s_before[8], s_total[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_words = n_pad >> 5;
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restri
   for (int w = threadIdx.x; w < n_words; w += 256) {
     const int c = __popc(even_mask[w]);
     total += c;
-    if (w < static_cast<int>(blockIdx.x)) before += c;
+    if (w < bx) before += c;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -185,12 +203,12 @@ __global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restri
     before += s_before[w];
     total += s_total[w];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) meta[kMetaNEven] = total;
-  const uint32_t word = even_mask[blockIdx.x];
+  if (bx == 0 && threadIdx.x == 0) meta[kMetaNEven] = total;
+  const uint32_t word = even_mask[bx];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int bit = warp * 4 + i;
-    const int r = blockIdx.x * 32 + bit;
+    const int r = bx * 32 + bit;
     const bool valid = r < n;
     const int ev_before = before + __popc(word & ((1u << bit) - 1u));
     const bool even = (word >> bit) & 1u;
@@ -226,6 +244,19 @@ __global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restri
       rowc[rank] = valid ? nrm[r] + 2 * kI8Cap : 0;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) convert_i8_kernel(const uint8_t* __restrict__ raw, int dim, int n, int n_pad,
+                                                         const int* __restrict__ nrm, const uint32_t* __restrict__ even_mask,
+                                                         uint8_t* __restrict__ form, int* __restrict__ perm,
+                                                         int* __restrict__ rowc, int* __restrict__ meta) {
+  convert_i8_body(raw, dim, n, n_pad, nrm, even_mask, form, perm, rowc, meta, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256) convert_i8_batch_kernel(const ConvJob* __restrict__ jobs, int dim) {
+  const ConvJob j = jobs[blockIdx.y];
+  if (static_cast<int>(blockIdx.x) * 32 >= j.n_pad) return;
+  convert_i8_body(j.raw, dim, j.n, j.n_pad, j.nrm, j.even_mask, j.form, j.perm, j.rowc, j.meta, blockIdx.x);
 }
 
 __global__ void __launch_bounds__(256) convert_hamming_kernel(const uint8_t* __restrict__ src, int nbytes, int n,
@@ -322,6 +353,15 @@ cudaError_t launch_convert(int norm, int raw_bytes, const void* src, int src_dty
     convert_hamming_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint8_t*>(src), raw_bytes, n, n_pad, raw,
                                                        a_form, b_form);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_convert_u8_batch(const ConvJob* d_jobs, int n_jobs, int max_n_pad, int raw_bytes, int* ctx_flag,
+                                    cudaStream_t stream) {
+  if (n_jobs <= 0 || max_n_pad <= 0) return cudaSuccess;
+  if (raw_bytes > 128 || (raw_bytes & 3) || n_jobs > 65535) return cudaErrorInvalidValue;
+  convert_l2_u8_batch_kernel<<<dim3(max_n_pad / 8, n_jobs), 256, 0, stream>>>(d_jobs, raw_bytes, ctx_flag);
+  convert_i8_batch_kernel<<<dim3(max_n_pad / 32, n_jobs), 256, 0, stream>>>(d_jobs, raw_bytes);
   return cudaGetLastError();
 }
 

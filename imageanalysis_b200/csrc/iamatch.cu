@@ -170,6 +170,10 @@ struct iam_ctx {
   unsigned long long h2d_bytes = 0;   // descriptor bytes copied host -> device by the current iam_match_images call
   int narrowed_images = 0;
   cudaEvent_t probe_ev[2] = {};  // last upload enqueued on each lane by iam_match_images
+  // batched conversion of a wave's uint8 images on the compute stream (iam_match_images)
+  Buffer conv_jobs_d;
+  iam::ConvJob* conv_jobs_h = nullptr;   // page-locked
+  int conv_jobs_cap = 0;
   cudaEvent_t span[4] = {};   // upload first/last, compute first/last of the last iam_match_images call
   bool span_pending = false;
   iam_timing timing{};
@@ -530,6 +534,8 @@ int iam_destroy(iam_ctx* c) {
   }
   c->narrow_pool.reset();
   if (c->narrow_arena) cudaFreeHost(c->narrow_arena);
+  if (c->conv_jobs_h) cudaFreeHost(c->conv_jobs_h);
+  c->conv_jobs_d.release();
   if (c->d_ctx_flag) cudaFree(c->d_ctx_flag);
   if (c->compute_done) cudaEventDestroy(c->compute_done);
   if (c->up_stream) cudaStreamDestroy(c->up_stream);
@@ -730,6 +736,43 @@ static int enqueue_upload(iam_ctx* c, int id, const void* src, bool src_on_host,
   if (c->feed_mode) CU(cudaEventRecord(c->probe_ev[lane2 ? 1 : 0], us));  // "has this lane run dry?" (host narrowing)
   im.seq = c->feed_mode ? 0 : ++c->up_seq;
   im.exact = (c->norm == IAM_NORM_L2 && dtype == IAM_DTYPE_F32) ? -1 : 1;  // resolved lazily (no sync per upload)
+  return IAM_OK;
+}
+
+// iam_match_images, uint8 source, byte layout: the rows are copied straight to their final place on an upload lane;
+// the conversion (norms, parity partition, byte form) is left to ONE batched launch per wave on the compute stream
+// (match_core), so that the matching kernel needs to leave no SMs free for per-image conversion kernels.
+static int enqueue_copy_u8(iam_ctx* c, int id, const void* src, iam::ConvJob* job) {
+  Image& im = c->images[id];
+  const int n = im.n, n_pad = im.n_pad;
+  const BlockLayout bl = block_layout(c, n_pad);
+  if (c->compute_pending) {  // WAR: kernels of the previous call may still read the operands we are about to replace
+    CU(cudaStreamWaitEvent(c->up_stream, c->compute_done, 0));
+    CU(cudaStreamWaitEvent(c->up_stream2, c->compute_done, 0));
+    c->compute_pending = false;
+  }
+  const bool lane2 = (c->up_rr++ & 1u) != 0u;
+  cudaStream_t us = lane2 ? c->up_stream2 : c->up_stream;
+  const size_t bytes = size_t(n) * c->desc_bytes;
+  CU(cudaMemsetAsync(im.block, 1, 2 * sizeof(int), us));   // flag words: non-zero = exact / byte layout usable
+  if (bytes) CU(cudaMemcpyAsync(im.block + bl.raw, src, bytes, cudaMemcpyHostToDevice, us));
+  c->h2d_bytes += bytes;
+  job->src = im.block + bl.raw;
+  job->raw = im.block + bl.raw;
+  job->meta = reinterpret_cast<int*>(im.block);
+  job->nrm = reinterpret_cast<int*>(im.block + bl.nrm);
+  job->even_mask = reinterpret_cast<uint32_t*>(im.block + bl.mask);
+  job->form = im.block + bl.i8_form;
+  job->perm = reinterpret_cast<int*>(im.block + bl.perm);
+  job->rowc = reinterpret_cast<int*>(im.block + bl.rowc);
+  job->n = n;
+  job->n_pad = n_pad;
+  im.has_wide = false;
+  im.has_i8 = true;
+  im.i8ok = -1;
+  CU(cudaEventRecord(c->probe_ev[lane2 ? 1 : 0], us));
+  im.seq = 0;
+  im.exact = 1;
   return IAM_OK;
 }
 
@@ -993,6 +1036,9 @@ struct UploadFeed {  // host-side sources for iam_match_images: enqueue an image
   iam::NarrowJob* jobs = nullptr;
   std::vector<int> job_of_slot;
   std::vector<cudaEvent_t> upload_waves;  // wave events of this call, in order (pacing of the enqueueing thread)
+  // uint8 rows go straight to their final place and are converted wave by wave on the compute stream
+  bool batch = false;
+  int conv_used = 0;      // jobs of earlier waves in conv_jobs_h / conv_jobs_d
 };
 
 int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_params* prm, int waves, UploadFeed* feed,
@@ -1108,6 +1154,28 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   // pairs per image) is compute-bound and runs 2.5 % faster end to end with 4 (361.3 -> 352.5 ms per 42 694 pairs;
   // with 2 the conversions fall behind: the upload span grows from 104 to 298 ms).
   c->reserve_sms = waves > 1 ? (n_images > 0 && n_pairs >= 8 * (long long)n_images ? 4 : 8) : 0;
+  // Batched conversion: when every image is expected to arrive as uint8 rows (native uint8 input, or float32 with
+  // enough narrowing workers to walk the list in order), the rows go straight to their final place and each wave is
+  // converted by two launches on the compute stream -- no per-image conversion kernels next to the matching kernel,
+  // so nothing is reserved for them.  IAM_BATCH_CONVERT=0 restores the per-image path (A/B aid).
+  feed.batch = c->norm == IAM_NORM_L2 && !wide && (dtype == IAM_DTYPE_U8 || (feed.narrow && c->narrow_pool && !feed.narrow_backward));
+  if (const char* env = getenv("IAM_BATCH_CONVERT")) feed.batch = feed.batch && atoi(env) != 0;
+  if (feed.batch) {
+    if (c->conv_jobs_cap < n_images) {
+      CU(cudaStreamSynchronize(c->up_stream));
+      if (c->conv_jobs_h) cudaFreeHost(c->conv_jobs_h);
+      c->conv_jobs_h = nullptr;
+      c->conv_jobs_cap = 0;
+      if (cudaHostAlloc(reinterpret_cast<void**>(&c->conv_jobs_h), size_t(n_images) * sizeof(iam::ConvJob), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        feed.batch = false;
+      } else {
+        c->conv_jobs_cap = n_images;
+      }
+    }
+    if (feed.batch) CU(c->conv_jobs_d.ensure(size_t(std::max(1, n_images)) * sizeof(iam::ConvJob)));
+    if (feed.batch) c->reserve_sms = 0;
+  }
   if (const char* env = getenv("IAM_RESERVE_SMS")) c->reserve_sms = waves > 1 ? std::max(0, atoi(env)) : 0;  // A/B aid
   rc = match_core(c, pairs, n_pairs, prm, waves, &feed, nullptr, nullptr);
   c->feed_mode = false;
@@ -1306,6 +1374,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
     if (p1 == p0) continue;
     if (feed) {  // enqueue the uploads this chunk is the first to need (upload stream; overlaps earlier chunks' kernels)
       bool any_upload = false;
+      int n_conv = 0, max_conv_pad = 0;   // images of this wave left to the batched conversion
       // With narrowing the enqueueing thread paces itself on the upload stream (at most two waves ahead): an image
       // is claimed for a float32 upload only when PCIe is about to run dry, which gives the workers time to get ahead.
       if (feed->narrow && feed->narrow_backward && !feed->narrow_always && feed->upload_waves.size() >= 2) CU(cudaEventSynchronize(feed->upload_waves[feed->upload_waves.size() - 2]));
@@ -1337,7 +1406,7 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
             while (st == iam::NarrowJob::kBusy || st == iam::NarrowJob::kFree) {
               // kFree is only still seen in forward order (the workers are about to reach this image): wait for
               // them while the bus has work queued, send the float32 rows as soon as it would run dry
-              if (st == iam::NarrowJob::kFree && cudaEventQuery(c->probe_ev[0]) == cudaSuccess &&
+              if (st == iam::NarrowJob::kFree && !feed->batch && cudaEventQuery(c->probe_ev[0]) == cudaSuccess &&
                   cudaEventQuery(c->probe_ev[1]) == cudaSuccess) {
                 int expect = iam::NarrowJob::kFree;
                 if (job.state.compare_exchange_strong(expect, iam::NarrowJob::kTaken, std::memory_order_acq_rel)) break;
@@ -1351,7 +1420,13 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
               c->narrowed_images++;
             }
           }
-          if ((rc = enqueue_upload(c, id, usrc, true, udtype, nullptr)) != IAM_OK) return rc;
+          if (feed->batch && udtype == IAM_DTYPE_U8 && feed->conv_used + n_conv < c->conv_jobs_cap) {
+            if ((rc = enqueue_copy_u8(c, id, usrc, &c->conv_jobs_h[feed->conv_used + n_conv])) != IAM_OK) return rc;
+            max_conv_pad = std::max(max_conv_pad, im.n_pad);
+            ++n_conv;
+          } else if ((rc = enqueue_upload(c, id, usrc, true, udtype, nullptr)) != IAM_OK) {
+            return rc;
+          }
           im.keys = keep;
           im.dev.kp_key = keep;
           if (hk && keep) CU(cudaMemcpyAsync(keep, hk, size_t(im.n) * sizeof(int), cudaMemcpyHostToDevice, c->up_stream));
@@ -1366,9 +1441,18 @@ int match_core(iam_ctx* c, const int32_t* pairs, int n_pairs, const iam_match_pa
         }
         CU(cudaEventRecord(c->lane2_ev, c->up_stream2));          // fold lane 2 into lane 1, then one event for both
         CU(cudaStreamWaitEvent(c->up_stream, c->lane2_ev, 0));
+        iam::ConvJob* d_jobs = c->conv_jobs_d.as<iam::ConvJob>() + feed->conv_used;
+        if (n_conv > 0)   // the wave's conversion jobs ride behind its rows
+          CU(cudaMemcpyAsync(d_jobs, c->conv_jobs_h + feed->conv_used, size_t(n_conv) * sizeof(iam::ConvJob), cudaMemcpyHostToDevice, c->up_stream));
         CU(cudaEventRecord(c->wave_ev[ch], c->up_stream));
         CU(cudaStreamWaitEvent(c->stream, c->wave_ev[ch], 0));
         feed->upload_waves.push_back(c->wave_ev[ch]);
+        if (n_conv > 0) {  // two launches convert the whole wave, on the stream (and all the SMs) of its matching kernel
+          cudaError_t ce = iam::launch_convert_u8_batch(d_jobs, n_conv, max_conv_pad, c->desc_bytes, c->d_ctx_flag, c->stream);
+          if (ce != cudaSuccess) return fail(IAM_E_CUDA, "batched convert launch: %s", cudaGetErrorString(ce));
+          c->timing.total_launches += 2;
+          feed->conv_used += n_conv;
+        }
       }
     } else if ((rc = wait_uploads(c, pairs, p0, p1)) != IAM_OK) {
       return rc;

@@ -35,6 +35,24 @@ struct I8Out {
   int* ctx_flag;        // optional context-wide sticky word, cleared when a row is not eligible
 };
 
+// One image of a batched byte-layout conversion (launch_convert_u8_batch); all device pointers.
+struct ConvJob {
+  const uint8_t* src;   // [n][raw_bytes] uint8 rows (may be `raw` itself: rows copied straight to their final place)
+  uint8_t* raw;         // [n_pad][raw_bytes]
+  int* meta;            // the image's flag words (pre-set non-zero)
+  int* nrm;
+  uint32_t* even_mask;
+  uint8_t* form;
+  int* perm;
+  int* rowc;
+  int n, n_pad;
+};
+
+// The byte-layout conversion of launch_convert(norm = L2, src_dtype = u8, wide forms skipped) for n_jobs images in
+// two launches (blockIdx.y = image).
+cudaError_t launch_convert_u8_batch(const ConvJob* d_jobs, int n_jobs, int max_n_pad, int raw_bytes, int* ctx_flag,
+                                    cudaStream_t stream);
+
 // Descriptor conversion: host-layout rows -> raw u8 rows + tiled operand forms.
 // src_dtype: 0 = u8, 1 = f32.  meta[kMetaExact] (pre-set non-zero) is cleared if any L2 component is not an
 // integer in [0,255]; with `i8`, meta[kMetaI8Ok] (pre-set non-zero) is cleared if a row is not eligible for the
