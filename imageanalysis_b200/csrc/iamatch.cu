@@ -1149,11 +1149,11 @@ int iam_match_images(iam_ctx* c, int n_images, const int32_t* image_ids, const v
   c->narrowed_images = 0;
   feed.narrow_backward = c->narrow_pool && c->narrow_pool->backward();
   c->feed_mode = true;
-  // SMs kept free of the matching kernel for the conversion kernels of later waves.  A strip (4 pairs per uploaded
-  // image) is upload-bound and wants 8 (4 / 6 / 12 reserved: 24.2 / 22.9 / 21.9 ms against 20.6); the survey job (15
-  // pairs per image) is compute-bound and runs 2.5 % faster end to end with 4 (361.3 -> 352.5 ms per 42 694 pairs;
-  // with 2 the conversions fall behind: the upload span grows from 104 to 298 ms).
-  c->reserve_sms = waves > 1 ? (n_images > 0 && n_pairs >= 8 * (long long)n_images ? 4 : 8) : 0;
+  // SMs kept free of the matching kernel for the per-image conversion kernels of later waves (the path float32 rows
+  // and few-worker ranks take): 8, measured on the upload-bound strip (4 / 6 / 12 reserved: 24.2 / 22.9 / 21.9 ms against
+  // 20.6) and the setting of the multi-GPU runs.  (A compute-bound single-GPU survey job ran 2.5 % faster with 4, but
+  // the upload span grew from 104 to 164 ms -- not something an upload-bound 8-rank job can afford.)
+  c->reserve_sms = waves > 1 ? 8 : 0;
   // Batched conversion: when every image is expected to arrive as uint8 rows (native uint8 input, or float32 with
   // enough narrowing workers to walk the list in order), the rows go straight to their final place and each wave is
   // converted by two launches on the compute stream -- no per-image conversion kernels next to the matching kernel,
